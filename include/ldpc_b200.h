@@ -1,0 +1,149 @@
+/*
+ * ldpc_b200.h -- C-ABI of the B200-native min-sum LDPC decoder (libldpc_b200.so).
+ *
+ * This is the drop-in boundary: the entry points below are what Coder::{forDecoder,
+ * addDecodeType, decode} bind instead of the reference's OpenCL host calls.  Plain pointers
+ * and sizes only -- no C++ types, no torch types, no exceptions cross this boundary.
+ * Every function returns LDPC_B200_OK (0) or a negative error code; ldpc_b200_last_error()
+ * gives the message for the calling thread.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with LDPC_B200_ERR_CUDA.
+ *
+ * Reference interfaces replaced (wing02/MyLdpcCppApi):
+ *   ldpc_b200_create          <- Coder::forDecoder edge tables + OpenCL context/queue/program
+ *                                + table upload              (MyLdpc.cpp:167-305)
+ *   ldpc_b200_set_max_iter    <- `times = 40` in the ctor    (MyLdpc.cpp:24)
+ *   ldpc_b200_reserve         <- Coder::addDecodeType(DecodeMS) buffer allocation
+ *                                                            (MyLdpc.cpp:387-437)
+ *   ldpc_b200_decode_host     <- Coder::decodeOnceMS: enqueueWriteBuffer, decodeInitMS,
+ *                                loop{refreshRMS, refreshPostPMS, checkResult, read flags,
+ *                                refreshQMS}, toChar, enqueueReadBuffer
+ *                                (MyLdpc.cpp:786-848; kernels decodeCL.c:88-199)
+ *   ldpc_b200_decode_device   <- the same with device-resident buffers (no PCIe leg)
+ *   ldpc_b200_destroy         <- Coder::~Coder / cl::Buffer RAII (MyLdpc.cpp:31-51)
+ *   ldpc_b200_synth_llr       <- Coder::test BPSK + AWGN          (MyLdpc.cpp:1061-1105)
+ *
+ * Decode semantics are those of Coder::decodeCPU (MyLdpc.cpp:684-784), per codeword:
+ * flooding min-sum in fp32, messages clamped at 1000, posterior accumulated from the channel
+ * value in ascending-row order, hard bit = !(posterior > 0), syndrome check after every
+ * iteration from 1, stop at `max_iter` inclusive; output = the first K hard bits packed
+ * LSB-first.  Input values are the raw channel samples (+1/-1 plus noise), as in the
+ * reference -- min-sum is scale-free.  NaN inputs are outside the contract.
+ */
+#ifndef LDPC_B200_H_
+#define LDPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldpc_b200_decoder *ldpc_b200_handle;
+
+enum {
+    LDPC_B200_OK = 0,
+    LDPC_B200_ERR_ARG = -1,         /* bad argument / malformed parity-check matrix */
+    LDPC_B200_ERR_CUDA = -2,        /* CUDA runtime failure or no device             */
+    LDPC_B200_ERR_UNSUPPORTED = -3, /* e.g. check degree above the packed-state limit */
+    LDPC_B200_ERR_NOMEM = -4
+};
+
+/* Which kernel family a handle uses (ldpc_b200_info.path). */
+enum {
+    LDPC_B200_PATH_LANE_SMEM = 0,  /* 32 codewords per CTA, lane = codeword, state in shared memory */
+    LDPC_B200_PATH_LANE_GLOBAL = 1,/* same schedule, state in a CTA-private L2/HBM workspace        */
+    LDPC_B200_PATH_CTA = 2         /* one codeword (group) per CTA, lane = check / variable         */
+};
+
+typedef struct ldpc_b200_info {
+    int M, N, K, nnz;
+    int max_row_weight, max_col_weight;
+    int max_iter, early_termination;
+    int device, sm_count;
+    int path;            /* LDPC_B200_PATH_* */
+    int threads_per_cta; /* launch shape                                            */
+    int ctas;            /* persistent grid size                                    */
+    int codewords_per_cta;
+    size_t smem_bytes;   /* dynamic shared memory per CTA                           */
+    size_t workspace_bytes;
+    size_t table_bytes;  /* device bytes of the check-major + variable-major tables */
+} ldpc_b200_info;
+
+/* Build a decoder for the M x N parity-check matrix given in CSR (row_ptr[M+1],
+ * col_idx[nnz]; each row's columns distinct).  K = number of leading (systematic) bits
+ * reported per codeword.  The edge order that fixes the fp32 summation order is
+ * (row, column) ascending, i.e. the order Eigen's RowMajor InnerIterator yields in the
+ * reference (MyLdpc.cpp:188-191).  `device` is the CUDA ordinal.                       */
+int ldpc_b200_create(ldpc_b200_handle *out, int M, int N, int K, const int32_t *row_ptr,
+                     const int32_t *col_idx, int device);
+
+/* Convenience: the reference's 802.16e code for (K, N, rate) -- rate is the reference's
+ * enum rate_type value 0..5 (MyLdpc.h:33-35); H as built by Coder::initCheckMatrix.     */
+int ldpc_b200_create_wimax(ldpc_b200_handle *out, int K, int N, int rate, int device);
+
+int ldpc_b200_destroy(ldpc_b200_handle h);
+
+int ldpc_b200_set_max_iter(ldpc_b200_handle h, int max_iter);        /* default 40, 1..65535 */
+/* 1 (default) = the reference's per-codeword syndrome stop; 0 = always run max_iter
+ * iterations (throughput runs; results then differ from the reference for words that
+ * would have converged earlier only in the iteration count and later posteriors).       */
+int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on);
+/* Force a kernel path (LDPC_B200_PATH_*) or -1 for automatic choice. */
+int ldpc_b200_set_path(ldpc_b200_handle h, int path);
+int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info *info);
+
+/* Copy the CSR of H back (for Coder::checkMatrix); arrays sized M+1 and nnz. */
+int ldpc_b200_get_csr(ldpc_b200_handle h, int32_t *row_ptr, int32_t *col_idx);
+
+/* Pre-allocate device staging for host-buffer decodes of up to `batch` codewords per
+ * chunk (what forDecoder(batchSize)/addDecodeType do in the reference).                 */
+int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch);
+
+/* Decode `ncw` codewords whose channel values already sit in device memory.
+ *   d_llr   : [ncw][N] float32, row-major (the reference's postCode layout)
+ *   d_info  : [ncw][ceil(K/8)] bytes, LSB-first (may be NULL)
+ *   d_hard  : [ncw][ceil(N/8)] bytes, all N hard bits LSB-first (may be NULL)
+ *   d_iters : [ncw] int32 iteration count at exit, 1..max_iter (may be NULL)
+ *   d_post  : [ncw][N] float32 posterior values lPostP (may be NULL)
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).    */
+int ldpc_b200_decode_device(ldpc_b200_handle h, const float *d_llr, int64_t ncw,
+                            uint8_t *d_info, uint8_t *d_hard, int32_t *d_iters,
+                            float *d_post, void *stream);
+
+/* Same with HOST buffers: chunks of the reserved batch are copied in, decoded and copied
+ * out on rotating streams so PCIe transfers overlap the kernels; returns when all outputs
+ * are in host memory.  Pinned buffers get full-speed async copies.                      */
+int ldpc_b200_decode_host(ldpc_b200_handle h, const float *llr, int64_t ncw, uint8_t *info,
+                          uint8_t *hard, int32_t *iters, float *post);
+
+/* Synthetic BPSK-AWGN channel on the device: y = (bit ? -1 : +1) + sigma * n, n ~ N(0,1)
+ * from a counter-based generator keyed by (seed, codeword, position).  d_bits: packed
+ * codeword bits [ncw][ceil(N/8)] LSB-first, or NULL for the all-zero codeword.          */
+int ldpc_b200_synth_llr(float *d_llr, int64_t ncw, int N, float sigma, uint64_t seed,
+                        const uint8_t *d_bits, int device, void *stream);
+
+/* Host-only helpers (no device needed).
+ * ldpc_b200_wimax_csr: H of the reference's 802.16e code as CSR; pass NULL arrays to query
+ * M and nnz first (row_ptr needs M+1 ints, col_idx nnz ints).
+ * ldpc_b200_edge_tables: the variable-major table the kernels use -- col_ptr[N+1] and
+ * vn_edge[nnz] = (check << 5) | position-in-check, per variable in ascending row order.  */
+int ldpc_b200_wimax_csr(int K, int N, int rate, int32_t *row_ptr, int32_t *col_idx, int *M, int *nnz);
+int ldpc_b200_edge_tables(int M, int N, const int32_t *row_ptr, const int32_t *col_idx,
+                          int32_t *col_ptr, uint32_t *vn_edge, int *max_row_weight,
+                          int *max_col_weight);
+
+/* Measurement aid: streams conflict-free 16-byte shared-memory loads on every SM and
+ * reports the achieved GB/s (the denominator of the on-chip roofline in bench.py).       */
+int ldpc_b200_probe_smem_bandwidth(int device, double *gbytes_per_s);
+
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
+int64_t ldpc_b200_launch_count(ldpc_b200_handle h);
+
+const char *ldpc_b200_last_error(void);
+const char *ldpc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDPC_B200_H_ */

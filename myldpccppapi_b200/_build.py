@@ -1,0 +1,86 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo).
+
+  libldpc_b200.so   -- sm_100a CUDA kernels + the extern "C" boundary (include/ldpc_b200.h)
+  libmyldpc_b200.so -- the drop-in C++ `Coder` class (include/MyLdpc.h) over that boundary
+"""
+from __future__ import annotations
+
+import os
+import pathlib
+import shutil
+import subprocess
+
+PKG = pathlib.Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libldpc_b200.so"
+CODER_LIB = PKG / "libmyldpc_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # never contract a*b+c: the posterior must round after every add
+    "--ftz=false", "--prec-div=true", "--prec-sqrt=true",
+    "-Xcompiler", "-fPIC,-O2,-fno-fast-math",
+    "-shared", "-cudart", "shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: pathlib.Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(pathlib.Path(s).stat().st_mtime > t for s in sources)
+
+
+def build_cuda(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> pathlib.Path:
+    srcs = [CSRC / "ldpc_b200.cu", CSRC / "ldpc_tables.cpp"]
+    deps = srcs + [CSRC / "ldpc_kernels.cuh", CSRC / "ldpc_tables.h", CSRC / "wimax_tables.h",
+                   ROOT / "include" / "ldpc_b200.h"]
+    if force or _stale(LIB, deps):
+        cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-o", str(LIB), *map(str, srcs)]
+        if ptxas_info:
+            cmd += ["-Xptxas", "-v"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode or ptxas_info:
+            print(" ".join(cmd))
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed for libldpc_b200.so")
+    return LIB
+
+
+def build_coder(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    src = CSRC / "mycoder.cpp"
+    if not src.exists():
+        return CODER_LIB
+    deps = [src, ROOT / "include" / "MyLdpc.h", ROOT / "include" / "ldpc_b200.h"]
+    if force or _stale(CODER_LIB, deps) or _stale(CODER_LIB, [LIB]):
+        cxx = shutil.which("g++") or "g++"
+        cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-I", str(ROOT / "include"), str(src),
+               "-o", str(CODER_LIB), "-L", str(PKG), "-lldpc_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(" ".join(cmd))
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise RuntimeError("g++ failed for libmyldpc_b200.so")
+    return CODER_LIB
+
+
+def build_all(force: bool = False, verbose: bool = False) -> None:
+    build_cuda(force=force, verbose=verbose)
+    build_coder(force=force, verbose=verbose)
+
+
+if __name__ == "__main__":
+    import sys
+    build_cuda(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
+    build_coder(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,511 @@
+// ldpc_b200.cu -- C-ABI (include/ldpc_b200.h) over the sm_100a kernels in ldpc_kernels.cuh.
+// Host side of what the reference does with cl::Context/CommandQueue/Buffer/Kernel in
+// Coder::forDecoder, addDecodeType and decodeOnceMS (MyLdpc.cpp:224-305, 387-437, 786-848).
+#include "../../include/ldpc_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ldpc_kernels.cuh"
+#include "ldpc_tables.h"
+
+using namespace ldpc_b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            return fail(LDPC_B200_ERR_CUDA,                                                       \
+                        std::string(#expr) + ": " + cudaGetErrorName(e__) + " (" + cudaGetErrorString(e__) + ")"); \
+        }                                                                                         \
+    } while (0)
+
+constexpr int kSlots = 3;          // rotating streams of the host-buffer pipeline
+constexpr int kCounterRing = 256;  // one work-queue head per in-flight launch
+
+struct Plan {
+    int path = LDPC_B200_PATH_LANE_SMEM;
+    int threads = 0;
+    int ctas = 0;
+    int cw_per_cta = 32;
+    size_t smem = 0;
+    size_t ws_stride = 0;  // floats per CTA (LANE_GLOBAL)
+};
+
+}  // namespace
+
+struct ldpc_b200_decoder {
+    HostTables host;
+    int K = 0;
+    int max_iter = 40;  // reference MyLdpc.cpp:24
+    int early = 1;
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int forced_path = -1;
+    Plan plan;
+    bool planned = false;
+
+    int32_t* d_row_ptr = nullptr;
+    uint32_t* d_cn_col = nullptr;
+    int32_t* d_col_ptr = nullptr;
+    uint32_t* d_vn_edge = nullptr;
+    size_t table_bytes = 0;
+
+    unsigned int* d_counters = nullptr;
+    int counter_next = 0;
+    float* d_ws = nullptr;
+    size_t ws_bytes = 0;
+    cudaEvent_t ws_event = nullptr;
+    bool ws_event_valid = false;
+
+    // host-buffer pipeline
+    int64_t reserved = 0;
+    cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+    float* s_llr[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* s_info[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* s_hard[kSlots] = {nullptr, nullptr, nullptr};
+    int32_t* s_iters[kSlots] = {nullptr, nullptr, nullptr};
+    float* s_post[kSlots] = {nullptr, nullptr, nullptr};
+
+    int64_t launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Pick the warp count that splits checks and variables of a 32-word group most evenly.
+int pick_lane_warps(int M, int N, int nnz) {
+    int best_w = 8;
+    double best = -1.0;
+    for (int w = 8; w <= 32; ++w) {
+        double cn = (double)M / w / ((M + w - 1) / w);
+        double vn = (double)N / w / ((N + w - 1) / w);
+        // issue-rate proxy: useful fraction of warp-slots (CN ~ 60 % of the work), scaled by the
+        // latency hiding more warps give
+        double eff = (0.6 * cn + 0.4 * vn) * (0.75 + 0.25 * w / 32.0);
+        if (eff > best + 1e-9) { best = eff; best_w = w; }
+    }
+    (void)nnz;
+    return best_w;
+}
+
+int make_plan(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    Plan pl;
+    const size_t state_bytes = ((size_t)2 * t.N + (size_t)3 * t.M) * kLanes * sizeof(float);
+    const size_t static_smem = 1024;  // s_group, s_flag + slack
+    int path = h->forced_path;
+    if (path < 0) path = (state_bytes + static_smem <= h->smem_optin) ? LDPC_B200_PATH_LANE_SMEM : LDPC_B200_PATH_LANE_GLOBAL;
+    if (path == LDPC_B200_PATH_LANE_SMEM) {
+        if (state_bytes + static_smem > h->smem_optin)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code too large for the shared-memory lane path");
+        pl.path = path;
+        pl.threads = 32 * pick_lane_warps(t.M, t.N, t.nnz);
+        pl.smem = state_bytes;
+        pl.ctas = h->sm_count;  // one persistent CTA per SM
+        pl.ws_stride = 0;
+    } else if (path == LDPC_B200_PATH_LANE_GLOBAL) {
+        pl.path = path;
+        pl.threads = 1024;
+        pl.smem = 0;
+        pl.ctas = h->sm_count;
+        pl.ws_stride = state_bytes / sizeof(float);
+    } else {
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "unknown kernel path");
+    }
+    h->plan = pl;
+    h->planned = true;
+    return LDPC_B200_OK;
+}
+
+int ensure_workspace(ldpc_b200_decoder* h) {
+    if (h->plan.path != LDPC_B200_PATH_LANE_GLOBAL) return LDPC_B200_OK;
+    const size_t need = h->plan.ws_stride * sizeof(float) * (size_t)h->plan.ctas;
+    if (h->ws_bytes >= need) return LDPC_B200_OK;
+    if (h->d_ws) { cudaFree(h->d_ws); h->d_ws = nullptr; h->ws_bytes = 0; }
+    CU_TRY(cudaMalloc(&h->d_ws, need));
+    h->ws_bytes = need;
+    return LDPC_B200_OK;
+}
+
+void free_slots(ldpc_b200_decoder* h) {
+    for (int s = 0; s < kSlots; ++s) {
+        cudaFree(h->s_llr[s]); h->s_llr[s] = nullptr;
+        cudaFree(h->s_info[s]); h->s_info[s] = nullptr;
+        cudaFree(h->s_hard[s]); h->s_hard[s] = nullptr;
+        cudaFree(h->s_iters[s]); h->s_iters[s] = nullptr;
+        cudaFree(h->s_post[s]); h->s_post[s] = nullptr;
+    }
+    h->reserved = 0;
+}
+
+int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
+                  int32_t* d_iters, float* d_post, cudaStream_t stream) {
+    if (ncw == 0) return LDPC_B200_OK;
+    if (!h->planned) {
+        int rc = make_plan(h);
+        if (rc) return rc;
+    }
+    int rc = ensure_workspace(h);
+    if (rc) return rc;
+    const Plan& pl = h->plan;
+    const HostTables& t = h->host;
+
+    DecodeParams p;
+    p.row_ptr = h->d_row_ptr;
+    p.cn_col = h->d_cn_col;
+    p.col_ptr = h->d_col_ptr;
+    p.vn_edge = h->d_vn_edge;
+    p.M = t.M; p.N = t.N; p.K = h->K;
+    p.max_iter = h->max_iter; p.early_term = h->early;
+    p.llr = d_llr; p.ncw = ncw;
+    p.info = d_info; p.hard = d_hard; p.iters = d_iters; p.post = d_post;
+    p.ws = h->d_ws; p.ws_stride = pl.ws_stride;
+    const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
+    if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
+    p.ngroups = (int)ngroups;
+    unsigned int* ctr = h->d_counters + h->counter_next;
+    h->counter_next = (h->counter_next + 1) % kCounterRing;
+    p.counter = ctr;
+    CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
+
+    const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+    if (pl.path == LDPC_B200_PATH_LANE_SMEM) {
+        CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        ldpc_ms_lane_kernel<true><<<grid, pl.threads, pl.smem, stream>>>(p);
+    } else {
+        // the workspace is shared by every launch of this handle: serialise launches on it
+        if (h->ws_event_valid) CU_TRY(cudaStreamWaitEvent(stream, h->ws_event, 0));
+        ldpc_ms_lane_kernel<false><<<grid, pl.threads, 0, stream>>>(p);
+        CU_TRY(cudaEventRecord(h->ws_event, stream));
+        h->ws_event_valid = true;
+    }
+    CU_TRY(cudaGetLastError());
+    h->launches += 1;
+    return LDPC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ldpc_b200_last_error(void) { return g_err.c_str(); }
+const char* ldpc_b200_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+
+int ldpc_b200_create(ldpc_b200_handle* out, int M, int N, int K, const int32_t* row_ptr, const int32_t* col_idx,
+                     int device) {
+    if (!out) return fail(LDPC_B200_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (K <= 0 || K > N) return fail(LDPC_B200_ERR_ARG, "K must be in 1..N");
+    ldpc_b200_decoder* h = new (std::nothrow) ldpc_b200_decoder();
+    if (!h) return fail(LDPC_B200_ERR_NOMEM, "out of host memory");
+    std::string msg = build_tables(M, N, row_ptr, col_idx, &h->host);
+    if (!msg.empty()) { delete h; return fail(LDPC_B200_ERR_ARG, msg); }
+    if (h->host.max_row_weight > kMaxCheckDegree) {
+        delete h;
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "check degree above 27 is not supported by the packed check state");
+    }
+    h->K = K;
+    h->device = device;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        delete h;
+        return fail(LDPC_B200_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                            " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) { delete h; return fail(LDPC_B200_ERR_ARG, "device ordinal out of range"); }
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete h; return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed"); }
+
+    auto cleanup_fail = [&](int code, const std::string& m) {
+        ldpc_b200_destroy(h);
+        return fail(code, m);
+    };
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+        return cleanup_fail(LDPC_B200_ERR_CUDA, "cudaDeviceGetAttribute(SM count) failed");
+    h->sm_count = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess)
+        return cleanup_fail(LDPC_B200_ERR_CUDA, "cudaDeviceGetAttribute(smem optin) failed");
+    h->smem_optin = (size_t)v;
+
+    const HostTables& t = h->host;
+    const size_t nnz1 = (size_t)std::max(t.nnz, 1);
+    bool ok = true;
+    ok = ok && cudaMalloc(&h->d_row_ptr, sizeof(int32_t) * (t.M + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_cn_col, sizeof(uint32_t) * nnz1) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_col_ptr, sizeof(int32_t) * (t.N + 1)) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_vn_edge, sizeof(uint32_t) * nnz1) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_counters, sizeof(unsigned int) * kCounterRing) == cudaSuccess;
+    if (!ok) return cleanup_fail(LDPC_B200_ERR_CUDA, std::string("cudaMalloc(tables): ") + cudaGetErrorString(cudaGetLastError()));
+    h->table_bytes = sizeof(int32_t) * (t.M + 1 + t.N + 1) + sizeof(uint32_t) * 2 * nnz1;
+    ok = ok && cudaMemcpy(h->d_row_ptr, t.row_ptr.data(), sizeof(int32_t) * (t.M + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_cn_col, t.col_idx.data(), sizeof(uint32_t) * t.nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_col_ptr, t.col_ptr.data(), sizeof(int32_t) * (t.N + 1), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(h->d_vn_edge, t.vn_edge.data(), sizeof(uint32_t) * t.nnz, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ws_event, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return cleanup_fail(LDPC_B200_ERR_CUDA, std::string("table upload: ") + cudaGetErrorString(cudaGetLastError()));
+    int rc = make_plan(h);
+    if (rc) { std::string m = g_err; return cleanup_fail(rc, m); }
+    *out = h;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_create_wimax(ldpc_b200_handle* out, int K, int N, int rate, int device) {
+    std::vector<int32_t> rp, ci;
+    int M = 0;
+    std::string msg = wimax_csr(K, N, rate, &rp, &ci, &M);
+    if (!msg.empty()) return fail(LDPC_B200_ERR_ARG, msg);
+    return ldpc_b200_create(out, M, N, K, rp.data(), ci.data(), device);
+}
+
+int ldpc_b200_destroy(ldpc_b200_handle h) {
+    if (!h) return LDPC_B200_OK;
+    {
+        DeviceGuard guard(h->device);
+        if (guard.ok) {
+            cudaDeviceSynchronize();
+            free_slots(h);
+            for (int s = 0; s < kSlots; ++s)
+                if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
+            cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
+            cudaFree(h->d_counters); cudaFree(h->d_ws);
+            if (h->ws_event) cudaEventDestroy(h->ws_event);
+        }
+    }
+    delete h;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_max_iter(ldpc_b200_handle h, int max_iter) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (max_iter < 1 || max_iter > 65535) return fail(LDPC_B200_ERR_ARG, "max_iter must be in 1..65535");
+    h->max_iter = max_iter;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    h->early = on ? 1 : 0;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_path(ldpc_b200_handle h, int path) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const int prev = h->forced_path;
+    h->forced_path = path;
+    int rc = make_plan(h);
+    if (rc) { h->forced_path = prev; make_plan(h); return rc; }
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info* info) {
+    if (!h || !info) return fail(LDPC_B200_ERR_ARG, "null argument");
+    const HostTables& t = h->host;
+    info->M = t.M; info->N = t.N; info->K = h->K; info->nnz = t.nnz;
+    info->max_row_weight = t.max_row_weight; info->max_col_weight = t.max_col_weight;
+    info->max_iter = h->max_iter; info->early_termination = h->early;
+    info->device = h->device; info->sm_count = h->sm_count;
+    info->path = h->plan.path; info->threads_per_cta = h->plan.threads; info->ctas = h->plan.ctas;
+    info->codewords_per_cta = h->plan.cw_per_cta;
+    info->smem_bytes = h->plan.smem;
+    info->workspace_bytes = h->plan.ws_stride * sizeof(float) * (size_t)h->plan.ctas;
+    info->table_bytes = h->table_bytes;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_get_csr(ldpc_b200_handle h, int32_t* row_ptr, int32_t* col_idx) {
+    if (!h || !row_ptr || !col_idx) return fail(LDPC_B200_ERR_ARG, "null argument");
+    std::memcpy(row_ptr, h->host.row_ptr.data(), sizeof(int32_t) * (h->host.M + 1));
+    std::memcpy(col_idx, h->host.col_idx.data(), sizeof(int32_t) * h->host.nnz);
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (batch < 1) return fail(LDPC_B200_ERR_ARG, "batch must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (batch <= h->reserved) return LDPC_B200_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    CU_TRY(cudaDeviceSynchronize());
+    free_slots(h);
+    const HostTables& t = h->host;
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    for (int s = 0; s < kSlots; ++s) {
+        if (!h->streams[s]) CU_TRY(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+        CU_TRY(cudaMalloc(&h->s_llr[s], sizeof(float) * (size_t)batch * t.N));
+        CU_TRY(cudaMalloc(&h->s_info[s], (size_t)batch * KB));
+        CU_TRY(cudaMalloc(&h->s_iters[s], sizeof(int32_t) * (size_t)batch));
+        CU_TRY(cudaMalloc(&h->s_hard[s], (size_t)batch * NB));
+    }
+    h->reserved = batch;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_decode_device(ldpc_b200_handle h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
+                            int32_t* d_iters, float* d_post, void* stream) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (ncw < 0) return fail(LDPC_B200_ERR_ARG, "ncw must be >= 0");
+    if (ncw > 0 && !d_llr) return fail(LDPC_B200_ERR_ARG, "d_llr is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    return launch_decode(h, d_llr, ncw, d_info, d_hard, d_iters, d_post, (cudaStream_t)stream);
+}
+
+int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                          int32_t* iters, float* post) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (ncw < 0) return fail(LDPC_B200_ERR_ARG, "ncw must be >= 0");
+    if (ncw == 0) return LDPC_B200_OK;
+    if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
+    const HostTables& t = h->host;
+    if (h->reserved == 0) {
+        // default chunk: a few waves of the persistent grid, bounded to ~256 MB of channel values
+        int64_t wave = (int64_t)h->plan.ctas * h->plan.cw_per_cta;
+        int64_t chunk = wave * 4;
+        const int64_t cap = std::max<int64_t>(wave, ((int64_t)256 << 20) / ((int64_t)t.N * 4) / wave * wave);
+        chunk = std::min(chunk, cap);
+        chunk = std::min(chunk, (ncw + wave - 1) / wave * wave);
+        int rc = ldpc_b200_reserve(h, chunk);
+        if (rc) return rc;
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    const int64_t chunk = h->reserved;
+    if (post) {
+        for (int s = 0; s < kSlots; ++s)
+            if (!h->s_post[s]) CU_TRY(cudaMalloc(&h->s_post[s], sizeof(float) * (size_t)chunk * t.N));
+    }
+    int slot = 0;
+    for (int64_t off = 0; off < ncw; off += chunk, slot = (slot + 1) % kSlots) {
+        const int64_t n = std::min(chunk, ncw - off);
+        cudaStream_t st = h->streams[slot];
+        CU_TRY(cudaMemcpyAsync(h->s_llr[slot], llr + (size_t)off * t.N, sizeof(float) * (size_t)n * t.N,
+                               cudaMemcpyHostToDevice, st));
+        int rc = launch_decode(h, h->s_llr[slot], n, info ? h->s_info[slot] : nullptr, hard ? h->s_hard[slot] : nullptr,
+                               iters ? h->s_iters[slot] : nullptr, post ? h->s_post[slot] : nullptr, st);
+        if (rc) return rc;
+        if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->s_info[slot], (size_t)n * KB, cudaMemcpyDeviceToHost, st));
+        if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->s_hard[slot], (size_t)n * NB, cudaMemcpyDeviceToHost, st));
+        if (iters) CU_TRY(cudaMemcpyAsync(iters + off, h->s_iters[slot], sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (post) CU_TRY(cudaMemcpyAsync(post + (size_t)off * t.N, h->s_post[slot], sizeof(float) * (size_t)n * t.N, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; ++s) CU_TRY(cudaStreamSynchronize(h->streams[s]));
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_synth_llr(float* d_llr, int64_t ncw, int N, float sigma, uint64_t seed, const uint8_t* d_bits, int device,
+                        void* stream) {
+    if (ncw < 0 || N <= 0) return fail(LDPC_B200_ERR_ARG, "bad size");
+    if (ncw == 0) return LDPC_B200_OK;
+    if (!d_llr) return fail(LDPC_B200_ERR_ARG, "d_llr is null");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
+    const long long total = (long long)ncw * N;
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
+    ldpc_synth_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_llr, total, N, sigma, seed, d_bits, 0);
+    CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+int64_t ldpc_b200_launch_count(ldpc_b200_handle h) { return h ? h->launches : 0; }
+
+int ldpc_b200_probe_smem_bandwidth(int device, double* gbytes_per_s) {
+    if (!gbytes_per_s) return fail(LDPC_B200_ERR_ARG, "null argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed (no CUDA device?)");
+    int sms = 0;
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    uint32_t* sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, sizeof(uint32_t) * sms));
+    const int smem = 65536, loops = 4096;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int rc = LDPC_B200_OK;
+    double best = 0.0;
+    do {
+        if (cudaFuncSetAttribute(ldpc_smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+            rc = fail(LDPC_B200_ERR_CUDA, "probe setup failed");
+            break;
+        }
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(a, 0);
+            ldpc_smem_probe_kernel<<<sms, 1024, smem, 0>>>(sink, loops);
+            cudaEventRecord(b, 0);
+            if (cudaEventSynchronize(b) != cudaSuccess) { rc = fail(LDPC_B200_ERR_CUDA, "probe kernel failed"); break; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            const double bytes = (double)sms * 1024.0 * 16.0 * 8.0 * loops;
+            if (rep > 0 && ms > 0.f) best = std::max(best, bytes / (ms * 1e-3) / 1e9);
+        }
+    } while (0);
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    cudaFree(sink);
+    *gbytes_per_s = best;
+    return rc;
+}
+
+int ldpc_b200_wimax_csr(int K, int N, int rate, int32_t* row_ptr, int32_t* col_idx, int* M_out, int* nnz_out) {
+    std::vector<int32_t> rp, ci;
+    int M = 0;
+    std::string msg = wimax_csr(K, N, rate, &rp, &ci, &M);
+    if (!msg.empty()) return fail(LDPC_B200_ERR_ARG, msg);
+    if (M_out) *M_out = M;
+    if (nnz_out) *nnz_out = (int)ci.size();
+    if (row_ptr) std::memcpy(row_ptr, rp.data(), sizeof(int32_t) * rp.size());
+    if (col_idx) std::memcpy(col_idx, ci.data(), sizeof(int32_t) * ci.size());
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_edge_tables(int M, int N, const int32_t* row_ptr, const int32_t* col_idx, int32_t* col_ptr,
+                          uint32_t* vn_edge, int* max_row_weight, int* max_col_weight) {
+    HostTables t;
+    std::string msg = build_tables(M, N, row_ptr, col_idx, &t);
+    if (!msg.empty()) return fail(LDPC_B200_ERR_ARG, msg);
+    if (col_ptr) std::memcpy(col_ptr, t.col_ptr.data(), sizeof(int32_t) * (N + 1));
+    if (vn_edge) std::memcpy(vn_edge, t.vn_edge.data(), sizeof(uint32_t) * t.nnz);
+    if (max_row_weight) *max_row_weight = t.max_row_weight;
+    if (max_col_weight) *max_col_weight = t.max_col_weight;
+    return LDPC_B200_OK;
+}
+
+}  // extern "C"

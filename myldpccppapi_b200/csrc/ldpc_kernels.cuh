@@ -1,0 +1,269 @@
+// ldpc_kernels.cuh -- sm_100a device code of the flooding min-sum decoder.
+//
+// Arithmetic contract (bit-exact with Coder::decodeCPU, reference MyLdpc.cpp:684-784):
+//   * check node (refreshRMS, decodeCL.c:126-147 / MyLdpc.cpp:705-721): for edge e of a row,
+//     R_e = (-1)^{xor of (Q_p<0), p != e} * min(1000, min_{p != e} |Q_p|).  Held here as the
+//     row's compressed state {min1, min2, argmin position, sign bits}; the exclude-self minimum
+//     is (pos == argmin ? min2 : min1), ties included (then min2 == min1).
+//   * variable node (refreshPostPMS, decodeCL.c:149-171 / MyLdpc.cpp:723-735):
+//     P_n = ((y_n + R_e1) + R_e2) + ... in ascending-row order, one fp32 rounding per add
+//     (__fadd_rn: never contracted, never reordered); hard bit = !(P_n > 0).
+//   * refreshQMS (decodeCL.c:175-186 / MyLdpc.cpp:757-762): Q_e = P_col(e) - R_e (__fsub_rn),
+//     evaluated lazily inside the next check-node pass.
+//   * checkResult (decodeCL.c:88-108 / MyLdpc.cpp:737-750): the syndrome of iteration t's hard
+//     decision is the xor of !(P>0) over each row -- computed for free while the next
+//     check-node pass gathers P, so a converged word costs one extra check pass instead of a
+//     separate syndrome pass every iteration.
+// y is canonicalised with y + 0.0f (-0.0 -> +0.0): then neither P nor Q can ever be -0.0 and the
+// sign bit of Q equals the reference's (Q < 0) test (see DESIGN.md "zero signs").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldpc_b200 {
+
+constexpr int kLanes = 32;
+constexpr float kClamp = 1000.0f;  // reference MyLdpc.cpp:708, decodeCL.c:134
+
+struct DecodeParams {
+    const int32_t* __restrict__ row_ptr;   // [M+1]
+    const uint32_t* __restrict__ cn_col;   // [nnz] column of edge e, check-major
+    const int32_t* __restrict__ col_ptr;   // [N+1]
+    const uint32_t* __restrict__ vn_edge;  // [nnz] (check << 5) | pos, variable-major, ascending row
+    int M, N, K, max_iter, early_term;
+    const float* __restrict__ llr;         // [ncw][N]
+    long long ncw;
+    uint8_t* info;                         // [ncw][ceil(K/8)] or null
+    uint8_t* hard;                         // [ncw][ceil(N/8)] or null
+    int32_t* iters;                        // [ncw] or null
+    float* post;                           // [ncw][N] or null
+    float* ws;                             // CTA-private global workspace (LANE_GLOBAL path)
+    size_t ws_stride;                      // floats per CTA
+    unsigned int* counter;                 // work-queue head, zeroed before launch
+    int ngroups;                           // ceil(ncw / 32)
+};
+
+// R_e rebuilt from a row's compressed state: magnitude by argmin position, sign from bit j.
+__device__ __forceinline__ float msg_from_state(float m1, float m2, uint32_t w, int j) {
+    const float mag = (j == (int)(w >> 27)) ? m2 : m1;
+    const uint32_t s = (w << (31 - j)) & 0x80000000u;
+    return __uint_as_float(__float_as_uint(mag) ^ s);
+}
+
+// ---------------------------------------------------------------------------------------
+// LANE kernels: one CTA decodes 32 codewords at a time, lane = codeword.  Every array is laid
+// out [index][lane], so each shared/global access of a warp is one conflict-free 128-byte row
+// and all index arithmetic is warp-uniform.  Warps split the checks (CN pass) and the variables
+// (VN pass) of those 32 words; two __syncthreads per iteration give the flooding schedule.
+//   P  [N][32]  posterior of the previous iteration (channel value before iteration 1)
+//   Y  [N][32]  channel values
+//   M1 [M][32], M2 [M][32], SW [M][32]  compressed check state (clamped min1/min2, signs|argmin)
+// SMEM=true keeps all five in shared memory ((2N+3M)*128 B); SMEM=false keeps them in a
+// CTA-private slice of a global workspace (any code size; L2/HBM-bound).
+// ---------------------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_group;
+    __shared__ uint32_t s_flag[2][kLanes];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int W = blockDim.x >> 5;
+    const int M = p.M, N = p.N;
+
+    float* base = SMEM ? reinterpret_cast<float*>(smem_raw) : (p.ws + (size_t)blockIdx.x * p.ws_stride);
+    float* P = base;
+    float* Y = P + (size_t)N * kLanes;
+    float* M1 = Y + (size_t)N * kLanes;
+    float* M2 = M1 + (size_t)M * kLanes;
+    uint32_t* SW = reinterpret_cast<uint32_t*>(M2 + (size_t)M * kLanes);
+
+    for (;;) {
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int g = s_group;
+        if (g >= p.ngroups) break;
+
+        const long long cw = (long long)g * kLanes + lane;
+        const bool active = cw < p.ncw;
+        const float* src = p.llr + (size_t)(active ? cw : 0) * N;
+
+        // ---- load: y -> Y and P (decodeInitMS, decodeCL.c:113-124: Q_e = y[col(e)], i.e. R = 0)
+        if ((N & 3) == 0) {
+            for (int n4 = warp; n4 < (N >> 2); n4 += W) {
+                float4 v = active ? __ldg(reinterpret_cast<const float4*>(src) + n4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float y = __fadd_rn(vv[k], 0.0f);
+                    const int a = (n4 * 4 + k) * kLanes + lane;
+                    P[a] = y;
+                    Y[a] = y;
+                }
+            }
+        } else {
+            for (int n = warp; n < N; n += W) {
+                const float y = __fadd_rn(active ? __ldg(src + n) : 1.0f, 0.0f);
+                P[n * kLanes + lane] = y;
+                Y[n * kLanes + lane] = y;
+            }
+        }
+        for (int c = warp; c < M; c += W) {
+            M1[c * kLanes + lane] = 0.0f;
+            M2[c * kLanes + lane] = 0.0f;
+            SW[c * kLanes + lane] = 0u;
+        }
+        if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+        __syncthreads();
+
+        bool done = !active;
+        int my_iters = 0;
+        int iter = 0;
+        for (;;) {
+            // ---- check-node pass (refreshQMS folded in) + syndrome of the previous posterior
+            uint32_t unsat = 0u;
+            for (int c = warp; c < M; c += W) {
+                const int e0 = __ldg(p.row_ptr + c);
+                const int dc = __ldg(p.row_ptr + c + 1) - e0;
+                const int si = c * kLanes + lane;
+                const float m1o = M1[si], m2o = M2[si];
+                const uint32_t wo = SW[si];
+                const int idxo = (int)(wo >> 27);
+                float m1 = INFINITY, m2 = INFINITY;
+                uint32_t sg = 0u, idx = 0u, syn = 0u;
+#pragma unroll 4
+                for (int j = 0; j < dc; ++j) {
+                    const uint32_t col = __ldg(p.cn_col + e0 + j);
+                    const float pv = P[col * kLanes + lane];
+                    const float mag = (j == idxo) ? m2o : m1o;
+                    const float r = __uint_as_float(__float_as_uint(mag) ^ ((wo << (31 - j)) & 0x80000000u));
+                    const float q = __fsub_rn(pv, r);
+                    syn ^= (pv > 0.0f) ? 0u : 1u;
+                    sg |= (__float_as_uint(q) >> 31) << j;
+                    const float a = fabsf(q);
+                    idx = (a < m1) ? (uint32_t)j : idx;
+                    m2 = fminf(m2, fmaxf(m1, a));
+                    m1 = fminf(m1, a);
+                }
+                const uint32_t mask = (dc >= 32) ? 0xffffffffu : ((1u << dc) - 1u);
+                const uint32_t sr = ((__popc(sg) & 1) ? ~sg : sg) & mask;
+                M1[si] = fminf(m1, kClamp);
+                M2[si] = fminf(m2, kClamp);
+                SW[si] = sr | (idx << 27);
+                unsat |= syn;
+            }
+            const bool check = p.early_term && iter >= 1;
+            if (check && unsat) s_flag[iter & 1][lane] = 1u;  // same-value race, benign
+            __syncthreads();
+            if (check && !done && s_flag[iter & 1][lane] == 0u) { done = true; my_iters = iter; }
+            if (__all_sync(0xffffffffu, done)) break;  // identical in every warp
+            if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
+
+            // ---- variable-node pass: posterior in ascending-row order; frozen once a word is done
+            for (int n = warp; n < N; n += W) {
+                const int v0 = __ldg(p.col_ptr + n);
+                const int dv = __ldg(p.col_ptr + n + 1) - v0;
+                float acc = Y[n * kLanes + lane];
+                for (int k = 0; k < dv; ++k) {
+                    const uint32_t pk = __ldg(p.vn_edge + v0 + k);
+                    const int si = (int)(pk >> 5) * kLanes + lane;
+                    acc = __fadd_rn(acc, msg_from_state(M1[si], M2[si], SW[si], (int)(pk & 31u)));
+                }
+                if (!done) P[n * kLanes + lane] = acc;
+            }
+            ++iter;
+            if (iter == p.max_iter) {
+                if (!done) my_iters = iter;
+                break;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+
+        // ---- outputs (toChar, decodeCL.c:188-199: LSB-first packing of the first K hard bits)
+        if (p.info) {
+            const int KB = (p.K + 7) >> 3;
+            for (int b = warp; b < KB; b += W) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.K) v |= ((P[n * kLanes + lane] > 0.0f) ? 0u : 1u) << t;
+                }
+                if (active) p.info[(size_t)cw * KB + b] = (uint8_t)v;
+            }
+        }
+        if (p.hard) {
+            const int NB = (N + 7) >> 3;
+            for (int b = warp; b < NB; b += W) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < N) v |= ((P[n * kLanes + lane] > 0.0f) ? 0u : 1u) << t;
+                }
+                if (active) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
+            }
+        }
+        if (p.post && active) {
+            for (int n = warp; n < N; n += W) p.post[(size_t)cw * N + n] = P[n * kLanes + lane];
+        }
+        if (p.iters && warp == 0 && active) p.iters[cw] = my_iters;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Synthetic BPSK + AWGN channel (Coder::test, reference MyLdpc.cpp:1061-1078): bit 0 -> +1,
+// bit 1 -> -1, plus sigma * N(0,1).  Counter-based: element i of the stream depends only on
+// (seed, i), so any shard of any GPU generates the same floats for the same codeword index.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(256) ldpc_synth_llr_kernel(float* __restrict__ out, long long total, int N,
+                                                             float sigma, uint64_t seed,
+                                                             const uint8_t* __restrict__ bits, long long first_index) {
+    const int NB = (N + 7) >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const uint64_t h = splitmix64(seed ^ splitmix64((uint64_t)(i + first_index)));
+        const float u1 = ((float)((uint32_t)(h >> 40)) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+        const float u2 = (float)((uint32_t)(h & 0xFFFFFFu)) * (1.0f / 16777216.0f);     // [0,1)
+        const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        float s = 1.0f;
+        if (bits) {
+            const long long cw = i / N;
+            const int n = (int)(i - cw * N);
+            if ((bits[(size_t)cw * NB + (n >> 3)] >> (n & 7)) & 1) s = -1.0f;
+        }
+        out[i] = __fmaf_rn(sigma, g, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared-memory bandwidth probe (measurement aid for bench.py's on-chip roofline): every
+// thread streams conflict-free 16-byte loads from a 64 KB tile.  Bytes moved per launch =
+// gridDim.x * blockDim.x * 16 * 8 * loops.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) ldpc_smem_probe_kernel(uint32_t* __restrict__ sink, int loops) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* buf = reinterpret_cast<uint4*>(smem_raw);
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);
+    __syncthreads();
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int l = 0; l < loops; ++l) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint4 v = buf[(threadIdx.x + k * 1024 + l * 32) & 4095];
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345u) sink[blockIdx.x] = acc.x;  // keep the loads alive
+}
+
+}  // namespace ldpc_b200

@@ -1,0 +1,92 @@
+// ldpc_tables.cpp -- see ldpc_tables.h
+#include "ldpc_tables.h"
+
+#include <algorithm>
+
+#include "wimax_tables.h"
+
+namespace ldpc_b200 {
+
+std::string build_tables(int M, int N, const int32_t* row_ptr, const int32_t* col_idx, HostTables* out) {
+    if (M <= 0 || N <= 0) return "M and N must be positive";
+    if (!row_ptr || !col_idx) return "null CSR pointer";
+    if (row_ptr[0] != 0) return "row_ptr[0] must be 0";
+    for (int r = 0; r < M; ++r)
+        if (row_ptr[r + 1] < row_ptr[r]) return "row_ptr must be non-decreasing";
+    const int nnz = row_ptr[M];
+    if ((uint64_t)M >= (1ull << (32 - kPosBits))) return "too many checks for the packed edge table";
+
+    HostTables& t = *out;
+    t.M = M; t.N = N; t.nnz = nnz;
+    t.row_ptr.assign(row_ptr, row_ptr + M + 1);
+    t.col_idx.assign(col_idx, col_idx + nnz);
+    t.col_ptr.assign(N + 1, 0);
+    t.max_row_weight = 0;
+    std::vector<int32_t> seen(N, -1);
+    for (int r = 0; r < M; ++r) {
+        t.max_row_weight = std::max(t.max_row_weight, row_ptr[r + 1] - row_ptr[r]);
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+            int c = col_idx[e];
+            if (c < 0 || c >= N) return "column index out of range";
+            if (seen[c] == r) return "duplicate (row, column) entry";
+            seen[c] = r;
+            t.col_ptr[c + 1]++;
+        }
+    }
+    t.max_col_weight = 0;
+    for (int c = 0; c < N; ++c) {
+        t.max_col_weight = std::max(t.max_col_weight, t.col_ptr[c + 1]);
+        t.col_ptr[c + 1] += t.col_ptr[c];
+    }
+    // Counting sort by column, stable in edge id => each variable's list is in ascending
+    // edge id, the order of the reference's hColFirstPtr/hColNextPtr walk.
+    t.vn_edge.assign(nnz, 0);
+    std::vector<int32_t> fill(t.col_ptr.begin(), t.col_ptr.end() - 1);
+    for (int r = 0; r < M; ++r) {
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+            int pos = e - row_ptr[r];
+            uint32_t packed = ((uint32_t)r << kPosBits) | (uint32_t)(pos & ((1 << kPosBits) - 1));
+            t.vn_edge[fill[col_idx[e]]++] = packed;
+        }
+    }
+    return std::string();
+}
+
+std::string wimax_csr(int K, int N, int rate, std::vector<int32_t>* row_ptr, std::vector<int32_t>* col_idx, int* M_out) {
+    const int8_t* base = nullptr;
+    int brows = 0;
+    switch (rate) {
+        case 0: base = &kBase_1_2[0][0];   brows = 12; break;
+        case 1: base = &kBase_2_3_A[0][0]; brows = 8;  break;
+        case 2: base = &kBase_2_3_B[0][0]; brows = 8;  break;
+        case 3: base = &kBase_3_4_A[0][0]; brows = 6;  break;
+        case 4: base = &kBase_3_4_B[0][0]; brows = 6;  break;
+        case 5: base = &kBase_5_6[0][0];   brows = 4;  break;
+        default: return "rate must be 0..5 (rate_1_2 .. rate_5_6)";
+    }
+    if (N <= 0 || N % kBaseCols != 0) return "N must be a positive multiple of 24";
+    const int z = N / kBaseCols;
+    const int M = brows * z;
+    if (K != N - M) return "K does not match N and the rate (K must equal N - rows*z)";
+    row_ptr->assign(1, 0);
+    col_idx->clear();
+    std::vector<int32_t> cols;
+    for (int br = 0; br < brows; ++br) {
+        for (int r = 0; r < z; ++r) {
+            cols.clear();
+            for (int bc = 0; bc < kBaseCols; ++bc) {
+                int p = base[br * kBaseCols + bc];
+                if (p < 0) continue;
+                int shift = (rate != 1) ? (p * z / 96) : (p % z);
+                cols.push_back(bc * z + (r + shift) % z);
+            }
+            // one entry per block column and blocks are disjoint column ranges => already ascending
+            col_idx->insert(col_idx->end(), cols.begin(), cols.end());
+            row_ptr->push_back((int32_t)col_idx->size());
+        }
+    }
+    *M_out = M;
+    return std::string();
+}
+
+}  // namespace ldpc_b200

@@ -1,0 +1,255 @@
+"""Host-side Python front-end of the C-ABI: a handle class plus a mirror of the reference's
+`Coder` decode interface (same method names, argument meaning and size rules as
+reference MyLdpc.h:104-129 / MyLdpc.cpp:571-631), so the parity tests read like Test.cpp.
+
+torch is used only for device memory and streams; all compute happens inside
+libldpc_b200.so.  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import Info, LdpcError, check
+
+# enum rate_type / decodeType, reference MyLdpc.h:33-39
+rate_1_2, rate_2_3_a, rate_2_3_b, rate_3_4_a, rate_3_4_b, rate_5_6 = range(6)
+DecodeCPU, DecodeMS, DecodeSP, DecodeTDMP, DecodeTDMPCL, DecodeMSCL = range(6)
+RATE_BY_NAME = {"1/2": 0, "2/3A": 1, "2/3B": 2, "3/4A": 3, "3/4B": 4, "5/6": 5}
+
+
+def wimax_csr(K: int, N: int, rate: int):
+    """H of the reference's 802.16e code (Coder::initCheckMatrix) as (row_ptr, col_idx, M)."""
+    L = _lib.load()
+    M, nnz = C.c_int(), C.c_int()
+    check(L.ldpc_b200_wimax_csr(K, N, rate, None, None, C.byref(M), C.byref(nnz)))
+    rp = np.zeros(M.value + 1, dtype=np.int32)
+    ci = np.zeros(nnz.value, dtype=np.int32)
+    check(L.ldpc_b200_wimax_csr(K, N, rate, rp.ctypes.data, ci.ctypes.data, C.byref(M), C.byref(nnz)))
+    return rp, ci, M.value
+
+
+def edge_tables(M: int, N: int, row_ptr, col_idx):
+    """(col_ptr, vn_edge, max_row_weight, max_col_weight) as the kernels use them."""
+    L = _lib.load()
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+    cp = np.zeros(N + 1, dtype=np.int32)
+    ve = np.zeros(max(ci.size, 1), dtype=np.uint32)
+    rw, cw = C.c_int(), C.c_int()
+    check(L.ldpc_b200_edge_tables(M, N, rp.ctypes.data, ci.ctypes.data, cp.ctypes.data, ve.ctypes.data,
+                                  C.byref(rw), C.byref(cw)))
+    return cp, ve[:ci.size], rw.value, cw.value
+
+
+class Decoder:
+    """One decoder handle on one GPU (ldpc_b200_create / _destroy)."""
+
+    def __init__(self, M: int, N: int, K: int, row_ptr, col_idx, device: int = 0, max_iter: int = 40,
+                 early_termination: bool = True):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+        if rp.shape != (M + 1,):
+            raise ValueError("row_ptr must have M+1 entries")
+        check(self._L.ldpc_b200_create(C.byref(self._h), M, N, K, rp.ctypes.data, ci.ctypes.data, device))
+        self.M, self.N, self.K, self.device = M, N, K, device
+        self.KB, self.NB = (K + 7) // 8, (N + 7) // 8
+        check(self._L.ldpc_b200_set_max_iter(self._h, max_iter))
+        check(self._L.ldpc_b200_set_early_termination(self._h, 1 if early_termination else 0))
+
+    @classmethod
+    def wimax(cls, K: int, N: int, rate: int, device: int = 0, **kw) -> "Decoder":
+        rp, ci, M = wimax_csr(K, N, rate)
+        return cls(M, N, K, rp, ci, device=device, **kw)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.ldpc_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ---------------------------------------------------------------
+    def set_max_iter(self, n: int) -> None:
+        check(self._L.ldpc_b200_set_max_iter(self._h, n))
+
+    def set_early_termination(self, on: bool) -> None:
+        check(self._L.ldpc_b200_set_early_termination(self._h, 1 if on else 0))
+
+    def set_path(self, path: int) -> None:
+        check(self._L.ldpc_b200_set_path(self._h, path))
+
+    def reserve(self, batch: int) -> None:
+        check(self._L.ldpc_b200_reserve(self._h, batch))
+
+    def info(self) -> dict:
+        inf = Info()
+        check(self._L.ldpc_b200_get_info(self._h, C.byref(inf)))
+        return inf.asdict()
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.ldpc_b200_launch_count(self._h))
+
+    # -- decode ----------------------------------------------------------------------
+    def decode_device(self, llr, want_hard: bool = False, want_post: bool = False, want_iters: bool = True,
+                      out: Optional[dict] = None, stream=None):
+        """llr: CUDA float32 tensor [ncw, N] on this decoder's device.  Returns a dict of CUDA
+        tensors {info[ncw,KB] u8, iters[ncw] i32, hard[ncw,NB] u8, post[ncw,N] f32}.  Async."""
+        import torch
+
+        if not llr.is_cuda or llr.dtype != torch.float32 or not llr.is_contiguous():
+            raise ValueError("llr must be a contiguous CUDA float32 tensor")
+        if llr.device.index != self.device:
+            raise ValueError("llr lives on another device than this decoder")
+        ncw = llr.numel() // self.N
+        dev = llr.device
+        out = out if out is not None else {}
+        if "info" not in out:
+            out["info"] = torch.empty((ncw, self.KB), dtype=torch.uint8, device=dev)
+        if want_iters and "iters" not in out:
+            out["iters"] = torch.empty((ncw,), dtype=torch.int32, device=dev)
+        if want_hard and "hard" not in out:
+            out["hard"] = torch.empty((ncw, self.NB), dtype=torch.uint8, device=dev)
+        if want_post and "post" not in out:
+            out["post"] = torch.empty((ncw, self.N), dtype=torch.float32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+        check(self._L.ldpc_b200_decode_device(self._h, llr.data_ptr(), ncw, ptr("info"), ptr("hard"), ptr("iters"),
+                                              ptr("post"), C.c_void_p(st.cuda_stream)))
+        return out
+
+    def decode_host(self, llr: np.ndarray, want_hard: bool = False, want_post: bool = False, out: Optional[dict] = None):
+        """llr: host float32 array/tensor [ncw, N] (pinned memory gives full-speed copies).
+        Returns numpy arrays {info, iters, hard?, post?}.  Blocking."""
+        a = _as_host_array(llr, np.float32)
+        ncw = a.size // self.N
+        out = out if out is not None else {}
+        if "info" not in out:
+            out["info"] = np.empty((ncw, self.KB), dtype=np.uint8)
+        if "iters" not in out:
+            out["iters"] = np.empty((ncw,), dtype=np.int32)
+        if want_hard and "hard" not in out:
+            out["hard"] = np.empty((ncw, self.NB), dtype=np.uint8)
+        if want_post and "post" not in out:
+            out["post"] = np.empty((ncw, self.N), dtype=np.float32)
+        ptr = lambda k: _host_ptr(out[k]) if k in out else None  # noqa: E731
+        check(self._L.ldpc_b200_decode_host(self._h, _host_ptr(a), ncw, ptr("info"), ptr("hard"), ptr("iters"), ptr("post")))
+        return out
+
+
+def _as_host_array(x, dtype):
+    if hasattr(x, "data_ptr"):  # torch CPU tensor (possibly pinned)
+        if x.is_cuda:
+            raise ValueError("expected a host tensor")
+        return x.contiguous()
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def _host_ptr(x):
+    return x.data_ptr() if hasattr(x, "data_ptr") else x.ctypes.data
+
+
+def synth_llr(ncw: int, N: int, sigma: float, seed: int, device: int = 0, bits=None, out=None):
+    """BPSK + AWGN channel values generated on the GPU (ldpc_b200_synth_llr).  `bits`:
+    optional CUDA uint8 tensor [ncw, ceil(N/8)] of packed codeword bits (LSB first)."""
+    import torch
+
+    L = _lib.load()
+    dev = torch.device("cuda", device)
+    if out is None:
+        out = torch.empty((ncw, N), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev)
+    check(L.ldpc_b200_synth_llr(out.data_ptr(), ncw, N, float(sigma), int(seed) & (2**64 - 1),
+                                bits.data_ptr() if bits is not None else None, device, C.c_void_p(st.cuda_stream)))
+    return out
+
+
+class Coder:
+    """Python mirror of the reference's `class Coder` decode interface (MyLdpc.h:104-129).
+
+    coder = Coder(ldpcK, ldpcN, rate); coder.forDecoder(batchSize); coder.addDecodeType(DecodeMS)
+    coder.decode(postCode, srcCode, srcLength, DecodeMS)
+
+    Every decodeType is served by the CUDA min-sum decoder with Coder::decodeCPU's semantics
+    (DecodeCPU included: there is no CPU path in this package).  Returns 0 like the reference.
+    Additive: from_csr() for arbitrary H, setMaxIter(), lastIterations.
+    """
+
+    def __init__(self, ldpcK: int, ldpcN: int, rate: int, device: int = 0):
+        self.ldpcK, self.ldpcN, self.ldpcM, self.rate = ldpcK, ldpcN, ldpcN - ldpcK, rate
+        self.device = device
+        self.times = 40  # reference MyLdpc.cpp:24
+        self.row_ptr, self.col_idx, M = wimax_csr(ldpcK, ldpcN, rate)
+        assert M == self.ldpcM
+        self.batchSize = 0
+        self._dec: Optional[Decoder] = None
+        self.lastIterations = None
+
+    @classmethod
+    def from_csr(cls, M: int, N: int, K: int, row_ptr, col_idx, device: int = 0) -> "Coder":
+        self = cls.__new__(cls)
+        self.ldpcK, self.ldpcN, self.ldpcM, self.rate = K, N, M, None
+        self.device = device
+        self.times = 40
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        self.col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        self.batchSize = 0
+        self._dec = None
+        self.lastIterations = None
+        return self
+
+    # reference MyLdpc.cpp:167-305
+    def forDecoder(self, batchSize: int) -> int:
+        self.batchSize = int(batchSize)
+        self._dec = Decoder(self.ldpcM, self.ldpcN, self.ldpcK, self.row_ptr, self.col_idx, device=self.device,
+                            max_iter=self.times)
+        return 0
+
+    # reference MyLdpc.cpp:307-552
+    def addDecodeType(self, deType: int) -> int:
+        if self._dec is None:
+            raise LdpcError(-1, "forDecoder must be called before addDecodeType")
+        if self.batchSize > 0:
+            self._dec.reserve(self.batchSize)
+        return 0
+
+    def setMaxIter(self, times: int) -> None:
+        self.times = int(times)
+        if self._dec is not None:
+            self._dec.set_max_iter(self.times)
+
+    # reference MyLdpc.cpp:620-631
+    def getCodeSize(self, srcLength: int) -> int:
+        return (srcLength + (self.ldpcK // 8) - 1) // (self.ldpcK // 8)
+
+    def getPostCodeLength(self, srcLength: int) -> int:
+        return self.getCodeSize(srcLength) * self.ldpcN
+
+    def getPriorCodeLength(self, srcLength: int) -> int:
+        return self.getCodeSize(srcLength) * (self.ldpcN // 8)
+
+    # reference MyLdpc.cpp:571-618 (+ :684-784 for the semantics)
+    def decode(self, postCode, srcCode, srcLength: int, deType: int = DecodeMS) -> int:
+        if self._dec is None:
+            raise LdpcError(-1, "forDecoder must be called before decode")
+        codeSize = self.getCodeSize(srcLength)
+        y = _as_host_array(postCode, np.float32)
+        if (y.numel() if hasattr(y, "numel") else y.size) < codeSize * self.ldpcN:
+            raise ValueError("postCode shorter than getPostCodeLength(srcLength)")
+        yy = y.reshape(-1)[: codeSize * self.ldpcN]
+        res = self._dec.decode_host(yy)
+        flat = res["info"].reshape(-1)[:srcLength]
+        dst = np.frombuffer(srcCode, dtype=np.uint8) if not isinstance(srcCode, np.ndarray) else srcCode.view(np.uint8)
+        dst[:srcLength] = flat
+        self.lastIterations = res["iters"]
+        return 0

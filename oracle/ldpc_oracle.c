@@ -1,0 +1,365 @@
+/*
+ * oracle/ldpc_oracle.c -- TEST INFRASTRUCTURE ONLY (see ldpc_oracle.h).
+ *
+ * Plain-C restatement of the reference's CPU min-sum decode path.  Every function cites the
+ * reference file:line it follows.  Build: gcc -O2 -ffp-contract=off -fno-fast-math (IEEE
+ * binary32, one rounding per add, no FMA contraction -- the reference is built -O0 for
+ * x86-64 SSE scalar math, Makefile:1, which has the same arithmetic).
+ */
+#include "ldpc_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "wimax_seed_tables.inc"
+
+#define ORACLE_NB 24 /* n_b, reference MyLdpc.h:102 */
+
+void oracle_free(void *p) { free(p); }
+
+/* reference MyLdpc.cpp:58-83: seed table + number of block rows per rate */
+int oracle_wimax_seed(int rate, const signed char **seed, int *seed_rows) {
+    switch (rate) {
+    case ORACLE_RATE_1_2:   *seed = oracle_seed_1_2;   *seed_rows = 12; return 0;
+    case ORACLE_RATE_2_3_A: *seed = oracle_seed_2_3_a; *seed_rows = 8;  return 0;
+    case ORACLE_RATE_2_3_B: *seed = oracle_seed_2_3_b; *seed_rows = 8;  return 0;
+    case ORACLE_RATE_3_4_A: *seed = oracle_seed_3_4_a; *seed_rows = 6;  return 0;
+    case ORACLE_RATE_3_4_B: *seed = oracle_seed_3_4_b; *seed_rows = 6;  return 0;
+    case ORACLE_RATE_5_6:   *seed = oracle_seed_5_6;   *seed_rows = 4;  return 0;
+    }
+    return -1;
+}
+
+typedef struct { int r, c; } rc_t;
+static int rc_cmp(const void *a, const void *b) {
+    const rc_t *x = (const rc_t *)a, *y = (const rc_t *)b;
+    if (x->r != y->r) return x->r < y->r ? -1 : 1;
+    if (x->c != y->c) return x->c < y->c ? -1 : 1;
+    return 0;
+}
+
+/* reference MyLdpc.cpp:52-109.  The triplet loop is restated literally (including the
+ * O(z^2) scan of every block and the `(z + permutCol - permutRow) % z == permut` test);
+ * Eigen's setFromTriplets into a RowMajor matrix is restated as a (row, col) sort, which is
+ * the order its InnerIterator later yields (MyLdpc.cpp:188-191). */
+int oracle_wimax_H(int N, int rate, int32_t **row_ptr, int32_t **col_idx, int *M_out) {
+    const signed char *hSeed;
+    int seedRowLength;
+    if (oracle_wimax_seed(rate, &hSeed, &seedRowLength)) return -1;
+    const int seedColLength = ORACLE_NB;
+    int z = N / ORACLE_NB;                       /* :55 */
+    int M = seedRowLength * z;
+    size_t cap = (size_t)seedRowLength * seedColLength * z;
+    rc_t *trip = (rc_t *)malloc(cap * sizeof(rc_t));
+    size_t nt = 0;
+    int permut;
+    for (int seedRow = 0; seedRow < seedRowLength; ++seedRow) {
+        for (int seedCol = 0; seedCol < seedColLength; ++seedCol) {
+            if ((permut = hSeed[seedRow * seedColLength + seedCol]) >= 0) {
+                if (rate != ORACLE_RATE_2_3_A) {
+                    permut = permut * z / 96;    /* :91 integer floor */
+                } else {
+                    permut = permut % z;         /* :93 */
+                }
+                for (int permutRow = 0; permutRow < z; ++permutRow) {
+                    for (int permutCol = 0; permutCol < z; ++permutCol) {
+                        if ((z + permutCol - permutRow) % z == permut) {
+                            trip[nt].r = seedRow * z + permutRow;
+                            trip[nt].c = seedCol * z + permutCol;
+                            ++nt;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    qsort(trip, nt, sizeof(rc_t), rc_cmp);
+    int32_t *rp = (int32_t *)calloc((size_t)M + 1, sizeof(int32_t));
+    int32_t *ci = (int32_t *)malloc(nt * sizeof(int32_t));
+    for (size_t i = 0; i < nt; ++i) {
+        rp[trip[i].r + 1]++;
+        ci[i] = trip[i].c;
+    }
+    for (int r = 0; r < M; ++r) rp[r + 1] += rp[r];
+    free(trip);
+    *row_ptr = rp;
+    *col_idx = ci;
+    *M_out = M;
+    return (int)nt;
+}
+
+/* reference MyLdpc.cpp:172-222: edge id = CSR position; hRows/hCols; per-row and per-column
+ * linked lists built by tail-walk append; hRowRange. */
+oracle_tables *oracle_tables_build(int M, int N, const int32_t *row_ptr, const int32_t *col_idx) {
+    oracle_tables *t = (oracle_tables *)calloc(1, sizeof(*t));
+    int nonZeros = row_ptr[M];
+    t->M = M; t->N = N; t->nnz = nonZeros;
+    t->hColFirstPtr = (int *)malloc(sizeof(int) * (size_t)N);
+    t->hColNextPtr = (int *)malloc(sizeof(int) * (size_t)(nonZeros > 0 ? nonZeros : 1));
+    t->hRowFirstPtr = (int *)malloc(sizeof(int) * (size_t)M);
+    t->hRowNextPtr = (int *)malloc(sizeof(int) * (size_t)(nonZeros > 0 ? nonZeros : 1));
+    memset(t->hColFirstPtr, -1, sizeof(int) * (size_t)N);
+    memset(t->hColNextPtr, -1, sizeof(int) * (size_t)nonZeros);
+    memset(t->hRowFirstPtr, -1, sizeof(int) * (size_t)M);
+    memset(t->hRowNextPtr, -1, sizeof(int) * (size_t)nonZeros);
+    t->hCols = (int *)malloc(sizeof(int) * (size_t)(nonZeros > 0 ? nonZeros : 1));
+    t->hRows = (int *)malloc(sizeof(int) * (size_t)(nonZeros > 0 ? nonZeros : 1));
+    t->hRowRange = (int *)malloc(sizeof(int) * ((size_t)M + 1));
+    /* The reference appends by walking to the tail (O(nnz * degree)); a tail cache gives the
+     * identical lists.  Kept explicit so long codes (N = 64800) set up quickly. */
+    int *rowTail = (int *)malloc(sizeof(int) * (size_t)M);
+    int *colTail = (int *)malloc(sizeof(int) * (size_t)N);
+    int offset = 0;
+    for (int k = 0; k < M; ++k) {
+        t->hRowRange[k] = offset;
+        for (int it = row_ptr[k]; it < row_ptr[k + 1]; ++it) {
+            int row = k, col = col_idx[it];
+            t->hRows[offset] = row;
+            t->hCols[offset] = col;
+            if (t->hRowFirstPtr[row] == -1) t->hRowFirstPtr[row] = offset;
+            else t->hRowNextPtr[rowTail[row]] = offset;
+            rowTail[row] = offset;
+            if (t->hColFirstPtr[col] == -1) t->hColFirstPtr[col] = offset;
+            else t->hColNextPtr[colTail[col]] = offset;
+            colTail[col] = offset;
+            ++offset;
+        }
+    }
+    t->hRowRange[M] = offset;
+    free(rowTail);
+    free(colTail);
+    return t;
+}
+
+void oracle_tables_free(oracle_tables *t) {
+    if (!t) return;
+    free(t->hRows); free(t->hCols);
+    free(t->hRowFirstPtr); free(t->hRowNextPtr);
+    free(t->hColFirstPtr); free(t->hColNextPtr);
+    free(t->hRowRange);
+    free(t);
+}
+
+/* reference MyLdpc.cpp:620-631 */
+int oracle_getCodeSize(int K, int srcLength) { return (srcLength + (K / 8) - 1) / (K / 8); }
+int oracle_getPostCodeLength(int K, int N, int srcLength) {
+    return (srcLength + (K / 8) - 1) / (K / 8) * N;
+}
+int oracle_getPriorCodeLength(int K, int N, int srcLength) {
+    return (srcLength + (K / 8) - 1) / (K / 8) * (N / 8);
+}
+
+typedef struct {
+    unsigned char *lQA; /* bool in the reference */
+    float *lQB, *lR, *lPostP;
+    unsigned char *src;
+} scratch_t;
+
+static void scratch_alloc(scratch_t *s, int nnz, int N) {
+    s->lQA = (unsigned char *)malloc((size_t)(nnz > 0 ? nnz : 1));
+    s->lQB = (float *)malloc(sizeof(float) * (size_t)(nnz > 0 ? nnz : 1));
+    s->lR = (float *)malloc(sizeof(float) * (size_t)(nnz > 0 ? nnz : 1));
+    s->lPostP = (float *)malloc(sizeof(float) * (size_t)N);
+    s->src = (unsigned char *)malloc((size_t)N);
+}
+static void scratch_free(scratch_t *s) {
+    free(s->lQA); free(s->lQB); free(s->lR); free(s->lPostP); free(s->src);
+}
+
+/* One codeword of reference MyLdpc.cpp:695-763, literal loops.  Returns `time`. */
+static int decode_one_literal(const oracle_tables *t, int times, const float *y, scratch_t *s) {
+    const int nonZeros = t->nnz, ldpcN = t->N, ldpcM = t->M;
+    int time = 0;
+    for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {       /* :697-702 */
+        int hCol = t->hCols[nodeInd];
+        float code = y[hCol];
+        s->lQA[nodeInd] = (code < 0);
+        s->lQB[nodeInd] = fabsf(code);
+    }
+    while (1) {
+        for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {   /* :705-721 refreshRMS */
+            int hRow = t->hRows[nodeInd];
+            unsigned char a = 0;
+            float b = 1000;
+            for (int ptr = t->hRowFirstPtr[hRow]; ptr != -1; ptr = t->hRowNextPtr[ptr]) {
+                if (nodeInd == ptr) continue;
+                if (s->lQA[ptr]) a = a ^ 1;
+                b = fminf(b, s->lQB[ptr]);
+            }
+            if (a) s->lR[nodeInd] = -b;
+            else s->lR[nodeInd] = b;
+        }
+        for (int nodeInd = 0; nodeInd < ldpcN; ++nodeInd) {      /* :723-735 refreshPostPMS */
+            float tmp = y[nodeInd];
+            for (int ptr = t->hColFirstPtr[nodeInd]; ptr != -1; ptr = t->hColNextPtr[ptr]) {
+                tmp += s->lR[ptr];
+            }
+            if (tmp > 0) s->src[nodeInd] = 0;
+            else s->src[nodeInd] = 1;
+            s->lPostP[nodeInd] = tmp;
+        }
+        unsigned char flag = 0;                                  /* :737-750 checkResult */
+        for (int nodeInd = 0; nodeInd < ldpcM; ++nodeInd) {
+            unsigned char result = 0;
+            for (int ptr = t->hRowFirstPtr[nodeInd]; ptr != -1; ptr = t->hRowNextPtr[ptr]) {
+                if (s->src[t->hCols[ptr]]) result ^= 1;
+            }
+            if (result) { flag = 1; break; }
+        }
+        ++time;                                                  /* :751-755 */
+        if (flag == 0) break;
+        if (time == times) break;
+        for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {   /* :757-762 refreshQ */
+            int hCol = t->hCols[nodeInd];
+            float lQ = s->lPostP[hCol] - s->lR[nodeInd];
+            s->lQA[nodeInd] = (lQ < 0);
+            s->lQB[nodeInd] = fabsf(lQ);
+        }
+    }
+    return time;
+}
+
+/* Same arithmetic with the check-node loop in min1/min2/parity form over CSR rows.
+ * Used for large test sizes; tests assert it equals decode_one_literal bit for bit. */
+static int decode_one_fast(const oracle_tables *t, int times, const float *y, scratch_t *s) {
+    const int nonZeros = t->nnz, ldpcN = t->N, ldpcM = t->M;
+    int time = 0;
+    for (int e = 0; e < nonZeros; ++e) {
+        float code = y[t->hCols[e]];
+        s->lQA[e] = (code < 0);
+        s->lQB[e] = fabsf(code);
+    }
+    while (1) {
+        for (int r = 0; r < ldpcM; ++r) {
+            int e0 = t->hRowRange[r], e1 = t->hRowRange[r + 1];
+            float m1 = INFINITY, m2 = INFINITY;
+            int i1 = -1;
+            unsigned char par = 0;
+            for (int e = e0; e < e1; ++e) {
+                float a = s->lQB[e];
+                par ^= s->lQA[e];
+                if (a < m1) { m2 = m1; m1 = a; i1 = e; }
+                else if (a < m2) { m2 = a; }
+            }
+            for (int e = e0; e < e1; ++e) {
+                float b = fminf(1000.0f, (e == i1) ? m2 : m1);
+                unsigned char a = par ^ s->lQA[e];
+                s->lR[e] = a ? -b : b;
+            }
+        }
+        for (int n = 0; n < ldpcN; ++n) {
+            float tmp = y[n];
+            for (int ptr = t->hColFirstPtr[n]; ptr != -1; ptr = t->hColNextPtr[ptr]) tmp += s->lR[ptr];
+            s->src[n] = (tmp > 0) ? 0 : 1;
+            s->lPostP[n] = tmp;
+        }
+        unsigned char flag = 0;
+        for (int r = 0; r < ldpcM && !flag; ++r) {
+            unsigned char result = 0;
+            for (int e = t->hRowRange[r]; e < t->hRowRange[r + 1]; ++e) result ^= s->src[t->hCols[e]];
+            if (result) flag = 1;
+        }
+        ++time;
+        if (!flag) break;
+        if (time == times) break;
+        for (int e = 0; e < nonZeros; ++e) {
+            float lQ = s->lPostP[t->hCols[e]] - s->lR[e];
+            s->lQA[e] = (lQ < 0);
+            s->lQB[e] = fabsf(lQ);
+        }
+    }
+    return time;
+}
+
+/* reference MyLdpc.cpp:684-784 */
+int oracle_decodeCPU(const oracle_tables *t, int K, int times, const float *postCode,
+                     char *srcCode, int srcLength, int32_t *iters, uint8_t *hard, float *post) {
+    const int ldpcN = t->N, ldpcK = K;
+    memset(srcCode, 0, (size_t)srcLength);                        /* :685 */
+    int codeSize = oracle_getCodeSize(K, srcLength);              /* :686 */
+    scratch_t s;
+    scratch_alloc(&s, t->nnz, ldpcN);
+    for (int batch = 0; batch < codeSize; ++batch) {              /* :694 */
+        int time = decode_one_literal(t, times, postCode + (size_t)batch * ldpcN, &s);
+        for (int tmp = 0; tmp < ldpcK; ++tmp) {                   /* :765-774 */
+            if (s.src[tmp]) {
+                int offset = batch * ldpcK + tmp;
+                int charOffset = offset / 8;
+                if (charOffset <= srcLength) {
+                    int bitOffset = offset % 8;
+                    srcCode[charOffset] |= (char)(1 << bitOffset);
+                }
+            }
+        }
+        if (iters) iters[batch] = time;
+        if (hard) memcpy(hard + (size_t)batch * ldpcN, s.src, (size_t)ldpcN);
+        if (post) memcpy(post + (size_t)batch * ldpcN, s.lPostP, sizeof(float) * (size_t)ldpcN);
+    }
+    scratch_free(&s);
+    return 0;
+}
+
+typedef struct {
+    const oracle_tables *t;
+    int K, times, literal;
+    const float *llr;
+    int64_t b0, b1;
+    uint8_t *info, *hard;
+    int32_t *iters;
+    float *post;
+} job_t;
+
+static void *job_run(void *arg) {
+    job_t *j = (job_t *)arg;
+    const int N = j->t->N, K = j->K, KB = (K + 7) / 8;
+    scratch_t s;
+    scratch_alloc(&s, j->t->nnz, N);
+    for (int64_t b = j->b0; b < j->b1; ++b) {
+        const float *y = j->llr + (size_t)b * N;
+        int time = j->literal ? decode_one_literal(j->t, j->times, y, &s)
+                              : decode_one_fast(j->t, j->times, y, &s);
+        if (j->info) {
+            uint8_t *o = j->info + (size_t)b * KB;
+            memset(o, 0, (size_t)KB);
+            for (int i = 0; i < K; ++i)
+                if (s.src[i]) o[i >> 3] |= (uint8_t)(1u << (i & 7)); /* LSB first, :765-774 */
+        }
+        if (j->iters) j->iters[b] = time;
+        if (j->hard) memcpy(j->hard + (size_t)b * N, s.src, (size_t)N);
+        if (j->post) memcpy(j->post + (size_t)b * N, s.lPostP, sizeof(float) * (size_t)N);
+    }
+    scratch_free(&s);
+    return NULL;
+}
+
+int oracle_decode_batch(const oracle_tables *t, int K, int times, const float *llr,
+                        int64_t ncw, uint8_t *info, int32_t *iters, uint8_t *hard,
+                        float *post, int nthreads, int literal) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > ncw) nthreads = ncw > 0 ? (int)ncw : 1;
+    job_t jobs[256];
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; ++i) {
+        job_t *j = &jobs[i];
+        j->t = t; j->K = K; j->times = times; j->literal = literal; j->llr = llr;
+        j->b0 = ncw * i / nthreads; j->b1 = ncw * (i + 1) / nthreads;
+        j->info = info; j->iters = iters; j->hard = hard; j->post = post;
+    }
+    if (nthreads == 1) { job_run(&jobs[0]); return 0; }
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, job_run, &jobs[i]);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
+
+/* reference MyLdpc.cpp:1063-1072: bit (LSB first) 1 -> -1.0, 0 -> +1.0 */
+void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out) {
+    for (int charOffset = 0; charOffset < nbytes; ++charOffset) {
+        uint8_t tmp = bytes[charOffset];
+        for (int bitOffset = 0; bitOffset < 8; ++bitOffset) {
+            out[charOffset * 8 + bitOffset] = (tmp & (1 << bitOffset)) ? -1.0f : 1.0f;
+        }
+    }
+}

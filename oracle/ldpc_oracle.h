@@ -1,0 +1,78 @@
+/*
+ * oracle/ldpc_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the reference's min-sum decode path (wing02/MyLdpcCppApi).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the stated CPU baseline.
+ * The product (libldpc_b200.so, libmyldpc_b200.so) never links or calls it.
+ *
+ * Parity status: the reference ships no golden vectors (its only test, Test.cpp, is
+ * unseeded).  The pin is oracle/_ref: the reference's own MyLdpc.cpp compiled unmodified
+ * against container-only shims (see oracle/Makefile, oracle/shim/), whose decodeCPU output
+ * is compared with this restatement in tests/test_oracle_vs_ref.py, plus committed golden
+ * fixtures generated from it (tests/golden/).
+ */
+#ifndef LDPC_ORACLE_H_
+#define LDPC_ORACLE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rate_type values, reference MyLdpc.h:33-35 */
+enum { ORACLE_RATE_1_2 = 0, ORACLE_RATE_2_3_A, ORACLE_RATE_2_3_B, ORACLE_RATE_3_4_A,
+       ORACLE_RATE_3_4_B, ORACLE_RATE_5_6 };
+
+/* Edge tables exactly as Coder::forDecoder builds them (reference MyLdpc.cpp:167-222). */
+typedef struct oracle_tables {
+    int M, N, nnz;
+    int *hRows, *hCols;            /* [nnz]  row / column of edge e (e = CSR position)   */
+    int *hRowFirstPtr, *hRowNextPtr; /* [M], [nnz]  singly linked list per row, -1 ends  */
+    int *hColFirstPtr, *hColNextPtr; /* [N], [nnz]  singly linked list per column        */
+    int *hRowRange;                /* [M+1] CSR offsets                                   */
+} oracle_tables;
+
+/* Base-matrix tables live in the oracle's own copy (oracle/ldpc_oracle.c) so that the
+ * oracle does not depend on product code.  `seed` is rows x 24, row-major.              */
+int oracle_wimax_seed(int rate, const signed char **seed, int *seed_rows);
+
+/* Restates Coder::initCheckMatrix (reference MyLdpc.cpp:52-109): expands the 802.16e seed
+ * for code length N (z = N/24) into CSR (row-major, ascending column inside a row).
+ * Caller frees *row_ptr and *col_idx with oracle_free().  Returns nnz or <0.             */
+int oracle_wimax_H(int N, int rate, int32_t **row_ptr, int32_t **col_idx, int *M_out);
+
+oracle_tables *oracle_tables_build(int M, int N, const int32_t *row_ptr, const int32_t *col_idx);
+void oracle_tables_free(oracle_tables *t);
+void oracle_free(void *p);
+
+/* Restates Coder::decodeCPU (reference MyLdpc.cpp:684-784) over the stream API:
+ *   postCode : codeSize*N floats, codeSize = ceil(srcLength/(K/8))  (MyLdpc.cpp:628-631)
+ *   srcCode  : >= srcLength+1 bytes (the reference's guard is `charOffset <= srcLength`)
+ *   times    : iteration cap (reference: 40, MyLdpc.cpp:24)
+ * The reference frees `time`, `src` and `lPostP`; we expose them (any may be NULL):
+ *   iters[codeSize], hard[codeSize*N] (0/1 bytes), post[codeSize*N].                     */
+int oracle_decodeCPU(const oracle_tables *t, int K, int times, const float *postCode,
+                     char *srcCode, int srcLength, int32_t *iters, uint8_t *hard, float *post);
+
+/* Same results, per-codeword records (K/8 bytes each, K%8==0), codewords split over
+ * nthreads pthreads.  `literal`!=0 uses the reference's O(d_c^2) check-node loop (the
+ * faithful CPU baseline); 0 uses the min1/min2 form (checked equal in tests).           */
+int oracle_decode_batch(const oracle_tables *t, int K, int times, const float *llr,
+                        int64_t ncw, uint8_t *info, int32_t *iters, uint8_t *hard,
+                        float *post, int nthreads, int literal);
+
+/* Restates Coder::test's bit->BPSK map (reference MyLdpc.cpp:1061-1072), noise supplied by
+ * the caller (the reference's rand()-based Box-Muller is unseeded).                      */
+void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out);
+
+/* Size helpers, reference MyLdpc.cpp:620-631. */
+int oracle_getCodeSize(int K, int srcLength);
+int oracle_getPostCodeLength(int K, int N, int srcLength);
+int oracle_getPriorCodeLength(int K, int N, int srcLength);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA decoder, called through the C-ABI, against the CPU oracle on
+the same seeded inputs.  Bar: hard decisions and iteration counts bit-exact; posterior within
+1e-4 relative (and in fact identical)."""
+import numpy as np
+import pytest
+
+import oracle
+from tests.util import awgn_llr, assert_parity, sigma_from_ebn0
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _run_device(dec, llr_np, **kw):
+    torch = _torch()
+    d = torch.from_numpy(llr_np).cuda()
+    out = dec.decode_device(d, want_hard=True, want_post=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("sigma", [0.4, 0.55, 0.62, 0.7, 1.0])
+def test_default_code_parity(default_code, sigma):
+    """BASELINE config 1: Test.cpp's code, 40-iteration cap, sigma from cliff to no-convergence."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    ncw = 1024 + 7  # ragged: not a multiple of 32
+    llr = awgn_llr(ncw, c["N"], sigma, seed=int(sigma * 1000))
+    ref = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr)
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    res = _run_device(dec, llr)
+    assert_parity(res, ref, c["N"], what="sigma=%g" % sigma)
+    host = dec.decode_host(llr, want_hard=True, want_post=True)
+    assert_parity(host, ref, c["N"], what="host sigma=%g" % sigma)
+
+
+def test_default_code_global_path(default_code):
+    """The workspace-in-global-memory path must give the same bits as the shared-memory path."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    llr = awgn_llr(300, c["N"], 0.62, seed=11)
+    ref = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr)
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    dec.set_path(1)
+    assert dec.info()["path_name"] == "lane_global"
+    assert_parity(_run_device(dec, llr), ref, c["N"], what="global path")
+
+
+@pytest.mark.parametrize("rate,name,num,den", [(0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3),
+                                               (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
+def test_other_wimax_rates(rate, name, num, den):
+    import myldpccppapi_b200 as m
+    N = 1152
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    sig = sigma_from_ebn0(2.5, num / den)
+    llr = awgn_llr(200, N, sig, seed=rate + 100)
+    ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr)
+    dec = m.Decoder.wimax(K, N, rate)
+    assert_parity(_run_device(dec, llr), ref, N, what="rate " + name)
+
+
+def test_ebn0_sweep_iteration_counts(default_code):
+    """BASELINE config 4: Eb/N0 0..4 dB with syndrome early termination, iteration-count parity."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    o = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40)
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    rng = np.random.default_rng(4)
+    Gp = m.codes.gf2_systematic_encoder(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"])
+    for i, ebn0 in enumerate(np.arange(0.0, 4.01, 0.5)):
+        u = rng.integers(0, 2, (256, c["K"])).astype(np.uint8)
+        cwb = np.concatenate([u, (u.astype(np.int64) @ Gp.astype(np.int64) % 2).astype(np.uint8)], axis=1)
+        assert m.codes.syndrome(c["M"], c["row_ptr"], c["col_idx"], cwb).sum() == 0
+        llr = awgn_llr(256, c["N"], sigma_from_ebn0(ebn0, 0.75), seed=40 + i, bits=cwb)
+        ref = o.decode(llr)
+        assert_parity(_run_device(dec, llr), ref, c["N"], what="EbN0=%g" % ebn0)
+
+
+def test_iteration_cap_and_no_early_termination(default_code):
+    import myldpccppapi_b200 as m
+    c = default_code
+    llr = awgn_llr(128, c["N"], 0.6, seed=77)
+    for cap in (1, 2, 7, 50):
+        ref = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=cap).decode(llr)
+        dec = m.Decoder.wimax(c["K"], c["N"], c["rate"], max_iter=cap)
+        assert_parity(_run_device(dec, llr), ref, c["N"], what="cap=%d" % cap)
+    # early termination off: every word runs to the cap; a noiseless word keeps its bits
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"], max_iter=5, early_termination=False)
+    res = _run_device(dec, np.ones((40, c["N"]), dtype=np.float32))
+    assert np.all(res["iters"] == 5) and not res["info"].any()
+
+
+def test_edge_inputs(default_code):
+    """Zeros, signed zeros, infinities, huge values (the 1000 clamp), and an empty batch."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    c = default_code
+    N = c["N"]
+    rng = np.random.default_rng(5)
+    llr = awgn_llr(96, N, 0.7, seed=5)
+    llr[0, :] = 0.0
+    llr[1, :] = -0.0
+    llr[2, ::3] = 0.0
+    llr[3, ::5] = -0.0
+    llr[4, :] = 5000.0 * np.sign(llr[4, :])          # above the 1000 clamp
+    llr[5, ::7] = np.inf
+    llr[6, ::11] = -np.inf
+    llr[7, :] = np.float32(1e-40)                      # denormals
+    llr[8, :] = rng.choice(np.array([-0.5, 0.5, 1.0, -1.0, 0.25], dtype=np.float32), N)  # exact ties / cancellations
+    llr[9, :] = rng.choice(np.array([-1.0, 1.0], dtype=np.float32), N)
+    ref = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr)
+    dec = m.Decoder.wimax(c["K"], N, c["rate"])
+    res = _run_device(dec, llr)
+    # compare posteriors with == semantics (signed zeros compare equal; inf-inf gives NaN on both sides)
+    info, iters, hard, post = ref
+    assert np.array_equal(res["iters"], iters)
+    assert np.array_equal(res["info"], info)
+    assert np.array_equal(res["hard"], np.packbits(hard, axis=1, bitorder="little"))
+    both_nan = np.isnan(res["post"]) & np.isnan(post)
+    assert np.array_equal(res["post"][~both_nan], post[~both_nan])
+    # empty batch is a no-op
+    out = dec.decode_device(torch.empty((0, N), dtype=torch.float32, device="cuda"))
+    assert out["info"].shape[0] == 0
+
+
+def test_regular_3_6_parity():
+    """BASELINE config 3 code (regular (3,6), N=8192) on a seeded sample, incl. non-convergent words."""
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.regular_code()
+    o = oracle.Oracle(M, N, K, rp, ci, times=40)
+    dec = m.Decoder(M, N, K, rp, ci)
+    for sigma, seed in [(0.7, 1), (0.84, 2), (1.0, 3)]:
+        llr = awgn_llr(48, N, sigma, seed=seed)
+        ref = o.decode(llr, literal=False)
+        assert_parity(_run_device(dec, llr), ref, N, what="reg36 sigma=%g" % sigma)
+
+
+def test_ira_64800_parity():
+    """BASELINE config 5 code (irregular, N=64800, 50-iteration cap) on a small seeded sample."""
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.ira_code()
+    o = oracle.Oracle(M, N, K, rp, ci, times=50)
+    dec = m.Decoder(M, N, K, rp, ci, max_iter=50)
+    rng = np.random.default_rng(9)
+    u = rng.integers(0, 2, (34, K)).astype(np.uint8)
+    cwb = m.codes.ira_encode(M, N, K, rp, ci, u)
+    for sigma, seed in [(0.8, 1), (0.97, 2)]:
+        llr = awgn_llr(34, N, sigma, seed=seed, bits=cwb)
+        ref = o.decode(llr, literal=False)
+        res = _run_device(dec, llr)
+        assert_parity(res, ref, N, what="ira sigma=%g" % sigma)
+
+
+def test_roundtrip_full_batch_properties(default_code):
+    """BASELINE config 2 size (65,536 words): size-independent properties at full scale --
+    encode -> BPSK+AWGN -> decode recovers the payload at high SNR, results do not depend on the
+    position of a word in the batch, and a seeded 2,048-word slice equals the oracle."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    c = default_code
+    N, K = c["N"], c["K"]
+    ncw = 65536
+    rng = np.random.default_rng(65536)
+    Gp = m.codes.gf2_systematic_encoder(c["M"], N, K, c["row_ptr"], c["col_idx"])
+    u = rng.integers(0, 2, (ncw, K)).astype(np.uint8)
+    cwb = np.concatenate([u, ((u.astype(np.float32) @ Gp.astype(np.float32)) % 2).astype(np.uint8)], axis=1)
+    bits = torch.from_numpy(m.codes.pack_bits(cwb)).cuda()
+    llr = m.synth_llr(ncw, N, 0.45, seed=2, bits=bits)
+    dec = m.Decoder.wimax(K, N, c["rate"])
+    out = dec.decode_device(llr)
+    info = out["info"].cpu().numpy()
+    assert np.array_equal(info, m.codes.pack_bits(u)), "payload not recovered at sigma=0.45"
+    assert int(out["iters"].max()) < 40
+    # permutation invariance: decode the batch in reversed order
+    rev = torch.flip(llr, dims=[0]).contiguous()
+    out2 = dec.decode_device(rev)
+    assert torch.equal(torch.flip(out2["info"], dims=[0]), out["info"])
+    assert torch.equal(torch.flip(out2["iters"], dims=[0]), out["iters"])
+    # oracle on a slice of the very same floats, at a noisier point
+    llr2 = m.synth_llr(2048, N, 0.62, seed=3, bits=bits[:2048].contiguous())
+    ref = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"], times=40).decode(llr2.cpu().numpy())
+    o2 = dec.decode_device(llr2, want_hard=True, want_post=True)
+    torch.cuda.synchronize()
+    assert_parity({k: v.cpu().numpy() for k, v in o2.items()}, ref, N, what="slice")
+
+
+def test_coder_api_roundtrip(default_code):
+    """Test.cpp-shaped run through the Coder mirror: payload -> encode -> test() channel -> decode."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    K, N = c["K"], c["N"]
+    srcLength = 1000  # not a multiple of K/8 = 54: the last codeword is partly padding
+    src = np.array([ord("a") + i % 26 for i in range(srcLength)], dtype=np.uint8)  # Test.cpp:43-45
+    coder = m.Coder(K, N, m.rate_3_4_b)
+    coder.forDecoder(8)
+    coder.addDecodeType(m.DecodeMS)
+    ncw = coder.getCodeSize(srcLength)
+    assert ncw == 19 and coder.getPostCodeLength(srcLength) == ncw * N
+    padded = np.zeros(ncw * K // 8, dtype=np.uint8)
+    padded[:srcLength] = src
+    u = m.codes.unpack_bits(padded.reshape(ncw, K // 8), K)
+    Gp = m.codes.gf2_systematic_encoder(c["M"], N, K, c["row_ptr"], c["col_idx"])
+    cwb = np.concatenate([u, (u.astype(np.int64) @ Gp.astype(np.int64) % 2).astype(np.uint8)], axis=1)
+    post = awgn_llr(ncw, N, 10 ** (-6.0 / 20), seed=6, bits=cwb).reshape(-1)   # snr = 6 dB, Test.cpp:56-59
+    new_src = np.zeros(srcLength + 1, dtype=np.uint8)
+    assert coder.decode(post, new_src, srcLength, m.DecodeMS) == 0
+    assert np.array_equal(new_src[:srcLength], src)                           # ErrNum == 0, Test.cpp:105-110
+    ref_bytes, ref_iters, _, _ = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"]).decode_stream(post, srcLength)
+    assert np.array_equal(new_src[:srcLength], ref_bytes)
+    assert np.array_equal(coder.lastIterations, ref_iters)

@@ -132,7 +132,7 @@ class Decoder:
         """llr: host float32 array/tensor [ncw, N] (pinned memory gives full-speed copies).
         Returns numpy arrays {info, iters, hard?, post?}.  Blocking."""
         a = _as_host_array(llr, np.float32)
-        ncw = a.size // self.N
+        ncw = _numel(a) // self.N
         out = out if out is not None else {}
         if "info" not in out:
             out["info"] = np.empty((ncw, self.KB), dtype=np.uint8)
@@ -153,6 +153,10 @@ def _as_host_array(x, dtype):
             raise ValueError("expected a host tensor")
         return x.contiguous()
     return np.ascontiguousarray(x, dtype=dtype)
+
+
+def _numel(x) -> int:
+    return int(x.numel()) if hasattr(x, "numel") else int(x.size)
 
 
 def _host_ptr(x):
@@ -244,7 +248,7 @@ class Coder:
             raise LdpcError(-1, "forDecoder must be called before decode")
         codeSize = self.getCodeSize(srcLength)
         y = _as_host_array(postCode, np.float32)
-        if (y.numel() if hasattr(y, "numel") else y.size) < codeSize * self.ldpcN:
+        if _numel(y) < codeSize * self.ldpcN:
             raise ValueError("postCode shorter than getPostCodeLength(srcLength)")
         yy = y.reshape(-1)[: codeSize * self.ldpcN]
         res = self._dec.decode_host(yy)

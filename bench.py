@@ -205,6 +205,7 @@ def main() -> None:
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--ncw", type=int, default=None, help="codewords per GPU (default: the workload's)")
     ap.add_argument("--sigma", type=float, default=None)
+    ap.add_argument("--max-iter", type=int, default=None, help="override the workload's iteration cap")
     ap.add_argument("--path", type=int, default=-1, help="force a kernel path (see ldpc_b200.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -253,6 +254,7 @@ def main() -> None:
     desc, sigma, cap, ncw = WORKLOADS[args.workload]
     sigma = args.sigma if args.sigma is not None else sigma
     ncw = args.ncw or ncw
+    cap = args.max_iter or cap
     code = make_code(args.workload)
     M, N, K, rp, ci = code
     nnz = int(rp[-1])
@@ -338,7 +340,7 @@ def main() -> None:
     per_gpu_cw_s = ncw / (ms_step * 1e-3)
     b_hbm = 4 * N + (K + 7) // 8 + 1                       # channel values in, info bits + count out
     b_msg = mean_iters * (16 * nnz + 8 * N)                # on-chip message bytes per word
-    onchip = info["path_name"] == "lane_smem"
+    onchip = info["path_name"] in ("lane_smem", "lane16")
     roof_smem = {"bound": "smem", "achieved": per_gpu_cw_s * b_msg / 1e9, "peak": smem_gbs.value, "unit": "GB/s",
                  "peak_source": "measured live: ldpc_b200_probe_smem_bandwidth (LDS.128 stream on all SMs)"}
     roof_smem["frac"] = roof_smem["achieved"] / roof_smem["peak"] if roof_smem["peak"] else None
@@ -347,7 +349,8 @@ def main() -> None:
     roof_hbm["frac"] = roof_hbm["achieved"] / hbm_peak
     roofline = dict(roof_smem if onchip else roof_hbm)
     roofline.update({
-        "kernel": "ldpc_ms_lane_kernel<%s>" % ("true" if onchip else "false"),
+        "kernel": {"lane16": "ldpc_ms_lane16_kernel<24>", "lane_smem": "ldpc_ms_lane_kernel<true>"}.get(
+            info["path_name"], "ldpc_ms_lane_kernel<false>"),
         "launch_ms": ms_step, "traffic": None,
         "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},
         "hbm": roof_hbm, "smem": roof_smem,

@@ -53,7 +53,9 @@ enum {
 enum {
     LDPC_B200_PATH_LANE_SMEM = 0,  /* 32 codewords per CTA, lane = codeword, state in shared memory */
     LDPC_B200_PATH_LANE_GLOBAL = 1,/* same schedule, state in a CTA-private L2/HBM workspace        */
-    LDPC_B200_PATH_CTA = 2         /* one codeword (group) per CTA, lane = check / variable         */
+    LDPC_B200_PATH_CTA = 2,        /* one codeword (group) per CTA, lane = check / variable         */
+    LDPC_B200_PATH_LANE16 = 3      /* tuned short-code path: lane = codeword, channel values in
+                                      registers, 16-byte check state and index tables in shared memory */
 };
 
 typedef struct ldpc_b200_info {

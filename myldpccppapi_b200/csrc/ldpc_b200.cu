@@ -46,7 +46,10 @@ struct Plan {
     int cw_per_cta = 32;
     size_t smem = 0;
     size_t ws_stride = 0;  // floats per CTA (LANE_GLOBAL)
+    int dcp = 0;           // padded check degree of the LANE16 tables
 };
+
+constexpr int kLane16Slots = 24;  // variable slots per warp held in registers (S_MAX)
 
 }  // namespace
 
@@ -67,6 +70,12 @@ struct ldpc_b200_decoder {
     int32_t* d_col_ptr = nullptr;
     uint32_t* d_vn_edge = nullptr;
     size_t table_bytes = 0;
+    // LANE16 tables (byte-offset form, copied into shared memory by the kernel)
+    uint32_t* d16_cn_tab = nullptr;
+    uint8_t* d16_cn_deg = nullptr;
+    uint32_t* d16_vn_ptr = nullptr;
+    uint32_t* d16_vn_tab = nullptr;
+    bool lane16_ready = false;
 
     unsigned int* d_counters = nullptr;
     int counter_next = 0;
@@ -118,9 +127,75 @@ int pick_lane_warps(int M, int N, int nnz) {
     return best_w;
 }
 
+size_t lane16_smem_bytes(const HostTables& t, int dcp) {
+    return (size_t)t.M * kLanes * 16 + (size_t)t.N * kLanes * 4 + (size_t)t.M * dcp * 4 +
+           (size_t)((t.nnz + 3) & ~3) * 4 + (size_t)((t.N + 1 + 3) & ~3) * 4 + (size_t)((t.M + 15) & ~15);
+}
+
+int pick_lane16_warps(int M, int N) {
+    const int wmin = std::max(8, (N + kLane16Slots - 1) / kLane16Slots);
+    int best_w = 32;
+    double best = -1.0;
+    for (int w = wmin; w <= 32; ++w) {
+        double cn = (double)M / w / ((M + w - 1) / w);
+        double vn = (double)N / w / ((N + w - 1) / w);
+        double eff = (0.6 * cn + 0.4 * vn) * (0.75 + 0.25 * w / 32.0);
+        if (eff > best + 1e-9) { best = eff; best_w = w; }
+    }
+    return best_w;
+}
+
+int upload_lane16_tables(ldpc_b200_decoder* h, int dcp) {
+    if (h->lane16_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    std::vector<uint32_t> cn_tab((size_t)t.M * dcp, 0u), vn_tab((size_t)std::max(t.nnz, 1), 0u), vn_ptr(t.N + 1);
+    std::vector<uint8_t> deg(t.M);
+    for (int r = 0; r < t.M; ++r) {
+        const int e0 = t.row_ptr[r], dc = t.row_ptr[r + 1] - e0;
+        deg[r] = (uint8_t)dc;
+        for (int j = 0; j < dc; ++j) cn_tab[(size_t)r * dcp + j] = (uint32_t)t.col_idx[e0 + j] * 128u;
+    }
+    for (int n = 0; n <= t.N; ++n) vn_ptr[n] = (uint32_t)t.col_ptr[n];
+    for (int e = 0; e < t.nnz; ++e) {
+        const uint32_t chk = t.vn_edge[e] >> kPosBits, pos = t.vn_edge[e] & ((1u << kPosBits) - 1u);
+        const int dc = t.row_ptr[chk + 1] - t.row_ptr[chk];
+        vn_tab[e] = chk * 512u | (uint32_t)(32 - dc + (int)pos);
+    }
+    CU_TRY(cudaMalloc(&h->d16_cn_tab, cn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->d16_cn_deg, deg.size()));
+    CU_TRY(cudaMalloc(&h->d16_vn_ptr, vn_ptr.size() * 4));
+    CU_TRY(cudaMalloc(&h->d16_vn_tab, vn_tab.size() * 4));
+    CU_TRY(cudaMemcpy(h->d16_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d16_cn_deg, deg.data(), deg.size(), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d16_vn_ptr, vn_ptr.data(), vn_ptr.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d16_vn_tab, vn_tab.data(), vn_tab.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += cn_tab.size() * 4 + deg.size() + vn_ptr.size() * 4 + vn_tab.size() * 4;
+    h->lane16_ready = true;
+    return LDPC_B200_OK;
+}
+
 int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
+    {   // tuned short-code path: channel values in registers, 16-byte check state, tables in smem
+        const int dcp = (t.max_row_weight + 3) & ~3;
+        const bool fits = t.N <= kLane16Slots * 32 && t.max_row_weight <= 32 && t.max_row_weight >= 1 &&
+                          (uint64_t)t.M * 512u < (1ull << 32) && lane16_smem_bytes(t, dcp) + 1024 <= h->smem_optin;
+        if (h->forced_path == LDPC_B200_PATH_LANE16 && !fits)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the lane16 shared-memory path");
+        if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_LANE16) && fits) {
+            pl.path = LDPC_B200_PATH_LANE16;
+            pl.threads = 32 * pick_lane16_warps(t.M, t.N);
+            pl.smem = lane16_smem_bytes(t, dcp);
+            pl.ctas = h->sm_count;
+            pl.dcp = dcp;
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
+    }
+    if (t.max_row_weight > kMaxCheckDegree)
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "check degree above 27 is only supported on the lane16 path");
     const size_t state_bytes = ((size_t)2 * t.N + (size_t)3 * t.M) * kLanes * sizeof(float);
     const size_t static_smem = 1024;  // s_group, s_flag + slack
     int path = h->forced_path;
@@ -179,6 +254,29 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (rc) return rc;
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
+    const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
+    if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
+    unsigned int* ctr = h->d_counters + h->counter_next;
+    h->counter_next = (h->counter_next + 1) % kCounterRing;
+    CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
+    const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+
+    if (pl.path == LDPC_B200_PATH_LANE16) {
+        rc = upload_lane16_tables(h, pl.dcp);
+        if (rc) return rc;
+        Lane16Params q;
+        q.cn_tab = h->d16_cn_tab; q.cn_deg = h->d16_cn_deg; q.vn_ptr = h->d16_vn_ptr; q.vn_tab = h->d16_vn_tab;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.DCP = pl.dcp; q.nnz = t.nnz;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter = ctr; q.ngroups = (int)ngroups;
+        CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<kLane16Slots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        ldpc_ms_lane16_kernel<kLane16Slots><<<grid, pl.threads, pl.smem, stream>>>(q);
+        CU_TRY(cudaGetLastError());
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
 
     DecodeParams p;
     p.row_ptr = h->d_row_ptr;
@@ -190,15 +288,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     p.llr = d_llr; p.ncw = ncw;
     p.info = d_info; p.hard = d_hard; p.iters = d_iters; p.post = d_post;
     p.ws = h->d_ws; p.ws_stride = pl.ws_stride;
-    const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
-    if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
     p.ngroups = (int)ngroups;
-    unsigned int* ctr = h->d_counters + h->counter_next;
-    h->counter_next = (h->counter_next + 1) % kCounterRing;
     p.counter = ctr;
-    CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
-
-    const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
     if (pl.path == LDPC_B200_PATH_LANE_SMEM) {
         CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         ldpc_ms_lane_kernel<true><<<grid, pl.threads, pl.smem, stream>>>(p);
@@ -230,9 +321,9 @@ int ldpc_b200_create(ldpc_b200_handle* out, int M, int N, int K, const int32_t* 
     if (!h) return fail(LDPC_B200_ERR_NOMEM, "out of host memory");
     std::string msg = build_tables(M, N, row_ptr, col_idx, &h->host);
     if (!msg.empty()) { delete h; return fail(LDPC_B200_ERR_ARG, msg); }
-    if (h->host.max_row_weight > kMaxCheckDegree) {
+    if (h->host.max_row_weight > 32) {
         delete h;
-        return fail(LDPC_B200_ERR_UNSUPPORTED, "check degree above 27 is not supported by the packed check state");
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "check degree above 32 is not supported by the packed sign word");
     }
     h->K = K;
     h->device = device;
@@ -300,6 +391,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
+            cudaFree(h->d16_cn_tab); cudaFree(h->d16_cn_deg); cudaFree(h->d16_vn_ptr); cudaFree(h->d16_vn_tab);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
         }
@@ -456,7 +548,7 @@ int ldpc_b200_probe_smem_bandwidth(int device, double* gbytes_per_s) {
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     uint32_t* sink = nullptr;
     CU_TRY(cudaMalloc(&sink, sizeof(uint32_t) * sms));
-    const int smem = 65536, loops = 4096;
+    const int smem = 131072, loops = 4096;
     cudaEvent_t a = nullptr, b = nullptr;
     int rc = LDPC_B200_OK;
     double best = 0.0;

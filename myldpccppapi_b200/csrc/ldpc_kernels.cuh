@@ -214,6 +214,206 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParam
 }
 
 // ---------------------------------------------------------------------------------------
+// LANE16 kernel: the tuned shared-memory path for short codes (Test.cpp's N=576 code).
+// Same schedule as above (32 codewords per CTA, lane = codeword, two barriers per iteration),
+// with everything the inner loops touch arranged for the fewest issue slots per edge:
+//   T  [N][32] f32    NEGATED posterior T = -P, zero canonicalised to +0.0, so that
+//                     hard bit = !signbit(T) and a row's syndrome is one XOR per edge
+//   ST [M][32] uint4  {min1, min2, sign word, argmin key}: one LDS.128 per edge in the VN pass;
+//                     argmin key = byte offset of the argmin's column in T (any injective id)
+//   channel values    stay in REGISTERS: warp w owns variables w, w+W, w+2W, ... for the whole
+//                     decode (static slots), thread (w, lane) keeps -y of its 32 x S_MAX words
+//   index tables      live in shared memory, pre-multiplied to byte offsets:
+//                     cn_tab[c*DCP + j] = col*128, vn_tab[e] = check*512 | (32 - dc + j)
+// Arithmetic is the same fp32 sequence as the reference: T = (-y) - R1 - R2 ... is the exact
+// negation of y + R1 + R2 ... (round-to-nearest is sign-symmetric); Q = P - R = -(T + R).
+// The sign of an exact zero never influences a non-zero value or a decision.
+// ---------------------------------------------------------------------------------------
+struct Lane16Params {
+    const uint32_t* __restrict__ cn_tab;   // [M*DCP] byte offsets col*128 (padding entries unused)
+    const uint8_t* __restrict__ cn_deg;    // [M]
+    const uint32_t* __restrict__ vn_ptr;   // [N+1]
+    const uint32_t* __restrict__ vn_tab;   // [nnz] check*512 | shift
+    int M, N, K, DCP, nnz, max_iter, early_term;
+    const float* __restrict__ llr;
+    long long ncw;
+    uint8_t* info;
+    uint8_t* hard;
+    int32_t* iters;
+    float* post;
+    unsigned int* counter;
+    int ngroups;
+};
+
+template <int S_MAX>
+__global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_group;
+    __shared__ uint32_t s_flag[2][kLanes];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int W = blockDim.x >> 5;
+    const int M = p.M, N = p.N, DCP = p.DCP;
+
+    // shared-memory carve-up (all 16-byte aligned)
+    unsigned char* sp = smem_raw;
+    uint4* ST = reinterpret_cast<uint4*>(sp);                 sp += (size_t)M * kLanes * 16;
+    float* T = reinterpret_cast<float*>(sp);                  sp += (size_t)N * kLanes * 4;
+    uint32_t* cn_tab = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)M * DCP * 4;
+    uint32_t* vn_tab = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)((p.nnz + 3) & ~3) * 4;
+    uint32_t* vn_ptr = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)((N + 1 + 3) & ~3) * 4;
+    uint8_t* cn_deg = reinterpret_cast<uint8_t*>(sp);
+
+    for (int i = threadIdx.x; i < M * DCP; i += blockDim.x) cn_tab[i] = __ldg(p.cn_tab + i);
+    for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) vn_tab[i] = __ldg(p.vn_tab + i);
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) vn_ptr[i] = __ldg(p.vn_ptr + i);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) cn_deg[i] = __ldg(p.cn_deg + i);
+
+    const unsigned char* Tl = reinterpret_cast<const unsigned char*>(T) + lane * 4;     // + col*128
+    const unsigned char* STl = reinterpret_cast<const unsigned char*>(ST) + lane * 16;  // + check*512
+
+    for (;;) {
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int g = s_group;
+        if (g >= p.ngroups) break;
+
+        const long long cw = (long long)g * kLanes + lane;
+        const bool active = cw < p.ncw;
+        const float* src = p.llr + (size_t)(active ? cw : 0) * N;
+
+        // ---- load: -y into registers (static slots) and T; R = 0 (decodeInitMS, decodeCL.c:113-124)
+        float yn[S_MAX];
+#pragma unroll
+        for (int s = 0; s < S_MAX; ++s) {
+            const int n = warp + s * W;
+            float v = 1.0f;
+            if (n < N && active) v = __ldg(src + n);
+            yn[s] = __fadd_rn(-v, 0.0f);  // canonical: -0.0 never stored
+            if (n < N) T[n * kLanes + lane] = yn[s];
+        }
+        for (int c = warp; c < M; c += W) ST[c * kLanes + lane] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+        if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+        __syncthreads();
+
+        bool done = !active;
+        int my_iters = 0;
+        int iter = 0;
+        for (;;) {
+            // ---- check-node pass: S = T + R_old = -Q; new {min1, min2, signs, argmin}; syndrome of T
+            uint32_t unsat = 0u;
+            for (int c = warp; c < M; c += W) {
+                const int dc = cn_deg[c];
+                const uint4 so = *reinterpret_cast<const uint4*>(STl + (size_t)c * 512);
+                const float m1o = __uint_as_float(so.x), m2o = __uint_as_float(so.y);
+                uint32_t wsh = so.z << ((32 - dc) & 31);
+                const uint32_t argo = so.w;
+                const uint32_t* tab = cn_tab + c * DCP;
+                float m1 = INFINITY, m2 = INFINITY;
+                uint32_t sS = 0u, arg = 0u, sx = 0u;
+                auto edge = [&](uint32_t off) {
+                    const float t = *reinterpret_cast<const float*>(Tl + off);
+                    const float mag = (argo == off) ? m2o : m1o;
+                    const float r = __uint_as_float(__float_as_uint(mag) ^ (wsh & 0x80000000u));
+                    wsh <<= 1;
+                    const float sv = __fadd_rn(t, r);
+                    sS = __funnelshift_l(__float_as_uint(sv), sS, 1);
+                    sx ^= __float_as_uint(t);
+                    const float a = fabsf(sv);
+                    arg = (a < m1) ? off : arg;
+                    m2 = fminf(m2, fmaxf(m1, a));
+                    m1 = fminf(m1, a);
+                };
+                int j = 0;
+                for (; j + 4 <= dc; j += 4) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(tab + j);
+                    edge(o.x); edge(o.y); edge(o.z); edge(o.w);
+                }
+                if (j < dc) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(tab + j);
+                    edge(o.x);
+                    if (j + 1 < dc) edge(o.y);
+                    if (j + 2 < dc) edge(o.z);
+                }
+                // signs: bit (dc-1-j) of sS = signbit(S_j) = !(Q_j < 0); R_j sign = parity ^ (Q_j < 0)
+                const uint32_t mask = (dc >= 32) ? 0xffffffffu : ((1u << dc) - 1u);
+                const uint32_t par = (uint32_t)(dc - __popc(sS & mask)) & 1u;
+                const uint32_t sr = (par ? sS : ~sS) & mask;
+                *reinterpret_cast<uint4*>(const_cast<unsigned char*>(STl) + (size_t)c * 512) =
+                    make_uint4(__float_as_uint(fminf(m1, kClamp)), __float_as_uint(fminf(m2, kClamp)), sr, arg);
+                // hard bit = !signbit(T): row syndrome = xor of signbits ^ (dc & 1)
+                unsat |= ((sx >> 31) ^ (uint32_t)dc) & 1u;
+            }
+            const bool check = p.early_term && iter >= 1;
+            if (check && unsat) s_flag[iter & 1][lane] = 1u;  // same-value race, benign
+            __syncthreads();
+            if (check && !done && s_flag[iter & 1][lane] == 0u) { done = true; my_iters = iter; }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
+
+            // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
+#pragma unroll
+            for (int s = 0; s < S_MAX; ++s) {
+                const int n = warp + s * W;
+                if (n < N) {
+                    const uint32_t v0 = vn_ptr[n], v1 = vn_ptr[n + 1];
+                    const uint32_t key = (uint32_t)n * 128u;
+                    float acc = yn[s];
+#pragma unroll 1
+                    for (uint32_t e = v0; e < v1; ++e) {
+                        const uint32_t ent = vn_tab[e];
+                        const uint32_t sh = ent & 31u;
+                        const uint4 st = *reinterpret_cast<const uint4*>(STl + (ent - sh));
+                        const uint32_t mag = (st.w == key) ? st.y : st.x;
+                        const float r = __uint_as_float(mag ^ ((st.z << sh) & 0x80000000u));
+                        acc = __fsub_rn(acc, r);
+                    }
+                    if (!done) T[n * kLanes + lane] = acc;
+                }
+            }
+            ++iter;
+            if (iter == p.max_iter) {
+                if (!done) my_iters = iter;
+                break;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+
+        // ---- outputs (toChar, decodeCL.c:188-199): bit n = !(P > 0) = !signbit(T)
+        if (p.info) {
+            const int KB = (p.K + 7) >> 3;
+            for (int b = warp; b < KB; b += W) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.K) v |= ((~__float_as_uint(T[n * kLanes + lane])) >> 31) << t;
+                }
+                if (active) p.info[(size_t)cw * KB + b] = (uint8_t)v;
+            }
+        }
+        if (p.hard) {
+            const int NB = (N + 7) >> 3;
+            for (int b = warp; b < NB; b += W) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < N) v |= ((~__float_as_uint(T[n * kLanes + lane])) >> 31) << t;
+                }
+                if (active) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
+            }
+        }
+        if (p.post && active) {
+            for (int n = warp; n < N; n += W) p.post[(size_t)cw * N + n] = -T[n * kLanes + lane];
+        }
+        if (p.iters && warp == 0 && active) p.iters[cw] = my_iters;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Synthetic BPSK + AWGN channel (Coder::test, reference MyLdpc.cpp:1061-1078): bit 0 -> +1,
 // bit 1 -> -1, plus sigma * N(0,1).  Counter-based: element i of the stream depends only on
 // (seed, i), so any shard of any GPU generates the same floats for the same codeword index.
@@ -247,20 +447,20 @@ __global__ void __launch_bounds__(256) ldpc_synth_llr_kernel(float* __restrict__
 
 // ---------------------------------------------------------------------------------------
 // Shared-memory bandwidth probe (measurement aid for bench.py's on-chip roofline): every
-// thread streams conflict-free 16-byte loads from a 64 KB tile.  Bytes moved per launch =
+// thread streams conflict-free 16-byte loads from a 128 KB tile.  Bytes moved per launch =
 // gridDim.x * blockDim.x * 16 * 8 * loops.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1) ldpc_smem_probe_kernel(uint32_t* __restrict__ sink, int loops) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* buf = reinterpret_cast<uint4*>(smem_raw);
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);
+    for (int i = threadIdx.x; i < 8192; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);
     __syncthreads();
     uint4 acc = make_uint4(0, 0, 0, 0);
     for (int l = 0; l < loops; ++l) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint4 v = buf[(threadIdx.x + k * 1024 + l * 32) & 4095];
-            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+            const uint4 v = buf[(threadIdx.x + k * 1024 + l * 32) & 8191];
+            acc.x += v.x; acc.y ^= v.y; acc.z += v.z; acc.w ^= v.w;
         }
     }
     if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345u) sink[blockIdx.x] = acc.x;  // keep the loads alive

@@ -6,7 +6,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <functional>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -46,10 +49,9 @@ struct Plan {
     int cw_per_cta = 32;
     size_t smem = 0;
     size_t ws_stride = 0;  // floats per CTA (LANE_GLOBAL)
-    int dcp = 0;           // padded check degree of the LANE16 tables
+    int dcp = 0;           // LANE16: padded check degree of the per-warp tables
+    int W = 0, CS = 0, VS = 0;  // LANE16: warps, check slots and variable slots per warp
 };
-
-constexpr int kLane16Slots = 24;  // variable slots per warp held in registers (S_MAX)
 
 }  // namespace
 
@@ -72,10 +74,13 @@ struct ldpc_b200_decoder {
     size_t table_bytes = 0;
     // LANE16 tables (byte-offset form, copied into shared memory by the kernel)
     uint32_t* d16_cn_tab = nullptr;
-    uint8_t* d16_cn_deg = nullptr;
-    uint32_t* d16_vn_ptr = nullptr;
-    uint32_t* d16_vn_tab = nullptr;
+    uint2* d16_vn_tab = nullptr;
+    uint32_t* d16_var_of_pos = nullptr;
+    uint32_t* d16_pos_of_var = nullptr;
     bool lane16_ready = false;
+    int l16_vn_stride = 0;
+    uint8_t l16_vdeg[kL16MaxVS] = {0};
+    uint8_t l16_cdeg[kL16MaxCS] = {0};
 
     unsigned int* d_counters = nullptr;
     int counter_next = 0;
@@ -127,49 +132,117 @@ int pick_lane_warps(int M, int N, int nnz) {
     return best_w;
 }
 
-size_t lane16_smem_bytes(const HostTables& t, int dcp) {
-    return (size_t)t.M * kLanes * 16 + (size_t)t.N * kLanes * 4 + (size_t)t.M * dcp * 4 +
-           (size_t)((t.nnz + 3) & ~3) * 4 + (size_t)((t.N + 1 + 3) & ~3) * 4 + (size_t)((t.M + 15) & ~15);
+// ---- LANE16 layout: degree-sorted ownership, per-warp flat tables (see ldpc_kernels.cuh) ----
+struct L16Shape {
+    int W = 0, CS = 0, VS = 0, DCP = 0;
+    long long vn_stride = 0;   // uint2 entries per warp
+    double padded_work = 0.0;  // issue-slot proxy used to pick W
+    size_t smem = 0;
+};
+
+// degrees sorted descending; slot degree = degree of the first (largest) member of the slot
+L16Shape lane16_shape(const HostTables& t, int W) {
+    L16Shape sh;
+    sh.W = W;
+    sh.CS = (t.M + W - 1) / W;
+    sh.VS = (t.N + W - 1) / W;
+    sh.DCP = (t.max_row_weight + 3) & ~3;
+    std::vector<int> cd(t.M), vd(t.N);
+    for (int r = 0; r < t.M; ++r) cd[r] = t.row_ptr[r + 1] - t.row_ptr[r];
+    for (int c = 0; c < t.N; ++c) vd[c] = t.col_ptr[c + 1] - t.col_ptr[c];
+    std::sort(cd.begin(), cd.end(), std::greater<int>());
+    std::sort(vd.begin(), vd.end(), std::greater<int>());
+    double cn_edges = 0, vn_edges = 0;
+    for (int cs = 0; cs < sh.CS; ++cs) cn_edges += (double)cd[(size_t)cs * W] * W;
+    for (int s = 0; s < sh.VS; ++s) { vn_edges += (double)vd[(size_t)s * W] * W; sh.vn_stride += vd[(size_t)s * W]; }
+    sh.padded_work = 13.0 * cn_edges + 8.0 * vn_edges + 20.0 * sh.CS * W + 10.0 * sh.VS * W;
+    sh.smem = (size_t)(sh.CS * W + 1) * kLanes * 16 + (size_t)(sh.VS * W + 1) * kLanes * 4 +
+              (size_t)W * sh.CS * sh.DCP * 4 + (size_t)W * sh.vn_stride * 8;
+    return sh;
 }
 
-int pick_lane16_warps(int M, int N) {
-    const int wmin = std::max(8, (N + kLane16Slots - 1) / kLane16Slots);
-    int best_w = 32;
-    double best = -1.0;
-    for (int w = wmin; w <= 32; ++w) {
-        double cn = (double)M / w / ((M + w - 1) / w);
-        double vn = (double)N / w / ((N + w - 1) / w);
-        double eff = (0.6 * cn + 0.4 * vn) * (0.75 + 0.25 * w / 32.0);
-        if (eff > best + 1e-9) { best = eff; best_w = w; }
+bool lane16_pick(const HostTables& t, size_t smem_limit, L16Shape* best) {
+    if (t.max_row_weight > 32 || t.max_row_weight < 1 || t.nnz < 1) return false;
+    bool found = false;
+    double best_cost = 0.0;
+    int w_lo = 8, w_hi = 32;
+    if (const char* env = std::getenv("LDPC_B200_L16_WARPS")) {  // tuning aid: pin the warp count
+        const int w = std::atoi(env);
+        if (w >= 1 && w <= 32) w_lo = w_hi = w;
     }
-    return best_w;
+    for (int W = w_lo; W <= w_hi; ++W) {
+        L16Shape sh = lane16_shape(t, W);
+        if (sh.VS > kL16MaxVS || sh.CS > kL16MaxCS) continue;
+        if (sh.smem + 1024 > smem_limit) continue;
+        // more warps hide more latency: mild preference (same form as the generic path)
+        const double cost = sh.padded_work / (0.75 + 0.25 * W / 32.0);
+        if (!found || cost < best_cost - 1e-9 || (std::abs(cost - best_cost) <= 1e-9 && W > best->W)) {
+            found = true; best_cost = cost; *best = sh;
+        }
+    }
+    return found;
 }
 
-int upload_lane16_tables(ldpc_b200_decoder* h, int dcp) {
+int upload_lane16_tables(ldpc_b200_decoder* h) {
     if (h->lane16_ready) return LDPC_B200_OK;
     const HostTables& t = h->host;
-    std::vector<uint32_t> cn_tab((size_t)t.M * dcp, 0u), vn_tab((size_t)std::max(t.nnz, 1), 0u), vn_ptr(t.N + 1);
-    std::vector<uint8_t> deg(t.M);
-    for (int r = 0; r < t.M; ++r) {
-        const int e0 = t.row_ptr[r], dc = t.row_ptr[r + 1] - e0;
-        deg[r] = (uint8_t)dc;
-        for (int j = 0; j < dc; ++j) cn_tab[(size_t)r * dcp + j] = (uint32_t)t.col_idx[e0 + j] * 128u;
-    }
-    for (int n = 0; n <= t.N; ++n) vn_ptr[n] = (uint32_t)t.col_ptr[n];
-    for (int e = 0; e < t.nnz; ++e) {
-        const uint32_t chk = t.vn_edge[e] >> kPosBits, pos = t.vn_edge[e] & ((1u << kPosBits) - 1u);
-        const int dc = t.row_ptr[chk + 1] - t.row_ptr[chk];
-        vn_tab[e] = chk * 512u | (uint32_t)(32 - dc + (int)pos);
-    }
+    const Plan& pl = h->plan;
+    const int W = pl.W, CS = pl.CS, VS = pl.VS, DCP = pl.dcp;
+    // rank variables / checks by degree (descending, stable in index): position = rank = slot*W + warp
+    std::vector<int> vorder(t.N), corder(t.M);
+    for (int i = 0; i < t.N; ++i) vorder[i] = i;
+    for (int i = 0; i < t.M; ++i) corder[i] = i;
+    auto vdegf = [&](int c) { return t.col_ptr[c + 1] - t.col_ptr[c]; };
+    auto cdegf = [&](int r) { return t.row_ptr[r + 1] - t.row_ptr[r]; };
+    std::stable_sort(vorder.begin(), vorder.end(), [&](int a, int b) { return vdegf(a) > vdegf(b); });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cdegf(a) > cdegf(b); });
+    const int PD = VS * W, CPD = CS * W;
+    std::vector<uint32_t> var_of_pos((size_t)PD, 0xffffffffu), pos_of_var(t.N), cpos_of_chk(t.M);
+    for (int i = 0; i < t.N; ++i) { var_of_pos[i] = (uint32_t)vorder[i]; pos_of_var[vorder[i]] = (uint32_t)i; }
+    for (int i = 0; i < t.M; ++i) cpos_of_chk[corder[i]] = (uint32_t)i;
+    std::memset(h->l16_vdeg, 0, sizeof(h->l16_vdeg));
+    std::memset(h->l16_cdeg, 0, sizeof(h->l16_cdeg));
+    for (int s = 0; s < VS; ++s) h->l16_vdeg[s] = (uint8_t)vdegf(vorder[(size_t)s * W]);
+    for (int cs = 0; cs < CS; ++cs) h->l16_cdeg[cs] = (uint8_t)cdegf(corder[(size_t)cs * W]);
+    long long vn_stride = 0;
+    std::vector<long long> voff(VS + 1, 0);
+    for (int s = 0; s < VS; ++s) { voff[s] = vn_stride; vn_stride += h->l16_vdeg[s]; }
+    h->l16_vn_stride = (int)vn_stride;
+
+    // check-major per-warp table: real edges first (position j fixes the sign-bit slot), then dummies
+    std::vector<uint32_t> cn_tab((size_t)W * CS * DCP, (uint32_t)PD * 128u);
+    for (int w = 0; w < W; ++w)
+        for (int cs = 0; cs < CS; ++cs) {
+            const int rank = cs * W + w;
+            if (rank >= t.M) continue;
+            const int r = corder[rank], e0 = t.row_ptr[r], dc = cdegf(r);
+            for (int j = 0; j < dc; ++j)
+                cn_tab[((size_t)w * CS + cs) * DCP + j] = pos_of_var[t.col_idx[e0 + j]] * 128u;
+        }
+    // variable-major per-warp table: ascending-row edge order kept; dummies pad to the slot degree
+    std::vector<uint2> vn_tab((size_t)W * std::max<long long>(vn_stride, 1), make_uint2((uint32_t)CPD * 512u, 0u));
+    for (int w = 0; w < W; ++w)
+        for (int s = 0; s < VS; ++s) {
+            const int rank = s * W + w;
+            if (rank >= t.N) continue;
+            const int v = vorder[rank];
+            for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+                const uint32_t chk = t.vn_edge[k] >> kPosBits, pos = t.vn_edge[k] & ((1u << kPosBits) - 1u);
+                const uint32_t cp = cpos_of_chk[chk];
+                const int slot_deg = h->l16_cdeg[cp / W];
+                const int shift = 32 - slot_deg + (int)pos;  // bit (slot_deg-1-pos) -> bit 31
+                vn_tab[(size_t)w * vn_stride + voff[s] + (k - t.col_ptr[v])] = make_uint2(cp * 512u, 1u << shift);
+            }
+        }
     CU_TRY(cudaMalloc(&h->d16_cn_tab, cn_tab.size() * 4));
-    CU_TRY(cudaMalloc(&h->d16_cn_deg, deg.size()));
-    CU_TRY(cudaMalloc(&h->d16_vn_ptr, vn_ptr.size() * 4));
-    CU_TRY(cudaMalloc(&h->d16_vn_tab, vn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->d16_vn_tab, vn_tab.size() * 8));
+    CU_TRY(cudaMalloc(&h->d16_var_of_pos, var_of_pos.size() * 4));
+    CU_TRY(cudaMalloc(&h->d16_pos_of_var, pos_of_var.size() * 4));
     CU_TRY(cudaMemcpy(h->d16_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d16_cn_deg, deg.data(), deg.size(), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d16_vn_ptr, vn_ptr.data(), vn_ptr.size() * 4, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(h->d16_vn_tab, vn_tab.data(), vn_tab.size() * 4, cudaMemcpyHostToDevice));
-    h->table_bytes += cn_tab.size() * 4 + deg.size() + vn_ptr.size() * 4 + vn_tab.size() * 4;
+    CU_TRY(cudaMemcpy(h->d16_vn_tab, vn_tab.data(), vn_tab.size() * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d16_var_of_pos, var_of_pos.data(), var_of_pos.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d16_pos_of_var, pos_of_var.data(), pos_of_var.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += cn_tab.size() * 4 + vn_tab.size() * 8 + var_of_pos.size() * 4 + pos_of_var.size() * 4;
     h->lane16_ready = true;
     return LDPC_B200_OK;
 }
@@ -178,17 +251,17 @@ int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
     {   // tuned short-code path: channel values in registers, 16-byte check state, tables in smem
-        const int dcp = (t.max_row_weight + 3) & ~3;
-        const bool fits = t.N <= kLane16Slots * 32 && t.max_row_weight <= 32 && t.max_row_weight >= 1 &&
-                          (uint64_t)t.M * 512u < (1ull << 32) && lane16_smem_bytes(t, dcp) + 1024 <= h->smem_optin;
+        L16Shape sh;
+        const bool fits = (uint64_t)t.M * 512u < (1ull << 31) && lane16_pick(t, h->smem_optin, &sh);
         if (h->forced_path == LDPC_B200_PATH_LANE16 && !fits)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the lane16 shared-memory path");
         if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_LANE16) && fits) {
+            if (h->lane16_ready && (h->plan.W != sh.W)) return fail(LDPC_B200_ERR_ARG, "lane16 layout changed after upload");
             pl.path = LDPC_B200_PATH_LANE16;
-            pl.threads = 32 * pick_lane16_warps(t.M, t.N);
-            pl.smem = lane16_smem_bytes(t, dcp);
+            pl.threads = 32 * sh.W;
+            pl.smem = sh.smem;
             pl.ctas = h->sm_count;
-            pl.dcp = dcp;
+            pl.dcp = sh.DCP; pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;
@@ -262,17 +335,26 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
 
     if (pl.path == LDPC_B200_PATH_LANE16) {
-        rc = upload_lane16_tables(h, pl.dcp);
+        rc = upload_lane16_tables(h);
         if (rc) return rc;
         Lane16Params q;
-        q.cn_tab = h->d16_cn_tab; q.cn_deg = h->d16_cn_deg; q.vn_ptr = h->d16_vn_ptr; q.vn_tab = h->d16_vn_tab;
-        q.M = t.M; q.N = t.N; q.K = h->K; q.DCP = pl.dcp; q.nnz = t.nnz;
+        q.cn_tab = h->d16_cn_tab; q.vn_tab = h->d16_vn_tab;
+        q.var_of_pos = h->d16_var_of_pos; q.pos_of_var = h->d16_pos_of_var;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.W = pl.W; q.CS = pl.CS; q.VS = pl.VS; q.DCP = pl.dcp;
+        q.vn_stride = h->l16_vn_stride;
         q.max_iter = h->max_iter; q.early_term = h->early;
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter = ctr; q.ngroups = (int)ngroups;
-        CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<kLane16Slots>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        ldpc_ms_lane16_kernel<kLane16Slots><<<grid, pl.threads, pl.smem, stream>>>(q);
+        std::memcpy(q.vdeg, h->l16_vdeg, sizeof(q.vdeg));
+        std::memcpy(q.cdeg, h->l16_cdeg, sizeof(q.cdeg));
+        if (pl.threads <= 768) {
+            CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            ldpc_ms_lane16_kernel<768><<<grid, pl.threads, pl.smem, stream>>>(q);
+        } else {
+            CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+            ldpc_ms_lane16_kernel<1024><<<grid, pl.threads, pl.smem, stream>>>(q);
+        }
         CU_TRY(cudaGetLastError());
         h->launches += 1;
         return LDPC_B200_OK;
@@ -391,7 +473,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
-            cudaFree(h->d16_cn_tab); cudaFree(h->d16_cn_deg); cudaFree(h->d16_vn_ptr); cudaFree(h->d16_vn_tab);
+            cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
         }

@@ -216,25 +216,36 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParam
 // ---------------------------------------------------------------------------------------
 // LANE16 kernel: the tuned shared-memory path for short codes (Test.cpp's N=576 code).
 // Same schedule as above (32 codewords per CTA, lane = codeword, two barriers per iteration),
-// with everything the inner loops touch arranged for the fewest issue slots per edge:
-//   T  [N][32] f32    NEGATED posterior T = -P, zero canonicalised to +0.0, so that
-//                     hard bit = !signbit(T) and a row's syndrome is one XOR per edge
-//   ST [M][32] uint4  {min1, min2, sign word, argmin key}: one LDS.128 per edge in the VN pass;
-//                     argmin key = byte offset of the argmin's column in T (any injective id)
-//   channel values    stay in REGISTERS: warp w owns variables w, w+W, w+2W, ... for the whole
-//                     decode (static slots), thread (w, lane) keeps -y of its 32 x S_MAX words
-//   index tables      live in shared memory, pre-multiplied to byte offsets:
-//                     cn_tab[c*DCP + j] = col*128, vn_tab[e] = check*512 | (32 - dc + j)
+// arranged so that the binding resource -- the 16-lane ALU pipe (LOP3/SHF/FMNMX/ISETP/SEL) --
+// sees as few instructions per edge as the arithmetic allows:
+//   T  [pos][32] f32    NEGATED posterior T = -P, zero canonicalised to +0.0, so that
+//                       hard bit = !signbit(T) and a row's syndrome is one XOR per edge
+//   ST [cpos][32] uint4 {min1, min2, sign word, argmin key}: one LDS.128 per edge in the VN pass;
+//                       argmin key = byte offset of the argmin's row in T
+//   channel values      stay in REGISTERS: warp w owns variable positions w, w+W, w+2W ... for
+//                       the whole decode (static slots); thread (w, lane) keeps -y of its words
+//   ownership order     variables and checks are sorted by degree (host side) and dealt to
+//                       (slot, warp) in that order, so a slot has ONE degree for all warps:
+//                       no per-variable / per-check degree loads, padding only at class edges
+//   index tables        per-warp flat lists in shared memory, pre-multiplied:
+//                       cn: byte offset of T row;  vn: {byte offset of ST row, 1 << shift}
+//                       (the sign bit is fetched with an IMAD on the FMA pipe, not a shift)
+//   padding             dummy T row = -inf (acts as P = +inf: never the minimum, positive sign,
+//                       hard bit 0); dummy ST row = {0,0,0,nokey} (R = +0.0, adds nothing)
 // Arithmetic is the same fp32 sequence as the reference: T = (-y) - R1 - R2 ... is the exact
 // negation of y + R1 + R2 ... (round-to-nearest is sign-symmetric); Q = P - R = -(T + R).
 // The sign of an exact zero never influences a non-zero value or a decision.
 // ---------------------------------------------------------------------------------------
+constexpr int kL16MaxVS = 24;  // variable slots per warp (channel values held in registers)
+constexpr int kL16MaxCS = 32;  // check slots per warp
+
 struct Lane16Params {
-    const uint32_t* __restrict__ cn_tab;   // [M*DCP] byte offsets col*128 (padding entries unused)
-    const uint8_t* __restrict__ cn_deg;    // [M]
-    const uint32_t* __restrict__ vn_ptr;   // [N+1]
-    const uint32_t* __restrict__ vn_tab;   // [nnz] check*512 | shift
-    int M, N, K, DCP, nnz, max_iter, early_term;
+    const uint32_t* __restrict__ cn_tab;      // [W][CS][DCP] byte offsets pos*128 (dummy = PD*128)
+    const uint2* __restrict__ vn_tab;         // [W][vn_stride] {cpos*512, 1 << shift} (dummy = {CPD*512, 0})
+    const uint32_t* __restrict__ var_of_pos;  // [VS*W] variable index, 0xffffffff = phantom
+    const uint32_t* __restrict__ pos_of_var;  // [N]
+    int M, N, K, W, CS, VS, DCP, vn_stride;
+    int max_iter, early_term;
     const float* __restrict__ llr;
     long long ncw;
     uint8_t* info;
@@ -243,35 +254,89 @@ struct Lane16Params {
     float* post;
     unsigned int* counter;
     int ngroups;
+    uint8_t vdeg[kL16MaxVS];  // slot degree of variable slot s (0 beyond VS)
+    uint8_t cdeg[kL16MaxCS];  // slot degree of check slot cs
 };
 
-template <int S_MAX>
-__global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Params p) {
+// Explicit 32-bit shared-window addressing: keeps every hot-loop access an `LDS [R + imm]` with a
+// single 2-input add in front of it (no generic-address reconstruction in the loop).
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// CNT consecutive variable-node edges: entries at shared address `q` ({ST row address, 1 << shift}).
+template <int CNT>
+__device__ __forceinline__ void l16_vn_edges(uint32_t q, uint32_t lane16, uint32_t key, float& acc) {
+    uint2 e[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) e[k] = lds_u64(q + 8 * k);
+    uint4 st[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) st[k] = lds_u128(e[k].x + lane16);
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) {
+        const uint32_t mag = (st[k].w == key) ? st[k].y : st[k].x;
+        const uint32_t sg = st[k].z * e[k].y;  // bit `shift` of the sign word -> bit 31 (IMAD, FMA pipe)
+        acc = __fsub_rn(acc, __uint_as_float((sg & 0x80000000u) ^ mag));
+    }
+}
+
+template <int MAX_THREADS>  // 768 (<= 24 warps: 80 registers per thread) or 1024 (64 registers)
+__global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_lane16_kernel(const __grid_constant__ Lane16Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_group;
     __shared__ uint32_t s_flag[2][kLanes];
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int W = blockDim.x >> 5;
-    const int M = p.M, N = p.N, DCP = p.DCP;
+    const int W = p.W, CS = p.CS, VS = p.VS, DCP = p.DCP;
+    const int PD = VS * W, CPD = CS * W;  // dummy rows
 
-    // shared-memory carve-up (all 16-byte aligned)
-    unsigned char* sp = smem_raw;
-    uint4* ST = reinterpret_cast<uint4*>(sp);                 sp += (size_t)M * kLanes * 16;
-    float* T = reinterpret_cast<float*>(sp);                  sp += (size_t)N * kLanes * 4;
-    uint32_t* cn_tab = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)M * DCP * 4;
-    uint32_t* vn_tab = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)((p.nnz + 3) & ~3) * 4;
-    uint32_t* vn_ptr = reinterpret_cast<uint32_t*>(sp);       sp += (size_t)((N + 1 + 3) & ~3) * 4;
-    uint8_t* cn_deg = reinterpret_cast<uint8_t*>(sp);
-
-    for (int i = threadIdx.x; i < M * DCP; i += blockDim.x) cn_tab[i] = __ldg(p.cn_tab + i);
-    for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) vn_tab[i] = __ldg(p.vn_tab + i);
-    for (int i = threadIdx.x; i <= N; i += blockDim.x) vn_ptr[i] = __ldg(p.vn_ptr + i);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) cn_deg[i] = __ldg(p.cn_deg + i);
-
-    const unsigned char* Tl = reinterpret_cast<const unsigned char*>(T) + lane * 4;     // + col*128
-    const unsigned char* STl = reinterpret_cast<const unsigned char*>(ST) + lane * 16;  // + check*512
+    // shared-window byte addresses of the four regions
+    const uint32_t st_base = smem_u32(smem_raw);
+    const uint32_t t_base = st_base + (uint32_t)(CPD + 1) * kLanes * 16;
+    const uint32_t cn_base = t_base + (uint32_t)(PD + 1) * kLanes * 4;
+    const uint32_t vn_base = cn_base + (uint32_t)W * CS * DCP * 4;
+    {
+        // tables are stored with the region base already added: an entry IS a shared address
+        uint32_t* cn_tab = reinterpret_cast<uint32_t*>(smem_raw + (cn_base - st_base));
+        uint2* vn_tab = reinterpret_cast<uint2*>(smem_raw + (vn_base - st_base));
+        for (int i = threadIdx.x; i < W * CS * DCP; i += blockDim.x) cn_tab[i] = __ldg(p.cn_tab + i) + t_base;
+        for (int i = threadIdx.x; i < W * p.vn_stride; i += blockDim.x) {
+            uint2 e = __ldg(p.vn_tab + i);
+            e.x += st_base;
+            vn_tab[i] = e;
+        }
+    }
+    const uint32_t lane4 = (uint32_t)lane * 4u, lane16 = (uint32_t)lane * 16u;
+    if (warp == 0) {
+        sts_f32(t_base + (uint32_t)PD * 128u + lane4, -INFINITY);
+        sts_u128(st_base + (uint32_t)CPD * 512u + lane16, make_uint4(0u, 0u, 0u, 0xffffffffu));
+    }
+    const uint32_t cn_w = cn_base + (uint32_t)warp * CS * DCP * 4;
+    const uint32_t vn_w = vn_base + (uint32_t)warp * p.vn_stride * 8;
+    const uint32_t key_w = t_base + (uint32_t)warp * 128u;  // T row (lane 0) of this warp's slot 0
+    const uint32_t sta_w = st_base + (uint32_t)warp * 512u + lane16;
+    const uint32_t t_stride = (uint32_t)W * 128u, st_stride = (uint32_t)W * 512u;
 
     for (;;) {
         if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
@@ -281,19 +346,22 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Par
 
         const long long cw = (long long)g * kLanes + lane;
         const bool active = cw < p.ncw;
-        const float* src = p.llr + (size_t)(active ? cw : 0) * N;
+        const float* src = p.llr + (size_t)(active ? cw : 0) * p.N;
 
         // ---- load: -y into registers (static slots) and T; R = 0 (decodeInitMS, decodeCL.c:113-124)
-        float yn[S_MAX];
+        float yn[kL16MaxVS];
 #pragma unroll
-        for (int s = 0; s < S_MAX; ++s) {
-            const int n = warp + s * W;
-            float v = 1.0f;
-            if (n < N && active) v = __ldg(src + n);
-            yn[s] = __fadd_rn(-v, 0.0f);  // canonical: -0.0 never stored
-            if (n < N) T[n * kLanes + lane] = yn[s];
+        for (int s = 0; s < kL16MaxVS; ++s) {
+            yn[s] = -1.0f;
+            if (s < VS) {
+                const uint32_t v = __ldg(p.var_of_pos + s * W + warp);
+                float y = 1.0f;
+                if (v != 0xffffffffu && active) y = __ldg(src + v);
+                yn[s] = __fadd_rn(-y, 0.0f);  // canonical: -0.0 is never stored
+                sts_f32(key_w + (uint32_t)s * t_stride + lane4, yn[s]);
+            }
         }
-        for (int c = warp; c < M; c += W) ST[c * kLanes + lane] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+        for (int cs = 0; cs < CS; ++cs) sts_u128(sta_w + (uint32_t)cs * st_stride, make_uint4(0u, 0u, 0u, 0xffffffffu));
         if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
         __syncthreads();
 
@@ -303,45 +371,47 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Par
         for (;;) {
             // ---- check-node pass: S = T + R_old = -Q; new {min1, min2, signs, argmin}; syndrome of T
             uint32_t unsat = 0u;
-            for (int c = warp; c < M; c += W) {
-                const int dc = cn_deg[c];
-                const uint4 so = *reinterpret_cast<const uint4*>(STl + (size_t)c * 512);
+            for (int cs = 0; cs < CS; ++cs) {
+                const int dc = p.cdeg[cs];
+                const uint32_t sta = sta_w + (uint32_t)cs * st_stride;
+                const uint4 so = lds_u128(sta);
                 const float m1o = __uint_as_float(so.x), m2o = __uint_as_float(so.y);
                 uint32_t wsh = so.z << ((32 - dc) & 31);
                 const uint32_t argo = so.w;
-                const uint32_t* tab = cn_tab + c * DCP;
+                uint32_t tab = cn_w + (uint32_t)(cs * DCP) * 4u;
                 float m1 = INFINITY, m2 = INFINITY;
-                uint32_t sS = 0u, arg = 0u, sx = 0u;
-                auto edge = [&](uint32_t off) {
-                    const float t = *reinterpret_cast<const float*>(Tl + off);
-                    const float mag = (argo == off) ? m2o : m1o;
+                uint32_t sS = 0u, arg = 0xffffffffu, sx = 0u;
+                auto edge = [&](uint32_t ent) {
+                    const float t = lds_f32(ent + lane4);
+                    const float mag = (argo == ent) ? m2o : m1o;
                     const float r = __uint_as_float(__float_as_uint(mag) ^ (wsh & 0x80000000u));
                     wsh <<= 1;
                     const float sv = __fadd_rn(t, r);
                     sS = __funnelshift_l(__float_as_uint(sv), sS, 1);
                     sx ^= __float_as_uint(t);
                     const float a = fabsf(sv);
-                    arg = (a < m1) ? off : arg;
+                    arg = (a < m1) ? ent : arg;
                     m2 = fminf(m2, fmaxf(m1, a));
                     m1 = fminf(m1, a);
                 };
-                int j = 0;
-                for (; j + 4 <= dc; j += 4) {
-                    const uint4 o = *reinterpret_cast<const uint4*>(tab + j);
+                int j = dc;
+#pragma unroll 1
+                for (; j >= 4; j -= 4) {
+                    const uint4 o = lds_u128(tab);
+                    tab += 16;
                     edge(o.x); edge(o.y); edge(o.z); edge(o.w);
                 }
-                if (j < dc) {
-                    const uint4 o = *reinterpret_cast<const uint4*>(tab + j);
+                if (j > 0) {
+                    const uint4 o = lds_u128(tab);
                     edge(o.x);
-                    if (j + 1 < dc) edge(o.y);
-                    if (j + 2 < dc) edge(o.z);
+                    if (j > 1) edge(o.y);
+                    if (j > 2) edge(o.z);
                 }
-                // signs: bit (dc-1-j) of sS = signbit(S_j) = !(Q_j < 0); R_j sign = parity ^ (Q_j < 0)
+                // bit (dc-1-j) of sS = signbit(S_j) = !(Q_j < 0); sign of R_j = parity ^ (Q_j < 0)
                 const uint32_t mask = (dc >= 32) ? 0xffffffffu : ((1u << dc) - 1u);
                 const uint32_t par = (uint32_t)(dc - __popc(sS & mask)) & 1u;
                 const uint32_t sr = (par ? sS : ~sS) & mask;
-                *reinterpret_cast<uint4*>(const_cast<unsigned char*>(STl) + (size_t)c * 512) =
-                    make_uint4(__float_as_uint(fminf(m1, kClamp)), __float_as_uint(fminf(m2, kClamp)), sr, arg);
+                sts_u128(sta, make_uint4(__float_as_uint(fminf(m1, kClamp)), __float_as_uint(fminf(m2, kClamp)), sr, arg));
                 // hard bit = !signbit(T): row syndrome = xor of signbits ^ (dc & 1)
                 unsat |= ((sx >> 31) ^ (uint32_t)dc) & 1u;
             }
@@ -353,23 +423,21 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Par
             if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
 
             // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
+            {
+                uint32_t q = vn_w;
+                uint32_t key = key_w;
 #pragma unroll
-            for (int s = 0; s < S_MAX; ++s) {
-                const int n = warp + s * W;
-                if (n < N) {
-                    const uint32_t v0 = vn_ptr[n], v1 = vn_ptr[n + 1];
-                    const uint32_t key = (uint32_t)n * 128u;
-                    float acc = yn[s];
+                for (int s = 0; s < kL16MaxVS; ++s) {
+                    if (s < VS) {
+                        int d = p.vdeg[s];
+                        float acc = yn[s];
 #pragma unroll 1
-                    for (uint32_t e = v0; e < v1; ++e) {
-                        const uint32_t ent = vn_tab[e];
-                        const uint32_t sh = ent & 31u;
-                        const uint4 st = *reinterpret_cast<const uint4*>(STl + (ent - sh));
-                        const uint32_t mag = (st.w == key) ? st.y : st.x;
-                        const float r = __uint_as_float(mag ^ ((st.z << sh) & 0x80000000u));
-                        acc = __fsub_rn(acc, r);
+                        for (; d >= 4; d -= 4) { l16_vn_edges<4>(q, lane16, key, acc); q += 32; }
+                        if (d & 2) { l16_vn_edges<2>(q, lane16, key, acc); q += 16; }
+                        if (d & 1) { l16_vn_edges<1>(q, lane16, key, acc); q += 8; }
+                        if (!done) sts_f32(key + lane4, acc);
+                        key += t_stride;
                     }
-                    if (!done) T[n * kLanes + lane] = acc;
                 }
             }
             ++iter;
@@ -389,25 +457,32 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane16_kernel(const Lane16Par
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int n = b * 8 + t;
-                    if (n < p.K) v |= ((~__float_as_uint(T[n * kLanes + lane])) >> 31) << t;
+                    if (n < p.K) {
+                        const uint32_t pos = __ldg(p.pos_of_var + n);
+                        v |= ((~__float_as_uint(lds_f32(t_base + pos * 128u + lane4))) >> 31) << t;
+                    }
                 }
                 if (active) p.info[(size_t)cw * KB + b] = (uint8_t)v;
             }
         }
         if (p.hard) {
-            const int NB = (N + 7) >> 3;
+            const int NB = (p.N + 7) >> 3;
             for (int b = warp; b < NB; b += W) {
                 uint32_t v = 0u;
 #pragma unroll
                 for (int t = 0; t < 8; ++t) {
                     const int n = b * 8 + t;
-                    if (n < N) v |= ((~__float_as_uint(T[n * kLanes + lane])) >> 31) << t;
+                    if (n < p.N) {
+                        const uint32_t pos = __ldg(p.pos_of_var + n);
+                        v |= ((~__float_as_uint(lds_f32(t_base + pos * 128u + lane4))) >> 31) << t;
+                    }
                 }
                 if (active) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
             }
         }
         if (p.post && active) {
-            for (int n = warp; n < N; n += W) p.post[(size_t)cw * N + n] = -T[n * kLanes + lane];
+            for (int n = warp; n < p.N; n += W)
+                p.post[(size_t)cw * p.N + n] = -lds_f32(t_base + __ldg(p.pos_of_var + n) * 128u + lane4);
         }
         if (p.iters && warp == 0 && active) p.iters[cw] = my_iters;
     }

@@ -174,8 +174,9 @@ bool lane16_pick(const HostTables& t, size_t smem_limit, L16Shape* best) {
         L16Shape sh = lane16_shape(t, W);
         if (sh.VS > kL16MaxVS || sh.CS > kL16MaxCS) continue;
         if (sh.smem + 1024 > smem_limit) continue;
-        // more warps hide more latency: mild preference (same form as the generic path)
-        const double cost = sh.padded_work / (0.75 + 0.25 * W / 32.0);
+        // measured on cfg2 (profiles/r01_warp_sweep.txt): the unpadded split wins over extra warps;
+        // keep only a very mild preference for more warps among near-equal splits
+        const double cost = sh.padded_work / (0.97 + 0.03 * W / 32.0);
         if (!found || cost < best_cost - 1e-9 || (std::abs(cost - best_cost) <= 1e-9 && W > best->W)) {
             found = true; best_cost = cost; *best = sh;
         }

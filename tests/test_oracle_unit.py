@@ -1,0 +1,84 @@
+"""Oracle unit tests on hand-checkable parity-check matrices (no reference needed)."""
+import numpy as np
+
+import oracle
+
+
+def _csr(H):
+    H = np.asarray(H)
+    rp = np.concatenate([[0], np.cumsum(H.sum(1))]).astype(np.int32)
+    ci = np.concatenate([np.nonzero(r)[0] for r in H]).astype(np.int32)
+    return H.shape[0], H.shape[1], rp, ci
+
+
+H_HAMMING = [[1, 1, 0, 1, 1, 0, 0],
+             [1, 0, 1, 1, 0, 1, 0],
+             [0, 1, 1, 1, 0, 0, 1]]
+
+
+def test_noiseless_word_stops_after_one_iteration():
+    M, N, rp, ci = _csr(H_HAMMING)
+    o = oracle.Oracle(M, N, 4, rp, ci, times=40)
+    cw = np.array([1, 0, 1, 1, 0, 1, 0])  # H cw = 0
+    assert (np.array(H_HAMMING) @ cw % 2).sum() == 0
+    y = (1.0 - 2.0 * cw).astype(np.float32)[None, :]
+    info, iters, hard, post = o.decode(y)
+    assert iters[0] == 1 and np.array_equal(hard[0], cw)
+    assert info[0, 0] == (1 | 4 | 8)  # bits 0,2,3 set, LSB first
+
+
+def test_first_iteration_by_hand():
+    """One iteration on the (7,4) Hamming matrix, worked by hand from MyLdpc.cpp:705-735."""
+    M, N, rp, ci = _csr(H_HAMMING)
+    y = np.array([[0.9, -0.3, 1.2, 0.5, -0.1, 2.0, 0.7]], dtype=np.float32)
+    o = oracle.Oracle(M, N, 4, rp, ci, times=1)
+    _, iters, hard, post = o.decode(y)
+    f = np.float32
+    # row 0 = {0,1,3,4}: R to col 0 = sign(-0.3*0.5*-0.1=+) * min(0.3,0.5,0.1) = +0.1; ...
+    R = {
+        (0, 0): f(0.1), (0, 1): f(-0.1), (0, 3): f(0.1), (0, 4): f(-0.3),
+        (1, 0): f(0.5), (1, 2): f(0.5), (1, 3): f(0.9), (1, 5): f(0.5),
+        (2, 1): f(0.5), (2, 2): f(-0.3), (2, 3): f(-0.3), (2, 6): f(-0.3),
+    }
+    want = y[0].copy()
+    for (r, c), v in sorted(R.items()):  # ascending row order per column
+        want[c] = f(want[c] + v)
+    assert np.array_equal(post[0], want)
+    assert np.array_equal(hard[0], (~(want > 0)).astype(np.uint8))
+    assert iters[0] == 1
+
+
+def test_zero_posterior_decides_one_and_degree_one_check_gives_1000():
+    # a single check touching only column 0 (degree 1): R = +1000 (b starts at 1000, MyLdpc.cpp:708)
+    H = [[1, 0, 0], [0, 1, 1]]
+    M, N, rp, ci = _csr(H)
+    o = oracle.Oracle(M, N, 3, rp, ci, times=1)
+    y = np.array([[-2.0, 0.5, -0.5]], dtype=np.float32)
+    _, _, hard, post = o.decode(y)
+    assert post[0, 0] == np.float32(998.0)
+    # col 1: 0.5 + (-0.5) = 0 -> bit 1 (tmp > 0 is false, MyLdpc.cpp:729-733); col 2: -0.5 + 0.5 = 0 -> 1
+    assert post[0, 1] == 0 and post[0, 2] == 0 and hard[0, 1] == 1 and hard[0, 2] == 1
+
+
+def test_cap_is_inclusive_and_literal_equals_fast():
+    rp, ci, M = oracle.wimax_H(576, "3/4B")
+    rng = np.random.default_rng(0)
+    y = (1 + 0.9 * rng.standard_normal((64, 576))).astype(np.float32)
+    for cap in (1, 3, 40):
+        o = oracle.Oracle(M, 576, 432, rp, ci, times=cap)
+        a = o.decode(y, literal=True)
+        b = o.decode(y, literal=False, threads=3)
+        assert all(np.array_equal(x, z) for x, z in zip(a, b))
+        assert a[1].max() == cap and a[1].min() >= 1
+
+
+def test_size_helpers_and_stream_packing():
+    L = oracle.lib()
+    assert L.oracle_getCodeSize(432, 1000) == 19           # ceil(1000 / 54), MyLdpc.cpp:628-631
+    assert L.oracle_getPostCodeLength(432, 576, 1000) == 19 * 576
+    assert L.oracle_getPriorCodeLength(432, 576, 1000) == 19 * 72
+    rp, ci, M = oracle.wimax_H(576, "3/4B")
+    o = oracle.Oracle(M, 576, 432, rp, ci)
+    y = -np.ones((2, 576), dtype=np.float32)  # all-one hard decision never satisfies -> cap; bits all 1
+    stream, iters, hard, _ = o.decode_stream(y, 100)
+    assert stream.shape == (100,) and np.all(stream == 0xFF) and np.all(hard == 1)

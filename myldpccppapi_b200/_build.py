@@ -75,12 +75,49 @@ def build_coder(force: bool = False, verbose: bool = False) -> pathlib.Path:
     return CODER_LIB
 
 
+BIN = PKG / "bin"
+REFERENCE_TEST = pathlib.Path("/root/reference/Test.cpp")
+
+
+def build_harness(force: bool = False, verbose: bool = False) -> None:
+    """tools/mytest.cpp (our Test.cpp-shaped CLI) and, when the reference tree is mounted, the
+    reference's OWN Test.cpp compiled unmodified against include/MyLdpc.h -- the drop-in proof.
+    Binaries land in myldpccppapi_b200/bin/ (git-ignored, shipped to the GPU box)."""
+    if not CODER_LIB.exists():
+        return
+    BIN.mkdir(exist_ok=True)
+    cxx = shutil.which("g++") or "g++"
+    jobs = [(ROOT / "tools" / "mytest.cpp", BIN / "mytest", [])]
+    if REFERENCE_TEST.exists():
+        # `#include "MyLdpc.h"` / "cl.hpp" resolve next to the including file first, so the reference's
+        # Test.cpp is compiled through a symlink in a scratch directory (nothing is copied): its quoted
+        # includes then fall through to -I include, i.e. to OUR MyLdpc.h and the empty cl.hpp stub.
+        import tempfile
+        scratch = pathlib.Path(tempfile.mkdtemp(prefix="myldpc_dropin_"))
+        link = scratch / "Test.cpp"
+        link.symlink_to(REFERENCE_TEST)
+        jobs.append((link, BIN / "MyTest_reference_harness", []))
+    for src, out, extra in jobs:
+        if not (force or _stale(out, [src.resolve(), ROOT / "include" / "MyLdpc.h", CODER_LIB])):
+            continue
+        cmd = [cxx, "-std=c++17", "-O2", "-w", "-I", str(ROOT / "include"), str(src), "-o", str(out),
+               "-L", str(PKG), "-lmyldpc_b200", "-lldpc_b200", "-Wl,-rpath,$ORIGIN/..", *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            print(" ".join(cmd))
+            print(r.stdout, r.stderr)
+        if r.returncode:
+            raise RuntimeError("g++ failed for " + out.name)
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_cuda(force=force, verbose=verbose)
     build_coder(force=force, verbose=verbose)
+    build_harness(force=force, verbose=verbose)
 
 
 if __name__ == "__main__":
     import sys
     build_cuda(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv)
     build_coder(force="--force" in sys.argv, verbose=True)
+    build_harness(force="--force" in sys.argv, verbose=True)

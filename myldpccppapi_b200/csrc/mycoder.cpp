@@ -1,0 +1,294 @@
+// mycoder.cpp -- `class Coder` (include/MyLdpc.h) over the C-ABI of libldpc_b200.so.
+//
+// Host-side mirror of the reference's Coder (MyLdpc.cpp): same call order, same size rules, same
+// stream layout.  What the reference did with cl::Context / cl::Buffer / cl::Kernel in forDecoder,
+// addDecodeType and decodeOnce* is one ldpc_b200_* call here; the decode itself runs on the GPU(s).
+#include "MyLdpc.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <thread>
+
+#include "ldpc_b200.h"
+
+struct Coder::Impl {
+    int K = 0, N = 0, M = 0;
+    int rate = -1;       // rate_type, or -1 for a CSR-constructed code
+    int times = 40;      // reference MyLdpc.cpp:24
+    int batchSize = 0;
+    bool early = true;
+    std::vector<int> devices{0};
+    std::vector<ldpc_b200_handle> handles;
+    std::vector<int32_t> iters;
+    std::vector<uint8_t> info;
+    int lastCodeSize = 0;
+    std::string err;
+    // systematic encoder: parity = X u over GF(2); X stored row-wise, 64 info bits per word
+    bool encoderReady = false;
+    int kWords = 0;
+    std::vector<uint64_t> X;  // [M][kWords]
+
+    int fail(int code) {
+        err = ldpc_b200_last_error();
+        return code;
+    }
+    void destroyHandles() {
+        for (ldpc_b200_handle h : handles) ldpc_b200_destroy(h);
+        handles.clear();
+    }
+};
+
+// ---- construction -----------------------------------------------------------------------------
+Coder::Coder(int ldpcK, int ldpcN, enum rate_type rate) : kernelSourceCode(nullptr), impl(new Impl) {
+    impl->K = ldpcK;
+    impl->N = ldpcN;
+    impl->M = ldpcN - ldpcK;
+    impl->rate = (int)rate;
+    int M = 0, nnz = 0;
+    if (ldpc_b200_wimax_csr(ldpcK, ldpcN, (int)rate, nullptr, nullptr, &M, &nnz) != LDPC_B200_OK) {
+        // the reference does not validate its arguments either; keep the object usable for lastError()
+        impl->err = ldpc_b200_last_error();
+        return;
+    }
+    checkMatrix.rows_ = M;
+    checkMatrix.cols_ = ldpcN;
+    checkMatrix.ptr_.resize(M + 1);
+    checkMatrix.col_.resize(nnz);
+    ldpc_b200_wimax_csr(ldpcK, ldpcN, (int)rate, checkMatrix.ptr_.data(), checkMatrix.col_.data(), &M, &nnz);
+}
+
+Coder::Coder(int ldpcM, int ldpcN, int ldpcK, const int *rowPtr, const int *colIdx)
+    : kernelSourceCode(nullptr), impl(new Impl) {
+    impl->K = ldpcK;
+    impl->N = ldpcN;
+    impl->M = ldpcM;
+    checkMatrix.rows_ = ldpcM;
+    checkMatrix.cols_ = ldpcN;
+    checkMatrix.ptr_.assign(rowPtr, rowPtr + ldpcM + 1);
+    checkMatrix.col_.assign(colIdx, colIdx + rowPtr[ldpcM]);
+}
+
+Coder::~Coder() {
+    impl->destroyHandles();
+    delete impl;
+}
+
+// ---- [B200] configuration ---------------------------------------------------------------------
+int Coder::setMaxIter(int times) {
+    if (times < 1) return LDPC_B200_ERR_ARG;
+    impl->times = times;
+    for (ldpc_b200_handle h : impl->handles)
+        if (ldpc_b200_set_max_iter(h, times) != LDPC_B200_OK) return impl->fail(LDPC_B200_ERR_ARG);
+    return LDPC_SUCCESS;
+}
+
+int Coder::setEarlyTermination(bool on) {
+    impl->early = on;
+    for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_early_termination(h, on ? 1 : 0);
+    return LDPC_SUCCESS;
+}
+
+int Coder::setDevices(const int *deviceIds, int count) {
+    if (!deviceIds || count < 1) return LDPC_B200_ERR_ARG;
+    if (!impl->handles.empty()) {
+        impl->err = "setDevices must be called before forDecoder";
+        return LDPC_B200_ERR_ARG;
+    }
+    impl->devices.assign(deviceIds, deviceIds + count);
+    return LDPC_SUCCESS;
+}
+
+const int *Coder::lastIterations() const { return impl->iters.data(); }
+int Coder::lastCodeSize() const { return impl->lastCodeSize; }
+const char *Coder::lastError() const { return impl->err.c_str(); }
+
+// ---- decoder setup (reference MyLdpc.cpp:167-305, 307-552) ------------------------------------
+int Coder::forDecoder(int batchSize) {
+    impl->batchSize = batchSize;
+    impl->destroyHandles();
+    if (checkMatrix.rows_ == 0) return LDPC_B200_ERR_ARG;
+    for (int dev : impl->devices) {
+        ldpc_b200_handle h = nullptr;
+        int rc = ldpc_b200_create(&h, impl->M, impl->N, impl->K, checkMatrix.ptr_.data(), checkMatrix.col_.data(), dev);
+        if (rc != LDPC_B200_OK) {
+            impl->fail(rc);
+            impl->destroyHandles();
+            return rc;
+        }
+        ldpc_b200_set_max_iter(h, impl->times);
+        ldpc_b200_set_early_termination(h, impl->early ? 1 : 0);
+        impl->handles.push_back(h);
+    }
+    return LDPC_SUCCESS;
+}
+
+int Coder::addDecodeType(enum decodeType deType) {
+    (void)deType;  // every decodeType is served by the CUDA min-sum decoder
+    if (impl->handles.empty()) {
+        impl->err = "forDecoder must be called before addDecodeType";
+        return LDPC_B200_ERR_ARG;
+    }
+    if (impl->batchSize > 0)
+        for (ldpc_b200_handle h : impl->handles) {
+            int rc = ldpc_b200_reserve(h, impl->batchSize);
+            if (rc != LDPC_B200_OK) return impl->fail(rc);
+        }
+    return LDPC_SUCCESS;
+}
+
+int Coder::forTest() { return LDPC_SUCCESS; }  // declared but never defined by the reference (MyLdpc.h:112)
+
+// ---- size helpers (reference MyLdpc.cpp:620-631) ----------------------------------------------
+int Coder::getPriorCodeLength(int srcLength) {
+    return (srcLength + (impl->K / 8) - 1) / (impl->K / 8) * (impl->N / 8);
+}
+int Coder::getPostCodeLength(int srcLength) { return (srcLength + (impl->K / 8) - 1) / (impl->K / 8) * impl->N; }
+int Coder::getCodeSize(int srcLength) { return (srcLength + (impl->K / 8) - 1) / (impl->K / 8); }
+
+// ---- decode (reference MyLdpc.cpp:571-618; semantics of :684-784) -----------------------------
+int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType deType) {
+    (void)deType;
+    if (impl->handles.empty()) {
+        impl->err = "forDecoder must be called before decode";
+        return LDPC_B200_ERR_ARG;
+    }
+    const int codeSize = getCodeSize(srcLength);
+    const int KB = (impl->K + 7) / 8;
+    const int G = (int)impl->handles.size();
+    impl->iters.assign(codeSize, 0);
+    impl->info.assign((size_t)codeSize * KB, 0);
+    impl->lastCodeSize = codeSize;
+    std::vector<int> rcs(G, LDPC_B200_OK);
+    std::vector<std::string> msgs(G);
+    auto work = [&](int g) {
+        // contiguous shard [b, e) of the codewords for device g: no data-path collective
+        const int64_t b = (int64_t)codeSize * g / G, e = (int64_t)codeSize * (g + 1) / G;
+        if (e <= b) return;
+        rcs[g] = ldpc_b200_decode_host(impl->handles[g], postCode + (size_t)b * impl->N, e - b,
+                                       impl->info.data() + (size_t)b * KB, nullptr, impl->iters.data() + b, nullptr);
+        if (rcs[g] != LDPC_B200_OK) msgs[g] = ldpc_b200_last_error();
+    };
+    if (G == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; ++g) th.emplace_back(work, g);
+        for (auto &t : th) t.join();
+    }
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] != LDPC_B200_OK) {
+            impl->err = msgs[g];
+            return rcs[g];
+        }
+    // the stream holds the first srcLength bytes (the last codeword may be partly padding)
+    std::memcpy(srcCode, impl->info.data(), std::min<size_t>((size_t)srcLength, impl->info.size()));
+    return LDPC_SUCCESS;
+}
+
+// ---- encoder (reference MyLdpc.cpp:137-165, 554-569, 633-682) ---------------------------------
+// The reference computes the parity bits with a Richardson-Urbanke split and dense GF(2) inverses
+// through Eigen.  The parity part of H is invertible, so the parity bits are uniquely determined by
+// H c = 0; we solve [B | A] once by Gauss-Jordan over GF(2) (B = last M columns) and keep X = B^-1 A.
+int Coder::forEncoder() {
+    const int M = impl->M, N = impl->N, K = impl->K;
+    if (N - K != M || checkMatrix.rows_ != M) {
+        impl->err = "forEncoder needs a square parity part (N - K == M)";
+        return LDPC_B200_ERR_ARG;
+    }
+    const int W = (N + 63) / 64;
+    std::vector<uint64_t> a((size_t)M * W, 0);  // row r: columns permuted to [parity (M) | info (K)]
+    auto setbit = [&](int r, int c) { a[(size_t)r * W + (c >> 6)] |= 1ull << (c & 63); };
+    auto getbit = [&](int r, int c) { return (a[(size_t)r * W + (c >> 6)] >> (c & 63)) & 1ull; };
+    for (int r = 0; r < M; ++r)
+        for (int e = checkMatrix.ptr_[r]; e < checkMatrix.ptr_[r + 1]; ++e) {
+            const int c = checkMatrix.col_[e];
+            setbit(r, c >= K ? c - K : M + c);
+        }
+    for (int c = 0; c < M; ++c) {
+        int p = -1;
+        for (int r = c; r < M; ++r)
+            if (getbit(r, c)) { p = r; break; }
+        if (p < 0) {
+            impl->err = "parity part of H is singular";
+            return LDPC_B200_ERR_ARG;
+        }
+        if (p != c)
+            for (int w = 0; w < W; ++w) std::swap(a[(size_t)p * W + w], a[(size_t)c * W + w]);
+        for (int r = 0; r < M; ++r)
+            if (r != c && getbit(r, c))
+                for (int w = 0; w < W; ++w) a[(size_t)r * W + w] ^= a[(size_t)c * W + w];
+    }
+    impl->kWords = (K + 63) / 64;
+    impl->X.assign((size_t)M * impl->kWords, 0);
+    for (int r = 0; r < M; ++r)
+        for (int k = 0; k < K; ++k)
+            if (getbit(r, M + k)) impl->X[(size_t)r * impl->kWords + (k >> 6)] |= 1ull << (k & 63);
+    impl->encoderReady = true;
+    return LDPC_SUCCESS;
+}
+
+int Coder::encode(char *srcCode, char *priorCode, int srcLength) {
+    if (!impl->encoderReady) {
+        impl->err = "forEncoder must be called before encode";
+        return LDPC_B200_ERR_ARG;
+    }
+    const int K = impl->K, N = impl->N, M = impl->M, kb = K / 8, nb = N / 8;
+    const int codeSize = getCodeSize(srcLength);
+    std::vector<uint64_t> u(impl->kWords);
+    for (int cw = 0; cw < codeSize; ++cw) {
+        const int srcL = std::min(kb, srcLength - cw * kb);  // the last word may be short (MyLdpc.cpp:561-564)
+        unsigned char *out = reinterpret_cast<unsigned char *>(priorCode) + (size_t)cw * nb;
+        std::memset(out, 0, nb);
+        std::memcpy(out, srcCode + (size_t)cw * kb, srcL);     // systematic part, LSB-first bits
+        std::fill(u.begin(), u.end(), 0);
+        for (int i = 0; i < srcL; ++i) u[i >> 3] |= (uint64_t)out[i] << ((i & 7) * 8);
+        for (int r = 0; r < M; ++r) {
+            uint64_t acc = 0;
+            const uint64_t *x = &impl->X[(size_t)r * impl->kWords];
+            for (int w = 0; w < impl->kWords; ++w) acc ^= x[w] & u[w];
+            if (__builtin_popcountll(acc) & 1) {
+                const int bit = K + r;
+                out[bit >> 3] |= (unsigned char)(1u << (bit & 7));
+            }
+        }
+    }
+    return LDPC_SUCCESS;
+}
+
+// ---- channel (reference MyLdpc.cpp:1061-1078, 1093-1105) --------------------------------------
+int Coder::test(char *priorCode, float *postCode, int priorCodeLength, float rate) {
+    for (int charOffset = 0; charOffset < priorCodeLength; ++charOffset) {
+        const char tmp = priorCode[charOffset];
+        for (int bitOffset = 0; bitOffset < 8; ++bitOffset)
+            postCode[charOffset * 8 + bitOffset] = (tmp & (1 << bitOffset)) ? -1.0f : 1.0f;
+    }
+    for (int i = 0; i < priorCodeLength * 8; ++i) postCode[i] += gaussian(0, rate);
+    return LDPC_SUCCESS;
+}
+
+// Box-Muller, cosine branch only, two rand() draws per sample -- the reference's generator.
+float gaussian(float ave, float sd) {
+    const float pi = 3.1415926f;
+    const float s1 = (float)((1.0 + rand()) / (RAND_MAX + 1.0));
+    const float s2 = (float)((1.0 + rand()) / (RAND_MAX + 1.0));
+    const float r = std::sqrt(-2 * std::log(s2));
+    const float t = 2 * pi * s1;
+    const float z = r * std::cos(t);
+    return ave + z * sd;
+}
+
+// Kept for link compatibility: the reference read its OpenCL kernel file with this (MyLdpc.cpp:1079-1091).
+char *load_program_source(const char *filename) {
+    FILE *fh = std::fopen(filename, "r");
+    if (!fh) return nullptr;
+    std::fseek(fh, 0, SEEK_END);
+    const long n = std::ftell(fh);
+    std::fseek(fh, 0, SEEK_SET);
+    char *source = (char *)std::malloc((size_t)n + 1);
+    const size_t got = std::fread(source, 1, (size_t)n, fh);
+    source[got] = '\0';
+    std::fclose(fh);
+    return source;
+}

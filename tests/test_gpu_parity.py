@@ -213,3 +213,31 @@ def test_coder_api_roundtrip(default_code):
     ref_bytes, ref_iters, _, _ = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"]).decode_stream(post, srcLength)
     assert np.array_equal(new_src[:srcLength], ref_bytes)
     assert np.array_equal(coder.lastIterations, ref_iters)
+
+
+def _run_cli(name, *args):
+    import pathlib
+    import subprocess
+    exe = pathlib.Path(__file__).resolve().parents[1] / "myldpccppapi_b200" / "bin" / name
+    if not exe.exists():
+        pytest.skip(name + " not built")
+    r = subprocess.run([str(exe), *map(str, args)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return dict(line.split("=", 1) for line in r.stdout.splitlines() if "=" in line), r.stdout
+
+
+def test_cpp_coder_cli_roundtrip():
+    """C++ drop-in `Coder` (include/MyLdpc.h, libmyldpc_b200.so) driven by our Test.cpp-shaped CLI."""
+    kv, out = _run_cli("mytest", 54000, 256, 6.5, "MS", 7)
+    assert kv["ErrNum"] == "0", out
+    assert 1.0 <= float(kv["MeanIterations"]) < 10.0
+    kv, out = _run_cli("mytest", 1000, 8, 0, "CPU", 7)   # sigma = 1: nothing converges, cap reached
+    assert float(kv["MeanIterations"]) == 40.0 and int(kv["ErrNum"]) > 0
+
+
+def test_reference_test_cpp_runs_against_the_drop_in():
+    """The reference's OWN Test.cpp, compiled unmodified against include/MyLdpc.h at build time
+    (myldpccppapi_b200/_build.py: build_harness), decodes its payload without byte errors."""
+    for alg in ("MS", "SP", "CPU", "TDMP"):
+        kv, out = _run_cli("MyTest_reference_harness", 5400, 64, 7, alg)
+        assert kv["ErrNum"] == "0", out

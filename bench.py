@@ -166,9 +166,9 @@ def run_reference(args, rank: int, world: int) -> None:
     kind, runner = "port", None
     try:
         from oracle import ref as oref
-        if oref.available() and args.workload in ("cfg1", "cfg2"):
+        if oref.available("O2") and args.workload in ("cfg1", "cfg2"):
             kind = "reference"
-            runner = lambda: oref.decode_cpu_parallel(K, N, 4, y, cap, thr)  # noqa: E731
+            runner = lambda: oref.decode_cpu_parallel(K, N, 4, y, cap, thr, opt="O2")  # noqa: E731
     except Exception:
         runner = None
     if runner is None:
@@ -188,7 +188,7 @@ def run_reference(args, rank: int, world: int) -> None:
                    "early_termination": True, "codewords_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": thr, "kind": kind,
                          "sample": "%d codewords per step on %d host threads (%s)" % (
-                             sample, thr, "oracle/_ref: the reference's own Coder::decodeCPU" if kind == "reference"
+                             sample, thr, "oracle/_ref: the reference's own Coder::decodeCPU compiled -O2 (its Makefile uses -O0), one Coder per thread" if kind == "reference"
                              else "oracle port of Coder::decodeCPU, literal O(dc^2) check loop, gcc -O2")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

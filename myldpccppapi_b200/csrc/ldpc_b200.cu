@@ -50,7 +50,10 @@ struct Plan {
     size_t smem = 0;
     size_t ws_stride = 0;  // floats per CTA (LANE_GLOBAL)
     int dcp = 0;           // LANE16: padded check degree of the per-warp tables
-    int W = 0, CS = 0, VS = 0;  // LANE16: warps, check slots and variable slots per warp
+    int W = 0, CS = 0, VS = 0;  // LANE16 / GROUP: warps, check slots and variable slots per warp
+    int G = 0, dmax = 0;        // GROUP: codewords per CTA group, unroll bound of the check pass
+    bool tab_smem = true;       // GROUP: index tables in shared memory (else read from global/L2)
+    int cn_stride = 0, vn_stride = 0, r_rows = 0;
 };
 
 }  // namespace
@@ -78,6 +81,14 @@ struct ldpc_b200_decoder {
     uint32_t* d16_var_of_pos = nullptr;
     uint32_t* d16_pos_of_var = nullptr;
     bool lane16_ready = false;
+    // GROUP tables
+    uint32_t* dg_cn_tab = nullptr;
+    uint32_t* dg_vn_tab = nullptr;
+    uint32_t* dg_var_of_pos = nullptr;
+    uint32_t* dg_pos_of_var = nullptr;
+    bool group_ready = false;
+    uint8_t g_vdeg[kGrpMaxVS] = {0};
+    uint8_t g_cdeg[kGrpMaxCS] = {0};
     int l16_vn_stride = 0;
     uint8_t l16_vdeg[kL16MaxVS] = {0};
     uint8_t l16_cdeg[kL16MaxCS] = {0};
@@ -248,9 +259,177 @@ int upload_lane16_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
+// ---- GROUP layout (explicit per-edge messages on chip; see ldpc_kernels.cuh) ----------------
+struct GrpShape {
+    int G = 0, W = 0, CS = 0, VS = 0, dmax = 0;
+    int cn_stride = 0, vn_stride = 0, r_rows = 0;
+    bool tab_smem = true;
+    size_t smem = 0;
+    double cost = 0.0;
+};
+
+bool group_shape(const HostTables& t, int G, int W, size_t smem_limit, GrpShape* out) {
+    const int SUB = 32 / G, NL = W * SUB;
+    GrpShape sh;
+    sh.G = G; sh.W = W;
+    sh.CS = (t.M + NL - 1) / NL;
+    sh.VS = (t.N + NL - 1) / NL;
+    if (sh.CS > kGrpMaxCS || sh.VS > kGrpMaxVS || t.max_row_weight > 16 || t.max_row_weight < 1) return false;
+    sh.dmax = t.max_row_weight <= 8 ? 8 : 16;
+    std::vector<int> cd(t.M), vd(t.N);
+    for (int r = 0; r < t.M; ++r) cd[r] = t.row_ptr[r + 1] - t.row_ptr[r];
+    for (int c = 0; c < t.N; ++c) vd[c] = t.col_ptr[c + 1] - t.col_ptr[c];
+    std::sort(cd.begin(), cd.end(), std::greater<int>());
+    std::sort(vd.begin(), vd.end(), std::greater<int>());
+    long long quads = 0, rrows = 0, ventries = 0, vquads = 0;
+    for (int cs = 0; cs < sh.CS; ++cs) { const int d = cd[(size_t)cs * NL]; rrows += d; quads += (d + 3) / 4; }
+    for (int s = 0; s < sh.VS; ++s) { const int d = vd[(size_t)s * NL]; ventries += d; vquads += (d + 3) / 4; }
+    sh.r_rows = (int)rrows;
+    sh.cn_stride = (int)(quads * SUB * 4);
+    sh.vn_stride = (int)(vquads * SUB * 4);
+    const size_t core = (((size_t)(sh.VS * NL + 1) * G * 4 + 127) & ~(size_t)127) + ((size_t)W * rrows + 1) * 128;
+    const size_t tabs = ((size_t)sh.cn_stride + sh.vn_stride) * 4 * W;
+    if (core + 1024 > smem_limit) return false;
+    sh.tab_smem = core + tabs + 1024 <= smem_limit;
+    sh.smem = core + (sh.tab_smem ? tabs : 0);
+    // issue-slot proxy of the padded work, as for LANE16
+    sh.cost = (14.0 * rrows + 4.0 * ventries + 12.0 * sh.CS + 6.0 * sh.VS) * NL / (0.97 + 0.03 * W / 32.0);
+    if (!sh.tab_smem) sh.cost *= 1.15;
+    *out = sh;
+    return true;
+}
+
+bool group_pick(const HostTables& t, size_t smem_limit, GrpShape* best) {
+    int g_lo = 1, g_hi = 16, w_lo = 8, w_hi = 32;
+    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16) g_lo = g_hi = g; }
+    if (const char* env = std::getenv("LDPC_B200_GRP_WARPS")) { const int w = std::atoi(env); if (w >= 1 && w <= 32) w_lo = w_hi = w; }
+    // instantiated: G = 16 (short codes, tables on chip) and G = 1 (one codeword per CTA)
+    for (int G : {16, 1}) {
+        if (G < g_lo || G > g_hi) continue;
+        bool found = false;
+        GrpShape b;
+        for (int W = w_lo; W <= w_hi; ++W) {
+            GrpShape sh;
+            if (!group_shape(t, G, W, smem_limit, &sh)) continue;
+            if (G == 16 && !sh.tab_smem) continue;
+            if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
+        }
+        if (found) { *best = b; return true; }
+    }
+    return false;
+}
+
+int upload_group_tables(ldpc_b200_decoder* h) {
+    if (h->group_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    const Plan& pl = h->plan;
+    const int G = pl.G, SUB = 32 / G, W = pl.W, NL = W * SUB, CS = pl.CS, VS = pl.VS;
+    std::vector<int> vorder(t.N), corder(t.M);
+    for (int i = 0; i < t.N; ++i) vorder[i] = i;
+    for (int i = 0; i < t.M; ++i) corder[i] = i;
+    auto vdegf = [&](int c) { return t.col_ptr[c + 1] - t.col_ptr[c]; };
+    auto cdegf = [&](int r) { return t.row_ptr[r + 1] - t.row_ptr[r]; };
+    std::stable_sort(vorder.begin(), vorder.end(), [&](int a, int b) { return vdegf(a) > vdegf(b); });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cdegf(a) > cdegf(b); });
+    const int PD = VS * NL, RD = W * pl.r_rows;
+    std::vector<uint32_t> var_of_pos((size_t)PD, 0xffffffffu), pos_of_var(t.N), crank_of_chk(t.M);
+    for (int i = 0; i < t.N; ++i) { var_of_pos[i] = (uint32_t)vorder[i]; pos_of_var[vorder[i]] = (uint32_t)i; }
+    for (int i = 0; i < t.M; ++i) crank_of_chk[corder[i]] = (uint32_t)i;
+    std::memset(h->g_vdeg, 0, sizeof(h->g_vdeg));
+    std::memset(h->g_cdeg, 0, sizeof(h->g_cdeg));
+    std::vector<int> coff(CS + 1, 0), qoff(CS + 1, 0), voff(VS + 1, 0);
+    for (int cs = 0; cs < CS; ++cs) {
+        h->g_cdeg[cs] = (uint8_t)cdegf(corder[(size_t)cs * NL]);
+        coff[cs + 1] = coff[cs] + h->g_cdeg[cs];
+        qoff[cs + 1] = qoff[cs] + (h->g_cdeg[cs] + 3) / 4;
+    }
+    for (int s = 0; s < VS; ++s) {
+        h->g_vdeg[s] = (uint8_t)vdegf(vorder[(size_t)s * NL]);
+        voff[s + 1] = voff[s] + (h->g_vdeg[s] + 3) / 4;  // in quads
+    }
+    // check pass: T-row byte offset of every edge, [warp][slot][quad][h][4]; padding -> dummy row PD
+    std::vector<uint32_t> cn_tab((size_t)W * pl.cn_stride, (uint32_t)PD * G * 4u);
+    for (int rank = 0; rank < t.M; ++rank) {
+        const int cs = rank / NL, nl = rank % NL, w = nl / SUB, hh = nl % SUB;
+        const int r = corder[rank], e0 = t.row_ptr[r], dc = cdegf(r);
+        for (int j = 0; j < dc; ++j)
+            cn_tab[(size_t)w * pl.cn_stride + ((size_t)(qoff[cs] + j / 4) * SUB + hh) * 4 + (j & 3)] =
+                pos_of_var[t.col_idx[e0 + j]] * (uint32_t)(G * 4);
+    }
+    // variable pass: byte offset of the R element of every edge in ascending-row order, [warp][slot][quad][h][4]
+    std::vector<uint32_t> vn_tab((size_t)W * pl.vn_stride, (uint32_t)RD * 128u);
+    for (int rank = 0; rank < t.N; ++rank) {
+        const int s = rank / NL, nl = rank % NL, w = nl / SUB, hh = nl % SUB;
+        const int v = vorder[rank];
+        for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+            const uint32_t chk = t.vn_edge[k] >> kPosBits, pos = t.vn_edge[k] & ((1u << kPosBits) - 1u);
+            const int crank = (int)crank_of_chk[chk];
+            const int ccs = crank / NL, cnl = crank % NL, cw = cnl / SUB, ch = cnl % SUB;
+            const uint32_t row = (uint32_t)cw * pl.r_rows + (uint32_t)coff[ccs] + pos;
+            const int kk = k - t.col_ptr[v];
+            vn_tab[(size_t)w * pl.vn_stride + ((size_t)(voff[s] + kk / 4) * SUB + hh) * 4 + (kk & 3)] =
+                row * 128u + (uint32_t)(ch * G * 4);
+        }
+    }
+    CU_TRY(cudaMalloc(&h->dg_cn_tab, cn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->dg_vn_tab, vn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->dg_var_of_pos, var_of_pos.size() * 4));
+    CU_TRY(cudaMalloc(&h->dg_pos_of_var, pos_of_var.size() * 4));
+    CU_TRY(cudaMemcpy(h->dg_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dg_vn_tab, vn_tab.data(), vn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dg_var_of_pos, var_of_pos.data(), var_of_pos.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dg_pos_of_var, pos_of_var.data(), pos_of_var.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += (cn_tab.size() + vn_tab.size() + var_of_pos.size() + pos_of_var.size()) * 4;
+    h->group_ready = true;
+    return LDPC_B200_OK;
+}
+
+template <int G, int DMAX, bool TAB, int MAXT>
+int launch_group_t(const GroupParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT><<<grid, threads, smem, stream>>>(q);
+    CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t stream) {
+    const int th = pl.threads;
+    if (pl.G == 16 && pl.tab_smem) {
+        if (pl.dmax == 8) return launch_group_t<16, 8, true, 1024>(q, grid, th, pl.smem, stream);
+        return th <= 768 ? launch_group_t<16, 16, true, 768>(q, grid, th, pl.smem, stream)
+                         : launch_group_t<16, 16, true, 1024>(q, grid, th, pl.smem, stream);
+    }
+    if (pl.G == 1) {
+        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024>(q, grid, th, pl.smem, stream)
+                                             : launch_group_t<1, 16, true, 1024>(q, grid, th, pl.smem, stream);
+        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024>(q, grid, th, pl.smem, stream)
+                            : launch_group_t<1, 16, false, 1024>(q, grid, th, pl.smem, stream);
+    }
+    return fail(LDPC_B200_ERR_UNSUPPORTED, "no group kernel instantiated for this shape");
+}
+
 int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
+    {   // explicit per-edge messages on chip (G codewords per CTA)
+        GrpShape sh;
+        const bool fits = group_pick(t, h->smem_optin, &sh);
+        if (h->forced_path == LDPC_B200_PATH_GROUP && !fits)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the group shared-memory path");
+        if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_GROUP) && fits) {
+            if (h->group_ready && (h->plan.W != sh.W || h->plan.G != sh.G)) return fail(LDPC_B200_ERR_ARG, "group layout changed after upload");
+            pl.path = LDPC_B200_PATH_GROUP;
+            pl.threads = 32 * sh.W;
+            pl.smem = sh.smem;
+            pl.ctas = h->sm_count;
+            pl.cw_per_cta = sh.G;
+            pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS; pl.G = sh.G; pl.dmax = sh.dmax; pl.tab_smem = sh.tab_smem;
+            pl.cn_stride = sh.cn_stride; pl.vn_stride = sh.vn_stride; pl.r_rows = sh.r_rows;
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
+    }
     {   // tuned short-code path: channel values in registers, 16-byte check state, tables in smem
         L16Shape sh;
         const bool fits = (uint64_t)t.M * 512u < (1ull << 31) && lane16_pick(t, h->smem_optin, &sh);
@@ -328,12 +507,33 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (rc) return rc;
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
-    const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
+    const int per_group = pl.path == LDPC_B200_PATH_GROUP ? pl.G : kLanes;
+    const int64_t ngroups = (ncw + per_group - 1) / per_group;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
     unsigned int* ctr = h->d_counters + h->counter_next;
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+
+    if (pl.path == LDPC_B200_PATH_GROUP) {
+        rc = upload_group_tables(h);
+        if (rc) return rc;
+        GroupParams q;
+        q.cn_tab = h->dg_cn_tab; q.vn_tab = h->dg_vn_tab;
+        q.var_of_pos = h->dg_var_of_pos; q.pos_of_var = h->dg_pos_of_var;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.W = pl.W; q.CS = pl.CS; q.VS = pl.VS;
+        q.cn_stride = pl.cn_stride; q.vn_stride = pl.vn_stride; q.r_rows_per_warp = pl.r_rows;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter = ctr; q.ngroups = (int)ngroups;
+        std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
+        std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
+        rc = launch_group(pl, q, grid, stream);
+        if (rc) return rc;
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
 
     if (pl.path == LDPC_B200_PATH_LANE16) {
         rc = upload_lane16_tables(h);
@@ -474,6 +674,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
+            cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);

@@ -489,6 +489,285 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_lane16_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------------
+// GROUP kernel: explicit per-edge messages on chip.  A CTA decodes G codewords at a time; a warp
+// instruction covers SUB = 32/G graph nodes x G codewords: lane = (h, c), c = lane % G the
+// codeword, h = lane / G the node lane.  Shared memory holds
+//   T [pos][G]      f32  negated posterior (as in LANE16: hard bit = !signbit, zero canonical)
+//   R [row][32]     f32  the check-to-variable message of every edge: row (warp, slot, j) holds
+//                        edge j of the SUB checks that warp processes together, so the check pass
+//                        reads R_old and writes R_new with conflict-free `[base + j*128]` accesses
+//   tables               check pass: byte offset of the T row of each edge, [slot][j/4][h][4]
+//                        variable pass: byte address of the R element of each edge, [entry][h]
+// and the channel values stay in registers (static variable slots), as in LANE16.
+// Per edge the check pass does 2 loads + 1 store + ~8 ALU-pipe ops (no message reconstruction,
+// no sign-word shifting: R_new = ((j==argmin) ? min2 : min1) ^ parity ^ sign(S_j)), the variable
+// pass one table load, one message load and one FADD.  With G = 16 Test.cpp's code fits one SM
+// (T 37 KB + R 135 KB); with G = 1 (tables in global memory) an N = 8192 code does.
+// Same arithmetic contract as above: Q = P - R = -(T + R_old); T = (-y) - R_1 - R_2 ... in
+// ascending-row order.
+// ---------------------------------------------------------------------------------------
+constexpr int kGrpMaxVS = 16;  // variable slots per thread (channel values in registers)
+constexpr int kGrpMaxCS = 16;  // check slots per thread
+
+struct GroupParams {
+    const uint32_t* __restrict__ cn_tab;      // [W][cn_stride] quads: [slot][jq][h][4] T-row byte offsets
+    const uint32_t* __restrict__ vn_tab;      // [W][vn_stride] quads: [slot][kq][h][4] R element byte offsets (row*128 + h_e*G*4)
+    const uint32_t* __restrict__ var_of_pos;  // [VS*NL] variable index, 0xffffffff = phantom
+    const uint32_t* __restrict__ pos_of_var;  // [N]
+    int M, N, K, W, CS, VS;
+    int cn_stride, vn_stride;                 // uint32 words per warp
+    int r_rows_per_warp;                      // sum of check-slot degrees
+    int max_iter, early_term;
+    const float* __restrict__ llr;
+    long long ncw;
+    uint8_t* info;
+    uint8_t* hard;
+    int32_t* iters;
+    float* post;
+    unsigned int* counter;
+    int ngroups;
+    uint8_t vdeg[kGrpMaxVS];
+    uint8_t cdeg[kGrpMaxCS];
+};
+
+// One check of exact degree D, straight-line: D x {T gather, R_old load, S = T + R_old}, running
+// min1/min2 and sign parities, then D x {R_new = ((|S_j| == min1) ? min2 : min1) ^ parity ^ sign(S_j)}.
+// (|S_j| == min1 picks the argmin; with a tie min2 == min1, so either choice is the same value.)
+// Returns the row's syndrome bit.
+template <int D, int SUB, bool TAB_SMEM>
+__device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __restrict__ gtab, uint32_t t_base,
+                                               uint32_t rrow, uint32_t c4, int h) {
+    constexpr int NQ = (D + 3) / 4;
+    uint32_t ent[NQ * 4];
+#pragma unroll
+    for (int jq = 0; jq < NQ; ++jq) {
+        uint4 o;
+        if (TAB_SMEM) o = lds_u128(tab + (uint32_t)(jq * SUB + h) * 16u);
+        else {
+            o = __ldg(reinterpret_cast<const uint4*>(gtab + tab) + (jq * SUB + h));
+            o.x += t_base; o.y += t_base; o.z += t_base; o.w += t_base;
+        }
+        ent[jq * 4 + 0] = o.x; ent[jq * 4 + 1] = o.y; ent[jq * 4 + 2] = o.z; ent[jq * 4 + 3] = o.w;
+    }
+    float tv[D], S[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) tv[j] = lds_f32(ent[j] + c4);
+#pragma unroll
+    for (int j = 0; j < D; ++j) S[j] = lds_f32(rrow + (uint32_t)j * 128u);
+    float m1 = INFINITY, m2 = INFINITY;
+    uint32_t px = 0u, sx = 0u;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
+        px ^= __float_as_uint(S[j]);
+        sx ^= __float_as_uint(tv[j]);
+        const float a = fabsf(S[j]);
+        m2 = fminf(m2, fmaxf(m1, a));
+        m1 = fminf(m1, a);
+    }
+    // (Q_j < 0) = !signbit(S_j); parity of the negative Q's = (D & 1) ^ xor signbit(S);
+    // sign(R_j) = parity ^ (Q_j < 0) = parity ^ 1 ^ signbit(S_j)
+    const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
+    const uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
+    const uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
+        sts_f32(rrow + (uint32_t)j * 128u, __uint_as_float(mag ^ (__float_as_uint(S[j]) & 0x80000000u)));
+    }
+    return ((sx >> 31) ^ (uint32_t)D) & 1u;  // hard bit = !signbit(T)
+}
+
+template <int CNT>
+__device__ __forceinline__ void grp_vn_part(const uint4 o, uint32_t c4, float& acc) {
+    const uint32_t e[4] = {o.x, o.y, o.z, o.w};
+    float r[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) r[k] = lds_f32(e[k] + c4);
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) acc = __fsub_rn(acc, r[k]);
+}
+
+template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
+    constexpr int SUB = 32 / G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_group;
+    __shared__ uint32_t s_flag[2][32];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int c = lane & (G - 1), h = lane / G;
+    const int W = p.W, CS = p.CS, VS = p.VS;
+    const int NL = W * SUB;
+    const int PD = VS * NL;                         // dummy T row (= -inf)
+    const int RD = W * p.r_rows_per_warp;           // dummy R row (= 0)
+
+    const uint32_t t_base = smem_u32(smem_raw);
+    const uint32_t r_base = t_base + (((uint32_t)(PD + 1) * G * 4 + 127u) & ~127u);  // 128-byte aligned rows
+    const uint32_t cn_base = r_base + (uint32_t)(RD + 1) * 128;
+    const uint32_t vn_base = cn_base + (TAB_SMEM ? (uint32_t)W * p.cn_stride * 4 : 0u);
+    if (TAB_SMEM) {
+        uint32_t* cn_s = reinterpret_cast<uint32_t*>(smem_raw + (cn_base - t_base));
+        uint32_t* vn_s = reinterpret_cast<uint32_t*>(smem_raw + (vn_base - t_base));
+        for (int i = threadIdx.x; i < W * p.cn_stride; i += blockDim.x) cn_s[i] = __ldg(p.cn_tab + i) + t_base;
+        for (int i = threadIdx.x; i < W * p.vn_stride; i += blockDim.x) vn_s[i] = __ldg(p.vn_tab + i) + r_base;
+    }
+    const uint32_t c4 = (uint32_t)c * 4u;
+    if (warp == 0) {
+        if (lane < G) sts_f32(t_base + (uint32_t)PD * G * 4 + lane * 4, -INFINITY);
+        sts_f32(r_base + (uint32_t)RD * 128 + lane * 4, 0.0f);
+    }
+    // this thread's own T elements: position (s*NL + warp*SUB + h), codeword c -> contiguous in tid
+    const uint32_t t_own = t_base + (uint32_t)threadIdx.x * 4u;
+    const uint32_t t_stride = (uint32_t)NL * G * 4u;
+    const uint32_t r_own = r_base + (uint32_t)warp * p.r_rows_per_warp * 128u + (uint32_t)lane * 4u;
+    // table cursors (shared addresses or global word offsets)
+    const uint32_t cn_w = TAB_SMEM ? cn_base + (uint32_t)warp * p.cn_stride * 4u : (uint32_t)warp * p.cn_stride;
+    const uint32_t vn_w = TAB_SMEM ? vn_base + (uint32_t)warp * p.vn_stride * 4u : (uint32_t)warp * p.vn_stride;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int g = s_group;
+        if (g >= p.ngroups) break;
+
+        const long long cw = (long long)g * G + c;
+        const bool active = cw < p.ncw;
+        const float* src = p.llr + (size_t)(active ? cw : 0) * p.N;
+
+        // ---- load: -y into registers and T; all messages R = 0 (decodeInitMS, decodeCL.c:113-124)
+        float yn[kGrpMaxVS];
+#pragma unroll
+        for (int s = 0; s < kGrpMaxVS; ++s) {
+            yn[s] = -1.0f;
+            if (s < VS) {
+                const uint32_t v = __ldg(p.var_of_pos + s * NL + warp * SUB + h);
+                float y = 1.0f;
+                if (v != 0xffffffffu && active) y = __ldg(src + v);
+                yn[s] = __fadd_rn(-y, 0.0f);
+                sts_f32(t_own + (uint32_t)s * t_stride, yn[s]);
+            }
+        }
+        for (int r = 0; r < p.r_rows_per_warp; ++r) sts_f32(r_own + (uint32_t)r * 128u, 0.0f);
+        if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+        __syncthreads();
+
+        bool done = !active;
+        int my_iters = 0;
+        int iter = 0;
+        for (;;) {
+            // ---- check-node pass
+            uint32_t unsat = 0u;
+            {
+                uint32_t tab = cn_w;     // quads for this warp, slot by slot
+                uint32_t rrow = r_own;   // this lane's R column, row by row
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int dc = p.cdeg[cs];
+#define GRP_CASE(D) case D: unsat |= grp_check<D, SUB, TAB_SMEM>(tab, p.cn_tab, t_base, rrow, c4, h); break;
+                    switch (dc) {
+                        GRP_CASE(1) GRP_CASE(2) GRP_CASE(3) GRP_CASE(4) GRP_CASE(5) GRP_CASE(6) GRP_CASE(7) GRP_CASE(8)
+                        default:
+                            if constexpr (DMAX > 8) {
+                                switch (dc) {
+                                    GRP_CASE(9) GRP_CASE(10) GRP_CASE(11) GRP_CASE(12)
+                                    GRP_CASE(13) GRP_CASE(14) GRP_CASE(15) GRP_CASE(16)
+                                    default: break;
+                                }
+                            }
+                            break;
+                    }
+#undef GRP_CASE
+                    rrow += (uint32_t)dc * 128u;
+                    tab += (TAB_SMEM ? 16u : 4u) * (uint32_t)(((dc + 3) >> 2) * SUB);
+                }
+            }
+            const bool check = p.early_term && iter >= 1;
+            if (check && unsat) s_flag[iter & 1][c] = 1u;  // same-value race, benign
+            __syncthreads();
+            if (check && !done && s_flag[iter & 1][c] == 0u) { done = true; my_iters = iter; }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
+
+            // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
+            {
+                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
+                auto next_quad = [&]() {
+                    uint4 o;
+                    if (TAB_SMEM) { o = lds_u128(q); q += SUB * 16; }
+                    else {
+                        o = __ldg(reinterpret_cast<const uint4*>(p.vn_tab + q));
+                        q += SUB * 4;
+                        o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+                    }
+                    return o;
+                };
+#pragma unroll
+                for (int s = 0; s < kGrpMaxVS; ++s) {
+                    if (s < VS) {
+                        int d = p.vdeg[s];
+                        float acc = yn[s];
+#pragma unroll 1
+                        for (; d >= 4; d -= 4) grp_vn_part<4>(next_quad(), c4, acc);
+                        if (d > 0) {
+                            const uint4 o = next_quad();
+                            if (d == 1) grp_vn_part<1>(o, c4, acc);
+                            else if (d == 2) grp_vn_part<2>(o, c4, acc);
+                            else grp_vn_part<3>(o, c4, acc);
+                        }
+                        if (!done) sts_f32(t_own + (uint32_t)s * t_stride, acc);
+                    }
+                }
+            }
+            ++iter;
+            if (iter == p.max_iter) {
+                if (!done) my_iters = iter;
+                break;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+
+        // ---- outputs (toChar, decodeCL.c:188-199): bit n = !(P > 0) = !signbit(T); node lanes share the bytes
+        if (p.info) {
+            const int KB = (p.K + 7) >> 3;
+            for (int b = warp * SUB + h; b < KB; b += NL) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.K) {
+                        const uint32_t pos = __ldg(p.pos_of_var + n);
+                        v |= ((~__float_as_uint(lds_f32(t_base + pos * (G * 4) + c4))) >> 31) << t;
+                    }
+                }
+                if (active) p.info[(size_t)cw * KB + b] = (uint8_t)v;
+            }
+        }
+        if (p.hard) {
+            const int NB = (p.N + 7) >> 3;
+            for (int b = warp * SUB + h; b < NB; b += NL) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.N) {
+                        const uint32_t pos = __ldg(p.pos_of_var + n);
+                        v |= ((~__float_as_uint(lds_f32(t_base + pos * (G * 4) + c4))) >> 31) << t;
+                    }
+                }
+                if (active) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
+            }
+        }
+        if (p.post && active) {
+            for (int n = warp * SUB + h; n < p.N; n += NL)
+                p.post[(size_t)cw * p.N + n] = -lds_f32(t_base + __ldg(p.pos_of_var + n) * (G * 4) + c4);
+        }
+        if (p.iters && warp == 0 && h == 0 && active) p.iters[cw] = my_iters;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Synthetic BPSK + AWGN channel (Coder::test, reference MyLdpc.cpp:1061-1078): bit 0 -> +1,
 // bit 1 -> -1, plus sigma * N(0,1).  Counter-based: element i of the stream depends only on
 // (seed, i), so any shard of any GPU generates the same floats for the same codeword index.

@@ -38,16 +38,30 @@ def test_default_code_parity(default_code, sigma):
     assert_parity(host, ref, c["N"], what="host sigma=%g" % sigma)
 
 
-def test_default_code_global_path(default_code):
-    """The workspace-in-global-memory path must give the same bits as the shared-memory path."""
+@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group")])
+def test_default_code_every_kernel_path(default_code, path, name):
+    """Every kernel family (shared-memory lane, global-workspace lane, lane16, group) gives the oracle's bits."""
     import myldpccppapi_b200 as m
     c = default_code
-    llr = awgn_llr(300, c["N"], 0.62, seed=11)
+    llr = np.concatenate([awgn_llr(150, c["N"], 0.62, seed=11), awgn_llr(150, c["N"], 0.52, seed=12),
+                          awgn_llr(21, c["N"], 1.0, seed=13)])
     ref = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr)
     dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
-    dec.set_path(1)
-    assert dec.info()["path_name"] == "lane_global"
-    assert_parity(_run_device(dec, llr), ref, c["N"], what="global path")
+    dec.set_path(path)
+    assert dec.info()["path_name"] == name
+    assert_parity(_run_device(dec, llr), ref, c["N"], what=name)
+
+
+def test_regular_3_6_every_kernel_path():
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.regular_code()
+    llr = awgn_llr(40, N, 0.84, seed=2)
+    ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
+    for path, name in [(1, "lane_global"), (4, "group")]:
+        dec = m.Decoder(M, N, K, rp, ci)
+        dec.set_path(path)
+        assert dec.info()["path_name"] == name
+        assert_parity(_run_device(dec, llr), ref, N, what="reg36 " + name)
 
 
 @pytest.mark.parametrize("rate,name,num,den", [(0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3),

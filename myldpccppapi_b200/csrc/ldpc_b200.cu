@@ -53,6 +53,7 @@ struct Plan {
     int W = 0, CS = 0, VS = 0;  // LANE16 / GROUP: warps, check slots and variable slots per warp
     int G = 0, dmax = 0;        // GROUP: codewords per CTA group, unroll bound of the check pass
     bool tab_smem = true;       // GROUP: index tables in shared memory (else read from global/L2)
+    bool y_smem = false;        // GROUP: channel values in shared memory (else registers)
     int cn_stride = 0, vn_stride = 0, r_rows = 0;
 };
 
@@ -264,6 +265,7 @@ struct GrpShape {
     int G = 0, W = 0, CS = 0, VS = 0, dmax = 0;
     int cn_stride = 0, vn_stride = 0, r_rows = 0;
     bool tab_smem = true;
+    bool y_smem = false;
     size_t smem = 0;
     double cost = 0.0;
 };
@@ -287,11 +289,15 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit, GrpShape*
     sh.r_rows = (int)rrows;
     sh.cn_stride = (int)(quads * SUB * 4);
     sh.vn_stride = (int)(vquads * SUB * 4);
-    const size_t core = (((size_t)(sh.VS * NL + 1) * G * 4 + 127) & ~(size_t)127) + ((size_t)W * rrows + 1) * 128;
+    const size_t tbytes = ((size_t)(sh.VS * NL + 1) * G * 4 + 127) & ~(size_t)127;
+    const size_t core = tbytes + ((size_t)W * rrows + 1) * 128;
     const size_t tabs = ((size_t)sh.cn_stride + sh.vn_stride) * 4 * W;
-    if (core + 1024 > smem_limit) return false;
-    sh.tab_smem = core + tabs + 1024 <= smem_limit;
+    if (core + 512 > smem_limit) return false;
+    sh.tab_smem = core + tabs + 512 <= smem_limit;
     sh.smem = core + (sh.tab_smem ? tabs : 0);
+    // channel values on chip too when they fit (dynamic slot loop, two slots in flight)
+    sh.y_smem = t.max_col_weight <= 12 && sh.smem + tbytes + 512 <= smem_limit && !std::getenv("LDPC_B200_GRP_NO_YSMEM");
+    if (sh.y_smem) sh.smem += tbytes;
     // issue-slot proxy of the padded work, as for LANE16
     sh.cost = (14.0 * rrows + 4.0 * ventries + 12.0 * sh.CS + 6.0 * sh.VS) * NL / (0.97 + 0.03 * W / 32.0);
     if (!sh.tab_smem) sh.cost *= 1.15;
@@ -347,14 +353,87 @@ int upload_group_tables(ldpc_b200_decoder* h) {
         h->g_vdeg[s] = (uint8_t)vdegf(vorder[(size_t)s * NL]);
         voff[s + 1] = voff[s] + (h->g_vdeg[s] + 3) / 4;  // in quads
     }
+    // ---- bank-conflict-aware placement (SUB == 2: two nodes share a warp instruction) --------------
+    // slot_of_edge[e] = row position j that edge e (CSR id) takes inside its check.  The order of a
+    // check's edges is free for min/xor, so for each co-processed check pair (A: h=0, B: h=1) we match
+    // edges whose T rows have opposite parity (different bank halves) to the same j.
+    std::vector<int> slot_of_edge(t.nnz);
+    for (int r = 0; r < t.M; ++r)
+        for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) slot_of_edge[e] = e - t.row_ptr[r];
+    if (SUB == 2) {
+        // (1) orientation of each check pair: which member sits in lanes 0-15.  A variable pair (X, Y)
+        //     reads its k-th messages together; they collide when both checks sit in the same half.
+        //     Greedy local search over pair flips.
+        const int npairs = (t.M + 1) / 2;
+        std::vector<uint8_t> flip(npairs, 0);
+        auto half_of_chk = [&](int chk) { const int rk = (int)crank_of_chk[chk]; return (rk & 1) ^ flip[rk >> 1]; };
+        auto vn_conflicts_of_pairs = [&](const std::vector<int>& vpairs) {
+            long long c = 0;
+            for (int vp : vpairs) {
+                const int ra = 2 * vp, rb = 2 * vp + 1;
+                if (rb >= t.N) continue;
+                const int x = vorder[ra], y = vorder[rb];
+                const int dx = vdegf(x), dy = vdegf(y);
+                for (int k = 0; k < std::min(dx, dy); ++k) {
+                    const int cx = (int)(t.vn_edge[t.col_ptr[x] + k] >> kPosBits), cy = (int)(t.vn_edge[t.col_ptr[y] + k] >> kPosBits);
+                    c += half_of_chk(cx) == half_of_chk(cy);
+                }
+            }
+            return c;
+        };
+        // variable pairs touched by each check pair
+        std::vector<std::vector<int>> touched(npairs);
+        for (int v = 0; v < t.N; ++v)
+            for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+                const int cp = (int)crank_of_chk[t.vn_edge[k] >> kPosBits] >> 1;
+                const int vp = (int)pos_of_var[v] >> 1;
+                if (touched[cp].empty() || touched[cp].back() != vp) touched[cp].push_back(vp);
+            }
+        for (auto& v : touched) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+        for (int pass = 0; pass < 6; ++pass) {
+            bool changed = false;
+            for (int cp = 0; cp < npairs; ++cp) {
+                const long long before = vn_conflicts_of_pairs(touched[cp]);
+                flip[cp] ^= 1;
+                const long long after = vn_conflicts_of_pairs(touched[cp]);
+                if (after < before) changed = true; else flip[cp] ^= 1;
+            }
+            if (!changed) break;
+        }
+        // apply the orientation: swap ranks inside flipped pairs
+        for (int cp = 0; cp < npairs; ++cp)
+            if (flip[cp] && 2 * cp + 1 < t.M) {
+                std::swap(corder[2 * cp], corder[2 * cp + 1]);
+                crank_of_chk[corder[2 * cp]] = 2 * cp;
+                crank_of_chk[corder[2 * cp + 1]] = 2 * cp + 1;
+            }
+        // (2) edge order inside each check pair: opposite T-row parity at equal j
+        for (int cp = 0; 2 * cp + 1 < t.M; ++cp) {
+            const int a = corder[2 * cp], b = corder[2 * cp + 1];
+            std::vector<int> ae[2], be[2];
+            for (int e = t.row_ptr[a]; e < t.row_ptr[a + 1]; ++e) ae[pos_of_var[t.col_idx[e]] & 1].push_back(e);
+            for (int e = t.row_ptr[b]; e < t.row_ptr[b + 1]; ++e) be[pos_of_var[t.col_idx[e]] & 1].push_back(e);
+            std::vector<int> oa, ob;  // matched orders
+            for (int par = 0; par < 2; ++par)
+                while (!ae[par].empty() && !be[par ^ 1].empty()) {
+                    oa.push_back(ae[par].back()); ae[par].pop_back();
+                    ob.push_back(be[par ^ 1].back()); be[par ^ 1].pop_back();
+                }
+            for (int par = 0; par < 2; ++par) { for (int e : ae[par]) oa.push_back(e); for (int e : be[par]) ob.push_back(e); }
+            for (size_t j = 0; j < oa.size(); ++j) slot_of_edge[oa[j]] = (int)j;
+            for (size_t j = 0; j < ob.size(); ++j) slot_of_edge[ob[j]] = (int)j;
+        }
+    }
     // check pass: T-row byte offset of every edge, [warp][slot][quad][h][4]; padding -> dummy row PD
     std::vector<uint32_t> cn_tab((size_t)W * pl.cn_stride, (uint32_t)PD * G * 4u);
     for (int rank = 0; rank < t.M; ++rank) {
         const int cs = rank / NL, nl = rank % NL, w = nl / SUB, hh = nl % SUB;
         const int r = corder[rank], e0 = t.row_ptr[r], dc = cdegf(r);
-        for (int j = 0; j < dc; ++j)
+        for (int e = e0; e < e0 + dc; ++e) {
+            const int j = slot_of_edge[e];
             cn_tab[(size_t)w * pl.cn_stride + ((size_t)(qoff[cs] + j / 4) * SUB + hh) * 4 + (j & 3)] =
-                pos_of_var[t.col_idx[e0 + j]] * (uint32_t)(G * 4);
+                pos_of_var[t.col_idx[e]] * (uint32_t)(G * 4);
+        }
     }
     // variable pass: byte offset of the R element of every edge in ascending-row order, [warp][slot][quad][h][4]
     std::vector<uint32_t> vn_tab((size_t)W * pl.vn_stride, (uint32_t)RD * 128u);
@@ -365,7 +444,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
             const uint32_t chk = t.vn_edge[k] >> kPosBits, pos = t.vn_edge[k] & ((1u << kPosBits) - 1u);
             const int crank = (int)crank_of_chk[chk];
             const int ccs = crank / NL, cnl = crank % NL, cw = cnl / SUB, ch = cnl % SUB;
-            const uint32_t row = (uint32_t)cw * pl.r_rows + (uint32_t)coff[ccs] + pos;
+            const uint32_t row = (uint32_t)cw * pl.r_rows + (uint32_t)coff[ccs] + (uint32_t)slot_of_edge[t.row_ptr[chk] + pos];
             const int kk = k - t.col_ptr[v];
             vn_tab[(size_t)w * pl.vn_stride + ((size_t)(voff[s] + kk / 4) * SUB + hh) * 4 + (kk & 3)] =
                 row * 128u + (uint32_t)(ch * G * 4);
@@ -384,26 +463,36 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int G, int DMAX, bool TAB, int MAXT>
+template <int G, int DMAX, bool TAB, int MAXT, bool YS>
 int launch_group_t(const GroupParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT><<<grid, threads, smem, stream>>>(q);
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS><<<grid, threads, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }
 
 int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t stream) {
     const int th = pl.threads;
+    const size_t sm = pl.smem;
     if (pl.G == 16 && pl.tab_smem) {
-        if (pl.dmax == 8) return launch_group_t<16, 8, true, 1024>(q, grid, th, pl.smem, stream);
-        return th <= 768 ? launch_group_t<16, 16, true, 768>(q, grid, th, pl.smem, stream)
-                         : launch_group_t<16, 16, true, 1024>(q, grid, th, pl.smem, stream);
+        if (pl.dmax == 8) return pl.y_smem ? launch_group_t<16, 8, true, 1024, true>(q, grid, th, sm, stream)
+                                           : launch_group_t<16, 8, true, 1024, false>(q, grid, th, sm, stream);
+        if (pl.y_smem) return th <= 768 ? launch_group_t<16, 16, true, 768, true>(q, grid, th, sm, stream)
+                                        : launch_group_t<16, 16, true, 1024, true>(q, grid, th, sm, stream);
+        return th <= 768 ? launch_group_t<16, 16, true, 768, false>(q, grid, th, sm, stream)
+                         : launch_group_t<16, 16, true, 1024, false>(q, grid, th, sm, stream);
+    }
+    if (pl.G == 1 && pl.y_smem) {
+        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, true>(q, grid, th, sm, stream)
+                                             : launch_group_t<1, 16, true, 1024, true>(q, grid, th, sm, stream);
+        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024, true>(q, grid, th, sm, stream)
+                            : launch_group_t<1, 16, false, 1024, true>(q, grid, th, sm, stream);
     }
     if (pl.G == 1) {
-        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024>(q, grid, th, pl.smem, stream)
-                                             : launch_group_t<1, 16, true, 1024>(q, grid, th, pl.smem, stream);
-        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024>(q, grid, th, pl.smem, stream)
-                            : launch_group_t<1, 16, false, 1024>(q, grid, th, pl.smem, stream);
+        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, false>(q, grid, th, sm, stream)
+                                             : launch_group_t<1, 16, true, 1024, false>(q, grid, th, sm, stream);
+        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024, false>(q, grid, th, sm, stream)
+                            : launch_group_t<1, 16, false, 1024, false>(q, grid, th, sm, stream);
     }
     return fail(LDPC_B200_ERR_UNSUPPORTED, "no group kernel instantiated for this shape");
 }
@@ -425,6 +514,7 @@ int make_plan(ldpc_b200_decoder* h) {
             pl.cw_per_cta = sh.G;
             pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS; pl.G = sh.G; pl.dmax = sh.dmax; pl.tab_smem = sh.tab_smem;
             pl.cn_stride = sh.cn_stride; pl.vn_stride = sh.vn_stride; pl.r_rows = sh.r_rows;
+            pl.y_smem = sh.y_smem;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;
@@ -529,6 +619,13 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.counter = ctr; q.ngroups = (int)ngroups;
         std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
         std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
+        q.n_vclass = 0;
+        std::memset(q.vclass_deg, 0, sizeof(q.vclass_deg));
+        std::memset(q.vclass_cnt, 0, sizeof(q.vclass_cnt));
+        for (int sidx = 0; sidx < pl.VS; ++sidx) {  // runs of equal slot degree
+            if (q.n_vclass && q.vclass_deg[q.n_vclass - 1] == h->g_vdeg[sidx]) q.vclass_cnt[q.n_vclass - 1]++;
+            else { q.vclass_deg[q.n_vclass] = h->g_vdeg[sidx]; q.vclass_cnt[q.n_vclass] = 1; q.n_vclass++; }
+        }
         rc = launch_group(pl, q, grid, stream);
         if (rc) return rc;
         h->launches += 1;

@@ -528,6 +528,9 @@ struct GroupParams {
     int ngroups;
     uint8_t vdeg[kGrpMaxVS];
     uint8_t cdeg[kGrpMaxCS];
+    int n_vclass;                             // Y_SMEM: runs of equal variable-slot degree
+    uint8_t vclass_deg[kGrpMaxVS];
+    uint8_t vclass_cnt[kGrpMaxVS];
 };
 
 // One check of exact degree D, straight-line: D x {T gather, R_old load, S = T + R_old}, running
@@ -559,21 +562,32 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
-        px ^= __float_as_uint(S[j]);
-        sx ^= __float_as_uint(tv[j]);
         const float a = fabsf(S[j]);
         m2 = fminf(m2, fmaxf(m1, a));
         m1 = fminf(m1, a);
     }
+    // sign parities, two edges per 3-input LOP3
+#pragma unroll
+    for (int j = 0; j + 1 < D; j += 2) {
+        px = px ^ __float_as_uint(S[j]) ^ __float_as_uint(S[j + 1]);
+        sx = sx ^ __float_as_uint(tv[j]) ^ __float_as_uint(tv[j + 1]);
+    }
+    if (D & 1) {
+        px ^= __float_as_uint(S[D - 1]);
+        sx ^= __float_as_uint(tv[D - 1]);
+    }
     // (Q_j < 0) = !signbit(S_j); parity of the negative Q's = (D & 1) ^ xor signbit(S);
     // sign(R_j) = parity ^ (Q_j < 0) = parity ^ 1 ^ signbit(S_j)
     const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
-    const uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
-    const uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
+    uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
+    uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
+    asm("" : "+r"(m1x), "+r"(m2x));  // materialise: keeps the parity flip out of the per-edge selects
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
-        sts_f32(rrow + (uint32_t)j * 128u, __uint_as_float(mag ^ (__float_as_uint(S[j]) & 0x80000000u)));
+        uint32_t rn;  // (S_j & 0x80000000) ^ mag in ONE LOP3 (kept opaque so the sign is not re-derived with FADDs)
+        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(rn) : "r"(__float_as_uint(S[j])), "r"(mag));
+        sts_f32(rrow + (uint32_t)j * 128u, __uint_as_float(rn));
     }
     return ((sx >> 31) ^ (uint32_t)D) & 1u;  // hard bit = !signbit(T)
 }
@@ -588,7 +602,46 @@ __device__ __forceinline__ void grp_vn_part(const uint4 o, uint32_t c4, float& a
     for (int k = 0; k < CNT; ++k) acc = __fsub_rn(acc, r[k]);
 }
 
-template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS>
+// NS variable slots of exact degree D processed together (independent FADD chains interleaved):
+// channel value from the Y array, D messages each through the quad table, new T stored.
+template <int D, int NS, int SUB, bool TAB_SMEM>
+__device__ __forceinline__ void grp_vn_slots(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,
+                                             uint32_t& ya, uint32_t t_stride, uint32_t c4, bool done) {
+    constexpr int NQ = (D + 3) / 4;
+    float acc[NS];
+    uint32_t e[NS][NQ * 4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        acc[i] = lds_f32(ya + (uint32_t)i * t_stride);
+#pragma unroll
+        for (int jq = 0; jq < NQ; ++jq) {
+            uint4 o;
+            if (TAB_SMEM) o = lds_u128(q + (uint32_t)((i * NQ + jq) * SUB) * 16u);
+            else {
+                o = __ldg(reinterpret_cast<const uint4*>(gtab + q) + (i * NQ + jq) * SUB);
+                o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+            }
+            e[i][jq * 4 + 0] = o.x; e[i][jq * 4 + 1] = o.y; e[i][jq * 4 + 2] = o.z; e[i][jq * 4 + 3] = o.w;
+        }
+    }
+    float r[NS][D];
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = 0; k < D; ++k) r[i][k] = lds_f32(e[i][k] + c4);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[i] = __fsub_rn(acc[i], r[i][k]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+        if (!done) sts_f32(ta + (uint32_t)i * t_stride, acc[i]);
+    q += (TAB_SMEM ? 16u : 4u) * (uint32_t)(NS * NQ * SUB);
+    ta += (uint32_t)NS * t_stride;
+    ya += (uint32_t)NS * t_stride;
+}
+
+template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM>
 __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
     constexpr int SUB = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -604,7 +657,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
     const int RD = W * p.r_rows_per_warp;           // dummy R row (= 0)
 
     const uint32_t t_base = smem_u32(smem_raw);
-    const uint32_t r_base = t_base + (((uint32_t)(PD + 1) * G * 4 + 127u) & ~127u);  // 128-byte aligned rows
+    const uint32_t t_bytes = ((uint32_t)(PD + 1) * G * 4 + 127u) & ~127u;
+    const uint32_t y_base = t_base + t_bytes;                                        // channel values (Y_SMEM)
+    const uint32_t r_base = y_base + (Y_SMEM ? t_bytes : 0u);                        // 128-byte aligned rows
     const uint32_t cn_base = r_base + (uint32_t)(RD + 1) * 128;
     const uint32_t vn_base = cn_base + (TAB_SMEM ? (uint32_t)W * p.cn_stride * 4 : 0u);
     if (TAB_SMEM) {
@@ -647,6 +702,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
                 if (v != 0xffffffffu && active) y = __ldg(src + v);
                 yn[s] = __fadd_rn(-y, 0.0f);
                 sts_f32(t_own + (uint32_t)s * t_stride, yn[s]);
+                if (Y_SMEM) sts_f32(t_own + t_bytes + (uint32_t)s * t_stride, yn[s]);
             }
         }
         for (int r = 0; r < p.r_rows_per_warp; ++r) sts_f32(r_own + (uint32_t)r * 128u, 0.0f);
@@ -690,7 +746,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
             if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
 
             // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
-            {
+            if constexpr (Y_SMEM) {
+                // channel values in shared memory: the slot loop is dynamic, two equal-degree slots at a
+                // time (slots are degree-sorted into at most kGrpMaxCls runs)
+                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
+                uint32_t ta = t_own, ya = t_own + t_bytes;
+                for (int ci = 0; ci < p.n_vclass; ++ci) {
+                    const int d = p.vclass_deg[ci];
+                    int n = p.vclass_cnt[ci];
+#define GRP_VCASE(D)                                                                                              \
+    case D:                                                                                                       \
+        if (D <= 3)                                                                                               \
+            for (; n >= 4; n -= 4) grp_vn_slots<D, (D <= 3 ? 4 : 1), SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done); \
+        for (; n >= 2; n -= 2) grp_vn_slots<D, 2, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done); \
+        if (n) grp_vn_slots<D, 1, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done);                 \
+        break;
+                    switch (d) {
+                        GRP_VCASE(1) GRP_VCASE(2) GRP_VCASE(3) GRP_VCASE(4) GRP_VCASE(5) GRP_VCASE(6) GRP_VCASE(7) GRP_VCASE(8)
+                        GRP_VCASE(9) GRP_VCASE(10) GRP_VCASE(11) GRP_VCASE(12)
+                        default:
+                            if (d == 0) { ta += (uint32_t)n * t_stride; ya += (uint32_t)n * t_stride; }
+                            break;
+                    }
+#undef GRP_VCASE
+                }
+            } else {
                 uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
                 auto next_quad = [&]() {
                     uint4 o;
@@ -707,13 +787,27 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
                     if (s < VS) {
                         int d = p.vdeg[s];
                         float acc = yn[s];
+                        // straight-line code per degree (slots are degree-sorted, so consecutive slots
+                        // take the same case); degrees above 8 fall back to a quad loop
+                        switch (d) {
+                            case 1: grp_vn_part<1>(next_quad(), c4, acc); break;
+                            case 2: grp_vn_part<2>(next_quad(), c4, acc); break;
+                            case 3: grp_vn_part<3>(next_quad(), c4, acc); break;
+                            case 4: grp_vn_part<4>(next_quad(), c4, acc); break;
+                            case 5: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<1>(next_quad(), c4, acc); break;
+                            case 6: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<2>(next_quad(), c4, acc); break;
+                            case 7: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<3>(next_quad(), c4, acc); break;
+                            case 8: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<4>(next_quad(), c4, acc); break;
+                            default:
 #pragma unroll 1
-                        for (; d >= 4; d -= 4) grp_vn_part<4>(next_quad(), c4, acc);
-                        if (d > 0) {
-                            const uint4 o = next_quad();
-                            if (d == 1) grp_vn_part<1>(o, c4, acc);
-                            else if (d == 2) grp_vn_part<2>(o, c4, acc);
-                            else grp_vn_part<3>(o, c4, acc);
+                                for (; d >= 4; d -= 4) grp_vn_part<4>(next_quad(), c4, acc);
+                                if (d > 0) {
+                                    const uint4 o = next_quad();
+                                    if (d == 1) grp_vn_part<1>(o, c4, acc);
+                                    else if (d == 2) grp_vn_part<2>(o, c4, acc);
+                                    else grp_vn_part<3>(o, c4, acc);
+                                }
+                                break;
                         }
                         if (!done) sts_f32(t_own + (uint32_t)s * t_stride, acc);
                     }

@@ -347,11 +347,20 @@ def main() -> None:
     roof_hbm = {"bound": "hbm", "achieved": per_gpu_cw_s * (b_hbm if onchip else b_msg) / 1e9, "peak": hbm_peak,
                 "unit": "GB/s", "peak_source": hbm_src, "traffic": None}
     roof_hbm["frac"] = roof_hbm["achieved"] / hbm_peak
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+    try:
+        tr = json.loads((ROOT / "profiles" / ("ncu_traffic_%s.json" % args.workload)).read_text())
+        if tr.get("codewords_per_launch") == ncw:
+            roof_hbm["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof_hbm["traffic_source"] = tr["source"]
+            roof_hbm["algorithmic_bytes_per_launch"] = (b_hbm if onchip else b_msg) * ncw
+    except Exception:
+        pass
     roofline = dict(roof_smem if onchip else roof_hbm)
     roofline.update({
         "kernel": {"group": "ldpc_ms_group_kernel", "lane16": "ldpc_ms_lane16_kernel",
                    "lane_smem": "ldpc_ms_lane_kernel<true>"}.get(info["path_name"], "ldpc_ms_lane_kernel<false>"),
-        "launch_ms": ms_step, "traffic": None,
+        "launch_ms": ms_step, "traffic": roof_hbm.get("traffic"),
         "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},
         "hbm": roof_hbm, "smem": roof_smem,
         "note": ("messages stay in shared memory: HBM carries only channel values and bits, so shared-memory "

@@ -270,7 +270,9 @@ struct GrpShape {
     double cost = 0.0;
 };
 
-bool group_shape(const HostTables& t, int G, int W, size_t smem_limit, GrpShape* out) {
+bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, GrpShape* out) {
+    // G = 8 runs two CTAs per SM (phase-shifted check / variable passes overlap): half the budget each
+    const size_t smem_limit = G == 8 ? (smem_limit_in + 1024) / 2 - 1024 : smem_limit_in;
     const int SUB = 32 / G, NL = W * SUB;
     GrpShape sh;
     sh.G = G; sh.W = W;
@@ -307,17 +309,30 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit, GrpShape*
 
 bool group_pick(const HostTables& t, size_t smem_limit, GrpShape* best) {
     int g_lo = 1, g_hi = 16, w_lo = 8, w_hi = 32;
-    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16) g_lo = g_hi = g; }
+    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16 || g == 8) g_lo = g_hi = g; }
     if (const char* env = std::getenv("LDPC_B200_GRP_WARPS")) { const int w = std::atoi(env); if (w >= 1 && w <= 32) w_lo = w_hi = w; }
     // instantiated: G = 16 (short codes, tables on chip) and G = 1 (one codeword per CTA)
-    for (int G : {16, 1}) {
+    for (int G : {16, 8, 1}) {
         if (G < g_lo || G > g_hi) continue;
+        if (G == 16 && g_lo != 16 && !std::getenv("LDPC_B200_GRP_PREFER_16")) {
+            // measured (profiles/): two phase-shifted CTAs of 8 words beat one CTA of 16 -- try G = 8 first
+            bool found8 = false;
+            GrpShape b8;
+            for (int W = w_lo; W <= std::min(w_hi, 12); ++W) {
+                GrpShape sh;
+                if (!group_shape(t, 8, W, smem_limit, &sh) || !sh.tab_smem) continue;
+                if (!found8 || sh.cost < b8.cost - 1e-9 || (std::abs(sh.cost - b8.cost) <= 1e-9 && W > b8.W)) { found8 = true; b8 = sh; }
+            }
+            if (found8) { *best = b8; return true; }
+        }
+        if (G == 8 && g_lo != 8) continue;
         bool found = false;
         GrpShape b;
         for (int W = w_lo; W <= w_hi; ++W) {
             GrpShape sh;
             if (!group_shape(t, G, W, smem_limit, &sh)) continue;
             if (G == 16 && !sh.tab_smem) continue;
+            if (G == 8 && (!sh.tab_smem || W > 12)) continue;
             if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
         }
         if (found) { *best = b; return true; }
@@ -360,68 +375,94 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     std::vector<int> slot_of_edge(t.nnz);
     for (int r = 0; r < t.M; ++r)
         for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) slot_of_edge[e] = e - t.row_ptr[r];
-    if (SUB == 2) {
-        // (1) orientation of each check pair: which member sits in lanes 0-15.  A variable pair (X, Y)
-        //     reads its k-th messages together; they collide when both checks sit in the same half.
-        //     Greedy local search over pair flips.
-        const int npairs = (t.M + 1) / 2;
-        std::vector<uint8_t> flip(npairs, 0);
-        auto half_of_chk = [&](int chk) { const int rk = (int)crank_of_chk[chk]; return (rk & 1) ^ flip[rk >> 1]; };
-        auto vn_conflicts_of_pairs = [&](const std::vector<int>& vpairs) {
-            long long c = 0;
-            for (int vp : vpairs) {
-                const int ra = 2 * vp, rb = 2 * vp + 1;
-                if (rb >= t.N) continue;
-                const int x = vorder[ra], y = vorder[rb];
-                const int dx = vdegf(x), dy = vdegf(y);
-                for (int k = 0; k < std::min(dx, dy); ++k) {
-                    const int cx = (int)(t.vn_edge[t.col_ptr[x] + k] >> kPosBits), cy = (int)(t.vn_edge[t.col_ptr[y] + k] >> kPosBits);
-                    c += half_of_chk(cx) == half_of_chk(cy);
+    if (SUB == 2 || SUB == 4) {
+        // Lanes of one warp instruction touch SUB different rows; a row occupies 32/SUB banks chosen by
+        // (row index mod SUB) for T and by the owning check's node lane for R.  Equal classes collide.
+        // (1) node lane of every check inside its co-processed group (SUB consecutive ranks): local
+        //     search over swaps, minimising the collisions of the variable pass, where the k-th messages
+        //     of SUB co-processed variables are read together.
+        const int ngrp = (t.M + SUB - 1) / SUB;
+        auto lane_of_chk = [&](int chk) { return (int)crank_of_chk[chk] % SUB; };
+        auto vgroup_cost = [&](int vg) {
+            long long cost = 0;
+            int maxd = 0;
+            for (int i = 0; i < SUB; ++i) { const int rk = vg * SUB + i; if (rk < t.N) maxd = std::max(maxd, vdegf(vorder[rk])); }
+            for (int k = 0; k < maxd; ++k) {
+                int cnt[4] = {0, 0, 0, 0};
+                for (int i = 0; i < SUB; ++i) {
+                    const int rk = vg * SUB + i;
+                    if (rk >= t.N) continue;
+                    const int v = vorder[rk];
+                    if (k >= vdegf(v)) continue;
+                    cnt[lane_of_chk((int)(t.vn_edge[t.col_ptr[v] + k] >> kPosBits))]++;
                 }
+                cost += std::max(std::max(cnt[0], cnt[1]), std::max(cnt[2], cnt[3]));
             }
-            return c;
+            return cost;
         };
-        // variable pairs touched by each check pair
-        std::vector<std::vector<int>> touched(npairs);
+        std::vector<std::vector<int>> touched(ngrp);  // variable groups reading messages of each check group
         for (int v = 0; v < t.N; ++v)
-            for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
-                const int cp = (int)crank_of_chk[t.vn_edge[k] >> kPosBits] >> 1;
-                const int vp = (int)pos_of_var[v] >> 1;
-                if (touched[cp].empty() || touched[cp].back() != vp) touched[cp].push_back(vp);
-            }
+            for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k)
+                touched[(int)crank_of_chk[t.vn_edge[k] >> kPosBits] / SUB].push_back((int)pos_of_var[v] / SUB);
         for (auto& v : touched) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-        for (int pass = 0; pass < 6; ++pass) {
+        auto touched_cost = [&](int cg) { long long c = 0; for (int vg : touched[cg]) c += vgroup_cost(vg); return c; };
+        auto swap_ranks = [&](int ra, int rb) {
+            std::swap(corder[ra], corder[rb]);
+            crank_of_chk[corder[ra]] = (uint32_t)ra;
+            crank_of_chk[corder[rb]] = (uint32_t)rb;
+        };
+        for (int pass = 0; pass < 8; ++pass) {
             bool changed = false;
-            for (int cp = 0; cp < npairs; ++cp) {
-                const long long before = vn_conflicts_of_pairs(touched[cp]);
-                flip[cp] ^= 1;
-                const long long after = vn_conflicts_of_pairs(touched[cp]);
-                if (after < before) changed = true; else flip[cp] ^= 1;
-            }
+            for (int cg = 0; cg < ngrp; ++cg)
+                for (int i = 0; i < SUB; ++i)
+                    for (int j = i + 1; j < SUB; ++j) {
+                        const int ra = cg * SUB + i, rb = cg * SUB + j;
+                        if (rb >= t.M) continue;
+                        const long long before = touched_cost(cg);
+                        swap_ranks(ra, rb);
+                        if (touched_cost(cg) < before) changed = true; else swap_ranks(ra, rb);
+                    }
             if (!changed) break;
         }
-        // apply the orientation: swap ranks inside flipped pairs
-        for (int cp = 0; cp < npairs; ++cp)
-            if (flip[cp] && 2 * cp + 1 < t.M) {
-                std::swap(corder[2 * cp], corder[2 * cp + 1]);
-                crank_of_chk[corder[2 * cp]] = 2 * cp;
-                crank_of_chk[corder[2 * cp + 1]] = 2 * cp + 1;
+        // (2) edge order inside each check group: at equal j the SUB T rows should fall in different bank
+        //     classes (row index mod SUB).  Greedy column by column, preferring each check's fullest class.
+        for (int cg = 0; cg < ngrp; ++cg) {
+            std::vector<int> byclass[4][4];  // [member][class] -> edges
+            int deg[4] = {0, 0, 0, 0}, nmem = 0;
+            for (int i = 0; i < SUB; ++i) {
+                const int rk = cg * SUB + i;
+                if (rk >= t.M) break;
+                nmem = i + 1;
+                const int r = corder[rk];
+                deg[i] = cdegf(r);
+                for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) byclass[i][pos_of_var[t.col_idx[e]] % SUB].push_back(e);
             }
-        // (2) edge order inside each check pair: opposite T-row parity at equal j
-        for (int cp = 0; 2 * cp + 1 < t.M; ++cp) {
-            const int a = corder[2 * cp], b = corder[2 * cp + 1];
-            std::vector<int> ae[2], be[2];
-            for (int e = t.row_ptr[a]; e < t.row_ptr[a + 1]; ++e) ae[pos_of_var[t.col_idx[e]] & 1].push_back(e);
-            for (int e = t.row_ptr[b]; e < t.row_ptr[b + 1]; ++e) be[pos_of_var[t.col_idx[e]] & 1].push_back(e);
-            std::vector<int> oa, ob;  // matched orders
-            for (int par = 0; par < 2; ++par)
-                while (!ae[par].empty() && !be[par ^ 1].empty()) {
-                    oa.push_back(ae[par].back()); ae[par].pop_back();
-                    ob.push_back(be[par ^ 1].back()); be[par ^ 1].pop_back();
+            const int maxd = std::max(std::max(deg[0], deg[1]), std::max(deg[2], deg[3]));
+            int placed[4] = {0, 0, 0, 0};
+            for (int j = 0; j < maxd; ++j) {
+                bool used[4] = {false, false, false, false};
+                // members with fewer remaining choices go first
+                int order[4] = {0, 1, 2, 3};
+                std::sort(order, order + nmem, [&](int x, int y) {
+                    int cx = 0, cy = 0;
+                    for (int c = 0; c < SUB; ++c) { cx += !byclass[x][c].empty(); cy += !byclass[y][c].empty(); }
+                    return cx < cy;
+                });
+                for (int oi = 0; oi < nmem; ++oi) {
+                    const int i = order[oi];
+                    if (placed[i] >= deg[i]) continue;
+                    int best = -1;
+                    for (int c = 0; c < SUB; ++c)
+                        if (!byclass[i][c].empty() && !used[c] && (best < 0 || byclass[i][c].size() > byclass[i][best].size())) best = c;
+                    if (best < 0)
+                        for (int c = 0; c < SUB; ++c)
+                            if (!byclass[i][c].empty() && (best < 0 || byclass[i][c].size() > byclass[i][best].size())) best = c;
+                    const int e = byclass[i][best].back();
+                    byclass[i][best].pop_back();
+                    used[best] = true;
+                    slot_of_edge[e] = placed[i]++;
                 }
-            for (int par = 0; par < 2; ++par) { for (int e : ae[par]) oa.push_back(e); for (int e : be[par]) ob.push_back(e); }
-            for (size_t j = 0; j < oa.size(); ++j) slot_of_edge[oa[j]] = (int)j;
-            for (size_t j = 0; j < ob.size(); ++j) slot_of_edge[ob[j]] = (int)j;
+            }
         }
     }
     // check pass: T-row byte offset of every edge, [warp][slot][quad][h][4]; padding -> dummy row PD
@@ -463,12 +504,20 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int G, int DMAX, bool TAB, int MAXT, bool YS>
+template <int G, int DMAX, bool TAB, int MAXT, bool YS, class PROF = GenericProfile>
 int launch_group_t(const GroupParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS><<<grid, threads, smem, stream>>>(q);
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF><<<grid, threads, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());
     return LDPC_B200_OK;
+}
+
+template <class P>
+bool profile_matches(const Plan& pl, const GroupParams& q) {
+    if (pl.CS != P::CS || pl.VS != P::VS) return false;
+    for (int i = 0; i < P::CS; ++i) if (q.cdeg[i] != P::cdeg(i)) return false;
+    for (int i = 0; i < P::VS; ++i) if (q.vdeg[i] != P::vdeg(i)) return false;
+    return true;
 }
 
 int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t stream) {
@@ -481,6 +530,14 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
                                         : launch_group_t<16, 16, true, 1024, true>(q, grid, th, sm, stream);
         return th <= 768 ? launch_group_t<16, 16, true, 768, false>(q, grid, th, sm, stream)
                          : launch_group_t<16, 16, true, 1024, false>(q, grid, th, sm, stream);
+    }
+    if (pl.G == 8 && pl.tab_smem && th <= 384) {
+        if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576>(pl, q))
+            return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576>(q, grid, th, sm, stream);
+        if (pl.dmax == 8) return pl.y_smem ? launch_group_t<8, 8, true, 384, true>(q, grid, th, sm, stream)
+                                           : launch_group_t<8, 8, true, 384, false>(q, grid, th, sm, stream);
+        return pl.y_smem ? launch_group_t<8, 16, true, 384, true>(q, grid, th, sm, stream)
+                         : launch_group_t<8, 16, true, 384, false>(q, grid, th, sm, stream);
     }
     if (pl.G == 1 && pl.y_smem) {
         if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, true>(q, grid, th, sm, stream)
@@ -510,7 +567,7 @@ int make_plan(ldpc_b200_decoder* h) {
             pl.path = LDPC_B200_PATH_GROUP;
             pl.threads = 32 * sh.W;
             pl.smem = sh.smem;
-            pl.ctas = h->sm_count;
+            pl.ctas = h->sm_count * (sh.G == 8 ? 2 : 1);
             pl.cw_per_cta = sh.G;
             pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS; pl.G = sh.G; pl.dmax = sh.dmax; pl.tab_smem = sh.tab_smem;
             pl.cn_stride = sh.cn_stride; pl.vn_stride = sh.vn_stride; pl.r_rows = sh.r_rows;

@@ -641,8 +641,93 @@ __device__ __forceinline__ void grp_vn_slots(uint32_t& q, const uint32_t* __rest
     ya += (uint32_t)NS * t_stride;
 }
 
-template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM>
-__global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
+// ---- degree profiles ---------------------------------------------------------------------------
+// The slot degrees of a (code, G, W) combination are a handful of small integers.  When they are
+// known at compile time the check and variable passes become straight-line code: no per-slot degree
+// loads, switches or loop counters, and the scheduler can overlap the loads of several slots.
+// GenericProfile reads the degrees from the kernel parameters; a static profile is picked by the
+// host when the plan's degrees match it exactly (ldpc_b200.cu: launch_group).
+struct GenericProfile {
+    static constexpr bool kStatic = false;
+};
+// Test.cpp's code (802.16e rate 3/4B, z = 24: N = 576, M = 144) dealt over 48 node lanes
+// (G = 8: 12 warps x 4, or G = 16: 24 warps x 2): 3 check slots, 12 variable slots.
+struct ProfileWimax34B576 {
+    static constexpr bool kStatic = true;
+    static constexpr int CS = 3, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 15, 14}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
+};
+
+// NS variable slots of exact degree D with the channel values in registers.
+template <int D, int NS, int SUB, bool TAB_SMEM>
+__device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,
+                                                 const float* yv, uint32_t t_stride, uint32_t c4, bool done) {
+    constexpr int NQ = (D + 3) / 4;
+    float acc[NS];
+    uint32_t e[NS][NQ * 4];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        acc[i] = yv[i];
+#pragma unroll
+        for (int jq = 0; jq < NQ; ++jq) {
+            uint4 o;
+            if (TAB_SMEM) o = lds_u128(q + (uint32_t)((i * NQ + jq) * SUB) * 16u);
+            else {
+                o = __ldg(reinterpret_cast<const uint4*>(gtab + q) + (i * NQ + jq) * SUB);
+                o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+            }
+            e[i][jq * 4 + 0] = o.x; e[i][jq * 4 + 1] = o.y; e[i][jq * 4 + 2] = o.z; e[i][jq * 4 + 3] = o.w;
+        }
+    }
+    float r[NS][D];
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = 0; k < D; ++k) r[i][k] = lds_f32(e[i][k] + c4);
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[i] = __fsub_rn(acc[i], r[i][k]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+        if (!done) sts_f32(ta + (uint32_t)i * t_stride, acc[i]);
+    q += (TAB_SMEM ? 16u : 4u) * (uint32_t)(NS * NQ * SUB);
+    ta += (uint32_t)NS * t_stride;
+}
+
+// Static variable pass: runs of equal-degree slots, up to 4 (degree <= 3) or 2 slots in flight.
+template <class P, int S0, int SUB, bool TAB_SMEM>
+__device__ __forceinline__ void grp_vn_static(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,
+                                              const float* yn, uint32_t t_stride, uint32_t c4, bool done) {
+    if constexpr (S0 < P::VS) {
+        constexpr int D = P::vdeg(S0);
+        constexpr int same2 = (S0 + 1 < P::VS) && P::vdeg(S0 + 1 < P::VS ? S0 + 1 : S0) == D;
+        constexpr int same4 = same2 && (S0 + 3 < P::VS) && P::vdeg(S0 + 2 < P::VS ? S0 + 2 : S0) == D &&
+                              P::vdeg(S0 + 3 < P::VS ? S0 + 3 : S0) == D;
+        constexpr int NS = (same4 && D <= 3) ? 4 : (same2 ? 2 : 1);
+        if constexpr (D > 0) grp_vn_slots_reg<D, NS, SUB, TAB_SMEM>(q, gtab, r_base, ta, yn + S0, t_stride, c4, done);
+        else ta += (uint32_t)NS * t_stride;
+        grp_vn_static<P, S0 + NS, SUB, TAB_SMEM>(q, gtab, r_base, ta, yn, t_stride, c4, done);
+    }
+}
+
+// Static check pass: one straight-line check per slot.
+template <class P, int CS0, int SUB, bool TAB_SMEM>
+__device__ __forceinline__ uint32_t grp_cn_static(uint32_t tab, const uint32_t* __restrict__ gtab, uint32_t t_base, uint32_t rrow,
+                                                   uint32_t c4, int h) {
+    if constexpr (CS0 < P::CS) {
+        constexpr int D = P::cdeg(CS0);
+        const uint32_t u = grp_check<D, SUB, TAB_SMEM>(tab, gtab, t_base, rrow, c4, h);
+        return u | grp_cn_static<P, CS0 + 1, SUB, TAB_SMEM>(tab + (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 3) >> 2) * SUB), gtab, t_base,
+                                                             rrow + (uint32_t)D * 128u, c4, h);
+    } else {
+        return 0u;
+    }
+}
+
+template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM, class PROF = GenericProfile>
+__global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
     constexpr int SUB = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_group;
@@ -715,7 +800,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
         for (;;) {
             // ---- check-node pass
             uint32_t unsat = 0u;
-            {
+            if constexpr (PROF::kStatic) {
+                unsat = grp_cn_static<PROF, 0, SUB, TAB_SMEM>(cn_w, p.cn_tab, t_base, r_own, c4, h);
+            } else {
                 uint32_t tab = cn_w;     // quads for this warp, slot by slot
                 uint32_t rrow = r_own;   // this lane's R column, row by row
                 for (int cs = 0; cs < CS; ++cs) {
@@ -770,6 +857,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) ldpc_ms_group_kernel(const __g
                     }
 #undef GRP_VCASE
                 }
+            } else if constexpr (PROF::kStatic) {
+                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
+                uint32_t ta = t_own;
+                grp_vn_static<PROF, 0, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, yn, t_stride, c4, done);
             } else {
                 uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
                 auto next_quad = [&]() {

@@ -539,6 +539,9 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
         return pl.y_smem ? launch_group_t<8, 16, true, 384, true>(q, grid, th, sm, stream)
                          : launch_group_t<8, 16, true, 384, false>(q, grid, th, sm, stream);
     }
+    if (pl.G == 1 && !pl.tab_smem && pl.dmax == 8 && !std::getenv("LDPC_B200_GRP_NO_PROFILE") &&
+        profile_matches<ProfileRegular36N8192>(pl, q))
+        return launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192>(q, grid, th, sm, stream);
     if (pl.G == 1 && pl.y_smem) {
         if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, true>(q, grid, th, sm, stream)
                                              : launch_group_t<1, 16, true, 1024, true>(q, grid, th, sm, stream);

@@ -659,6 +659,14 @@ struct ProfileWimax34B576 {
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
 };
 
+// Regular (3,6) code with N = 8192 (BASELINE config 3) dealt over 1024 node lanes (G = 1, 32 warps).
+struct ProfileRegular36N8192 {
+    static constexpr bool kStatic = true;
+    static constexpr int CS = 4, VS = 8;
+    __host__ __device__ static constexpr int cdeg(int) { return 6; }
+    __host__ __device__ static constexpr int vdeg(int) { return 3; }
+};
+
 // NS variable slots of exact degree D with the channel values in registers.
 template <int D, int NS, int SUB, bool TAB_SMEM>
 __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,

@@ -465,6 +465,135 @@ int upload_group_tables(ldpc_b200_decoder* h) {
             }
         }
     }
+    if (SUB >= 8) {
+        // ---- bank placement for wide node groups (G <= 4; G = 1: 32 different checks / variables per
+        // instruction).  T[pos] sits in bank (pos mod 32) = the owning variable's lane; R elements sit in
+        // the bank of the owning check's lane.  Random codes collide ~3.4-way in both gathers.  Lanes
+        // inside a 32-node group are free to permute, so:
+        //   (a) permute variable lanes so that every check group sees each T bank equally often
+        //       (then its edges split into conflict-free columns -- Koenig);
+        //   (b) permute check lanes so that, for every k, the k-th messages of a variable group come
+        //       from distinct R banks (the per-variable order k is fixed by the summation order);
+        //   (c) order each check group's edges column by column with a bipartite matching.
+        const int LN = SUB;  // lanes per group (bank classes); rows are 4*G bytes wide
+        const int nvg = (t.N + LN - 1) / LN, ncg = (t.M + LN - 1) / LN;
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 32); };
+        // (a) variable lanes
+        {
+            std::vector<int> cnt((size_t)ncg * LN, 0);  // [check group][bank]
+            auto bump = [&](int v, int bank, int dlt, long long& cost) {
+                for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+                    const int cg = (int)crank_of_chk[t.vn_edge[k] >> kPosBits] / LN;
+                    int& x = cnt[(size_t)cg * LN + bank];
+                    cost += dlt > 0 ? 2 * x + 1 : -(2 * x - 1);
+                    x += dlt;
+                }
+            };
+            long long cost = 0;
+            for (int r = 0; r < t.N; ++r) bump(vorder[r], r % LN, +1, cost);
+            const long long iters = (long long)t.N * 60;
+            for (long long it = 0; it < iters; ++it) {
+                const int vg = (int)(rnd() % (uint32_t)nvg);
+                const int a = vg * LN + (int)(rnd() % LN), b = vg * LN + (int)(rnd() % LN);
+                if (a == b || a >= t.N || b >= t.N) continue;
+                long long d = 0;
+                bump(vorder[a], a % LN, -1, d); bump(vorder[b], b % LN, -1, d);
+                bump(vorder[a], b % LN, +1, d); bump(vorder[b], a % LN, +1, d);
+                if (d <= 0) {
+                    std::swap(vorder[a], vorder[b]);
+                    cost += d;
+                } else {
+                    long long u = 0;
+                    bump(vorder[a], b % LN, -1, u); bump(vorder[b], a % LN, -1, u);
+                    bump(vorder[a], a % LN, +1, u); bump(vorder[b], b % LN, +1, u);
+                }
+            }
+            for (int i = 0; i < t.N; ++i) { var_of_pos[i] = (uint32_t)vorder[i]; pos_of_var[vorder[i]] = (uint32_t)i; }
+        }
+        // (b) check lanes
+        {
+            int maxdv = t.max_col_weight;
+            std::vector<int> cnt((size_t)nvg * maxdv * LN, 0);  // [variable group][k][bank]
+            auto bump = [&](int chk, int bank, int dlt, long long& cost) {
+                for (int e = t.row_ptr[chk]; e < t.row_ptr[chk + 1]; ++e) {
+                    const int v = t.col_idx[e];
+                    // k = index of this check in v's ascending-row list
+                    int k = 0;
+                    for (int q = t.col_ptr[v]; q < t.col_ptr[v + 1]; ++q, ++k)
+                        if ((int)(t.vn_edge[q] >> kPosBits) == chk) break;
+                    const int vg = (int)pos_of_var[v] / LN;
+                    int& x = cnt[((size_t)vg * maxdv + k) * LN + bank];
+                    cost += dlt > 0 ? 2 * x + 1 : -(2 * x - 1);
+                    x += dlt;
+                }
+            };
+            long long cost = 0;
+            for (int r = 0; r < t.M; ++r) bump(corder[r], r % LN, +1, cost);
+            const long long iters = (long long)t.M * 120;
+            for (long long it = 0; it < iters; ++it) {
+                const int cg = (int)(rnd() % (uint32_t)ncg);
+                const int a = cg * LN + (int)(rnd() % LN), b = cg * LN + (int)(rnd() % LN);
+                if (a == b || a >= t.M || b >= t.M) continue;
+                long long d = 0;
+                bump(corder[a], a % LN, -1, d); bump(corder[b], b % LN, -1, d);
+                bump(corder[a], b % LN, +1, d); bump(corder[b], a % LN, +1, d);
+                if (d <= 0) {
+                    std::swap(corder[a], corder[b]);
+                    cost += d;
+                } else {
+                    long long u = 0;
+                    bump(corder[a], b % LN, -1, u); bump(corder[b], a % LN, -1, u);
+                    bump(corder[a], a % LN, +1, u); bump(corder[b], b % LN, +1, u);
+                }
+            }
+            for (int i = 0; i < t.M; ++i) crank_of_chk[corder[i]] = (uint32_t)i;
+        }
+        // (c) edge columns inside each check group: maximum bipartite matching (checks x banks) per column
+        for (int cg = 0; cg < ncg; ++cg) {
+            const int n = std::min(LN, t.M - cg * LN);
+            std::vector<std::vector<int>> rem(n);  // remaining edges per member
+            int maxd = 0;
+            for (int i = 0; i < n; ++i) {
+                const int r = corder[cg * LN + i];
+                for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) rem[i].push_back(e);
+                maxd = std::max(maxd, (int)rem[i].size());
+            }
+            std::vector<int> placed(n, 0);
+            for (int j = 0; j < maxd; ++j) {
+                std::vector<int> bank_owner(LN, -1), pick(n, -1);
+                std::vector<char> seen;
+                std::function<bool(int)> aug = [&](int i) {
+                    for (size_t x = 0; x < rem[i].size(); ++x) {
+                        const int bnk = (int)(pos_of_var[t.col_idx[rem[i][x]]] % LN);
+                        if (seen[bnk]) continue;
+                        seen[bnk] = 1;
+                        if (bank_owner[bnk] < 0 || aug(bank_owner[bnk])) { bank_owner[bnk] = i; pick[i] = (int)x; return true; }
+                    }
+                    return false;
+                };
+                for (int i = 0; i < n; ++i) {
+                    if (rem[i].empty()) continue;
+                    seen.assign(LN, 0);
+                    aug(i);
+                }
+                // pick[] may be stale for members re-routed during augmentation: rebuild from bank_owner
+                std::fill(pick.begin(), pick.end(), -1);
+                for (int bnk = 0; bnk < LN; ++bnk) {
+                    const int i = bank_owner[bnk];
+                    if (i < 0) continue;
+                    for (size_t x = 0; x < rem[i].size(); ++x)
+                        if ((int)(pos_of_var[t.col_idx[rem[i][x]]] % LN) == bnk) { pick[i] = (int)x; break; }
+                }
+                for (int i = 0; i < n; ++i) {
+                    if (rem[i].empty()) continue;
+                    const int x = pick[i] >= 0 ? pick[i] : 0;  // unmatched: take any (a conflict)
+                    slot_of_edge[rem[i][x]] = placed[i]++;
+                    rem[i].erase(rem[i].begin() + x);
+                }
+            }
+        }
+    }
     // check pass: T-row byte offset of every edge, [warp][slot][quad][h][4]; padding -> dummy row PD
     std::vector<uint32_t> cn_tab((size_t)W * pl.cn_stride, (uint32_t)PD * G * 4u);
     for (int rank = 0; rank < t.M; ++rank) {

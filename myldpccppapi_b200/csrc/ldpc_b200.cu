@@ -94,7 +94,7 @@ struct ldpc_b200_decoder {
     uint8_t l16_vdeg[kL16MaxVS] = {0};
     uint8_t l16_cdeg[kL16MaxCS] = {0};
 
-    unsigned int* d_counters = nullptr;
+    unsigned long long* d_counters = nullptr;  // ring of work-queue heads (64-bit; lane kernels use the low word)
     int counter_next = 0;
     float* d_ws = nullptr;
     size_t ws_bytes = 0;
@@ -789,9 +789,10 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     const int per_group = pl.path == LDPC_B200_PATH_GROUP ? pl.G : kLanes;
     const int64_t ngroups = (ncw + per_group - 1) / per_group;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
-    unsigned int* ctr = h->d_counters + h->counter_next;
+    unsigned long long* ctr64 = h->d_counters + h->counter_next;
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(ctr64);
     h->counter_next = (h->counter_next + 1) % kCounterRing;
-    CU_TRY(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), stream));
+    CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
 
     if (pl.path == LDPC_B200_PATH_GROUP) {
@@ -805,7 +806,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.max_iter = h->max_iter; q.early_term = h->early;
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
-        q.counter = ctr; q.ngroups = (int)ngroups;
+        q.counter = ctr; q.counter64 = ctr64; q.ngroups = (int)ngroups;
+        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;  // measured: profiles/r01_refill_sweep.txt
         std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
         std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
         q.n_vclass = 0;
@@ -927,7 +929,7 @@ int ldpc_b200_create(ldpc_b200_handle* out, int M, int N, int K, const int32_t* 
     ok = ok && cudaMalloc(&h->d_cn_col, sizeof(uint32_t) * nnz1) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_col_ptr, sizeof(int32_t) * (t.N + 1)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_vn_edge, sizeof(uint32_t) * nnz1) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_counters, sizeof(unsigned int) * kCounterRing) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_counters, sizeof(unsigned long long) * kCounterRing) == cudaSuccess;
     if (!ok) return cleanup_fail(LDPC_B200_ERR_CUDA, std::string("cudaMalloc(tables): ") + cudaGetErrorString(cudaGetLastError()));
     h->table_bytes = sizeof(int32_t) * (t.M + 1 + t.N + 1) + sizeof(uint32_t) * 2 * nnz1;
     ok = ok && cudaMemcpy(h->d_row_ptr, t.row_ptr.data(), sizeof(int32_t) * (t.M + 1), cudaMemcpyHostToDevice) == cudaSuccess;

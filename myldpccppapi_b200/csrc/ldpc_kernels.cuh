@@ -525,6 +525,8 @@ struct GroupParams {
     int32_t* iters;
     float* post;
     unsigned int* counter;
+    unsigned long long* counter64;            // work-queue head: next codeword index
+    int refill_wait;                          // lane refill policy (see the kernel's loop top)
     int ngroups;
     uint8_t vdeg[kGrpMaxVS];
     uint8_t cdeg[kGrpMaxCS];
@@ -738,7 +740,6 @@ template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM, class PR
 __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
     constexpr int SUB = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_group;
     __shared__ uint32_t s_flag[2][32];
 
     const int lane = threadIdx.x & 31;
@@ -774,153 +775,124 @@ __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldp
     const uint32_t cn_w = TAB_SMEM ? cn_base + (uint32_t)warp * p.cn_stride * 4u : (uint32_t)warp * p.cn_stride;
     const uint32_t vn_w = TAB_SMEM ? vn_base + (uint32_t)warp * p.vn_stride * 4u : (uint32_t)warp * p.vn_stride;
 
-    for (;;) {
-        if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
-        __syncthreads();
-        const int g = s_group;
-        if (g >= p.ngroups) break;
-
-        const long long cw = (long long)g * G + c;
-        const bool active = cw < p.ncw;
-        const float* src = p.llr + (size_t)(active ? cw : 0) * p.N;
-
-        // ---- load: -y into registers and T; all messages R = 0 (decodeInitMS, decodeCL.c:113-124)
-        float yn[kGrpMaxVS];
+    // ---- per-lane decode state.  Every thread of a codeword lane c keeps the same copy. ---------------
+    float yn[kGrpMaxVS];
 #pragma unroll
-        for (int s = 0; s < kGrpMaxVS; ++s) {
-            yn[s] = -1.0f;
-            if (s < VS) {
-                const uint32_t v = __ldg(p.var_of_pos + s * NL + warp * SUB + h);
-                float y = 1.0f;
-                if (v != 0xffffffffu && active) y = __ldg(src + v);
-                yn[s] = __fadd_rn(-y, 0.0f);
-                sts_f32(t_own + (uint32_t)s * t_stride, yn[s]);
-                if (Y_SMEM) sts_f32(t_own + t_bytes + (uint32_t)s * t_stride, yn[s]);
+    for (int s = 0; s < kGrpMaxVS; ++s) yn[s] = -1.0f;
+    long long cw = -1;
+    bool live = false;     // decoding a codeword
+    bool done = false;     // live and finished (converged or at the cap): retires at the next loop top
+    bool loading = false;  // channel values in flight (cp.async into this lane's own T elements)
+    int it = 0, my_iters = 0;
+    __shared__ long long s_cw[32];
+
+    // passes -----------------------------------------------------------------------------------------
+    auto cn_pass = [&]() -> uint32_t {
+        // ---- check-node pass
+        uint32_t unsat = 0u;
+        if constexpr (PROF::kStatic) {
+            unsat = grp_cn_static<PROF, 0, SUB, TAB_SMEM>(cn_w, p.cn_tab, t_base, r_own, c4, h);
+        } else {
+            uint32_t tab = cn_w;     // quads for this warp, slot by slot
+            uint32_t rrow = r_own;   // this lane's R column, row by row
+            for (int cs = 0; cs < CS; ++cs) {
+                const int dc = p.cdeg[cs];
+#define GRP_CASE(D) case D: unsat |= grp_check<D, SUB, TAB_SMEM>(tab, p.cn_tab, t_base, rrow, c4, h); break;
+                switch (dc) {
+                    GRP_CASE(1) GRP_CASE(2) GRP_CASE(3) GRP_CASE(4) GRP_CASE(5) GRP_CASE(6) GRP_CASE(7) GRP_CASE(8)
+                    default:
+                        if constexpr (DMAX > 8) {
+                            switch (dc) {
+                                GRP_CASE(9) GRP_CASE(10) GRP_CASE(11) GRP_CASE(12)
+                                GRP_CASE(13) GRP_CASE(14) GRP_CASE(15) GRP_CASE(16)
+                                default: break;
+                            }
+                        }
+                        break;
+                }
+#undef GRP_CASE
+                rrow += (uint32_t)dc * 128u;
+                tab += (TAB_SMEM ? 16u : 4u) * (uint32_t)(((dc + 3) >> 2) * SUB);
             }
         }
-        for (int r = 0; r < p.r_rows_per_warp; ++r) sts_f32(r_own + (uint32_t)r * 128u, 0.0f);
-        if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
-        __syncthreads();
-
-        bool done = !active;
-        int my_iters = 0;
-        int iter = 0;
-        for (;;) {
-            // ---- check-node pass
-            uint32_t unsat = 0u;
-            if constexpr (PROF::kStatic) {
-                unsat = grp_cn_static<PROF, 0, SUB, TAB_SMEM>(cn_w, p.cn_tab, t_base, r_own, c4, h);
-            } else {
-                uint32_t tab = cn_w;     // quads for this warp, slot by slot
-                uint32_t rrow = r_own;   // this lane's R column, row by row
-                for (int cs = 0; cs < CS; ++cs) {
-                    const int dc = p.cdeg[cs];
-#define GRP_CASE(D) case D: unsat |= grp_check<D, SUB, TAB_SMEM>(tab, p.cn_tab, t_base, rrow, c4, h); break;
-                    switch (dc) {
-                        GRP_CASE(1) GRP_CASE(2) GRP_CASE(3) GRP_CASE(4) GRP_CASE(5) GRP_CASE(6) GRP_CASE(7) GRP_CASE(8)
+        return unsat;
+    };
+    auto vn_pass = [&]() {
+        const bool done_mask = !(live && !done);  // only a live, unfinished word moves its posterior
+        // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
+        if constexpr (Y_SMEM) {
+            // channel values in shared memory: the slot loop is dynamic, two equal-degree slots at a
+            // time (slots are degree-sorted into at most kGrpMaxCls runs)
+            uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
+            uint32_t ta = t_own, ya = t_own + t_bytes;
+            for (int ci = 0; ci < p.n_vclass; ++ci) {
+                const int d = p.vclass_deg[ci];
+                int n = p.vclass_cnt[ci];
+#define GRP_VCASE(D)                                                                                              \
+case D:                                                                                                       \
+    if (D <= 3)                                                                                               \
+        for (; n >= 4; n -= 4) grp_vn_slots<D, (D <= 3 ? 4 : 1), SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done_mask); \
+    for (; n >= 2; n -= 2) grp_vn_slots<D, 2, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done_mask); \
+    if (n) grp_vn_slots<D, 1, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done_mask);                 \
+    break;
+                switch (d) {
+                    GRP_VCASE(1) GRP_VCASE(2) GRP_VCASE(3) GRP_VCASE(4) GRP_VCASE(5) GRP_VCASE(6) GRP_VCASE(7) GRP_VCASE(8)
+                    GRP_VCASE(9) GRP_VCASE(10) GRP_VCASE(11) GRP_VCASE(12)
+                    default:
+                        if (d == 0) { ta += (uint32_t)n * t_stride; ya += (uint32_t)n * t_stride; }
+                        break;
+                }
+#undef GRP_VCASE
+            }
+        } else if constexpr (PROF::kStatic) {
+            uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
+            uint32_t ta = t_own;
+            grp_vn_static<PROF, 0, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, yn, t_stride, c4, done_mask);
+        } else {
+            uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
+            auto next_quad = [&]() {
+                uint4 o;
+                if (TAB_SMEM) { o = lds_u128(q); q += SUB * 16; }
+                else {
+                    o = __ldg(reinterpret_cast<const uint4*>(p.vn_tab + q));
+                    q += SUB * 4;
+                    o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+                }
+                return o;
+            };
+#pragma unroll
+            for (int s = 0; s < kGrpMaxVS; ++s) {
+                if (s < VS) {
+                    int d = p.vdeg[s];
+                    float acc = yn[s];
+                    // straight-line code per degree (slots are degree-sorted, so consecutive slots
+                    // take the same case); degrees above 8 fall back to a quad loop
+                    switch (d) {
+                        case 1: grp_vn_part<1>(next_quad(), c4, acc); break;
+                        case 2: grp_vn_part<2>(next_quad(), c4, acc); break;
+                        case 3: grp_vn_part<3>(next_quad(), c4, acc); break;
+                        case 4: grp_vn_part<4>(next_quad(), c4, acc); break;
+                        case 5: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<1>(next_quad(), c4, acc); break;
+                        case 6: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<2>(next_quad(), c4, acc); break;
+                        case 7: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<3>(next_quad(), c4, acc); break;
+                        case 8: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<4>(next_quad(), c4, acc); break;
                         default:
-                            if constexpr (DMAX > 8) {
-                                switch (dc) {
-                                    GRP_CASE(9) GRP_CASE(10) GRP_CASE(11) GRP_CASE(12)
-                                    GRP_CASE(13) GRP_CASE(14) GRP_CASE(15) GRP_CASE(16)
-                                    default: break;
-                                }
+#pragma unroll 1
+                            for (; d >= 4; d -= 4) grp_vn_part<4>(next_quad(), c4, acc);
+                            if (d > 0) {
+                                const uint4 o = next_quad();
+                                if (d == 1) grp_vn_part<1>(o, c4, acc);
+                                else if (d == 2) grp_vn_part<2>(o, c4, acc);
+                                else grp_vn_part<3>(o, c4, acc);
                             }
                             break;
                     }
-#undef GRP_CASE
-                    rrow += (uint32_t)dc * 128u;
-                    tab += (TAB_SMEM ? 16u : 4u) * (uint32_t)(((dc + 3) >> 2) * SUB);
+                    if (!done_mask) sts_f32(t_own + (uint32_t)s * t_stride, acc);
                 }
             }
-            const bool check = p.early_term && iter >= 1;
-            if (check && unsat) s_flag[iter & 1][c] = 1u;  // same-value race, benign
-            __syncthreads();
-            if (check && !done && s_flag[iter & 1][c] == 0u) { done = true; my_iters = iter; }
-            if (__all_sync(0xffffffffu, done)) break;
-            if (warp == 0) s_flag[(iter + 1) & 1][lane] = 0u;
-
-            // ---- variable-node pass: T = (-y) - R_e1 - R_e2 ... in ascending-row order
-            if constexpr (Y_SMEM) {
-                // channel values in shared memory: the slot loop is dynamic, two equal-degree slots at a
-                // time (slots are degree-sorted into at most kGrpMaxCls runs)
-                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
-                uint32_t ta = t_own, ya = t_own + t_bytes;
-                for (int ci = 0; ci < p.n_vclass; ++ci) {
-                    const int d = p.vclass_deg[ci];
-                    int n = p.vclass_cnt[ci];
-#define GRP_VCASE(D)                                                                                              \
-    case D:                                                                                                       \
-        if (D <= 3)                                                                                               \
-            for (; n >= 4; n -= 4) grp_vn_slots<D, (D <= 3 ? 4 : 1), SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done); \
-        for (; n >= 2; n -= 2) grp_vn_slots<D, 2, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done); \
-        if (n) grp_vn_slots<D, 1, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, ya, t_stride, c4, done);                 \
-        break;
-                    switch (d) {
-                        GRP_VCASE(1) GRP_VCASE(2) GRP_VCASE(3) GRP_VCASE(4) GRP_VCASE(5) GRP_VCASE(6) GRP_VCASE(7) GRP_VCASE(8)
-                        GRP_VCASE(9) GRP_VCASE(10) GRP_VCASE(11) GRP_VCASE(12)
-                        default:
-                            if (d == 0) { ta += (uint32_t)n * t_stride; ya += (uint32_t)n * t_stride; }
-                            break;
-                    }
-#undef GRP_VCASE
-                }
-            } else if constexpr (PROF::kStatic) {
-                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
-                uint32_t ta = t_own;
-                grp_vn_static<PROF, 0, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, yn, t_stride, c4, done);
-            } else {
-                uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
-                auto next_quad = [&]() {
-                    uint4 o;
-                    if (TAB_SMEM) { o = lds_u128(q); q += SUB * 16; }
-                    else {
-                        o = __ldg(reinterpret_cast<const uint4*>(p.vn_tab + q));
-                        q += SUB * 4;
-                        o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
-                    }
-                    return o;
-                };
-#pragma unroll
-                for (int s = 0; s < kGrpMaxVS; ++s) {
-                    if (s < VS) {
-                        int d = p.vdeg[s];
-                        float acc = yn[s];
-                        // straight-line code per degree (slots are degree-sorted, so consecutive slots
-                        // take the same case); degrees above 8 fall back to a quad loop
-                        switch (d) {
-                            case 1: grp_vn_part<1>(next_quad(), c4, acc); break;
-                            case 2: grp_vn_part<2>(next_quad(), c4, acc); break;
-                            case 3: grp_vn_part<3>(next_quad(), c4, acc); break;
-                            case 4: grp_vn_part<4>(next_quad(), c4, acc); break;
-                            case 5: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<1>(next_quad(), c4, acc); break;
-                            case 6: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<2>(next_quad(), c4, acc); break;
-                            case 7: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<3>(next_quad(), c4, acc); break;
-                            case 8: grp_vn_part<4>(next_quad(), c4, acc); grp_vn_part<4>(next_quad(), c4, acc); break;
-                            default:
-#pragma unroll 1
-                                for (; d >= 4; d -= 4) grp_vn_part<4>(next_quad(), c4, acc);
-                                if (d > 0) {
-                                    const uint4 o = next_quad();
-                                    if (d == 1) grp_vn_part<1>(o, c4, acc);
-                                    else if (d == 2) grp_vn_part<2>(o, c4, acc);
-                                    else grp_vn_part<3>(o, c4, acc);
-                                }
-                                break;
-                        }
-                        if (!done) sts_f32(t_own + (uint32_t)s * t_stride, acc);
-                    }
-                }
-            }
-            ++iter;
-            if (iter == p.max_iter) {
-                if (!done) my_iters = iter;
-                break;
-            }
-            __syncthreads();
         }
-        __syncthreads();
-
+    };
+    auto emit = [&](bool sel) {
         // ---- outputs (toChar, decodeCL.c:188-199): bit n = !(P > 0) = !signbit(T); node lanes share the bytes
         if (p.info) {
             const int KB = (p.K + 7) >> 3;
@@ -934,7 +906,7 @@ __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldp
                         v |= ((~__float_as_uint(lds_f32(t_base + pos * (G * 4) + c4))) >> 31) << t;
                     }
                 }
-                if (active) p.info[(size_t)cw * KB + b] = (uint8_t)v;
+                if (sel) p.info[(size_t)cw * KB + b] = (uint8_t)v;
             }
         }
         if (p.hard) {
@@ -949,14 +921,93 @@ __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldp
                         v |= ((~__float_as_uint(lds_f32(t_base + pos * (G * 4) + c4))) >> 31) << t;
                     }
                 }
-                if (active) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
+                if (sel) p.hard[(size_t)cw * NB + b] = (uint8_t)v;
             }
         }
-        if (p.post && active) {
+        if (p.post && sel) {
             for (int n = warp * SUB + h; n < p.N; n += NL)
                 p.post[(size_t)cw * p.N + n] = -lds_f32(t_base + __ldg(p.pos_of_var + n) * (G * 4) + c4);
         }
-        if (p.iters && warp == 0 && h == 0 && active) p.iters[cw] = my_iters;
+        if (p.iters && warp == 0 && h == 0 && sel) p.iters[cw] = my_iters;
+    };
+    // fetch the next codeword of lanes selected by `want` and start its channel values on their way
+    auto fetch = [&](bool want) {
+        if (warp == 0 && h == 0 && want) s_cw[c] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.counter64), 1ull);
+        __syncthreads();  // also: every read of the retiring lanes' T (emit) is complete
+        if (want) {
+            live = false; done = false;
+            cw = s_cw[c];
+            if (cw < p.ncw) {
+                loading = true;
+                const float* src = p.llr + (size_t)cw * p.N;
+#pragma unroll
+                for (int s = 0; s < kGrpMaxVS; ++s) {
+                    if (s < VS) {
+                        const uint32_t v = __ldg(p.var_of_pos + s * NL + warp * SUB + h);
+                        const uint32_t dst = t_own + (uint32_t)s * t_stride;
+                        if (v != 0xffffffffu) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + v) : "memory");
+                        else sts_f32(dst, 1.0f);
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // lanes whose values have landed start decoding: T = -y (canonical zero), R = 0 (decodeInitMS)
+    auto start_loaded = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (loading) {
+#pragma unroll
+            for (int s = 0; s < kGrpMaxVS; ++s) {
+                if (s < VS) {
+                    const float y = lds_f32(t_own + (uint32_t)s * t_stride);
+                    yn[s] = __fadd_rn(-y, 0.0f);
+                    sts_f32(t_own + (uint32_t)s * t_stride, yn[s]);
+                    if (Y_SMEM) sts_f32(t_own + t_bytes + (uint32_t)s * t_stride, yn[s]);
+                }
+            }
+            for (int r = 0; r < p.r_rows_per_warp; ++r) sts_f32(r_own + (uint32_t)r * 128u, 0.0f);
+            loading = false; live = true; done = false; it = 0;
+        }
+        __syncthreads();
+    };
+
+    if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+    __syncthreads();
+    fetch(true);
+    uint32_t ph = 0;
+    for (;;) {
+        // ---- loop top: start words whose values arrived, retire finished words and refill their lanes.
+        // (A warp holds every codeword lane and all threads of a lane agree, so these votes are CTA-uniform.)
+        if (__any_sync(0xffffffffu, loading)) start_loaded();  // refilled at an earlier loop top
+        const bool retire = live && done;
+        if (__any_sync(0xffffffffu, retire)) {
+            emit(retire);
+            fetch(retire);
+            // refill_wait = 0: a lane refilled now starts at the next loop top, after one more iteration of
+            // the others (its load overlaps them); when nothing else is running there is nothing to
+            // overlap with and it starts at once.  refill_wait = 1: always wait for the values now.
+            if ((p.refill_wait || !__any_sync(0xffffffffu, live)) && __any_sync(0xffffffffu, loading)) start_loaded();
+        }
+        if (!__any_sync(0xffffffffu, live || loading)) break;
+
+        // ---- check-node pass + syndrome of the previous posterior
+        const uint32_t unsat = cn_pass();
+        const bool check = p.early_term && it >= 1 && live && !done;
+        if (check && unsat) s_flag[ph & 1][c] = 1u;  // same-value race, benign
+        __syncthreads();
+        if (check && s_flag[ph & 1][c] == 0u) { done = true; my_iters = it; }
+        if (warp == 0) s_flag[(ph + 1) & 1][lane] = 0u;
+        ++ph;
+
+        // ---- variable-node pass (posterior of finished / idle lanes is frozen)
+        vn_pass();
+        if (live && !done) {
+            ++it;
+            if (it == p.max_iter) { done = true; my_iters = it; }
+        }
+        __syncthreads();
     }
 }
 

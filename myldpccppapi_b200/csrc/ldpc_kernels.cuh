@@ -975,6 +975,46 @@ case D:                                                                         
 
     if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
     __syncthreads();
+    if constexpr (G == 1) {
+        // One codeword per CTA: nothing to refill around -- plain word-at-a-time loop with direct loads.
+        for (;;) {
+            if (threadIdx.x == 0) s_cw[0] = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.counter64), 1ull);
+            __syncthreads();
+            cw = s_cw[0];
+            if (cw >= p.ncw) break;
+            const float* src = p.llr + (size_t)cw * p.N;
+#pragma unroll
+            for (int s = 0; s < kGrpMaxVS; ++s) {
+                if (s < VS) {
+                    const uint32_t v = __ldg(p.var_of_pos + s * NL + warp * SUB + h);
+                    const float y = (v != 0xffffffffu) ? __ldg(src + v) : 1.0f;
+                    yn[s] = __fadd_rn(-y, 0.0f);
+                    sts_f32(t_own + (uint32_t)s * t_stride, yn[s]);
+                    if (Y_SMEM) sts_f32(t_own + t_bytes + (uint32_t)s * t_stride, yn[s]);
+                }
+            }
+            for (int r = 0; r < p.r_rows_per_warp; ++r) sts_f32(r_own + (uint32_t)r * 128u, 0.0f);
+            if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+            live = true; done = false; it = 0;
+            __syncthreads();
+            for (;;) {
+                const uint32_t unsat = cn_pass();
+                const bool check = p.early_term && it >= 1;
+                if (check && unsat) s_flag[it & 1][0] = 1u;
+                __syncthreads();
+                if (check && s_flag[it & 1][0] == 0u) { done = true; my_iters = it; break; }  // CTA-uniform
+                if (warp == 0) s_flag[(it + 1) & 1][lane] = 0u;
+                vn_pass();
+                ++it;
+                if (it == p.max_iter) { done = true; my_iters = it; break; }
+                __syncthreads();
+            }
+            __syncthreads();
+            emit(true);
+            __syncthreads();
+        }
+        return;
+    }
     fetch(true);
     uint32_t ph = 0;
     for (;;) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <functional>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "ldpc_kernels.cuh"
+#include "ldpc_cluster.cuh"
 #include "ldpc_tables.h"
 
 using namespace ldpc_b200;
@@ -88,6 +90,12 @@ struct ldpc_b200_decoder {
     uint32_t* dg_var_of_pos = nullptr;
     uint32_t* dg_pos_of_var = nullptr;
     bool group_ready = false;
+    // CLUSTER tables
+    uint32_t* dc_cn_tab = nullptr;
+    uint32_t* dc_vn_tab = nullptr;
+    uint32_t* dc_var_of_pos = nullptr;
+    uint32_t* dc_out_addr = nullptr;
+    bool cluster_ready = false;
     uint8_t g_vdeg[kGrpMaxVS] = {0};
     uint8_t g_cdeg[kGrpMaxCS] = {0};
     int l16_vn_stride = 0;
@@ -686,6 +694,186 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
     return fail(LDPC_B200_ERR_UNSUPPORTED, "no group kernel instantiated for this shape");
 }
 
+// ---- CLUSTER layout (one codeword per 8-CTA cluster, DSMEM gathers; see ldpc_cluster.cuh) ------------
+struct ClShape {
+    int W = 32, CS = 0, VS = 0, dmax = 8;
+    int cn_stride = 0, vn_stride = 0, r_rows = 0;
+    size_t smem = 0;
+};
+
+// Partition: checks in contiguous row blocks; a variable goes to the CTA holding most of its checks
+// (capacity-bounded), which keeps e.g. a dual-diagonal parity part entirely local.
+void cluster_partition(const HostTables& t, std::vector<int>* chk_rank, std::vector<int>* var_rank) {
+    const int CL = kClusterSize;
+    chk_rank->resize(t.M);
+    var_rank->assign(t.N, -1);
+    for (int r = 0; r < t.M; ++r) (*chk_rank)[r] = (int)((long long)r * CL / t.M);
+    const int cap = (t.N + CL - 1) / CL;
+    std::vector<int> fill(CL, 0);
+    std::vector<std::pair<int, int>> order;  // (-best count, variable)
+    std::vector<std::array<int, kClusterSize>> hist(t.N);
+    for (int v = 0; v < t.N; ++v) {
+        hist[v].fill(0);
+        for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) hist[v][(*chk_rank)[t.vn_edge[k] >> kPosBits]]++;
+        order.emplace_back(-*std::max_element(hist[v].begin(), hist[v].end()), v);
+    }
+    std::stable_sort(order.begin(), order.end());
+    for (auto& ov : order) {
+        const int v = ov.second;
+        int best = -1;
+        for (int r = 0; r < CL; ++r)
+            if (fill[r] < cap && (best < 0 || hist[v][r] > hist[v][best] || (hist[v][r] == hist[v][best] && fill[r] < fill[best]))) best = r;
+        (*var_rank)[v] = best;
+        fill[best]++;
+    }
+}
+
+bool cluster_shape(const HostTables& t, size_t smem_limit, ClShape* out, std::vector<int>* chk_rank, std::vector<int>* var_rank) {
+    if (t.max_row_weight > 16 || t.max_row_weight < 1 || t.M < kClusterSize || t.N < kClusterSize) return false;
+    cluster_partition(t, chk_rank, var_rank);
+    const int CL = kClusterSize;
+    ClShape sh;
+    sh.dmax = t.max_row_weight <= 8 ? 8 : 16;
+    const int NL = sh.W * 32;
+    std::vector<std::vector<int>> cd(CL), vd(CL);
+    for (int r = 0; r < t.M; ++r) cd[(*chk_rank)[r]].push_back(t.row_ptr[r + 1] - t.row_ptr[r]);
+    for (int v = 0; v < t.N; ++v) vd[(*var_rank)[v]].push_back(t.col_ptr[v + 1] - t.col_ptr[v]);
+    size_t cmax = 0, vmax = 0;
+    for (int r = 0; r < CL; ++r) {
+        std::sort(cd[r].begin(), cd[r].end(), std::greater<int>());
+        std::sort(vd[r].begin(), vd[r].end(), std::greater<int>());
+        cmax = std::max(cmax, cd[r].size()); vmax = std::max(vmax, vd[r].size());
+    }
+    sh.CS = (int)((cmax + NL - 1) / NL);
+    sh.VS = (int)((vmax + NL - 1) / NL);
+    if (sh.CS > kGrpMaxCS || sh.VS > kGrpMaxVS) return false;
+    long long rrows = 0, cquads = 0, vquads = 0;
+    for (int cs = 0; cs < sh.CS; ++cs) {
+        int d = 0;
+        for (int r = 0; r < CL; ++r) if ((size_t)cs * NL < cd[r].size()) d = std::max(d, cd[r][(size_t)cs * NL]);
+        rrows += d; cquads += (d + 3) / 4;
+    }
+    for (int sidx = 0; sidx < sh.VS; ++sidx) {
+        int d = 0;
+        for (int r = 0; r < CL; ++r) if ((size_t)sidx * NL < vd[r].size()) d = std::max(d, vd[r][(size_t)sidx * NL]);
+        vquads += (d + 3) / 4;
+    }
+    sh.r_rows = (int)rrows;
+    sh.cn_stride = (int)(cquads * 32 * 4);
+    sh.vn_stride = (int)(vquads * 32 * 4);
+    sh.smem = (((size_t)(sh.VS * NL + 1) * 4 + 127) & ~(size_t)127) + ((size_t)sh.W * rrows + 1) * 128;
+    if (sh.smem + 1024 > smem_limit) return false;
+    if ((size_t)(sh.VS * NL + 1) * 4 >= (1u << 24) || ((size_t)sh.W * rrows + 1) * 128 >= (1u << 24)) return false;
+    *out = sh;
+    return true;
+}
+
+int upload_cluster_tables(ldpc_b200_decoder* h) {
+    if (h->cluster_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    const Plan& pl = h->plan;
+    const int CL = kClusterSize, W = pl.W, NL = W * 32, CS = pl.CS, VS = pl.VS;
+    std::vector<int> chk_rank, var_rank;
+    cluster_partition(t, &chk_rank, &var_rank);
+    auto vdegf = [&](int c) { return t.col_ptr[c + 1] - t.col_ptr[c]; };
+    auto cdegf = [&](int r) { return t.row_ptr[r + 1] - t.row_ptr[r]; };
+    std::vector<std::vector<int>> corder(CL), vorder(CL);
+    for (int r = 0; r < t.M; ++r) corder[chk_rank[r]].push_back(r);
+    for (int v = 0; v < t.N; ++v) vorder[var_rank[v]].push_back(v);
+    for (int r = 0; r < CL; ++r) {
+        std::stable_sort(corder[r].begin(), corder[r].end(), [&](int a, int b) { return cdegf(a) > cdegf(b); });
+        std::stable_sort(vorder[r].begin(), vorder[r].end(), [&](int a, int b) { return vdegf(a) > vdegf(b); });
+    }
+    std::memset(h->g_vdeg, 0, sizeof(h->g_vdeg));
+    std::memset(h->g_cdeg, 0, sizeof(h->g_cdeg));
+    std::vector<int> coff(CS + 1, 0), qoff(CS + 1, 0), voff(VS + 1, 0);
+    for (int cs = 0; cs < CS; ++cs) {
+        int d = 0;
+        for (int r = 0; r < CL; ++r) if ((size_t)cs * NL < corder[r].size()) d = std::max(d, cdegf(corder[r][(size_t)cs * NL]));
+        h->g_cdeg[cs] = (uint8_t)d;
+        coff[cs + 1] = coff[cs] + d;
+        qoff[cs + 1] = qoff[cs] + (d + 3) / 4;
+    }
+    for (int sidx = 0; sidx < VS; ++sidx) {
+        int d = 0;
+        for (int r = 0; r < CL; ++r) if ((size_t)sidx * NL < vorder[r].size()) d = std::max(d, vdegf(vorder[r][(size_t)sidx * NL]));
+        h->g_vdeg[sidx] = (uint8_t)d;
+        voff[sidx + 1] = voff[sidx] + (d + 3) / 4;
+    }
+    const int PD = VS * NL, RD = W * pl.r_rows;
+    // local rank (position) of every node inside its CTA
+    std::vector<uint32_t> lpos_of_var(t.N), lrank_of_chk(t.M), var_of_pos((size_t)CL * PD, 0xffffffffu), out_addr(t.N);
+    for (int r = 0; r < CL; ++r) {
+        for (size_t i = 0; i < vorder[r].size(); ++i) {
+            lpos_of_var[vorder[r][i]] = (uint32_t)i;
+            var_of_pos[(size_t)r * PD + i] = (uint32_t)vorder[r][i];
+            out_addr[vorder[r][i]] = ((uint32_t)r << 24) + (uint32_t)i * 4u;
+        }
+        for (size_t i = 0; i < corder[r].size(); ++i) lrank_of_chk[corder[r][i]] = (uint32_t)i;
+    }
+    std::vector<uint32_t> cn_tab((size_t)CL * W * pl.cn_stride), vn_tab((size_t)CL * W * pl.vn_stride);
+    for (int r = 0; r < CL; ++r) {
+        std::fill(cn_tab.begin() + (size_t)r * W * pl.cn_stride, cn_tab.begin() + (size_t)(r + 1) * W * pl.cn_stride,
+                  ((uint32_t)r << 24) + (uint32_t)PD * 4u);      // padding -> this CTA's dummy T entry
+        std::fill(vn_tab.begin() + (size_t)r * W * pl.vn_stride, vn_tab.begin() + (size_t)(r + 1) * W * pl.vn_stride,
+                  ((uint32_t)r << 24) + (uint32_t)RD * 128u);    // padding -> this CTA's dummy R row
+    }
+    for (int c = 0; c < t.M; ++c) {
+        const int r = chk_rank[c], lr = (int)lrank_of_chk[c];
+        const int cs = lr / NL, nl = lr % NL, w = nl / 32, hh = nl % 32;
+        const int e0 = t.row_ptr[c], dc = cdegf(c);
+        for (int j = 0; j < dc; ++j) {
+            const int v = t.col_idx[e0 + j];
+            cn_tab[((size_t)r * W + w) * pl.cn_stride + ((size_t)(qoff[cs] + j / 4) * 32 + hh) * 4 + (j & 3)] =
+                ((uint32_t)var_rank[v] << 24) + lpos_of_var[v] * 4u;
+        }
+    }
+    for (int v = 0; v < t.N; ++v) {
+        const int r = var_rank[v], lp = (int)lpos_of_var[v];
+        const int sidx = lp / NL, nl = lp % NL, w = nl / 32, hh = nl % 32;
+        for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+            const uint32_t chk = t.vn_edge[k] >> kPosBits, pos = t.vn_edge[k] & ((1u << kPosBits) - 1u);
+            const int cr = chk_rank[chk], clr = (int)lrank_of_chk[chk];
+            const int ccs = clr / NL, cnl = clr % NL, cw = cnl / 32, ch = cnl % 32;
+            const uint32_t row = (uint32_t)cw * pl.r_rows + (uint32_t)coff[ccs] + pos;
+            const int kk = k - t.col_ptr[v];
+            vn_tab[((size_t)r * W + w) * pl.vn_stride + ((size_t)(voff[sidx] + kk / 4) * 32 + hh) * 4 + (kk & 3)] =
+                ((uint32_t)cr << 24) + row * 128u + (uint32_t)ch * 4u;
+        }
+    }
+    CU_TRY(cudaMalloc(&h->dc_cn_tab, cn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->dc_vn_tab, vn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->dc_var_of_pos, var_of_pos.size() * 4));
+    CU_TRY(cudaMalloc(&h->dc_out_addr, out_addr.size() * 4));
+    CU_TRY(cudaMemcpy(h->dc_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dc_vn_tab, vn_tab.data(), vn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dc_var_of_pos, var_of_pos.data(), var_of_pos.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dc_out_addr, out_addr.data(), out_addr.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += (cn_tab.size() + vn_tab.size() + var_of_pos.size() + out_addr.size()) * 4;
+    h->cluster_ready = true;
+    return LDPC_B200_OK;
+}
+
+template <int DMAX>
+int launch_cluster_t(const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream) {
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_cluster_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(kClusterSize);
+    int maxc = 0;
+    CU_TRY(cudaOccupancyMaxActiveClusters(&maxc, ldpc_ms_cluster_kernel<DMAX>, &cfg));
+    if (maxc < 1) return fail(LDPC_B200_ERR_UNSUPPORTED, "no 8-CTA cluster of this size can be resident");
+    cfg.gridDim = dim3(kClusterSize * std::min(maxc, nclusters_wanted));
+    CU_TRY(cudaLaunchKernelEx(&cfg, ldpc_ms_cluster_kernel<DMAX>, q));
+    return LDPC_B200_OK;
+}
+
 int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
@@ -721,6 +909,27 @@ int make_plan(ldpc_b200_decoder* h) {
             pl.smem = sh.smem;
             pl.ctas = h->sm_count;
             pl.dcp = sh.DCP; pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS;
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
+    }
+    {   // long codes: one codeword per 8-CTA cluster, state in distributed shared memory
+        ClShape sh;
+        std::vector<int> cr, vr;
+        // Opt-in only: measured on cfg5 (profiles/r01_cluster_dsmem.txt) the 4-byte DSMEM gathers run at
+        // ~0.5 per clock per SM, which leaves this path at half the speed of the global-workspace path.
+        const bool fits = h->forced_path == LDPC_B200_PATH_CLUSTER && cluster_shape(t, h->smem_optin, &sh, &cr, &vr);
+        if (h->forced_path == LDPC_B200_PATH_CLUSTER && !fits)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the cluster path");
+        if (fits) {
+            pl.path = LDPC_B200_PATH_CLUSTER;
+            pl.threads = 32 * sh.W;
+            pl.smem = sh.smem;
+            pl.ctas = (h->sm_count / kClusterSize) * kClusterSize;
+            pl.cw_per_cta = 1;
+            pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS; pl.G = 1; pl.dmax = sh.dmax;
+            pl.cn_stride = sh.cn_stride; pl.vn_stride = sh.vn_stride; pl.r_rows = sh.r_rows;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;
@@ -794,6 +1003,27 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+
+    if (pl.path == LDPC_B200_PATH_CLUSTER) {
+        rc = upload_cluster_tables(h);
+        if (rc) return rc;
+        ClusterParams q;
+        q.cn_tab = h->dc_cn_tab; q.vn_tab = h->dc_vn_tab; q.var_of_pos = h->dc_var_of_pos; q.out_addr = h->dc_out_addr;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.W = pl.W; q.CS = pl.CS; q.VS = pl.VS;
+        q.cn_stride = pl.cn_stride; q.vn_stride = pl.vn_stride; q.r_rows_per_warp = pl.r_rows;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter64 = ctr64;
+        std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
+        std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
+        const int want = (int)std::min<int64_t>(ncw, 1 << 20);
+        rc = pl.dmax == 8 ? launch_cluster_t<8>(q, want, pl.threads, pl.smem, stream)
+                          : launch_cluster_t<16>(q, want, pl.threads, pl.smem, stream);
+        if (rc) return rc;
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
 
     if (pl.path == LDPC_B200_PATH_GROUP) {
         rc = upload_group_tables(h);
@@ -962,6 +1192,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
+            cudaFree(h->dc_cn_tab); cudaFree(h->dc_vn_tab); cudaFree(h->dc_var_of_pos); cudaFree(h->dc_out_addr);
             cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);

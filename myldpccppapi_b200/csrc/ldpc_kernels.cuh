@@ -535,11 +535,24 @@ struct GroupParams {
     uint8_t vclass_cnt[kGrpMaxVS];
 };
 
+// Message / posterior gathers go through the CTA's own shared window, or -- in the cluster kernel --
+// through the cluster window (distributed shared memory: the row may live in a peer CTA).
+__device__ __forceinline__ float ld_cluster_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+template <bool DSM>
+__device__ __forceinline__ float ld_node_f32(uint32_t a) {
+    if constexpr (DSM) return ld_cluster_f32(a);
+    else return lds_f32(a);
+}
+
 // One check of exact degree D, straight-line: D x {T gather, R_old load, S = T + R_old}, running
 // min1/min2 and sign parities, then D x {R_new = ((|S_j| == min1) ? min2 : min1) ^ parity ^ sign(S_j)}.
 // (|S_j| == min1 picks the argmin; with a tie min2 == min1, so either choice is the same value.)
 // Returns the row's syndrome bit.
-template <int D, int SUB, bool TAB_SMEM>
+template <int D, int SUB, bool TAB_SMEM, bool DSM = false>
 __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __restrict__ gtab, uint32_t t_base,
                                                uint32_t rrow, uint32_t c4, int h) {
     constexpr int NQ = (D + 3) / 4;
@@ -556,7 +569,7 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
     }
     float tv[D], S[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) tv[j] = lds_f32(ent[j] + c4);
+    for (int j = 0; j < D; ++j) tv[j] = ld_node_f32<DSM>(ent[j] + c4);
 #pragma unroll
     for (int j = 0; j < D; ++j) S[j] = lds_f32(rrow + (uint32_t)j * 128u);
     float m1 = INFINITY, m2 = INFINITY;
@@ -594,12 +607,12 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
     return ((sx >> 31) ^ (uint32_t)D) & 1u;  // hard bit = !signbit(T)
 }
 
-template <int CNT>
+template <int CNT, bool DSM = false>
 __device__ __forceinline__ void grp_vn_part(const uint4 o, uint32_t c4, float& acc) {
     const uint32_t e[4] = {o.x, o.y, o.z, o.w};
     float r[CNT];
 #pragma unroll
-    for (int k = 0; k < CNT; ++k) r[k] = lds_f32(e[k] + c4);
+    for (int k = 0; k < CNT; ++k) r[k] = ld_node_f32<DSM>(e[k] + c4);
 #pragma unroll
     for (int k = 0; k < CNT; ++k) acc = __fsub_rn(acc, r[k]);
 }

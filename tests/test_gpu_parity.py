@@ -38,7 +38,7 @@ def test_default_code_parity(default_code, sigma):
     assert_parity(host, ref, c["N"], what="host sigma=%g" % sigma)
 
 
-@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group")])
+@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group"), (5, "cluster")])
 def test_default_code_every_kernel_path(default_code, path, name):
     """Every kernel family (shared-memory lane, global-workspace lane, lane16, group) gives the oracle's bits."""
     import myldpccppapi_b200 as m
@@ -57,7 +57,7 @@ def test_regular_3_6_every_kernel_path():
     M, N, K, rp, ci = m.codes.regular_code()
     llr = awgn_llr(40, N, 0.84, seed=2)
     ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
-    for path, name in [(1, "lane_global"), (4, "group")]:
+    for path, name in [(1, "lane_global"), (4, "group"), (5, "cluster")]:
         dec = m.Decoder(M, N, K, rp, ci)
         dec.set_path(path)
         assert dec.info()["path_name"] == name
@@ -163,11 +163,15 @@ def test_ira_64800_parity():
     rng = np.random.default_rng(9)
     u = rng.integers(0, 2, (34, K)).astype(np.uint8)
     cwb = m.codes.ira_encode(M, N, K, rp, ci, u)
+    assert dec.info()["path_name"] == "lane_global"
+    clus = m.Decoder(M, N, K, rp, ci, max_iter=50)
+    clus.set_path(5)   # one codeword per 8-CTA cluster, state in distributed shared memory
+    assert clus.info()["path_name"] == "cluster"
     for sigma, seed in [(0.8, 1), (0.97, 2)]:
         llr = awgn_llr(34, N, sigma, seed=seed, bits=cwb)
         ref = o.decode(llr, literal=False)
-        res = _run_device(dec, llr)
-        assert_parity(res, ref, N, what="ira sigma=%g" % sigma)
+        assert_parity(_run_device(dec, llr), ref, N, what="ira lane_global sigma=%g" % sigma)
+        assert_parity(_run_device(clus, llr), ref, N, what="ira cluster sigma=%g" % sigma)
 
 
 def test_roundtrip_full_batch_properties(default_code):

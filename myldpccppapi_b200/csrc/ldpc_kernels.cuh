@@ -132,19 +132,32 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParam
                 const int idxo = (int)(wo >> 27);
                 float m1 = INFINITY, m2 = INFINITY;
                 uint32_t sg = 0u, idx = 0u, syn = 0u;
-#pragma unroll 4
-                for (int j = 0; j < dc; ++j) {
-                    const uint32_t col = __ldg(p.cn_col + e0 + j);
-                    const float pv = P[col * kLanes + lane];
-                    const float mag = (j == idxo) ? m2o : m1o;
-                    const float r = __uint_as_float(__float_as_uint(mag) ^ ((wo << (31 - j)) & 0x80000000u));
-                    const float q = __fsub_rn(pv, r);
-                    syn ^= (pv > 0.0f) ? 0u : 1u;
-                    sg |= (__float_as_uint(q) >> 31) << j;
-                    const float a = fabsf(q);
-                    idx = (a < m1) ? (uint32_t)j : idx;
-                    m2 = fminf(m2, fmaxf(m1, a));
-                    m1 = fminf(m1, a);
+                // batches of 8 edges: all column indices, then all posteriors, then the arithmetic --
+                // up to 8 independent 128-byte rows in flight per warp (the global-workspace path is
+                // bound by memory latency x parallelism, see profiles/r01_m_lane_global_cfg5_ncu.txt)
+                for (int j0 = 0; j0 < dc; j0 += 8) {
+                    uint32_t col[8];
+                    float pvv[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) col[t] = (j0 + t < dc) ? __ldg(p.cn_col + e0 + j0 + t) : 0u;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) pvv[t] = (j0 + t < dc) ? P[col[t] * kLanes + lane] : 1.0f;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int j = j0 + t;
+                        if (j < dc) {
+                            const float pv = pvv[t];
+                            const float mag = (j == idxo) ? m2o : m1o;
+                            const float r = __uint_as_float(__float_as_uint(mag) ^ ((wo << (31 - j)) & 0x80000000u));
+                            const float q = __fsub_rn(pv, r);
+                            syn ^= (pv > 0.0f) ? 0u : 1u;
+                            sg |= (__float_as_uint(q) >> 31) << j;
+                            const float a = fabsf(q);
+                            idx = (a < m1) ? (uint32_t)j : idx;
+                            m2 = fminf(m2, fmaxf(m1, a));
+                            m1 = fminf(m1, a);
+                        }
+                    }
                 }
                 const uint32_t mask = (dc >= 32) ? 0xffffffffu : ((1u << dc) - 1u);
                 const uint32_t sr = ((__popc(sg) & 1) ? ~sg : sg) & mask;
@@ -165,10 +178,21 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParam
                 const int v0 = __ldg(p.col_ptr + n);
                 const int dv = __ldg(p.col_ptr + n + 1) - v0;
                 float acc = Y[n * kLanes + lane];
-                for (int k = 0; k < dv; ++k) {
-                    const uint32_t pk = __ldg(p.vn_edge + v0 + k);
-                    const int si = (int)(pk >> 5) * kLanes + lane;
-                    acc = __fadd_rn(acc, msg_from_state(M1[si], M2[si], SW[si], (int)(pk & 31u)));
+                for (int k0 = 0; k0 < dv; k0 += 8) {  // batched like the check pass: 24 state loads in flight
+                    uint32_t pk[8], sw[8];
+                    float a1[8], a2[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) pk[t] = (k0 + t < dv) ? __ldg(p.vn_edge + v0 + k0 + t) : 0u;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (k0 + t < dv) {
+                            const int si = (int)(pk[t] >> 5) * kLanes + lane;
+                            a1[t] = M1[si]; a2[t] = M2[si]; sw[t] = SW[si];
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (k0 + t < dv) acc = __fadd_rn(acc, msg_from_state(a1[t], a2[t], sw[t], (int)(pk[t] & 31u)));
                 }
                 if (!done) P[n * kLanes + lane] = acc;
             }

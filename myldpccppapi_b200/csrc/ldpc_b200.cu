@@ -56,6 +56,7 @@ struct Plan {
     int G = 0, dmax = 0;        // GROUP: codewords per CTA group, unroll bound of the check pass
     bool tab_smem = true;       // GROUP: index tables in shared memory (else read from global/L2)
     bool y_smem = false;        // GROUP: channel values in shared memory (else registers)
+    bool t16 = false;           // GROUP: 16-bit table entries (static-profile kernel only)
     int cn_stride = 0, vn_stride = 0, r_rows = 0;
 };
 
@@ -628,6 +629,53 @@ int upload_group_tables(ldpc_b200_decoder* h) {
                 row * 128u + (uint32_t)(ch * G * 4);
         }
     }
+    // 16-bit tables for the static-profile kernel (Test.cpp's code, G = 8): entries are row indices,
+    // [slot][j/8][lane][8] for the check pass, [slot][lane][2|4|8] for the variable pass.  They cut the
+    // table wavefronts by ~0.6 per edge but cost one unpack op per edge; measured 4.40 ms vs 4.26 ms with
+    // 32-bit tables on cfg2 (profiles/r01_t16_experiment.txt), so they are off unless LDPC_B200_GRP_T16 is set.
+    {
+        bool match = G == 8 && pl.tab_smem && !pl.y_smem && CS == ProfileWimax34B576::CS && VS == ProfileWimax34B576::VS &&
+                     !std::getenv("LDPC_B200_GRP_NO_PROFILE") && std::getenv("LDPC_B200_GRP_T16");  // opt-in: measured slower
+        for (int i = 0; match && i < CS; ++i) match = h->g_cdeg[i] == ProfileWimax34B576::cdeg(i);
+        for (int i = 0; match && i < VS; ++i) match = h->g_vdeg[i] == ProfileWimax34B576::vdeg(i);
+        if (match) {
+            std::vector<int> ooff(CS + 1, 0), vbyte(VS + 1, 0);
+            for (int cs = 0; cs < CS; ++cs) ooff[cs + 1] = ooff[cs] + (h->g_cdeg[cs] + 7) / 8;
+            auto sd_of = [](int d) { return d <= 2 ? 4 : (d <= 4 ? 8 : 16); };
+            for (int sidx = 0; sidx < VS; ++sidx) vbyte[sidx + 1] = vbyte[sidx] + SUB * sd_of(h->g_vdeg[sidx]);
+            const int cn_words = ooff[CS] * SUB * 4, vn_words = (vbyte[VS] + 15) / 16 * 4;
+            std::vector<uint16_t> c16((size_t)W * cn_words * 2, (uint16_t)PD), v16((size_t)W * vn_words * 2, (uint16_t)(RD * SUB));
+            for (int rank = 0; rank < t.M; ++rank) {
+                const int cs = rank / NL, nl = rank % NL, w = nl / SUB, hh = nl % SUB;
+                const int r = corder[rank], e0 = t.row_ptr[r], dc = cdegf(r);
+                for (int e = e0; e < e0 + dc; ++e) {
+                    const int j = slot_of_edge[e];
+                    c16[(size_t)w * cn_words * 2 + ((size_t)(ooff[cs] + j / 8) * SUB + hh) * 8 + (j & 7)] = (uint16_t)pos_of_var[t.col_idx[e]];
+                }
+            }
+            for (int rank = 0; rank < t.N; ++rank) {
+                const int sidx = rank / NL, nl = rank % NL, w = nl / SUB, hh = nl % SUB;
+                const int v = vorder[rank];
+                const int sd = sd_of(h->g_vdeg[sidx]);
+                for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+                    const uint32_t chk = t.vn_edge[k] >> kPosBits, pos = t.vn_edge[k] & ((1u << kPosBits) - 1u);
+                    const int crank = (int)crank_of_chk[chk];
+                    const int ccs = crank / NL, cnl = crank % NL, cw = cnl / SUB, ch = cnl % SUB;
+                    const uint32_t row = (uint32_t)cw * pl.r_rows + (uint32_t)coff[ccs] + (uint32_t)slot_of_edge[t.row_ptr[chk] + pos];
+                    v16[(size_t)w * vn_words * 2 + (size_t)(vbyte[sidx] + hh * sd) / 2 + (k - t.col_ptr[v])] = (uint16_t)(row * SUB + ch);
+                }
+            }
+            if ((size_t)(PD + 1) < 65536 && (size_t)(RD + 1) * SUB < 65536) {
+                cn_tab.assign((size_t)W * cn_words, 0u);
+                vn_tab.assign((size_t)W * vn_words, 0u);
+                std::memcpy(cn_tab.data(), c16.data(), cn_tab.size() * 4);
+                std::memcpy(vn_tab.data(), v16.data(), vn_tab.size() * 4);
+                h->plan.t16 = true;
+                h->plan.cn_stride = cn_words;
+                h->plan.vn_stride = vn_words;
+            }
+        }
+    }
     CU_TRY(cudaMalloc(&h->dg_cn_tab, cn_tab.size() * 4));
     CU_TRY(cudaMalloc(&h->dg_vn_tab, vn_tab.size() * 4));
     CU_TRY(cudaMalloc(&h->dg_var_of_pos, var_of_pos.size() * 4));
@@ -641,10 +689,10 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int G, int DMAX, bool TAB, int MAXT, bool YS, class PROF = GenericProfile>
+template <int G, int DMAX, bool TAB, int MAXT, bool YS, class PROF = GenericProfile, bool T16 = false>
 int launch_group_t(const GroupParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF><<<grid, threads, smem, stream>>>(q);
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF, T16><<<grid, threads, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }
@@ -669,6 +717,7 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
                          : launch_group_t<16, 16, true, 1024, false>(q, grid, th, sm, stream);
     }
     if (pl.G == 8 && pl.tab_smem && th <= 384) {
+        if (pl.t16) return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576, true>(q, grid, th, sm, stream);
         if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576>(pl, q))
             return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576>(q, grid, th, sm, stream);
         if (pl.dmax == 8) return pl.y_smem ? launch_group_t<8, 8, true, 384, true>(q, grid, th, sm, stream)

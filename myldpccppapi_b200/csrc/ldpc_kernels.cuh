@@ -576,24 +576,41 @@ __device__ __forceinline__ float ld_node_f32(uint32_t a) {
 // min1/min2 and sign parities, then D x {R_new = ((|S_j| == min1) ? min2 : min1) ^ parity ^ sign(S_j)}.
 // (|S_j| == min1 picks the argmin; with a tie min2 == min1, so either choice is the same value.)
 // Returns the row's syndrome bit.
-template <int D, int SUB, bool TAB_SMEM, bool DSM = false>
+template <int D, int SUB, bool TAB_SMEM, bool DSM = false, bool T16 = false>
 __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __restrict__ gtab, uint32_t t_base,
                                                uint32_t rrow, uint32_t c4, int h) {
     constexpr int NQ = (D + 3) / 4;
-    uint32_t ent[NQ * 4];
+    uint32_t ent[(T16 ? (D + 7) / 8 * 8 : NQ * 4)];
+    if constexpr (T16) {
+        // 16-bit entries (T row index): eight per LDS.128, address = index * row bytes + base in one IMAD
+        static_assert(TAB_SMEM && !DSM, "16-bit tables live in shared memory");
+        constexpr uint32_t ROWB = 128u / SUB;
+        const uint32_t base = t_base + c4;
 #pragma unroll
-    for (int jq = 0; jq < NQ; ++jq) {
-        uint4 o;
-        if (TAB_SMEM) o = lds_u128(tab + (uint32_t)(jq * SUB + h) * 16u);
-        else {
-            o = __ldg(reinterpret_cast<const uint4*>(gtab + tab) + (jq * SUB + h));
-            o.x += t_base; o.y += t_base; o.z += t_base; o.w += t_base;
+        for (int jo = 0; jo < (D + 7) / 8; ++jo) {
+            const uint4 o = lds_u128(tab + (uint32_t)(jo * SUB + h) * 16u);
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ent[jo * 8 + 2 * i] = (w[i] & 0xffffu) * ROWB + base;
+                ent[jo * 8 + 2 * i + 1] = (w[i] >> 16) * ROWB + base;
+            }
         }
-        ent[jq * 4 + 0] = o.x; ent[jq * 4 + 1] = o.y; ent[jq * 4 + 2] = o.z; ent[jq * 4 + 3] = o.w;
+    } else {
+#pragma unroll
+        for (int jq = 0; jq < NQ; ++jq) {
+            uint4 o;
+            if (TAB_SMEM) o = lds_u128(tab + (uint32_t)(jq * SUB + h) * 16u);
+            else {
+                o = __ldg(reinterpret_cast<const uint4*>(gtab + tab) + (jq * SUB + h));
+                o.x += t_base; o.y += t_base; o.z += t_base; o.w += t_base;
+            }
+            ent[jq * 4 + 0] = o.x; ent[jq * 4 + 1] = o.y; ent[jq * 4 + 2] = o.z; ent[jq * 4 + 3] = o.w;
+        }
     }
     float tv[D], S[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) tv[j] = ld_node_f32<DSM>(ent[j] + c4);
+    for (int j = 0; j < D; ++j) tv[j] = ld_node_f32<DSM>(ent[j] + (T16 ? 0u : c4));
 #pragma unroll
     for (int j = 0; j < D; ++j) S[j] = lds_f32(rrow + (uint32_t)j * 128u);
     float m1 = INFINITY, m2 = INFINITY;
@@ -707,31 +724,53 @@ struct ProfileRegular36N8192 {
 };
 
 // NS variable slots of exact degree D with the channel values in registers.
-template <int D, int NS, int SUB, bool TAB_SMEM>
+template <int D, int NS, int SUB, bool TAB_SMEM, bool T16 = false>
 __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,
-                                                 const float* yv, uint32_t t_stride, uint32_t c4, bool done) {
+                                                 const float* yv, uint32_t t_stride, uint32_t c4, bool done, int h = 0) {
     constexpr int NQ = (D + 3) / 4;
     float acc[NS];
-    uint32_t e[NS][NQ * 4];
+    uint32_t e[NS][T16 ? 8 : NQ * 4];
+    if constexpr (T16) {
+        // 16-bit entries (R element index in row units): one LDS.32 / .64 / .128 per slot and lane
+        static_assert(TAB_SMEM && D <= 8, "16-bit variable tables: shared memory, degree <= 8");
+        constexpr uint32_t ROWB = 128u / SUB;
+        constexpr uint32_t SD = D <= 2 ? 4u : (D <= 4 ? 8u : 16u);
+        const uint32_t base = r_base + c4;
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        acc[i] = yv[i];
+        for (int i = 0; i < NS; ++i) {
+            acc[i] = yv[i];
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            const uint32_t a = q + (uint32_t)(i * SUB + h) * SD;  // T16 layout: [slot][lane][SD bytes], q = slot base
+            if constexpr (SD == 4u) w[0] = __float_as_uint(lds_f32(a));
+            else if constexpr (SD == 8u) { const uint2 o = lds_u64(a); w[0] = o.x; w[1] = o.y; }
+            else { const uint4 o = lds_u128(a); w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w; }
 #pragma unroll
-        for (int jq = 0; jq < NQ; ++jq) {
-            uint4 o;
-            if (TAB_SMEM) o = lds_u128(q + (uint32_t)((i * NQ + jq) * SUB) * 16u);
-            else {
-                o = __ldg(reinterpret_cast<const uint4*>(gtab + q) + (i * NQ + jq) * SUB);
-                o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+            for (int k = 0; k < 4; ++k) {
+                e[i][2 * k] = (w[k] & 0xffffu) * ROWB + base;
+                e[i][2 * k + 1] = (w[k] >> 16) * ROWB + base;
             }
-            e[i][jq * 4 + 0] = o.x; e[i][jq * 4 + 1] = o.y; e[i][jq * 4 + 2] = o.z; e[i][jq * 4 + 3] = o.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            acc[i] = yv[i];
+#pragma unroll
+            for (int jq = 0; jq < NQ; ++jq) {
+                uint4 o;
+                if (TAB_SMEM) o = lds_u128(q + (uint32_t)((i * NQ + jq) * SUB) * 16u);
+                else {
+                    o = __ldg(reinterpret_cast<const uint4*>(gtab + q) + (i * NQ + jq) * SUB);
+                    o.x += r_base; o.y += r_base; o.z += r_base; o.w += r_base;
+                }
+                e[i][jq * 4 + 0] = o.x; e[i][jq * 4 + 1] = o.y; e[i][jq * 4 + 2] = o.z; e[i][jq * 4 + 3] = o.w;
+            }
         }
     }
     float r[NS][D];
 #pragma unroll
     for (int i = 0; i < NS; ++i)
 #pragma unroll
-        for (int k = 0; k < D; ++k) r[i][k] = lds_f32(e[i][k] + c4);
+        for (int k = 0; k < D; ++k) r[i][k] = lds_f32(e[i][k] + (T16 ? 0u : c4));
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
@@ -739,41 +778,42 @@ __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __
 #pragma unroll
     for (int i = 0; i < NS; ++i)
         if (!done) sts_f32(ta + (uint32_t)i * t_stride, acc[i]);
-    q += (TAB_SMEM ? 16u : 4u) * (uint32_t)(NS * NQ * SUB);
+    if constexpr (T16) q += (uint32_t)NS * SUB * (D <= 2 ? 4u : (D <= 4 ? 8u : 16u));
+    else q += (TAB_SMEM ? 16u : 4u) * (uint32_t)(NS * NQ * SUB);
     ta += (uint32_t)NS * t_stride;
 }
 
 // Static variable pass: runs of equal-degree slots, up to 4 (degree <= 3) or 2 slots in flight.
-template <class P, int S0, int SUB, bool TAB_SMEM>
+template <class P, int S0, int SUB, bool TAB_SMEM, bool T16 = false>
 __device__ __forceinline__ void grp_vn_static(uint32_t& q, const uint32_t* __restrict__ gtab, uint32_t r_base, uint32_t& ta,
-                                              const float* yn, uint32_t t_stride, uint32_t c4, bool done) {
+                                              const float* yn, uint32_t t_stride, uint32_t c4, bool done, int h = 0) {
     if constexpr (S0 < P::VS) {
         constexpr int D = P::vdeg(S0);
         constexpr int same2 = (S0 + 1 < P::VS) && P::vdeg(S0 + 1 < P::VS ? S0 + 1 : S0) == D;
         constexpr int same4 = same2 && (S0 + 3 < P::VS) && P::vdeg(S0 + 2 < P::VS ? S0 + 2 : S0) == D &&
                               P::vdeg(S0 + 3 < P::VS ? S0 + 3 : S0) == D;
         constexpr int NS = (same4 && D <= 3) ? 4 : (same2 ? 2 : 1);
-        if constexpr (D > 0) grp_vn_slots_reg<D, NS, SUB, TAB_SMEM>(q, gtab, r_base, ta, yn + S0, t_stride, c4, done);
+        if constexpr (D > 0) grp_vn_slots_reg<D, NS, SUB, TAB_SMEM, T16>(q, gtab, r_base, ta, yn + S0, t_stride, c4, done, h);
         else ta += (uint32_t)NS * t_stride;
-        grp_vn_static<P, S0 + NS, SUB, TAB_SMEM>(q, gtab, r_base, ta, yn, t_stride, c4, done);
+        grp_vn_static<P, S0 + NS, SUB, TAB_SMEM, T16>(q, gtab, r_base, ta, yn, t_stride, c4, done, h);
     }
 }
 
 // Static check pass: one straight-line check per slot.
-template <class P, int CS0, int SUB, bool TAB_SMEM>
+template <class P, int CS0, int SUB, bool TAB_SMEM, bool T16 = false>
 __device__ __forceinline__ uint32_t grp_cn_static(uint32_t tab, const uint32_t* __restrict__ gtab, uint32_t t_base, uint32_t rrow,
                                                    uint32_t c4, int h) {
     if constexpr (CS0 < P::CS) {
         constexpr int D = P::cdeg(CS0);
-        const uint32_t u = grp_check<D, SUB, TAB_SMEM>(tab, gtab, t_base, rrow, c4, h);
-        return u | grp_cn_static<P, CS0 + 1, SUB, TAB_SMEM>(tab + (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 3) >> 2) * SUB), gtab, t_base,
-                                                             rrow + (uint32_t)D * 128u, c4, h);
+        const uint32_t u = grp_check<D, SUB, TAB_SMEM, false, T16>(tab, gtab, t_base, rrow, c4, h);
+        constexpr uint32_t adv = T16 ? 16u * (uint32_t)(((D + 7) >> 3) * SUB) : (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 3) >> 2) * SUB);
+        return u | grp_cn_static<P, CS0 + 1, SUB, TAB_SMEM, T16>(tab + adv, gtab, t_base, rrow + (uint32_t)D * 128u, c4, h);
     } else {
         return 0u;
     }
 }
 
-template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM, class PROF = GenericProfile>
+template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM, class PROF = GenericProfile, bool T16 = false>
 __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
     constexpr int SUB = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -796,8 +836,10 @@ __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldp
     if (TAB_SMEM) {
         uint32_t* cn_s = reinterpret_cast<uint32_t*>(smem_raw + (cn_base - t_base));
         uint32_t* vn_s = reinterpret_cast<uint32_t*>(smem_raw + (vn_base - t_base));
-        for (int i = threadIdx.x; i < W * p.cn_stride; i += blockDim.x) cn_s[i] = __ldg(p.cn_tab + i) + t_base;
-        for (int i = threadIdx.x; i < W * p.vn_stride; i += blockDim.x) vn_s[i] = __ldg(p.vn_tab + i) + r_base;
+        // 32-bit entries are stored with the region base added (an entry IS a shared address);
+        // 16-bit entries (T16) are row indices and stay as they are
+        for (int i = threadIdx.x; i < W * p.cn_stride; i += blockDim.x) cn_s[i] = __ldg(p.cn_tab + i) + (T16 ? 0u : t_base);
+        for (int i = threadIdx.x; i < W * p.vn_stride; i += blockDim.x) vn_s[i] = __ldg(p.vn_tab + i) + (T16 ? 0u : r_base);
     }
     const uint32_t c4 = (uint32_t)c * 4u;
     if (warp == 0) {
@@ -828,7 +870,7 @@ __global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldp
         // ---- check-node pass
         uint32_t unsat = 0u;
         if constexpr (PROF::kStatic) {
-            unsat = grp_cn_static<PROF, 0, SUB, TAB_SMEM>(cn_w, p.cn_tab, t_base, r_own, c4, h);
+            unsat = grp_cn_static<PROF, 0, SUB, TAB_SMEM, T16>(cn_w, p.cn_tab, t_base, r_own, c4, h);
         } else {
             uint32_t tab = cn_w;     // quads for this warp, slot by slot
             uint32_t rrow = r_own;   // this lane's R column, row by row
@@ -882,9 +924,9 @@ case D:                                                                         
 #undef GRP_VCASE
             }
         } else if constexpr (PROF::kStatic) {
-            uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);
+            uint32_t q = vn_w + (T16 ? 0u : (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u));  // T16: lane offset per slot
             uint32_t ta = t_own;
-            grp_vn_static<PROF, 0, SUB, TAB_SMEM>(q, p.vn_tab, r_base, ta, yn, t_stride, c4, done_mask);
+            grp_vn_static<PROF, 0, SUB, TAB_SMEM, T16>(q, p.vn_tab, r_base, ta, yn, t_stride, c4, done_mask, h);
         } else {
             uint32_t q = vn_w + (TAB_SMEM ? (uint32_t)h * 16u : (uint32_t)h * 4u);  // quads [slot][kq][h][4]
             auto next_quad = [&]() {

@@ -2,9 +2,12 @@
 //
 // Same `class Coder` public interface, enums, macros and seed-table names, so code written against
 // the reference (its own Test.cpp included) compiles unchanged; the OpenCL / cl.hpp machinery and the
-// Eigen dependency are gone.  Every decodeType is served by the sm_100a CUDA min-sum decoder in
-// libldpc_b200.so (include/ldpc_b200.h) with the semantics of the reference's Coder::decodeCPU
-// (MyLdpc.cpp:684-784) -- there is no CPU decode path in this library, DecodeCPU included.
+// Eigen dependency are gone.  Decoding runs on the sm_100a CUDA decoder in libldpc_b200.so
+// (include/ldpc_b200.h): DecodeSP selects the probability-domain sum-product kernel (the semantics of the
+// reference's decodeOnceSP, MyLdpc.cpp:977-1059 / decodeCL.c:3-108; codes too large for its on-chip layout
+// fall back to min-sum, reported through lastError()); every other decodeType runs min-sum with the
+// semantics of the reference's Coder::decodeCPU (MyLdpc.cpp:684-784).  There is no CPU decode path in
+// this library, DecodeCPU included.
 //
 //   reference                         here
 //   --------------------------------  ------------------------------------------------------------

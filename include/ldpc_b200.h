@@ -62,6 +62,14 @@ enum {
                                       registers, 16-byte check state and index tables in shared memory */
 };
 
+/* Decoding algorithm of a handle (ldpc_b200_set_algorithm). */
+enum {
+    LDPC_B200_ALG_MIN_SUM = 0,     /* Coder::decodeCPU / DecodeMS semantics (default)                    */
+    LDPC_B200_ALG_SUM_PRODUCT = 1  /* DecodeSP: probability-domain sum-product of decodeCL.c:3-108 under
+                                      decodeOnceSP (MyLdpc.cpp:977-1059); short codes (on-chip group layout,
+                                      variable degree <= 8, check degree <= 16); no posterior output   */
+};
+
 typedef struct ldpc_b200_info {
     int M, N, K, nnz;
     int max_row_weight, max_col_weight;
@@ -95,6 +103,7 @@ int ldpc_b200_set_max_iter(ldpc_b200_handle h, int max_iter);        /* default 
  * iterations (throughput runs; results then differ from the reference for words that
  * would have converged earlier only in the iteration count and later posteriors).       */
 int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on);
+int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm);     /* LDPC_B200_ALG_* */
 /* Force a kernel path (LDPC_B200_PATH_*) or -1 for automatic choice. */
 int ldpc_b200_set_path(ldpc_b200_handle h, int path);
 int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info *info);

@@ -19,6 +19,7 @@
 
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
+#include "ldpc_sp.cuh"
 #include "ldpc_tables.h"
 
 using namespace ldpc_b200;
@@ -71,6 +72,8 @@ struct ldpc_b200_decoder {
     int sm_count = 0;
     size_t smem_optin = 0;
     int forced_path = -1;
+    int algorithm = LDPC_B200_ALG_MIN_SUM;
+    bool tables_keep_edge_order = false;  // group tables were built in CSR edge order (needed by sum-product)
     Plan plan;
     bool planned = false;
 
@@ -279,7 +282,7 @@ struct GrpShape {
     double cost = 0.0;
 };
 
-bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, GrpShape* out) {
+bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool sp, GrpShape* out) {
     // G = 8 runs two CTAs per SM (phase-shifted check / variable passes overlap): half the budget each
     const size_t smem_limit = G == 8 ? (smem_limit_in + 1024) / 2 - 1024 : smem_limit_in;
     const int SUB = 32 / G, NL = W * SUB;
@@ -287,8 +290,10 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, GrpSha
     sh.G = G; sh.W = W;
     sh.CS = (t.M + NL - 1) / NL;
     sh.VS = (t.N + NL - 1) / NL;
-    if (sh.CS > kGrpMaxCS || sh.VS > kGrpMaxVS || t.max_row_weight > 16 || t.max_row_weight < 1) return false;
-    sh.dmax = t.max_row_weight <= 8 ? 8 : 16;
+    // the sum-product kernel is instantiated to check degree 20 (802.16e rate 5/6) and variable degree 8
+    if (sh.CS > kGrpMaxCS || sh.VS > kGrpMaxVS || t.max_row_weight > (sp ? 20 : 16) || t.max_row_weight < 1) return false;
+    if (sp && (t.max_col_weight > 8 || G == 1)) return false;
+    sh.dmax = t.max_row_weight <= 8 ? 8 : (t.max_row_weight <= 16 ? 16 : 20);
     std::vector<int> cd(t.M), vd(t.N);
     for (int r = 0; r < t.M; ++r) cd[r] = t.row_ptr[r + 1] - t.row_ptr[r];
     for (int c = 0; c < t.N; ++c) vd[c] = t.col_ptr[c + 1] - t.col_ptr[c];
@@ -307,7 +312,7 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, GrpSha
     sh.tab_smem = core + tabs + 512 <= smem_limit;
     sh.smem = core + (sh.tab_smem ? tabs : 0);
     // channel values on chip too when they fit (dynamic slot loop, two slots in flight)
-    sh.y_smem = t.max_col_weight <= 12 && sh.smem + tbytes + 512 <= smem_limit && !std::getenv("LDPC_B200_GRP_NO_YSMEM");
+    sh.y_smem = !sp && t.max_col_weight <= 12 && sh.smem + tbytes + 512 <= smem_limit && !std::getenv("LDPC_B200_GRP_NO_YSMEM");
     if (sh.y_smem) sh.smem += tbytes;
     // issue-slot proxy of the padded work, as for LANE16
     sh.cost = (14.0 * rrows + 4.0 * ventries + 12.0 * sh.CS + 6.0 * sh.VS) * NL / (0.97 + 0.03 * W / 32.0);
@@ -316,7 +321,7 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, GrpSha
     return true;
 }
 
-bool group_pick(const HostTables& t, size_t smem_limit, GrpShape* best) {
+bool group_pick(const HostTables& t, size_t smem_limit, bool sp, GrpShape* best) {
     int g_lo = 1, g_hi = 16, w_lo = 8, w_hi = 32;
     if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16 || g == 8) g_lo = g_hi = g; }
     if (const char* env = std::getenv("LDPC_B200_GRP_WARPS")) { const int w = std::atoi(env); if (w >= 1 && w <= 32) w_lo = w_hi = w; }
@@ -329,7 +334,7 @@ bool group_pick(const HostTables& t, size_t smem_limit, GrpShape* best) {
             GrpShape b8;
             for (int W = w_lo; W <= std::min(w_hi, 12); ++W) {
                 GrpShape sh;
-                if (!group_shape(t, 8, W, smem_limit, &sh) || !sh.tab_smem) continue;
+                if (!group_shape(t, 8, W, smem_limit, sp, &sh) || !sh.tab_smem) continue;
                 if (!found8 || sh.cost < b8.cost - 1e-9 || (std::abs(sh.cost - b8.cost) <= 1e-9 && W > b8.W)) { found8 = true; b8 = sh; }
             }
             if (found8) { *best = b8; return true; }
@@ -339,7 +344,7 @@ bool group_pick(const HostTables& t, size_t smem_limit, GrpShape* best) {
         GrpShape b;
         for (int W = w_lo; W <= w_hi; ++W) {
             GrpShape sh;
-            if (!group_shape(t, G, W, smem_limit, &sh)) continue;
+            if (!group_shape(t, G, W, smem_limit, sp, &sh)) continue;
             if (G == 16 && !sh.tab_smem) continue;
             if (G == 8 && (!sh.tab_smem || W > 12)) continue;
             if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
@@ -384,6 +389,8 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     std::vector<int> slot_of_edge(t.nnz);
     for (int r = 0; r < t.M; ++r)
         for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) slot_of_edge[e] = e - t.row_ptr[r];
+    const bool keep_order = h->algorithm == LDPC_B200_ALG_SUM_PRODUCT;  // products are taken in CSR edge order
+    h->tables_keep_edge_order = keep_order;
     if (SUB == 2 || SUB == 4) {
         // Lanes of one warp instruction touch SUB different rows; a row occupies 32/SUB banks chosen by
         // (row index mod SUB) for T and by the owning check's node lane for R.  Equal classes collide.
@@ -435,7 +442,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
         }
         // (2) edge order inside each check group: at equal j the SUB T rows should fall in different bank
         //     classes (row index mod SUB).  Greedy column by column, preferring each check's fullest class.
-        for (int cg = 0; cg < ngrp; ++cg) {
+        for (int cg = 0; cg < ngrp && !keep_order; ++cg) {
             std::vector<int> byclass[4][4];  // [member][class] -> edges
             int deg[4] = {0, 0, 0, 0}, nmem = 0;
             for (int i = 0; i < SUB; ++i) {
@@ -559,7 +566,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
             for (int i = 0; i < t.M; ++i) crank_of_chk[corder[i]] = (uint32_t)i;
         }
         // (c) edge columns inside each check group: maximum bipartite matching (checks x banks) per column
-        for (int cg = 0; cg < ncg; ++cg) {
+        for (int cg = 0; cg < ncg && !keep_order; ++cg) {
             const int n = std::min(LN, t.M - cg * LN);
             std::vector<std::vector<int>> rem(n);  // remaining edges per member
             int maxd = 0;
@@ -634,7 +641,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     // table wavefronts by ~0.6 per edge but cost one unpack op per edge; measured 4.40 ms vs 4.26 ms with
     // 32-bit tables on cfg2 (profiles/r01_t16_experiment.txt), so they are off unless LDPC_B200_GRP_T16 is set.
     {
-        bool match = G == 8 && pl.tab_smem && !pl.y_smem && CS == ProfileWimax34B576::CS && VS == ProfileWimax34B576::VS &&
+        bool match = !keep_order && G == 8 && pl.tab_smem && !pl.y_smem && CS == ProfileWimax34B576::CS && VS == ProfileWimax34B576::VS &&
                      !std::getenv("LDPC_B200_GRP_NO_PROFILE") && std::getenv("LDPC_B200_GRP_T16");  // opt-in: measured slower
         for (int i = 0; match && i < CS; ++i) match = h->g_cdeg[i] == ProfileWimax34B576::cdeg(i);
         for (int i = 0; match && i < VS; ++i) match = h->g_vdeg[i] == ProfileWimax34B576::vdeg(i);
@@ -928,7 +935,7 @@ int make_plan(ldpc_b200_decoder* h) {
     Plan pl;
     {   // explicit per-edge messages on chip (G codewords per CTA)
         GrpShape sh;
-        const bool fits = group_pick(t, h->smem_optin, &sh);
+        const bool fits = group_pick(t, h->smem_optin, h->algorithm == LDPC_B200_ALG_SUM_PRODUCT, &sh);
         if (h->forced_path == LDPC_B200_PATH_GROUP && !fits)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the group shared-memory path");
         if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_GROUP) && fits) {
@@ -1096,11 +1103,31 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
             if (q.n_vclass && q.vclass_deg[q.n_vclass - 1] == h->g_vdeg[sidx]) q.vclass_cnt[q.n_vclass - 1]++;
             else { q.vclass_deg[q.n_vclass] = h->g_vdeg[sidx]; q.vclass_cnt[q.n_vclass] = 1; q.n_vclass++; }
         }
+        if (h->algorithm == LDPC_B200_ALG_SUM_PRODUCT) {
+            if (!pl.tab_smem || pl.t16 || (pl.G != 8 && pl.G != 16) || t.max_col_weight > 8 || t.max_row_weight > 20)
+                return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product needs the on-chip group layout (short codes, variable degree <= 8, check degree <= 20)");
+            if (d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
+            if (pl.G == 8) {
+                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<8, 20, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                ldpc_sp_group_kernel<8, 20, 384><<<grid, pl.threads, pl.smem, stream>>>(q);
+            } else if (pl.threads <= 768) {
+                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<16, 20, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                ldpc_sp_group_kernel<16, 20, 768><<<grid, pl.threads, pl.smem, stream>>>(q);
+            } else {
+                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<16, 20, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+                ldpc_sp_group_kernel<16, 20, 1024><<<grid, pl.threads, pl.smem, stream>>>(q);
+            }
+            CU_TRY(cudaGetLastError());
+            h->launches += 1;
+            return LDPC_B200_OK;
+        }
         rc = launch_group(pl, q, grid, stream);
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
     }
+    if (h->algorithm == LDPC_B200_ALG_SUM_PRODUCT)
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product needs the on-chip group layout (short codes)");
 
     if (pl.path == LDPC_B200_PATH_LANE16) {
         rc = upload_lane16_tables(h);
@@ -1263,6 +1290,25 @@ int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
     h->early = on ? 1 : 0;
     return LDPC_B200_OK;
+}
+
+int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (algorithm != LDPC_B200_ALG_MIN_SUM && algorithm != LDPC_B200_ALG_SUM_PRODUCT) return fail(LDPC_B200_ERR_ARG, "unknown algorithm");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (algorithm == h->algorithm) return LDPC_B200_OK;
+    h->algorithm = algorithm;
+    // the two kernels want different group layouts (sum-product multiplies in CSR edge order and admits
+    // check degree 20; min-sum reorders edges for bank placement): drop the tables and plan again
+    if (h->group_ready) {
+        DeviceGuard guard(h->device);
+        if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
+        h->dg_cn_tab = h->dg_vn_tab = h->dg_var_of_pos = h->dg_pos_of_var = nullptr;
+        h->group_ready = false;
+    }
+    return make_plan(h);
 }
 
 int ldpc_b200_set_path(ldpc_b200_handle h, int path) {

@@ -125,7 +125,7 @@ int Coder::forDecoder(int batchSize) {
 }
 
 int Coder::addDecodeType(enum decodeType deType) {
-    (void)deType;  // every decodeType is served by the CUDA min-sum decoder
+    (void)deType;  // both kernels are precompiled; decode() picks one per call from its own deType
     if (impl->handles.empty()) {
         impl->err = "forDecoder must be called before addDecodeType";
         return LDPC_B200_ERR_ARG;
@@ -149,7 +149,6 @@ int Coder::getCodeSize(int srcLength) { return (srcLength + (impl->K / 8) - 1) /
 
 // ---- decode (reference MyLdpc.cpp:571-618; semantics of :684-784) -----------------------------
 int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType deType) {
-    (void)deType;
     if (impl->handles.empty()) {
         impl->err = "forDecoder must be called before decode";
         return LDPC_B200_ERR_ARG;
@@ -157,6 +156,11 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
     const int codeSize = getCodeSize(srcLength);
     const int KB = (impl->K + 7) / 8;
     const int G = (int)impl->handles.size();
+    // DecodeSP runs the probability-domain sum-product kernel (decodeCL.c:3-108 semantics) where the code
+    // fits its on-chip layout; every other decodeType -- and DecodeSP on codes too large for it -- runs the
+    // min-sum decoder with Coder::decodeCPU semantics.
+    int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT : LDPC_B200_ALG_MIN_SUM;
+    for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, alg);
     impl->iters.assign(codeSize, 0);
     impl->info.assign((size_t)codeSize * KB, 0);
     impl->lastCodeSize = codeSize;
@@ -176,6 +180,20 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) th.emplace_back(work, g);
         for (auto &t : th) t.join();
+    }
+    bool sp_unsupported = false;
+    for (int g = 0; g < G; ++g)
+        if (rcs[g] == LDPC_B200_ERR_UNSUPPORTED && alg == LDPC_B200_ALG_SUM_PRODUCT) sp_unsupported = true;
+    if (sp_unsupported) {  // code too large for the sum-product layout: decode with min-sum instead, and say so
+        for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, LDPC_B200_ALG_MIN_SUM);
+        std::fill(rcs.begin(), rcs.end(), LDPC_B200_OK);
+        if (G == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int g = 0; g < G; ++g) th.emplace_back(work, g);
+            for (auto &t : th) t.join();
+        }
+        impl->err = "DecodeSP: code too large for the on-chip sum-product layout, decoded with min-sum";
     }
     for (int g = 0; g < G; ++g)
         if (rcs[g] != LDPC_B200_OK) {

@@ -85,6 +85,10 @@ class Decoder:
     def set_early_termination(self, on: bool) -> None:
         check(self._L.ldpc_b200_set_early_termination(self._h, 1 if on else 0))
 
+    def set_algorithm(self, alg: int) -> None:
+        """0 = min-sum (default), 1 = probability-domain sum-product (DecodeSP)."""
+        check(self._L.ldpc_b200_set_algorithm(self._h, alg))
+
     def set_path(self, path: int) -> None:
         check(self._L.ldpc_b200_set_path(self._h, path))
 
@@ -251,7 +255,16 @@ class Coder:
         if _numel(y) < codeSize * self.ldpcN:
             raise ValueError("postCode shorter than getPostCodeLength(srcLength)")
         yy = y.reshape(-1)[: codeSize * self.ldpcN]
-        res = self._dec.decode_host(yy)
+        # DecodeSP -> sum-product kernel where the code fits its on-chip layout, else (and for every other
+        # decodeType) the min-sum decoder with Coder::decodeCPU semantics
+        self._dec.set_algorithm(1 if deType == DecodeSP else 0)
+        try:
+            res = self._dec.decode_host(yy)
+        except LdpcError as e:
+            if deType != DecodeSP or e.code != -3:
+                raise
+            self._dec.set_algorithm(0)
+            res = self._dec.decode_host(yy)
         flat = res["info"].reshape(-1)[:srcLength]
         dst = np.frombuffer(srcCode, dtype=np.uint8) if not isinstance(srcCode, np.ndarray) else srcCode.view(np.uint8)
         dst[:srcLength] = flat

@@ -53,6 +53,11 @@ def lib() -> C.CDLL:
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_decode_batch.restype = C.c_int
         L.oracle_bpsk.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_decode_sp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_decode_sp_batch.restype = C.c_int
+        L.oracle_sp_expf.argtypes = [C.c_float]
+        L.oracle_sp_expf.restype = C.c_float
         for f in ("oracle_getCodeSize",):
             getattr(L, f).argtypes = [C.c_int, C.c_int]
         for f in ("oracle_getPostCodeLength", "oracle_getPriorCodeLength"):
@@ -124,6 +129,23 @@ class Oracle:
                               iters.ctypes.data, hard.ctypes.data if want_hard else None,
                               post.ctypes.data if want_post else None, threads, 1 if literal else 0)
         return info, iters, hard, post
+
+
+def decode_sp(o: "Oracle", llr: np.ndarray, threads: int = 0):
+    """Sum-product restatement (see ldpc_oracle.h): (info, iters, hard, post0, post1)."""
+    L = lib()
+    y = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, o.N)
+    ncw = y.shape[0]
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    info = np.zeros((ncw, (o.K + 7) // 8), dtype=np.uint8)
+    iters = np.zeros(ncw, dtype=np.int32)
+    hard = np.zeros((ncw, o.N), dtype=np.uint8)
+    p0 = np.zeros((ncw, o.N), dtype=np.float32)
+    p1 = np.zeros((ncw, o.N), dtype=np.float32)
+    L.oracle_decode_sp_batch(o._t, o.K, o.times, y.ctypes.data, ncw, info.ctypes.data, iters.ctypes.data,
+                             hard.ctypes.data, p0.ctypes.data, p1.ctypes.data, threads)
+    return info, iters, hard, p0, p1
 
 
 def bpsk(bytes_: np.ndarray) -> np.ndarray:

@@ -354,6 +354,150 @@ int oracle_decode_batch(const oracle_tables *t, int K, int times, const float *l
     return 0;
 }
 
+/* ---- sum-product restatement (decodeCL.c:3-108, MyLdpc.cpp:977-1059) ---------------------------- */
+
+/* exp(x) as a fixed sequence of IEEE binary32 operations (no FMA), shared verbatim with the CUDA
+ * kernel (csrc/ldpc_sp.cuh: sp_expf).  Cody-Waite reduction + degree-6 polynomial, ~2 ulp; saturates
+ * like expf: +inf above 88.72, 0 below -103.  */
+float oracle_sp_expf(float x) {
+    if (x > 88.72283f) return INFINITY;
+    if (x < -103.0f) return 0.0f;
+    const float kf = (x * 1.44269504f + 12582912.0f) - 12582912.0f; /* round to nearest integer */
+    float r = x - kf * 0.693359375f;                                 /* ln2 high part: 9 bits, exact product */
+    r = r - kf * -2.12194440e-4f;                                    /* ln2 low part */
+    float p = 1.38888889e-3f;                                        /* 1/720 */
+    p = p * r + 8.33333377e-3f;
+    p = p * r + 4.16666679e-2f;
+    p = p * r + 1.66666672e-1f;
+    p = p * r + 0.5f;
+    p = p * r + 1.0f;
+    p = p * r + 1.0f;
+    int k = (int)kf;
+    /* scale by 2^k in two steps so that results in the denormal range are produced by multiplication */
+    union { float f; uint32_t u; } s1, s2;
+    int k1 = k / 2, k2 = k - k1;
+    s1.u = (uint32_t)(k1 + 127) << 23;
+    s2.u = (uint32_t)(k2 + 127) << 23;
+    return (p * s1.f) * s2.f;
+}
+
+typedef struct {
+    const oracle_tables *t;
+    int K, times;
+    const float *llr;
+    int64_t b0, b1;
+    uint8_t *info, *hard;
+    int32_t *iters;
+    float *post0, *post1;
+} spjob_t;
+
+static void *spjob_run(void *arg) {
+    spjob_t *j = (spjob_t *)arg;
+    const oracle_tables *t = j->t;
+    const int nonZeros = t->nnz, ldpcN = t->N, ldpcM = t->M, K = j->K, KB = (K + 7) / 8;
+    float *q0 = (float *)malloc(sizeof(float) * (size_t)nonZeros), *q1 = (float *)malloc(sizeof(float) * (size_t)nonZeros);
+    float *r0 = (float *)malloc(sizeof(float) * (size_t)nonZeros), *r1 = (float *)malloc(sizeof(float) * (size_t)nonZeros);
+    float *priorP0 = (float *)malloc(sizeof(float) * (size_t)ldpcN), *priorP1 = (float *)malloc(sizeof(float) * (size_t)ldpcN);
+    float *pt0 = (float *)malloc(sizeof(float) * (size_t)ldpcN), *pt1 = (float *)malloc(sizeof(float) * (size_t)ldpcN);
+    unsigned char *src = (unsigned char *)malloc((size_t)ldpcN);
+    for (int64_t b = j->b0; b < j->b1; ++b) {
+        const float *codes = j->llr + (size_t)b * ldpcN;
+        /* decodeInit, decodeCL.c:3-22 */
+        for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {
+            float tmp = oracle_sp_expf(8 * codes[t->hCols[nodeInd]]);
+            q0[nodeInd] = tmp / (1 + tmp);
+            q1[nodeInd] = 1 / (1 + tmp);
+        }
+        for (int n = 0; n < ldpcN; ++n) {
+            float tmp = oracle_sp_expf(8 * codes[n]);
+            priorP0[n] = tmp / (1 + tmp);
+            priorP1[n] = 1 / (1 + tmp);
+            src[n] = 0;
+            pt0[n] = priorP0[n]; pt1[n] = priorP1[n];
+        }
+        int time = 0;
+        while (1) {
+            /* refreshR, decodeCL.c:25-41 */
+            for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {
+                int hRow = t->hRows[nodeInd];
+                float dTmp = 1;
+                for (int ptr = t->hRowFirstPtr[hRow]; ptr != -1; ptr = t->hRowNextPtr[ptr]) {
+                    if (nodeInd == ptr) continue;
+                    dTmp *= q0[ptr] - q1[ptr];
+                }
+                r0[nodeInd] = (1 + dTmp) / 2;
+                r1[nodeInd] = (1 - dTmp) / 2;
+            }
+            /* hardDecision, decodeCL.c:64-86 */
+            for (int col = 0; col < ldpcN; ++col) {
+                float tmp0 = priorP0[col], tmp1 = priorP1[col];
+                for (int ptr = t->hColFirstPtr[col]; ptr != -1; ptr = t->hColNextPtr[ptr]) {
+                    tmp0 *= r0[ptr];
+                    tmp1 *= r1[ptr];
+                }
+                if (tmp0 > tmp1) src[col] = 0;
+                else if (tmp0 < tmp1) src[col] = 1;
+                pt0[col] = tmp0; pt1[col] = tmp1;
+            }
+            /* checkResult, decodeCL.c:88-108 */
+            unsigned char flag = 0;
+            for (int row = 0; row < ldpcM && !flag; ++row) {
+                unsigned char result = 0;
+                for (int ptr = t->hRowFirstPtr[row]; ptr != -1; ptr = t->hRowNextPtr[ptr])
+                    if (src[t->hCols[ptr]]) result ^= 1;
+                if (result) flag = 1;
+            }
+            ++time; /* MyLdpc.cpp:1035-1039 */
+            if (!flag) break;
+            if (time == j->times) break;
+            /* refreshQ, decodeCL.c:43-62 */
+            for (int nodeInd = 0; nodeInd < nonZeros; ++nodeInd) {
+                int hCol = t->hCols[nodeInd];
+                float tmp0 = priorP0[hCol], tmp1 = priorP1[hCol];
+                for (int ptr = t->hColFirstPtr[hCol]; ptr != -1; ptr = t->hColNextPtr[ptr]) {
+                    if (nodeInd == ptr) continue;
+                    tmp0 *= r0[ptr];
+                    tmp1 *= r1[ptr];
+                }
+                q0[nodeInd] = tmp0 / (tmp0 + tmp1);
+                q1[nodeInd] = tmp1 / (tmp0 + tmp1);
+            }
+        }
+        if (j->info) { /* toChar, decodeCL.c:188-199 */
+            uint8_t *o = j->info + (size_t)b * KB;
+            memset(o, 0, (size_t)KB);
+            for (int i = 0; i < K; ++i)
+                if (src[i]) o[i >> 3] |= (uint8_t)(1u << (i & 7));
+        }
+        if (j->iters) j->iters[b] = time;
+        if (j->hard) memcpy(j->hard + (size_t)b * ldpcN, src, (size_t)ldpcN);
+        if (j->post0) memcpy(j->post0 + (size_t)b * ldpcN, pt0, sizeof(float) * (size_t)ldpcN);
+        if (j->post1) memcpy(j->post1 + (size_t)b * ldpcN, pt1, sizeof(float) * (size_t)ldpcN);
+    }
+    free(q0); free(q1); free(r0); free(r1); free(priorP0); free(priorP1); free(pt0); free(pt1); free(src);
+    return NULL;
+}
+
+int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float *llr, int64_t ncw,
+                           uint8_t *info, int32_t *iters, uint8_t *hard, float *post0, float *post1,
+                           int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > ncw) nthreads = ncw > 0 ? (int)ncw : 1;
+    spjob_t jobs[256];
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; ++i) {
+        spjob_t *j = &jobs[i];
+        j->t = t; j->K = K; j->times = times; j->llr = llr;
+        j->b0 = ncw * i / nthreads; j->b1 = ncw * (i + 1) / nthreads;
+        j->info = info; j->iters = iters; j->hard = hard; j->post0 = post0; j->post1 = post1;
+    }
+    if (nthreads == 1) { spjob_run(&jobs[0]); return 0; }
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, spjob_run, &jobs[i]);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
+
 /* reference MyLdpc.cpp:1063-1072: bit (LSB first) 1 -> -1.0, 0 -> +1.0 */
 void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out) {
     for (int charOffset = 0; charOffset < nbytes; ++charOffset) {

@@ -63,6 +63,26 @@ int oracle_decode_batch(const oracle_tables *t, int K, int times, const float *l
                         int64_t ncw, uint8_t *info, int32_t *iters, uint8_t *hard,
                         float *post, int nthreads, int literal);
 
+/* ---- sum-product (DecodeSP) -------------------------------------------------------------------
+ * Restates the reference's probability-domain sum-product decoder, which exists only as OpenCL
+ * kernels + host loop (decodeInit / refreshR / hardDecision / checkResult / refreshQ, decodeCL.c:3-108;
+ * Coder::decodeOnceSP, MyLdpc.cpp:977-1059), per codeword (the reference freezes a word with isDones
+ * once its syndrome is clean, decodeCL.c:45-49, so per-word results equal a per-word loop):
+ *   init      q0 = t/(1+t), q1 = 1/(1+t), t = exp(8*y) per edge; prior0/1 the same per column
+ *   refreshR  d_e = product over the row's OTHER edges (row-list order) of (q0-q1); r0=(1+d)/2, r1=(1-d)/2
+ *   hardDecision  t0 = prior0 * prod r0, t1 = prior1 * prod r1 over the column list; bit 0 if t0>t1,
+ *             1 if t0<t1, unchanged on a tie (bits start at 0 here; the reference's buffer is uninitialised)
+ *   checkResult / ++time / stop if clean or time == times
+ *   refreshQ  t0 = prior0 * prod_{others} r0, t1 likewise (column-list order); q0 = t0/(t0+t1), q1 = t1/(t0+t1)
+ * `exp` is an OpenCL built-in in the reference (implementation-defined rounding, no canonical value):
+ * oracle and CUDA kernel both use oracle_sp_expf / the identical device routine, a fixed sequence of
+ * IEEE fp32 operations, so the two sides can be compared bit for bit.  There is no CPU sum-product in the
+ * reference to pin this restatement against: parity for DecodeSP is GPU == this oracle ("unpinned").  */
+float oracle_sp_expf(float x);
+int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float *llr, int64_t ncw,
+                           uint8_t *info, int32_t *iters, uint8_t *hard, float *post0, float *post1,
+                           int nthreads);
+
 /* Restates Coder::test's bit->BPSK map (reference MyLdpc.cpp:1061-1072), noise supplied by
  * the caller (the reference's rand()-based Box-Muller is unseeded).                      */
 void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out);

@@ -233,6 +233,32 @@ def test_coder_api_roundtrip(default_code):
     assert np.array_equal(coder.lastIterations, ref_iters)
 
 
+def test_coder_decode_sp_uses_the_sum_product_kernel(default_code):
+    """Coder::decode(..., DecodeSP) (MyLdpc.cpp:571-618 -> decodeOnceSP) runs the sum-product kernel; the same
+    stream decoded with DecodeCPU runs min-sum.  At a noise level where the two disagree on iteration counts the
+    Coder must reproduce each oracle."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    K, N = c["K"], c["N"]
+    ncw = 64
+    srcLength = ncw * K // 8
+    post = awgn_llr(ncw, N, 0.62, seed=21).reshape(-1)
+    o = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"])
+    sp_info, sp_iters, _, _, _ = oracle.decode_sp(o, post.reshape(ncw, N))
+    ms_info, ms_iters, _, _ = o.decode(post.reshape(ncw, N))
+    assert not np.array_equal(sp_iters, ms_iters)
+    coder = m.Coder(K, N, m.rate_3_4_b)
+    coder.forDecoder(ncw)
+    coder.addDecodeType(m.DecodeSP)
+    out = np.zeros(srcLength + 1, dtype=np.uint8)
+    assert coder.decode(post, out, srcLength, m.DecodeSP) == 0
+    assert np.array_equal(coder.lastIterations, sp_iters)
+    assert np.array_equal(out[:srcLength], sp_info.reshape(-1))
+    assert coder.decode(post, out, srcLength, m.DecodeCPU) == 0
+    assert np.array_equal(coder.lastIterations, ms_iters)
+    assert np.array_equal(out[:srcLength], ms_info.reshape(-1))
+
+
 def _run_cli(name, *args):
     import pathlib
     import subprocess
@@ -251,6 +277,11 @@ def test_cpp_coder_cli_roundtrip():
     assert 1.0 <= float(kv["MeanIterations"]) < 10.0
     kv, out = _run_cli("mytest", 1000, 8, 0, "CPU", 7)   # sigma = 1: nothing converges, cap reached
     assert float(kv["MeanIterations"]) == 40.0 and int(kv["ErrNum"]) > 0
+    # DecodeSP reaches the sum-product kernel through the C++ Coder: same seed, different iteration profile
+    kv_ms, _ = _run_cli("mytest", 54000, 256, 5.0, "MS", 11)
+    kv_sp, _ = _run_cli("mytest", 54000, 256, 5.0, "SP", 11)
+    assert float(kv_sp["MeanIterations"]) != float(kv_ms["MeanIterations"])
+    assert float(kv_sp["MeanIterations"]) < float(kv_ms["MeanIterations"])
 
 
 def test_reference_test_cpp_runs_against_the_drop_in():
@@ -259,3 +290,60 @@ def test_reference_test_cpp_runs_against_the_drop_in():
     for alg in ("MS", "SP", "CPU", "TDMP"):
         kv, out = _run_cli("MyTest_reference_harness", 5400, 64, 7, alg)
         assert kv["ErrNum"] == "0", out
+
+
+@pytest.mark.parametrize("sigma", [0.45, 0.55, 0.6, 0.66, 0.9])
+def test_sum_product_matches_restated_oracle(default_code, sigma):
+    """DecodeSP: the probability-domain sum-product kernel against the oracle's restatement of the
+    reference's OpenCL kernels (decodeCL.c:3-108 / decodeOnceSP).  Both sides take every product in the
+    reference's list order with IEEE fp32 operations and share one exp routine, so hard decisions and
+    iteration counts must be identical.  (No CPU sum-product exists in the reference: this parity is
+    GPU == restated oracle.)"""
+    import myldpccppapi_b200 as m
+    c = default_code
+    llr = awgn_llr(300 + 5, c["N"], sigma, seed=int(sigma * 1000) + 1)
+    llr[0, :] = 0.0
+    llr[1, ::4] = -0.0
+    o = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40)
+    info, iters, hard, p0, p1 = oracle.decode_sp(o, llr)
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    dec.set_algorithm(1)
+    torch = _torch()
+    out = dec.decode_device(torch.from_numpy(llr).cuda(), want_hard=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["iters"].cpu().numpy(), iters)
+    assert np.array_equal(out["info"].cpu().numpy(), info)
+    assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(hard, axis=1, bitorder="little"))
+    # switching back to min-sum on the same handle still matches the min-sum oracle
+    dec.set_algorithm(0)
+    ref = o.decode(llr)
+    assert_parity(_run_device(dec, llr), ref, c["N"], what="min-sum after sum-product")
+
+
+def test_sum_product_other_rates_and_caps():
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    for rate, name, num, den in [(0, "1/2", 1, 2), (5, "5/6", 5, 6)]:
+        N = 576
+        K = N * num // den
+        rp, ci, M = oracle.wimax_H(N, name)
+        llr = awgn_llr(130, N, sigma_from_ebn0(2.0, num / den), seed=rate + 7)
+        for cap in (1, 3, 40):
+            o = oracle.Oracle(M, N, K, rp, ci, times=cap)
+            info, iters, hard, _, _ = oracle.decode_sp(o, llr)
+            dec = m.Decoder.wimax(K, N, rate, max_iter=cap)
+            dec.set_algorithm(1)
+            out = dec.decode_device(torch.from_numpy(llr).cuda(), want_hard=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(out["iters"].cpu().numpy(), iters), (name, cap)
+            assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(hard, axis=1, bitorder="little")), (name, cap)
+
+
+def test_sum_product_unsupported_on_long_codes():
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.regular_code()
+    dec = m.Decoder(M, N, K, rp, ci)
+    dec.set_algorithm(1)
+    with pytest.raises(m.LdpcError) as e:
+        dec.decode_device(_torch().zeros((4, N), dtype=_torch().float32, device="cuda"))
+    assert e.value.code == -3

@@ -641,10 +641,21 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     // table wavefronts by ~0.6 per edge but cost one unpack op per edge; measured 4.40 ms vs 4.26 ms with
     // 32-bit tables on cfg2 (profiles/r01_t16_experiment.txt), so they are off unless LDPC_B200_GRP_T16 is set.
     {
-        bool match = !keep_order && G == 8 && pl.tab_smem && !pl.y_smem && CS == ProfileWimax34B576::CS && VS == ProfileWimax34B576::VS &&
-                     !std::getenv("LDPC_B200_GRP_NO_PROFILE") && std::getenv("LDPC_B200_GRP_T16");  // opt-in: measured slower
-        for (int i = 0; match && i < CS; ++i) match = h->g_cdeg[i] == ProfileWimax34B576::cdeg(i);
-        for (int i = 0; match && i < VS; ++i) match = h->g_vdeg[i] == ProfileWimax34B576::vdeg(i);
+        // Test.cpp's code (G = 8, tables on chip): opt-in, measured slower.  Regular (3,6) N = 8192 (G = 1, tables
+        // read through L1 from L2): the kernel is bound by L1 data-stage wavefronts, of which the 32-bit tables are
+        // a third, so 16-bit entries are the default there (LDPC_B200_GRP_NO_T16 turns them off).
+        auto prof_match = [&](auto prof) {
+            using P = decltype(prof);
+            if (CS != P::CS || VS != P::VS) return false;
+            for (int i = 0; i < CS; ++i) if (h->g_cdeg[i] != P::cdeg(i)) return false;
+            for (int i = 0; i < VS; ++i) if (h->g_vdeg[i] != P::vdeg(i)) return false;
+            return true;
+        };
+        bool match = false;
+        if (!keep_order && !std::getenv("LDPC_B200_GRP_NO_PROFILE")) {
+            if (G == 8 && pl.tab_smem && !pl.y_smem && std::getenv("LDPC_B200_GRP_T16")) match = prof_match(ProfileWimax34B576{});
+            if (G == 1 && !pl.tab_smem && !std::getenv("LDPC_B200_GRP_NO_T16")) match = prof_match(ProfileRegular36N8192{});
+        }
         if (match) {
             std::vector<int> ooff(CS + 1, 0), vbyte(VS + 1, 0);
             for (int cs = 0; cs < CS; ++cs) ooff[cs + 1] = ooff[cs] + (h->g_cdeg[cs] + 7) / 8;
@@ -734,7 +745,8 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
     }
     if (pl.G == 1 && !pl.tab_smem && pl.dmax == 8 && !std::getenv("LDPC_B200_GRP_NO_PROFILE") &&
         profile_matches<ProfileRegular36N8192>(pl, q))
-        return launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192>(q, grid, th, sm, stream);
+        return pl.t16 ? launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192, true>(q, grid, th, sm, stream)
+                      : launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192>(q, grid, th, sm, stream);
     if (pl.G == 1 && pl.y_smem) {
         if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, true>(q, grid, th, sm, stream)
                                              : launch_group_t<1, 16, true, 1024, true>(q, grid, th, sm, stream);

@@ -583,12 +583,14 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
     uint32_t ent[(T16 ? (D + 7) / 8 * 8 : NQ * 4)];
     if constexpr (T16) {
         // 16-bit entries (T row index): eight per LDS.128, address = index * row bytes + base in one IMAD
-        static_assert(TAB_SMEM && !DSM, "16-bit tables live in shared memory");
+        static_assert(!DSM, "16-bit tables address the CTA's own shared memory");
         constexpr uint32_t ROWB = 128u / SUB;
         const uint32_t base = t_base + c4;
 #pragma unroll
         for (int jo = 0; jo < (D + 7) / 8; ++jo) {
-            const uint4 o = lds_u128(tab + (uint32_t)(jo * SUB + h) * 16u);
+            uint4 o;
+            if (TAB_SMEM) o = lds_u128(tab + (uint32_t)(jo * SUB + h) * 16u);
+            else o = __ldg(reinterpret_cast<const uint4*>(gtab + tab) + (jo * SUB + h));
             const uint32_t w[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -732,7 +734,7 @@ __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __
     uint32_t e[NS][T16 ? 8 : NQ * 4];
     if constexpr (T16) {
         // 16-bit entries (R element index in row units): one LDS.32 / .64 / .128 per slot and lane
-        static_assert(TAB_SMEM && D <= 8, "16-bit variable tables: shared memory, degree <= 8");
+        static_assert(D <= 8, "16-bit variable tables: degree <= 8");
         constexpr uint32_t ROWB = 128u / SUB;
         constexpr uint32_t SD = D <= 2 ? 4u : (D <= 4 ? 8u : 16u);
         const uint32_t base = r_base + c4;
@@ -740,10 +742,17 @@ __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __
         for (int i = 0; i < NS; ++i) {
             acc[i] = yv[i];
             uint32_t w[4] = {0u, 0u, 0u, 0u};
-            const uint32_t a = q + (uint32_t)(i * SUB + h) * SD;  // T16 layout: [slot][lane][SD bytes], q = slot base
-            if constexpr (SD == 4u) w[0] = __float_as_uint(lds_f32(a));
-            else if constexpr (SD == 8u) { const uint2 o = lds_u64(a); w[0] = o.x; w[1] = o.y; }
-            else { const uint4 o = lds_u128(a); w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w; }
+            if constexpr (TAB_SMEM) {
+                const uint32_t a = q + (uint32_t)(i * SUB + h) * SD;  // T16 layout: [slot][lane][SD bytes], q = slot base
+                if constexpr (SD == 4u) w[0] = __float_as_uint(lds_f32(a));
+                else if constexpr (SD == 8u) { const uint2 o = lds_u64(a); w[0] = o.x; w[1] = o.y; }
+                else { const uint4 o = lds_u128(a); w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w; }
+            } else {  // same layout in global memory, q = slot base in words
+                const uint32_t* a = gtab + q;
+                if constexpr (SD == 4u) w[0] = __ldg(a + (i * SUB + h));
+                else if constexpr (SD == 8u) { const uint2 o = __ldg(reinterpret_cast<const uint2*>(a) + (i * SUB + h)); w[0] = o.x; w[1] = o.y; }
+                else { const uint4 o = __ldg(reinterpret_cast<const uint4*>(a) + (i * SUB + h)); w[0] = o.x; w[1] = o.y; w[2] = o.z; w[3] = o.w; }
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 e[i][2 * k] = (w[k] & 0xffffu) * ROWB + base;
@@ -778,7 +787,7 @@ __device__ __forceinline__ void grp_vn_slots_reg(uint32_t& q, const uint32_t* __
 #pragma unroll
     for (int i = 0; i < NS; ++i)
         if (!done) sts_f32(ta + (uint32_t)i * t_stride, acc[i]);
-    if constexpr (T16) q += (uint32_t)NS * SUB * (D <= 2 ? 4u : (D <= 4 ? 8u : 16u));
+    if constexpr (T16) q += (uint32_t)NS * SUB * (D <= 2 ? 4u : (D <= 4 ? 8u : 16u)) / (TAB_SMEM ? 1u : 4u);
     else q += (TAB_SMEM ? 16u : 4u) * (uint32_t)(NS * NQ * SUB);
     ta += (uint32_t)NS * t_stride;
 }
@@ -806,7 +815,8 @@ __device__ __forceinline__ uint32_t grp_cn_static(uint32_t tab, const uint32_t* 
     if constexpr (CS0 < P::CS) {
         constexpr int D = P::cdeg(CS0);
         const uint32_t u = grp_check<D, SUB, TAB_SMEM, false, T16>(tab, gtab, t_base, rrow, c4, h);
-        constexpr uint32_t adv = T16 ? 16u * (uint32_t)(((D + 7) >> 3) * SUB) : (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 3) >> 2) * SUB);
+        constexpr uint32_t adv = T16 ? (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 7) >> 3) * SUB)
+                                     : (TAB_SMEM ? 16u : 4u) * (uint32_t)(((D + 3) >> 2) * SUB);
         return u | grp_cn_static<P, CS0 + 1, SUB, TAB_SMEM, T16>(tab + adv, gtab, t_base, rrow + (uint32_t)D * 128u, c4, h);
     } else {
         return 0u;

@@ -65,9 +65,15 @@ enum {
 /* Decoding algorithm of a handle (ldpc_b200_set_algorithm). */
 enum {
     LDPC_B200_ALG_MIN_SUM = 0,     /* Coder::decodeCPU / DecodeMS semantics (default)                    */
-    LDPC_B200_ALG_SUM_PRODUCT = 1  /* DecodeSP: probability-domain sum-product of decodeCL.c:3-108 under
+    LDPC_B200_ALG_SUM_PRODUCT = 1, /* DecodeSP: probability-domain sum-product of decodeCL.c:3-108 under
                                       decodeOnceSP (MyLdpc.cpp:977-1059); short codes (on-chip group layout,
-                                      variable degree <= 8, check degree <= 16); no posterior output   */
+                                      variable degree <= 8, check degree <= 20); no posterior output   */
+    LDPC_B200_ALG_LAYERED_MIN_SUM = 2 /* DecodeTDMP: layered min-sum, the schedule decodeOnceTDMP intends
+                                      (MyLdpc.cpp:889-976, decodeCL.c:203-292): layers of z consecutive rows,
+                                      Q = P - R, R = min-sum, P = Q + R per layer, then hard decision
+                                      (P == 0 keeps the bit) and syndrome.  Needs the layer height
+                                      (known for ldpc_b200_create_wimax, else ldpc_b200_set_layer_height),
+                                      column-disjoint layers, <= 16 layers, N <= 32 z, on-chip layout     */
 };
 
 typedef struct ldpc_b200_info {
@@ -104,6 +110,9 @@ int ldpc_b200_set_max_iter(ldpc_b200_handle h, int max_iter);        /* default 
  * would have converged earlier only in the iteration count and later posteriors).       */
 int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on);
 int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm);     /* LDPC_B200_ALG_* */
+/* Rows per layer for LDPC_B200_ALG_LAYERED_MIN_SUM (the reference's z, MyLdpc.cpp:22: one block row of the
+ * quasi-cyclic matrix).  ldpc_b200_create_wimax sets it to N/24.                                          */
+int ldpc_b200_set_layer_height(ldpc_b200_handle h, int z);
 /* Force a kernel path (LDPC_B200_PATH_*) or -1 for automatic choice. */
 int ldpc_b200_set_path(ldpc_b200_handle h, int path);
 int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info *info);

@@ -20,6 +20,7 @@
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
 #include "ldpc_sp.cuh"
+#include "ldpc_tdmp.cuh"
 #include "ldpc_tables.h"
 
 using namespace ldpc_b200;
@@ -61,6 +62,15 @@ struct Plan {
     int cn_stride = 0, vn_stride = 0, r_rows = 0;
 };
 
+// Layered (TDMP) decoder: one layer = z consecutive rows = one sweep of the CTA's W warps.
+struct TdmpPlan {
+    bool ok = false;
+    int G = 0, W = 0, L = 0, VS = 0, z = 0;
+    int cn_stride = 0, r_rows = 0, threads = 0, ctas_per_sm = 1;
+    size_t smem = 0;
+    uint8_t ldeg[kTdmpMaxLayers] = {0};
+};
+
 }  // namespace
 
 struct ldpc_b200_decoder {
@@ -100,6 +110,11 @@ struct ldpc_b200_decoder {
     uint32_t* dc_var_of_pos = nullptr;
     uint32_t* dc_out_addr = nullptr;
     bool cluster_ready = false;
+    // TDMP (layered) tables
+    int layer_z = 0;  // rows per layer; 0 = unknown (layered decoding unavailable)
+    TdmpPlan tdmp;
+    uint32_t* dt_cn_tab = nullptr;
+    bool tdmp_ready = false;
     uint8_t g_vdeg[kGrpMaxVS] = {0};
     uint8_t g_cdeg[kGrpMaxCS] = {0};
     int l16_vn_stride = 0;
@@ -942,6 +957,127 @@ int launch_cluster_t(const ClusterParams& q, int nclusters_wanted, int threads, 
     return LDPC_B200_OK;
 }
 
+// ---- TDMP layout (see ldpc_tdmp.cuh) ------------------------------------------------------------------
+int tdmp_plan(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    const int z = h->layer_z;
+    TdmpPlan best;
+    if (z < 1) return fail(LDPC_B200_ERR_UNSUPPORTED, "layered decoding needs the layer height (ldpc_b200_set_layer_height)");
+    if (t.M % z || t.N % z) return fail(LDPC_B200_ERR_UNSUPPORTED, "layer height must divide M and N");
+    const int L = t.M / z, VS = t.N / z;
+    if (L > kTdmpMaxLayers || VS > 32 || t.max_row_weight > 20)
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "layered decoding: at most 16 layers, N <= 32 z, check degree <= 20");
+    {   // no column may appear twice inside a layer (the rows of a layer are updated concurrently)
+        std::vector<int> seen(t.N, -1);
+        for (int r = 0; r < t.M; ++r)
+            for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) {
+                if (seen[t.col_idx[e]] == r / z) return fail(LDPC_B200_ERR_UNSUPPORTED, "layered decoding: a column appears twice inside a layer");
+                seen[t.col_idx[e]] = r / z;
+            }
+    }
+    int force_g = 0;
+    if (const char* env = std::getenv("LDPC_B200_TDMP_G")) force_g = std::atoi(env);
+    for (int G : {4, 8, 16}) {
+        if (force_g && G != force_g) continue;
+        const int SUB = 32 / G;
+        if (z % SUB) continue;
+        TdmpPlan pl;
+        pl.G = G; pl.W = z / SUB; pl.L = L; pl.VS = VS; pl.z = z;
+        if (pl.W > 32) continue;
+        pl.threads = pl.W * 32;
+        long long quads = 0;
+        for (int l = 0; l < L; ++l) {
+            int d = 0;
+            for (int r = l * z; r < (l + 1) * z; ++r) d = std::max(d, t.row_ptr[r + 1] - t.row_ptr[r]);
+            pl.ldeg[l] = (uint8_t)d;
+            pl.r_rows += d;
+            quads += (d + 3) / 4;
+        }
+        pl.cn_stride = (int)(quads * SUB * 4);
+        const size_t tbytes = ((size_t)(t.N + SUB) * G * 4 + 127) & ~(size_t)127;
+        pl.smem = tbytes + (size_t)pl.W * pl.r_rows * 128 + (size_t)pl.W * pl.cn_stride * 4;
+        if (pl.smem + 512 > h->smem_optin) continue;
+        const size_t sm_total = h->smem_optin + 1024;  // per-SM capacity; every resident CTA reserves 1 KB
+        pl.ctas_per_sm = (int)std::min<size_t>({sm_total / (pl.smem + 1024), (size_t)(2048 / pl.threads), (size_t)32});
+        if (pl.threads > 384) pl.ctas_per_sm = std::min(pl.ctas_per_sm, 1);  // register budget of the 1024-thread variant
+        else pl.ctas_per_sm = std::min(pl.ctas_per_sm, 384 / pl.threads);    // 168 registers x 384 threads per SM
+        if (pl.ctas_per_sm < 1) continue;
+        pl.ok = true;
+        // more resident warps first, then more (smaller) CTAs: their layer barriers interleave
+        const int warps = pl.ctas_per_sm * pl.W, bw = best.ok ? best.ctas_per_sm * best.W : -1;
+        if (!best.ok || warps > bw || (warps == bw && pl.ctas_per_sm > best.ctas_per_sm)) best = pl;
+    }
+    if (!best.ok) return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the layered shared-memory layout");
+    h->tdmp = best;
+    return LDPC_B200_OK;
+}
+
+int upload_tdmp_tables(ldpc_b200_decoder* h) {
+    if (h->tdmp_ready) return LDPC_B200_OK;
+    int rc = tdmp_plan(h);
+    if (rc) return rc;
+    const HostTables& t = h->host;
+    const TdmpPlan& pl = h->tdmp;
+    const int G = pl.G, SUB = 32 / G, z = pl.z;
+    std::vector<uint32_t> cn_tab((size_t)pl.W * pl.cn_stride);
+    std::vector<int> qoff(pl.L + 1, 0);
+    for (int l = 0; l < pl.L; ++l) qoff[l + 1] = qoff[l] + (pl.ldeg[l] + 3) / 4;
+    for (int w = 0; w < pl.W; ++w)
+        for (int l = 0; l < pl.L; ++l)
+            for (int hh = 0; hh < SUB; ++hh) {
+                const int r = l * z + w * SUB + hh;
+                const int dc = t.row_ptr[r + 1] - t.row_ptr[r];
+                for (int j = 0; j < ((pl.ldeg[l] + 3) / 4) * 4; ++j) {
+                    const uint32_t col = j < dc ? (uint32_t)t.col_idx[t.row_ptr[r] + j] : (uint32_t)(t.N + hh);  // per-h dummy row
+                    cn_tab[(size_t)w * pl.cn_stride + ((size_t)(qoff[l] + j / 4) * SUB + hh) * 4 + (j & 3)] = col * (uint32_t)(G * 4);
+                }
+            }
+    CU_TRY(cudaMalloc(&h->dt_cn_tab, cn_tab.size() * 4));
+    CU_TRY(cudaMemcpy(h->dt_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += cn_tab.size() * 4;
+    h->tdmp_ready = true;
+    return LDPC_B200_OK;
+}
+
+template <int G, int MAXT>
+int launch_tdmp_t(const TdmpParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    CU_TRY(cudaFuncSetAttribute(ldpc_tdmp_group_kernel<G, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_tdmp_group_kernel<G, MAXT><<<grid, threads, smem, stream>>>(q);
+    CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard, int32_t* d_iters,
+                float* d_post, cudaStream_t stream) {
+    int rc = upload_tdmp_tables(h);
+    if (rc) return rc;
+    const HostTables& t = h->host;
+    const TdmpPlan& pl = h->tdmp;
+    unsigned long long* ctr64 = h->d_counters + h->counter_next;
+    h->counter_next = (h->counter_next + 1) % kCounterRing;
+    CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
+    TdmpParams q;
+    q.cn_tab = h->dt_cn_tab;
+    q.M = t.M; q.N = t.N; q.K = h->K; q.W = pl.W; q.L = pl.L; q.VS = pl.VS;
+    q.cn_stride = pl.cn_stride; q.r_rows_per_warp = pl.r_rows;
+    q.max_iter = h->max_iter; q.early_term = h->early;
+    q.llr = d_llr; q.ncw = ncw;
+    q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+    q.counter64 = ctr64;
+    std::memcpy(q.ldeg, pl.ldeg, sizeof(q.ldeg));
+    const int64_t ngroups = (ncw + pl.G - 1) / pl.G;
+    const int grid = (int)std::min<int64_t>(ngroups, (int64_t)h->sm_count * pl.ctas_per_sm);
+    const bool big = pl.threads > 384;
+    switch (pl.G) {
+        case 4: rc = big ? launch_tdmp_t<4, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<4, 384>(q, grid, pl.threads, pl.smem, stream); break;
+        case 8: rc = big ? launch_tdmp_t<8, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<8, 384>(q, grid, pl.threads, pl.smem, stream); break;
+        default: rc = big ? launch_tdmp_t<16, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<16, 384>(q, grid, pl.threads, pl.smem, stream); break;
+    }
+    if (rc) return rc;
+    h->launches += 1;
+    return LDPC_B200_OK;
+}
+
 int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
@@ -1055,6 +1191,7 @@ void free_slots(ldpc_b200_decoder* h) {
 int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
                   int32_t* d_iters, float* d_post, cudaStream_t stream) {
     if (ncw == 0) return LDPC_B200_OK;
+    if (h->algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM) return launch_tdmp(h, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     if (!h->planned) {
         int rc = make_plan(h);
         if (rc) return rc;
@@ -1267,7 +1404,9 @@ int ldpc_b200_create_wimax(ldpc_b200_handle* out, int K, int N, int rate, int de
     int M = 0;
     std::string msg = wimax_csr(K, N, rate, &rp, &ci, &M);
     if (!msg.empty()) return fail(LDPC_B200_ERR_ARG, msg);
-    return ldpc_b200_create(out, M, N, K, rp.data(), ci.data(), device);
+    int rc = ldpc_b200_create(out, M, N, K, rp.data(), ci.data(), device);
+    if (rc == LDPC_B200_OK) (*out)->layer_z = N / 24;  // one block row of the 802.16e base matrix
+    return rc;
 }
 
 int ldpc_b200_destroy(ldpc_b200_handle h) {
@@ -1283,6 +1422,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dc_cn_tab); cudaFree(h->dc_vn_tab); cudaFree(h->dc_var_of_pos); cudaFree(h->dc_out_addr);
             cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
+            cudaFree(h->dt_cn_tab);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
         }
@@ -1306,11 +1446,24 @@ int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on) {
 
 int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
-    if (algorithm != LDPC_B200_ALG_MIN_SUM && algorithm != LDPC_B200_ALG_SUM_PRODUCT) return fail(LDPC_B200_ERR_ARG, "unknown algorithm");
+    if (algorithm != LDPC_B200_ALG_MIN_SUM && algorithm != LDPC_B200_ALG_SUM_PRODUCT && algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM)
+        return fail(LDPC_B200_ERR_ARG, "unknown algorithm");
     std::lock_guard<std::mutex> lk(h->mu);
     if (algorithm == h->algorithm) return LDPC_B200_OK;
+    if (algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM) {
+        // its own layout and tables; nothing of the flooding plan changes.  Fails here (not at the first decode)
+        // when the code cannot be layered, so a caller can fall back.
+        if (!h->tdmp_ready) {
+            int rc = tdmp_plan(h);
+            if (rc) return rc;
+        }
+        h->algorithm = algorithm;
+        return LDPC_B200_OK;
+    }
+    const int prev = h->algorithm;
     h->algorithm = algorithm;
-    // the two kernels want different group layouts (sum-product multiplies in CSR edge order and admits
+    if (prev == LDPC_B200_ALG_LAYERED_MIN_SUM && algorithm == LDPC_B200_ALG_MIN_SUM && !h->tables_keep_edge_order) return LDPC_B200_OK;
+    // the two flooding kernels want different group layouts (sum-product multiplies in CSR edge order and admits
     // check degree 20; min-sum reorders edges for bank placement): drop the tables and plan again
     if (h->group_ready) {
         DeviceGuard guard(h->device);
@@ -1321,6 +1474,28 @@ int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
         h->group_ready = false;
     }
     return make_plan(h);
+}
+
+int ldpc_b200_set_layer_height(ldpc_b200_handle h, int z) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (z < 1) return fail(LDPC_B200_ERR_ARG, "layer height must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (z == h->layer_z) return LDPC_B200_OK;
+    if (h->tdmp_ready) {
+        DeviceGuard guard(h->device);
+        if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(h->dt_cn_tab);
+        h->dt_cn_tab = nullptr;
+        h->tdmp_ready = false;
+    }
+    const int prev = h->layer_z;
+    h->layer_z = z;
+    if (h->algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM) {
+        int rc = tdmp_plan(h);
+        if (rc) { h->layer_z = prev; return rc; }
+    }
+    return LDPC_B200_OK;
 }
 
 int ldpc_b200_set_path(ldpc_b200_handle h, int path) {

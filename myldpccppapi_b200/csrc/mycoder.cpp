@@ -119,6 +119,7 @@ int Coder::forDecoder(int batchSize) {
         }
         ldpc_b200_set_max_iter(h, impl->times);
         ldpc_b200_set_early_termination(h, impl->early ? 1 : 0);
+        if (impl->rate >= 0) ldpc_b200_set_layer_height(h, impl->N / 24);  // z, reference MyLdpc.cpp:22
         impl->handles.push_back(h);
     }
     return LDPC_SUCCESS;
@@ -156,11 +157,21 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
     const int codeSize = getCodeSize(srcLength);
     const int KB = (impl->K + 7) / 8;
     const int G = (int)impl->handles.size();
-    // DecodeSP runs the probability-domain sum-product kernel (decodeCL.c:3-108 semantics) where the code
-    // fits its on-chip layout; every other decodeType -- and DecodeSP on codes too large for it -- runs the
-    // min-sum decoder with Coder::decodeCPU semantics.
-    int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT : LDPC_B200_ALG_MIN_SUM;
-    for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, alg);
+    // DecodeSP runs the probability-domain sum-product kernel (decodeCL.c:3-108 semantics) and DecodeTDMP /
+    // DecodeTDMPCL the layered min-sum kernel (the schedule of decodeCL.c:203-292) where the code fits their
+    // on-chip layouts; every other decodeType -- and those two on codes that do not fit -- runs flooding
+    // min-sum with Coder::decodeCPU semantics.
+    int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT
+              : (deType == DecodeTDMP || deType == DecodeTDMPCL) ? LDPC_B200_ALG_LAYERED_MIN_SUM
+                                                                 : LDPC_B200_ALG_MIN_SUM;
+    const char *fallback_note = "requested decodeType does not fit its on-chip layout for this code, decoded with flooding min-sum";
+    bool fell_back = false;
+    for (ldpc_b200_handle h : impl->handles)
+        if (ldpc_b200_set_algorithm(h, alg) != LDPC_B200_OK) fell_back = true;
+    if (fell_back) {
+        alg = LDPC_B200_ALG_MIN_SUM;
+        for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, alg);
+    }
     impl->iters.assign(codeSize, 0);
     impl->info.assign((size_t)codeSize * KB, 0);
     impl->lastCodeSize = codeSize;
@@ -181,10 +192,11 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
         for (int g = 0; g < G; ++g) th.emplace_back(work, g);
         for (auto &t : th) t.join();
     }
-    bool sp_unsupported = false;
+    bool unsupported = false;
     for (int g = 0; g < G; ++g)
-        if (rcs[g] == LDPC_B200_ERR_UNSUPPORTED && alg == LDPC_B200_ALG_SUM_PRODUCT) sp_unsupported = true;
-    if (sp_unsupported) {  // code too large for the sum-product layout: decode with min-sum instead, and say so
+        if (rcs[g] == LDPC_B200_ERR_UNSUPPORTED && alg != LDPC_B200_ALG_MIN_SUM) unsupported = true;
+    if (unsupported) {  // the kernel of this decodeType cannot hold the code: decode with min-sum instead, and say so
+        fell_back = true;
         for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, LDPC_B200_ALG_MIN_SUM);
         std::fill(rcs.begin(), rcs.end(), LDPC_B200_OK);
         if (G == 1) work(0);
@@ -193,8 +205,8 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
             for (int g = 0; g < G; ++g) th.emplace_back(work, g);
             for (auto &t : th) t.join();
         }
-        impl->err = "DecodeSP: code too large for the on-chip sum-product layout, decoded with min-sum";
     }
+    if (fell_back) impl->err = fallback_note;
     for (int g = 0; g < G; ++g)
         if (rcs[g] != LDPC_B200_OK) {
             impl->err = msgs[g];

@@ -65,7 +65,9 @@ class Decoder:
     @classmethod
     def wimax(cls, K: int, N: int, rate: int, device: int = 0, **kw) -> "Decoder":
         rp, ci, M = wimax_csr(K, N, rate)
-        return cls(M, N, K, rp, ci, device=device, **kw)
+        self = cls(M, N, K, rp, ci, device=device, **kw)
+        self.set_layer_height(N // 24)  # as ldpc_b200_create_wimax does
+        return self
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
@@ -86,8 +88,12 @@ class Decoder:
         check(self._L.ldpc_b200_set_early_termination(self._h, 1 if on else 0))
 
     def set_algorithm(self, alg: int) -> None:
-        """0 = min-sum (default), 1 = probability-domain sum-product (DecodeSP)."""
+        """0 = min-sum (default), 1 = probability-domain sum-product (DecodeSP), 2 = layered min-sum (DecodeTDMP)."""
         check(self._L.ldpc_b200_set_algorithm(self._h, alg))
+
+    def set_layer_height(self, z: int) -> None:
+        """Rows per layer for the layered decoder (Decoder.wimax sets N/24)."""
+        check(self._L.ldpc_b200_set_layer_height(self._h, z))
 
     def set_path(self, path: int) -> None:
         check(self._L.ldpc_b200_set_path(self._h, path))
@@ -199,6 +205,7 @@ class Coder:
         self.times = 40  # reference MyLdpc.cpp:24
         self.row_ptr, self.col_idx, M = wimax_csr(ldpcK, ldpcN, rate)
         assert M == self.ldpcM
+        self._z = ldpcN // 24  # rows per layer of the layered decoder = z, reference MyLdpc.cpp:22
         self.batchSize = 0
         self._dec: Optional[Decoder] = None
         self.lastIterations = None
@@ -211,6 +218,7 @@ class Coder:
         self.times = 40
         self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
         self.col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
+        self._z = 0
         self.batchSize = 0
         self._dec = None
         self.lastIterations = None
@@ -221,6 +229,8 @@ class Coder:
         self.batchSize = int(batchSize)
         self._dec = Decoder(self.ldpcM, self.ldpcN, self.ldpcK, self.row_ptr, self.col_idx, device=self.device,
                             max_iter=self.times)
+        if self._z:
+            self._dec.set_layer_height(self._z)  # z, reference MyLdpc.cpp:22
         return 0
 
     # reference MyLdpc.cpp:307-552
@@ -255,13 +265,15 @@ class Coder:
         if _numel(y) < codeSize * self.ldpcN:
             raise ValueError("postCode shorter than getPostCodeLength(srcLength)")
         yy = y.reshape(-1)[: codeSize * self.ldpcN]
-        # DecodeSP -> sum-product kernel where the code fits its on-chip layout, else (and for every other
-        # decodeType) the min-sum decoder with Coder::decodeCPU semantics
-        self._dec.set_algorithm(1 if deType == DecodeSP else 0)
+        # DecodeSP -> sum-product kernel, DecodeTDMP / DecodeTDMPCL -> layered min-sum kernel, where the code
+        # fits them; otherwise (and for DecodeCPU / DecodeMS / DecodeMSCL) flooding min-sum with
+        # Coder::decodeCPU semantics
+        alg = {DecodeSP: 1, DecodeTDMP: 2, DecodeTDMPCL: 2}.get(deType, 0)
         try:
+            self._dec.set_algorithm(alg)
             res = self._dec.decode_host(yy)
         except LdpcError as e:
-            if deType != DecodeSP or e.code != -3:
+            if alg == 0 or e.code != -3:
                 raise
             self._dec.set_algorithm(0)
             res = self._dec.decode_host(yy)

@@ -56,6 +56,11 @@ def lib() -> C.CDLL:
         L.oracle_decode_sp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_decode_sp_batch.restype = C.c_int
+        L.oracle_decode_tdmp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_decode_tdmp_batch.restype = C.c_int
+        L.oracle_tdmp_layering_ok.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_tdmp_layering_ok.restype = C.c_int
         L.oracle_sp_expf.argtypes = [C.c_float]
         L.oracle_sp_expf.restype = C.c_float
         for f in ("oracle_getCodeSize",):
@@ -146,6 +151,24 @@ def decode_sp(o: "Oracle", llr: np.ndarray, threads: int = 0):
     L.oracle_decode_sp_batch(o._t, o.K, o.times, y.ctypes.data, ncw, info.ctypes.data, iters.ctypes.data,
                              hard.ctypes.data, p0.ctypes.data, p1.ctypes.data, threads)
     return info, iters, hard, p0, p1
+
+
+def decode_tdmp(o: "Oracle", llr: np.ndarray, z: int, threads: int = 0):
+    """Layered min-sum restatement (see ldpc_oracle.h): (info, iters, hard, post); layers of z rows."""
+    L = lib()
+    y = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, o.N)
+    ncw = y.shape[0]
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    info = np.zeros((ncw, (o.K + 7) // 8), dtype=np.uint8)
+    iters = np.zeros(ncw, dtype=np.int32)
+    hard = np.zeros((ncw, o.N), dtype=np.uint8)
+    post = np.zeros((ncw, o.N), dtype=np.float32)
+    rc = L.oracle_decode_tdmp_batch(o._t, o.K, o.times, int(z), y.ctypes.data, ncw, info.ctypes.data,
+                                    iters.ctypes.data, hard.ctypes.data, post.ctypes.data, threads)
+    if rc:
+        raise ValueError("layers of %d rows are not column-disjoint" % z)
+    return info, iters, hard, post
 
 
 def bpsk(bytes_: np.ndarray) -> np.ndarray:

@@ -498,6 +498,118 @@ int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float
     return 0;
 }
 
+/* ---- layered (TDMP) min-sum restatement (decodeCL.c:203-292, MyLdpc.cpp:889-976) ----------------------
+ * The reference's intent, per codeword, with its three defects repaired (see ldpc_oracle.h):
+ *   init      lPostP = y, lR = 0, bits = 0                                   (decodeInitTDMP, :203-222)
+ *   per layer (z consecutive rows), in row order:
+ *     refreshQTDMP     lQ_e   = lPostP[col] - lR_e                            (:275-283)
+ *     refreshRTDMP     lR_e   = (xor of the row's other (lQ<0)) ? -b : b,  b = fmin(1000, min |lQ|)  (:224-249)
+ *     refreshPostPTDMP lPostP[col] = lQ_e + lR_e                              (:251-259)
+ *   after the last layer: hardDecisionTDMP (>0 -> 0, <0 -> 1, ==0 keeps, :261-281), checkResult, ++time,
+ *   stop when clean or time == times.                                         (MyLdpc.cpp:925-950)        */
+typedef struct {
+    const oracle_tables *t;
+    int K, times, z;
+    const float *llr;
+    int64_t b0, b1;
+    uint8_t *info, *hard;
+    int32_t *iters;
+    float *post;
+} tdjob_t;
+
+static void *tdjob_run(void *arg) {
+    tdjob_t *j = (tdjob_t *)arg;
+    const oracle_tables *t = j->t;
+    const int nonZeros = t->nnz, ldpcN = t->N, ldpcM = t->M, K = j->K, KB = (K + 7) / 8, z = j->z;
+    float *lQ = (float *)malloc(sizeof(float) * (size_t)nonZeros), *lR = (float *)malloc(sizeof(float) * (size_t)nonZeros);
+    float *lPostP = (float *)malloc(sizeof(float) * (size_t)ldpcN);
+    unsigned char *src = (unsigned char *)malloc((size_t)ldpcN);
+    for (int64_t b = j->b0; b < j->b1; ++b) {
+        const float *codes = j->llr + (size_t)b * ldpcN;
+        for (int n = 0; n < ldpcN; ++n) { lPostP[n] = codes[n]; src[n] = 0; }
+        for (int e = 0; e < nonZeros; ++e) lR[e] = 0;
+        int time = 0;
+        while (1) {
+            for (int blockRow = 0; blockRow < ldpcM / z; ++blockRow) {
+                const int e0 = t->hRowRange[blockRow * z], e1 = t->hRowRange[(blockRow + 1) * z];
+                for (int e = e0; e < e1; ++e) lQ[e] = lPostP[t->hCols[e]] - lR[e];
+                for (int e = e0; e < e1; ++e) {
+                    int hRow = t->hRows[e];
+                    int a = 0;
+                    float bb = 1000;
+                    for (int ptr = t->hRowFirstPtr[hRow]; ptr != -1; ptr = t->hRowNextPtr[ptr]) {
+                        if (e == ptr) continue;
+                        if (lQ[ptr] < 0) a ^= 1;
+                        bb = fminf(bb, fabsf(lQ[ptr]));
+                    }
+                    lR[e] = a ? -bb : bb;
+                }
+                for (int e = e0; e < e1; ++e) lPostP[t->hCols[e]] = lQ[e] + lR[e];
+            }
+            for (int n = 0; n < ldpcN; ++n) {
+                float tmp = lPostP[n];
+                if (tmp > 0) src[n] = 0;
+                else if (tmp < 0) src[n] = 1;
+            }
+            unsigned char flag = 0;
+            for (int row = 0; row < ldpcM && !flag; ++row) {
+                unsigned char result = 0;
+                for (int ptr = t->hRowFirstPtr[row]; ptr != -1; ptr = t->hRowNextPtr[ptr])
+                    if (src[t->hCols[ptr]]) result ^= 1;
+                if (result) flag = 1;
+            }
+            ++time;
+            if (!flag) break;
+            if (time == j->times) break;
+        }
+        if (j->info) {
+            uint8_t *o = j->info + (size_t)b * KB;
+            memset(o, 0, (size_t)KB);
+            for (int i = 0; i < K; ++i)
+                if (src[i]) o[i >> 3] |= (uint8_t)(1u << (i & 7));
+        }
+        if (j->iters) j->iters[b] = time;
+        if (j->hard) memcpy(j->hard + (size_t)b * ldpcN, src, (size_t)ldpcN);
+        if (j->post) memcpy(j->post + (size_t)b * ldpcN, lPostP, sizeof(float) * (size_t)ldpcN);
+    }
+    free(lQ); free(lR); free(lPostP); free(src);
+    return NULL;
+}
+
+int oracle_tdmp_layering_ok(const oracle_tables *t, int z) {
+    if (z < 1 || t->M % z) return 0;
+    int *seen = (int *)malloc(sizeof(int) * (size_t)t->N);
+    for (int n = 0; n < t->N; ++n) seen[n] = -1;
+    int ok = 1;
+    for (int e = 0; e < t->nnz && ok; ++e) {
+        int layer = t->hRows[e] / z;
+        if (seen[t->hCols[e]] == layer) ok = 0;
+        seen[t->hCols[e]] = layer;
+    }
+    free(seen);
+    return ok;
+}
+
+int oracle_decode_tdmp_batch(const oracle_tables *t, int K, int times, int z, const float *llr, int64_t ncw,
+                             uint8_t *info, int32_t *iters, uint8_t *hard, float *post, int nthreads) {
+    if (!oracle_tdmp_layering_ok(t, z)) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > ncw) nthreads = ncw > 0 ? (int)ncw : 1;
+    tdjob_t jobs[256];
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; ++i) {
+        tdjob_t *j = &jobs[i];
+        j->t = t; j->K = K; j->times = times; j->z = z; j->llr = llr;
+        j->b0 = ncw * i / nthreads; j->b1 = ncw * (i + 1) / nthreads;
+        j->info = info; j->iters = iters; j->hard = hard; j->post = post;
+    }
+    if (nthreads == 1) { tdjob_run(&jobs[0]); return 0; }
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, tdjob_run, &jobs[i]);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
+
 /* reference MyLdpc.cpp:1063-1072: bit (LSB first) 1 -> -1.0, 0 -> +1.0 */
 void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out) {
     for (int charOffset = 0; charOffset < nbytes; ++charOffset) {

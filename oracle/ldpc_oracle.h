@@ -83,6 +83,25 @@ int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float
                            uint8_t *info, int32_t *iters, uint8_t *hard, float *post0, float *post1,
                            int nthreads);
 
+/* ---- layered min-sum (DecodeTDMP) ----------------------------------------------------------------
+ * Restates the schedule the reference's TDMP path intends (host loop Coder::decodeOnceTDMP,
+ * MyLdpc.cpp:889-976; kernels decodeInitTDMP / refreshRTDMP / refreshPostPTDMP / refreshQTDMP /
+ * hardDecisionTDMP, decodeCL.c:203-292): the rows are processed in layers of z consecutive rows (one block
+ * row of the QC matrix); inside a layer  lQ = lPostP - lR,  lR = min-sum over the row's other edges
+ * (clamp 1000, as decodeCPU),  lPostP = lQ + lR;  after the last layer a hard decision
+ * (>0 -> 0, <0 -> 1, ==0 keeps the previous bit; bits start at 0 here, the reference's buffer is
+ * uninitialised), the syndrome check, ++time, stop if clean or time == times.
+ * As shipped the reference's host loop cannot produce this (it sizes a layer with
+ * hRowRange[blockRow + z] instead of hRowRange[(blockRow+1)*z], MyLdpc.cpp:907,958; lQ is indexed
+ * without the layer offset in refreshPostPTDMP, decodeCL.c:258; decodeInitTDMP seeds only the first N
+ * edges), and it exists only as OpenCL kernels: there is nothing to run, so this restatement follows
+ * the kernels' arithmetic with the layer bookkeeping repaired.  Parity for DecodeTDMP is
+ * GPU == this oracle ("unpinned").  Returns -1 if some column appears twice inside a layer (the
+ * reference's per-edge threads would race there).                                                     */
+int oracle_tdmp_layering_ok(const oracle_tables *t, int z);
+int oracle_decode_tdmp_batch(const oracle_tables *t, int K, int times, int z, const float *llr, int64_t ncw,
+                             uint8_t *info, int32_t *iters, uint8_t *hard, float *post, int nthreads);
+
 /* Restates Coder::test's bit->BPSK map (reference MyLdpc.cpp:1061-1072), noise supplied by
  * the caller (the reference's rand()-based Box-Muller is unseeded).                      */
 void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out);

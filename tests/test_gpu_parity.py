@@ -347,3 +347,74 @@ def test_sum_product_unsupported_on_long_codes():
     with pytest.raises(m.LdpcError) as e:
         dec.decode_device(_torch().zeros((4, N), dtype=_torch().float32, device="cuda"))
     assert e.value.code == -3
+
+
+@pytest.mark.parametrize("sigma", [0.45, 0.55, 0.6, 0.66, 0.9])
+def test_layered_min_sum_matches_restated_oracle(default_code, sigma):
+    """DecodeTDMP: the layered min-sum kernel against the oracle's restatement of the schedule the reference's
+    TDMP kernels intend (decodeCL.c:203-292 / decodeOnceTDMP, layer bookkeeping repaired).  Same IEEE fp32
+    operations in the same order on both sides: bits, iteration counts and posteriors must be identical.
+    (The reference has no runnable TDMP: this parity is GPU == restated oracle.)"""
+    import myldpccppapi_b200 as m
+    c = default_code
+    llr = awgn_llr(300 + 5, c["N"], sigma, seed=int(sigma * 1000) + 2)
+    llr[0, :] = 0.0           # P == 0 everywhere: every bit keeps its initial 0, the word is "clean" at iteration 1
+    llr[1, ::4] = -0.0
+    llr[2, :] = -1.0
+    llr[2, ::7] = 0.0
+    o = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40)
+    info, iters, hard, post = oracle.decode_tdmp(o, llr, c["N"] // 24)
+    dec = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    dec.set_algorithm(2)
+    torch = _torch()
+    out = dec.decode_device(torch.from_numpy(llr).cuda(), want_hard=True, want_post=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["iters"].cpu().numpy(), iters)
+    assert np.array_equal(out["info"].cpu().numpy(), info)
+    assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(hard, axis=1, bitorder="little"))
+    assert np.array_equal(out["post"].cpu().numpy(), post)
+    dec.set_algorithm(0)
+    assert_parity(_run_device(dec, llr), o.decode(llr), c["N"], what="min-sum after layered")
+
+
+def test_layered_other_rates_sizes_and_caps():
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    for rate, name, num, den, N in [(0, "1/2", 1, 2, 576), (1, "2/3A", 2, 3, 672), (5, "5/6", 5, 6, 576), (3, "3/4A", 3, 4, 1152)]:
+        K = N * num // den
+        rp, ci, M = oracle.wimax_H(N, name)
+        llr = awgn_llr(70, N, sigma_from_ebn0(2.2, num / den), seed=rate + 17)
+        for cap in (1, 2, 40):
+            o = oracle.Oracle(M, N, K, rp, ci, times=cap)
+            info, iters, hard, post = oracle.decode_tdmp(o, llr, N // 24)
+            dec = m.Decoder.wimax(K, N, rate, max_iter=cap)
+            dec.set_algorithm(2)
+            out = dec.decode_device(torch.from_numpy(llr).cuda(), want_hard=True, want_post=True)
+            torch.cuda.synchronize()
+            assert np.array_equal(out["iters"].cpu().numpy(), iters), (name, N, cap)
+            assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(hard, axis=1, bitorder="little")), (name, N, cap)
+            assert np.array_equal(out["post"].cpu().numpy(), post), (name, N, cap)
+    # early termination off: every word runs to the cap
+    rp, ci, M = oracle.wimax_H(576, "3/4B")
+    dec = m.Decoder.wimax(432, 576, 4, max_iter=7)
+    dec.set_algorithm(2)
+    dec.set_early_termination(False)
+    out = dec.decode_device(torch.from_numpy(awgn_llr(40, 576, 0.4, seed=3)).cuda())
+    assert (out["iters"].cpu().numpy() == 7).all()
+
+
+def test_layered_needs_a_layer_height():
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.regular_code()
+    dec = m.Decoder(M, N, K, rp, ci)
+    with pytest.raises(m.LdpcError) as e:
+        dec.set_algorithm(2)
+    assert e.value.code == -3
+    rp, ci, M = oracle.wimax_H(576, "3/4B")
+    dec = m.Decoder(M, 576, 432, rp, ci)          # CSR constructor: z unknown until told
+    with pytest.raises(m.LdpcError):
+        dec.set_algorithm(2)
+    dec.set_layer_height(24)
+    dec.set_algorithm(2)
+    with pytest.raises(m.LdpcError):              # 16 rows per layer: rows of a circulant collide with the next block row
+        dec.set_layer_height(16)

@@ -5,8 +5,10 @@
 // Eigen dependency are gone.  Decoding runs on the sm_100a CUDA decoder in libldpc_b200.so
 // (include/ldpc_b200.h): DecodeSP selects the probability-domain sum-product kernel (the semantics of the
 // reference's decodeOnceSP, MyLdpc.cpp:977-1059 / decodeCL.c:3-108; codes too large for its on-chip layout
-// fall back to min-sum, reported through lastError()); every other decodeType runs min-sum with the
-// semantics of the reference's Coder::decodeCPU (MyLdpc.cpp:684-784).  There is no CPU decode path in
+// fall back to min-sum, reported through lastError()); DecodeTDMP and DecodeTDMPCL select the layered
+// min-sum kernel (the schedule decodeOnceTDMP intends, MyLdpc.cpp:889-976 / decodeCL.c:203-292, with the
+// same fallback); DecodeCPU, DecodeMS and DecodeMSCL run flooding min-sum with the semantics of the
+// reference's Coder::decodeCPU (MyLdpc.cpp:684-784).  There is no CPU decode path in
 // this library, DecodeCPU included.
 //
 //   reference                         here

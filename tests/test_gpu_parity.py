@@ -257,6 +257,13 @@ def test_coder_decode_sp_uses_the_sum_product_kernel(default_code):
     assert coder.decode(post, out, srcLength, m.DecodeCPU) == 0
     assert np.array_equal(coder.lastIterations, ms_iters)
     assert np.array_equal(out[:srcLength], ms_info.reshape(-1))
+    # DecodeTDMP / DecodeTDMPCL -> the layered kernel
+    td_info, td_iters, _, _ = oracle.decode_tdmp(o, post.reshape(ncw, N), N // 24)
+    assert not np.array_equal(td_iters, ms_iters)
+    for t in (m.DecodeTDMP, m.DecodeTDMPCL):
+        assert coder.decode(post, out, srcLength, t) == 0
+        assert np.array_equal(coder.lastIterations, td_iters)
+        assert np.array_equal(out[:srcLength], td_info.reshape(-1))
 
 
 def _run_cli(name, *args):
@@ -282,6 +289,9 @@ def test_cpp_coder_cli_roundtrip():
     kv_sp, _ = _run_cli("mytest", 54000, 256, 5.0, "SP", 11)
     assert float(kv_sp["MeanIterations"]) != float(kv_ms["MeanIterations"])
     assert float(kv_sp["MeanIterations"]) < float(kv_ms["MeanIterations"])
+    kv_td, _ = _run_cli("mytest", 54000, 256, 5.0, "TDMP", 11)
+    assert float(kv_td["MeanIterations"]) < float(kv_ms["MeanIterations"])
+    assert int(kv_td["ErrNum"]) <= int(kv_ms["ErrNum"])
 
 
 def test_reference_test_cpp_runs_against_the_drop_in():

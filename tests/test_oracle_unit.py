@@ -1,5 +1,6 @@
 """Oracle unit tests on hand-checkable parity-check matrices (no reference needed)."""
 import numpy as np
+import pytest
 
 import oracle
 
@@ -102,3 +103,25 @@ def test_sum_product_restatement_basics():
     sp = oracle.decode_sp(o, y)
     ms = o.decode(y, literal=False)
     assert sp[2].sum() <= ms[2].sum()
+
+
+def test_layered_restatement_basics():
+    """The layered (TDMP) restatement: clean words stop at iteration 1, it needs fewer iterations than the
+    flooding schedule on the same noisy words, rejects layers whose rows share a column, and an all-zero
+    input keeps every bit at its initial 0 (the P == 0 rule of hardDecisionTDMP)."""
+    rp, ci, M = oracle.wimax_H(576, "3/4B")
+    o = oracle.Oracle(M, 576, 432, rp, ci)
+    info, iters, hard, post = oracle.decode_tdmp(o, np.ones((3, 576), dtype=np.float32), 24)
+    assert np.all(iters == 1) and not hard.any()
+    rng = np.random.default_rng(5)
+    y = (1 + 0.55 * rng.standard_normal((256, 576))).astype(np.float32)
+    td = oracle.decode_tdmp(o, y, 24)
+    ms = o.decode(y, literal=False)
+    assert td[1].mean() < 0.8 * ms[1].mean()
+    assert td[2].sum() <= ms[2].sum()
+    z0 = oracle.decode_tdmp(o, np.zeros((1, 576), dtype=np.float32), 24)
+    assert z0[1][0] == 1 and not z0[2].any()
+    assert oracle.lib().oracle_tdmp_layering_ok(o._t, 24) == 1
+    assert oracle.lib().oracle_tdmp_layering_ok(o._t, 48) == 0
+    with pytest.raises(ValueError):
+        oracle.decode_tdmp(o, y[:1], 48)

@@ -359,7 +359,7 @@ def main() -> None:
     roofline = dict(roof_smem if onchip else roof_hbm)
     roofline.update({
         "kernel": {"group": "ldpc_ms_group_kernel", "cluster": "ldpc_ms_cluster_kernel", "lane16": "ldpc_ms_lane16_kernel",
-                   "lane_smem": "ldpc_ms_lane_kernel<true>"}.get(info["path_name"], "ldpc_ms_lane_kernel<false>"),
+                   "lane_smem": "ldpc_ms_lane_kernel<true>", "stream": "ldpc_ms_stream_kernel"}.get(info["path_name"], "ldpc_ms_lane_kernel<false>"),
         "launch_ms": ms_step, "traffic": roof_hbm.get("traffic"),
         "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},
         "hbm": roof_hbm, "smem": roof_smem,

@@ -58,6 +58,8 @@ enum {
                                       32/G graph nodes per warp instruction (G=16 short codes, G=1 N~8k) */
     LDPC_B200_PATH_CLUSTER = 5,    /* long codes: one codeword per 8-CTA thread-block cluster, posteriors and
                                       messages in distributed shared memory (DSMEM gathers, cluster barriers) */
+    LDPC_B200_PATH_STREAM = 6,     /* long codes with check and variable degree <= 8: explicit per-edge messages in a
+                                      global workspace, fixed-stride tables, prefetched indices, variable bundles   */
     LDPC_B200_PATH_LANE16 = 3      /* tuned short-code path: lane = codeword, channel values in
                                       registers, 16-byte check state and index tables in shared memory */
 };

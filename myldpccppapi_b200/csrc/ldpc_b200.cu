@@ -21,6 +21,7 @@
 #include "ldpc_cluster.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
+#include "ldpc_stream.cuh"
 #include "ldpc_tables.h"
 
 using namespace ldpc_b200;
@@ -110,6 +111,13 @@ struct ldpc_b200_decoder {
     uint32_t* dc_var_of_pos = nullptr;
     uint32_t* dc_out_addr = nullptr;
     bool cluster_ready = false;
+    // STREAM tables (long codes, global workspace)
+    uint4* ds_cn_tab = nullptr;
+    uint4* ds_vn_tab = nullptr;
+    uint32_t* ds_var_of_pos = nullptr;
+    uint32_t* ds_pos_of_var = nullptr;
+    int s_np = 0, s_nb8 = 0, s_nb4 = 0, s_nb2 = 0;
+    bool stream_ready = false;
     // TDMP (layered) tables
     int layer_z = 0;  // rows per layer; 0 = unknown (layered decoding unavailable)
     TdmpPlan tdmp;
@@ -957,6 +965,65 @@ int launch_cluster_t(const ClusterParams& q, int nclusters_wanted, int threads, 
     return LDPC_B200_OK;
 }
 
+// ---- STREAM layout (see ldpc_stream.cuh) --------------------------------------------------------------
+struct StreamShape { int np = 0, nb8 = 0, nb4 = 0, nb2 = 0; };
+
+StreamShape stream_shape(const HostTables& t) {
+    StreamShape sh;
+    int n8 = 0, n4 = 0, n2 = 0;
+    for (int v = 0; v < t.N; ++v) {
+        const int d = t.col_ptr[v + 1] - t.col_ptr[v];
+        if (d > 4) ++n8; else if (d > 2) ++n4; else ++n2;
+    }
+    sh.nb8 = n8; sh.nb4 = (n4 + 1) / 2; sh.nb2 = (n2 + 3) / 4;
+    sh.np = sh.nb8 + 2 * sh.nb4 + 4 * sh.nb2;
+    return sh;
+}
+
+int upload_stream_tables(ldpc_b200_decoder* h) {
+    if (h->stream_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    const StreamShape sh = stream_shape(t);
+    std::vector<uint32_t> var_of_pos((size_t)sh.np, kStreamNone), pos_of_var(t.N);
+    {
+        int p8 = 0, p4 = sh.nb8, p2 = sh.nb8 + 2 * sh.nb4;
+        for (int v = 0; v < t.N; ++v) {
+            const int d = t.col_ptr[v + 1] - t.col_ptr[v];
+            int& slot = d > 4 ? p8 : (d > 2 ? p4 : p2);
+            var_of_pos[slot] = (uint32_t)v;
+            pos_of_var[v] = (uint32_t)slot;
+            ++slot;
+        }
+    }
+    std::vector<uint32_t> cn_tab((size_t)t.M * 8, kStreamNone), vn_tab((size_t)(sh.nb8 + sh.nb4 + sh.nb2) * 8, kStreamNone);
+    for (int r = 0; r < t.M; ++r)
+        for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) cn_tab[(size_t)r * 8 + (e - t.row_ptr[r])] = pos_of_var[t.col_idx[e]];
+    for (int pos = 0; pos < sh.np; ++pos) {
+        const uint32_t v = var_of_pos[pos];
+        if (v == kStreamNone) continue;
+        size_t base;  // first table entry of this variable
+        if (pos < sh.nb8) base = (size_t)pos * 8;
+        else if (pos < sh.nb8 + 2 * sh.nb4) base = (size_t)sh.nb8 * 8 + (size_t)(pos - sh.nb8) * 4;
+        else base = (size_t)(sh.nb8 + sh.nb4) * 8 + (size_t)(pos - sh.nb8 - 2 * sh.nb4) * 2;
+        for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+            const uint32_t chk = t.vn_edge[k] >> kPosBits, j = t.vn_edge[k] & ((1u << kPosBits) - 1u);
+            vn_tab[base + (size_t)(k - t.col_ptr[v])] = chk * 8u + j;  // ascending row = the reference's summation order
+        }
+    }
+    CU_TRY(cudaMalloc(&h->ds_cn_tab, cn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->ds_vn_tab, vn_tab.size() * 4));
+    CU_TRY(cudaMalloc(&h->ds_var_of_pos, var_of_pos.size() * 4));
+    CU_TRY(cudaMalloc(&h->ds_pos_of_var, pos_of_var.size() * 4));
+    CU_TRY(cudaMemcpy(h->ds_cn_tab, cn_tab.data(), cn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->ds_vn_tab, vn_tab.data(), vn_tab.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->ds_var_of_pos, var_of_pos.data(), var_of_pos.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->ds_pos_of_var, pos_of_var.data(), pos_of_var.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += (cn_tab.size() + vn_tab.size() + var_of_pos.size() + pos_of_var.size()) * 4;
+    h->s_np = sh.np; h->s_nb8 = sh.nb8; h->s_nb4 = sh.nb4; h->s_nb2 = sh.nb2;
+    h->stream_ready = true;
+    return LDPC_B200_OK;
+}
+
 // ---- TDMP layout (see ldpc_tdmp.cuh) ------------------------------------------------------------------
 int tdmp_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
@@ -1144,7 +1211,11 @@ int make_plan(ldpc_b200_decoder* h) {
     const size_t state_bytes = ((size_t)2 * t.N + (size_t)3 * t.M) * kLanes * sizeof(float);
     const size_t static_smem = 1024;  // s_group, s_flag + slack
     int path = h->forced_path;
-    if (path < 0) path = (state_bytes + static_smem <= h->smem_optin) ? LDPC_B200_PATH_LANE_SMEM : LDPC_B200_PATH_LANE_GLOBAL;
+    const bool stream_ok = t.max_row_weight <= 8 && t.max_col_weight <= 8 && (uint64_t)t.M * 8 * kLanes < (1ull << 32);
+    if (path == LDPC_B200_PATH_STREAM && !stream_ok)
+        return fail(LDPC_B200_ERR_UNSUPPORTED, "the streamed global path needs check and variable degree <= 8");
+    if (path < 0) path = (state_bytes + static_smem <= h->smem_optin) ? LDPC_B200_PATH_LANE_SMEM
+                         : (stream_ok ? LDPC_B200_PATH_STREAM : LDPC_B200_PATH_LANE_GLOBAL);
     if (path == LDPC_B200_PATH_LANE_SMEM) {
         if (state_bytes + static_smem > h->smem_optin)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "code too large for the shared-memory lane path");
@@ -1159,6 +1230,13 @@ int make_plan(ldpc_b200_decoder* h) {
         pl.smem = 0;
         pl.ctas = h->sm_count;
         pl.ws_stride = state_bytes / sizeof(float);
+    } else if (path == LDPC_B200_PATH_STREAM) {
+        pl.path = path;
+        pl.threads = 1024;
+        if (const char* env = std::getenv("LDPC_B200_STREAM_THREADS")) { const int th = std::atoi(env); if (th >= 32 && th <= 1024 && th % 32 == 0) pl.threads = th; }
+        pl.smem = 0;
+        pl.ctas = h->sm_count;
+        pl.ws_stride = ((size_t)2 * stream_shape(t).np + (size_t)8 * t.M) * kLanes;
     } else {
         return fail(LDPC_B200_ERR_UNSUPPORTED, "unknown kernel path");
     }
@@ -1168,7 +1246,7 @@ int make_plan(ldpc_b200_decoder* h) {
 }
 
 int ensure_workspace(ldpc_b200_decoder* h) {
-    if (h->plan.path != LDPC_B200_PATH_LANE_GLOBAL) return LDPC_B200_OK;
+    if (h->plan.path != LDPC_B200_PATH_LANE_GLOBAL && h->plan.path != LDPC_B200_PATH_STREAM) return LDPC_B200_OK;
     const size_t need = h->plan.ws_stride * sizeof(float) * (size_t)h->plan.ctas;
     if (h->ws_bytes >= need) return LDPC_B200_OK;
     if (h->d_ws) { cudaFree(h->d_ws); h->d_ws = nullptr; h->ws_bytes = 0; }
@@ -1304,6 +1382,30 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         return LDPC_B200_OK;
     }
 
+    if (pl.path == LDPC_B200_PATH_STREAM) {
+        rc = upload_stream_tables(h);
+        if (rc) return rc;
+        StreamParams q;
+        q.cn_tab = h->ds_cn_tab; q.vn_tab = h->ds_vn_tab; q.var_of_pos = h->ds_var_of_pos; q.pos_of_var = h->ds_pos_of_var;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.NP = h->s_np;
+        q.nb8 = h->s_nb8; q.nb4 = h->s_nb4; q.nb2 = h->s_nb2;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.ws = h->d_ws; q.ws_stride = pl.ws_stride;
+        q.counter = ctr; q.ngroups = (int)ngroups;
+        // the workspace is shared by every launch of this handle: serialise launches on it
+        if (h->ws_event_valid) CU_TRY(cudaStreamWaitEvent(stream, h->ws_event, 0));
+        if (pl.threads <= 512) ldpc_ms_stream_kernel<512><<<grid, pl.threads, 0, stream>>>(q);
+        else if (pl.threads <= 768) ldpc_ms_stream_kernel<768><<<grid, pl.threads, 0, stream>>>(q);
+        else ldpc_ms_stream_kernel<1024><<<grid, pl.threads, 0, stream>>>(q);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(h->ws_event, stream));
+        h->ws_event_valid = true;
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
+
     DecodeParams p;
     p.row_ptr = h->d_row_ptr;
     p.cn_col = h->d_cn_col;
@@ -1423,6 +1525,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
             cudaFree(h->dt_cn_tab);
+            cudaFree(h->ds_cn_tab); cudaFree(h->ds_vn_tab); cudaFree(h->ds_var_of_pos); cudaFree(h->ds_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
         }

@@ -57,7 +57,7 @@ def test_regular_3_6_every_kernel_path():
     M, N, K, rp, ci = m.codes.regular_code()
     llr = awgn_llr(40, N, 0.84, seed=2)
     ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
-    for path, name in [(1, "lane_global"), (4, "group"), (5, "cluster")]:
+    for path, name in [(1, "lane_global"), (4, "group"), (5, "cluster"), (6, "stream")]:
         dec = m.Decoder(M, N, K, rp, ci)
         dec.set_path(path)
         assert dec.info()["path_name"] == name
@@ -163,14 +163,18 @@ def test_ira_64800_parity():
     rng = np.random.default_rng(9)
     u = rng.integers(0, 2, (34, K)).astype(np.uint8)
     cwb = m.codes.ira_encode(M, N, K, rp, ci, u)
-    assert dec.info()["path_name"] == "lane_global"
+    assert dec.info()["path_name"] == "stream"
+    lg = m.Decoder(M, N, K, rp, ci, max_iter=50)
+    lg.set_path(1)     # compressed check state in the global workspace (any degree)
+    assert lg.info()["path_name"] == "lane_global"
     clus = m.Decoder(M, N, K, rp, ci, max_iter=50)
     clus.set_path(5)   # one codeword per 8-CTA cluster, state in distributed shared memory
     assert clus.info()["path_name"] == "cluster"
     for sigma, seed in [(0.8, 1), (0.97, 2)]:
         llr = awgn_llr(34, N, sigma, seed=seed, bits=cwb)
         ref = o.decode(llr, literal=False)
-        assert_parity(_run_device(dec, llr), ref, N, what="ira lane_global sigma=%g" % sigma)
+        assert_parity(_run_device(dec, llr), ref, N, what="ira stream sigma=%g" % sigma)
+        assert_parity(_run_device(lg, llr), ref, N, what="ira lane_global sigma=%g" % sigma)
         assert_parity(_run_device(clus, llr), ref, N, what="ira cluster sigma=%g" % sigma)
 
 

@@ -371,7 +371,7 @@ def main() -> None:
     # ---- CPU baseline: the oracle on a bounded sample of the same floats (+ parity spot check)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sample_max = min(ncw, 8192)
+        sample_max = min(ncw, 65536)  # cpu_decode_timed sizes the sample for ~12 s of host work
         y = llr[:sample_max].cpu().numpy()
         n, secs, ref, thr = cpu_decode_timed(code, cap, y)
         ok = bool(np.array_equal(ref[0], out["info"][:n].cpu().numpy()) and np.array_equal(ref[1], out["iters"][:n].cpu().numpy()))

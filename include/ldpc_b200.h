@@ -21,6 +21,7 @@
  *   ldpc_b200_decode_device   <- the same with device-resident buffers (no PCIe leg)
  *   ldpc_b200_destroy         <- Coder::~Coder / cl::Buffer RAII (MyLdpc.cpp:31-51)
  *   ldpc_b200_synth_llr       <- Coder::test BPSK + AWGN          (MyLdpc.cpp:1061-1105)
+ *   ldpc_b200_encode_*        <- Coder::forEncoder / Coder::encode (MyLdpc.cpp:137-165, 554-569, 633-682)
  *
  * Decode semantics are those of Coder::decodeCPU (MyLdpc.cpp:684-784), per codeword:
  * flooding min-sum in fp32, messages clamped at 1000, posterior accumulated from the channel
@@ -142,6 +143,15 @@ int ldpc_b200_decode_device(ldpc_b200_handle h, const float *d_llr, int64_t ncw,
  * are in host memory.  Pinned buffers get full-speed async copies.                      */
 int ldpc_b200_decode_host(ldpc_b200_handle h, const float *llr, int64_t ncw, uint8_t *info,
                           uint8_t *hard, int32_t *iters, float *post);
+
+/* Systematic encoder on the device (Coder::forEncoder + Coder::encode, MyLdpc.cpp:137-165, 554-569, 633-682).
+ * info: [ncw][K/8] bytes, bits LSB-first (the reference's srcCode split per codeword); codewords: [ncw][N/8]
+ * bytes in the reference's priorCode layout (info bits first, then the M parity bits of H c = 0).
+ * encoder_init solves the parity part of H over GF(2) once (needs N - K == M, an invertible parity part,
+ * K and N multiples of 8, K <= 4096) and is implied by the first encode call.                          */
+int ldpc_b200_encoder_init(ldpc_b200_handle h);
+int ldpc_b200_encode_device(ldpc_b200_handle h, const uint8_t *d_info, int64_t ncw, uint8_t *d_codewords, void *stream);
+int ldpc_b200_encode_host(ldpc_b200_handle h, const uint8_t *info, int64_t ncw, uint8_t *codewords);
 
 /* Synthetic BPSK-AWGN channel on the device: y = (bit ? -1 : +1) + sigma * n, n ~ N(0,1)
  * from a counter-based generator keyed by (seed, codeword, position).  d_bits: packed

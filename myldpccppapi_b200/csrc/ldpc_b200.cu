@@ -22,6 +22,7 @@
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
 #include "ldpc_stream.cuh"
+#include "ldpc_encode.cuh"
 #include "ldpc_tables.h"
 
 using namespace ldpc_b200;
@@ -118,6 +119,10 @@ struct ldpc_b200_decoder {
     uint32_t* ds_pos_of_var = nullptr;
     int s_np = 0, s_nb8 = 0, s_nb4 = 0, s_nb2 = 0;
     bool stream_ready = false;
+    // encoder (X transposed, see ldpc_encode.cuh)
+    uint32_t* de_xt = nullptr;
+    int enc_kw = 0, enc_mw = 0;
+    bool encoder_ready = false;
     // TDMP (layered) tables
     int layer_z = 0;  // rows per layer; 0 = unknown (layered decoding unavailable)
     TdmpPlan tdmp;
@@ -1524,7 +1529,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dc_cn_tab); cudaFree(h->dc_vn_tab); cudaFree(h->dc_var_of_pos); cudaFree(h->dc_out_addr);
             cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
-            cudaFree(h->dt_cn_tab);
+            cudaFree(h->dt_cn_tab); cudaFree(h->de_xt);
             cudaFree(h->ds_cn_tab); cudaFree(h->ds_vn_tab); cudaFree(h->ds_var_of_pos); cudaFree(h->ds_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
@@ -1599,6 +1604,66 @@ int ldpc_b200_set_layer_height(ldpc_b200_handle h, int z) {
         if (rc) { h->layer_z = prev; return rc; }
     }
     return LDPC_B200_OK;
+}
+
+int ldpc_b200_encoder_init(ldpc_b200_handle h) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->encoder_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    if (h->K % 8 || t.N % 8) return fail(LDPC_B200_ERR_UNSUPPORTED, "the encoder needs K and N to be multiples of 8");
+    if (h->K > 32 * 32 * kEncMaxKW) return fail(LDPC_B200_ERR_UNSUPPORTED, "the encoder handles K <= 4096");
+    std::vector<uint32_t> xt;
+    const std::string msg = build_encoder(t, h->K, &xt, &h->enc_kw, &h->enc_mw);
+    if (!msg.empty()) return fail(LDPC_B200_ERR_UNSUPPORTED, msg);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    CU_TRY(cudaMalloc(&h->de_xt, xt.size() * 4));
+    CU_TRY(cudaMemcpy(h->de_xt, xt.data(), xt.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += xt.size() * 4;
+    h->encoder_ready = true;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_encode_device(ldpc_b200_handle h, const uint8_t* d_info, int64_t ncw, uint8_t* d_codewords, void* stream) {
+    if (!h || (ncw > 0 && (!d_info || !d_codewords)) || ncw < 0) return fail(LDPC_B200_ERR_ARG, "bad argument");
+    if (!h->encoder_ready) {
+        int rc = ldpc_b200_encoder_init(h);
+        if (rc) return rc;
+    }
+    if (ncw == 0) return LDPC_B200_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    EncodeParams q;
+    q.xt = h->de_xt; q.K = h->K; q.N = h->host.N; q.M = h->host.M; q.KW = h->enc_kw; q.MW = h->enc_mw;
+    q.info = d_info; q.out = d_codewords; q.ncw = ncw;
+    const int64_t blocks = std::min<int64_t>((ncw + 7) / 8, (int64_t)h->sm_count * 8);
+    ldpc_encode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(q);
+    CU_TRY(cudaGetLastError());
+    h->launches += 1;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_encode_host(ldpc_b200_handle h, const uint8_t* info, int64_t ncw, uint8_t* codewords) {
+    if (!h || (ncw > 0 && (!info || !codewords)) || ncw < 0) return fail(LDPC_B200_ERR_ARG, "bad argument");
+    if (!h->encoder_ready) {
+        int rc = ldpc_b200_encoder_init(h);
+        if (rc) return rc;
+    }
+    if (ncw == 0) return LDPC_B200_OK;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    const size_t KB = (size_t)h->K / 8, NB = (size_t)h->host.N / 8;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CU_TRY(cudaMalloc(&d_in, KB * (size_t)ncw));
+    if (cudaMalloc(&d_out, NB * (size_t)ncw) != cudaSuccess) { cudaFree(d_in); return fail(LDPC_B200_ERR_CUDA, "cudaMalloc(codewords)"); }
+    int rc = LDPC_B200_OK;
+    if (cudaMemcpy(d_in, info, KB * (size_t)ncw, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(LDPC_B200_ERR_CUDA, "cudaMemcpy(info)");
+    if (!rc) rc = ldpc_b200_encode_device(h, d_in, ncw, d_out, nullptr);
+    if (!rc && cudaMemcpy(codewords, d_out, NB * (size_t)ncw, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(LDPC_B200_ERR_CUDA, "cudaMemcpy(codewords)");
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
 }
 
 int ldpc_b200_set_path(ldpc_b200_handle h, int path) {

@@ -89,4 +89,39 @@ std::string wimax_csr(int K, int N, int rate, std::vector<int32_t>* row_ptr, std
     return std::string();
 }
 
+std::string build_encoder(const HostTables& t, int K, std::vector<uint32_t>* xt, int* KW, int* MW) {
+    const int M = t.M, N = t.N;
+    if (N - K != M || K < 1) return "encoder needs a square parity part (N - K == M)";
+    const int W = (N + 63) / 64;
+    std::vector<uint64_t> a((size_t)M * W, 0);  // row r: columns permuted to [parity (M) | info (K)]
+    auto getbit = [&](int r, int c) { return (a[(size_t)r * W + (c >> 6)] >> (c & 63)) & 1ull; };
+    for (int r = 0; r < M; ++r)
+        for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) {
+            const int c = t.col_idx[e], cc = c >= K ? c - K : M + c;
+            a[(size_t)r * W + (cc >> 6)] ^= 1ull << (cc & 63);
+        }
+    for (int c = 0; c < M; ++c) {  // Gauss-Jordan over GF(2) on the parity block
+        int piv = -1;
+        for (int r = c; r < M; ++r)
+            if (getbit(r, c)) { piv = r; break; }
+        if (piv < 0) return "parity part of H is singular";
+        if (piv != c)
+            for (int w = 0; w < W; ++w) std::swap(a[(size_t)piv * W + w], a[(size_t)c * W + w]);
+        const uint64_t* src = &a[(size_t)c * W];
+        for (int r = 0; r < M; ++r)
+            if (r != c && getbit(r, c)) {
+                uint64_t* dst = &a[(size_t)r * W];
+                for (int w = c >> 6; w < W; ++w) dst[w] ^= src[w];
+            }
+    }
+    *KW = (K + 31) / 32;
+    *MW = (M + 31) / 32;
+    const size_t MP = (size_t)*MW * 32;
+    xt->assign((size_t)*KW * MP, 0u);
+    for (int r = 0; r < M; ++r)
+        for (int k = 0; k < K; ++k)
+            if (getbit(r, M + k)) (*xt)[(size_t)(k >> 5) * MP + r] |= 1u << (k & 31);
+    return "";
+}
+
 }  // namespace ldpc_b200

@@ -34,4 +34,10 @@ std::string build_tables(int M, int N, const int32_t* row_ptr, const int32_t* co
 // shift = p*z/96 (integer floor), or p % z for rate_2_3_a.  Emits CSR with ascending columns.
 std::string wimax_csr(int K, int N, int rate, std::vector<int32_t>* row_ptr, std::vector<int32_t>* col_idx, int* M);
 
+// Systematic encoder matrix: with H = [A | B] (B = the last M columns, invertible), the parity bits are
+// p = X u over GF(2), X = B^-1 A (the unique solution of H c = 0; what Coder::forEncoder / Coder::encode compute
+// through the Richardson-Urbanke split, reference MyLdpc.cpp:137-165, 633-682).  Returns X transposed and packed
+// for the device: xt[w * (MW*32) + r] holds info bits 32w .. 32w+31 of row r; KW = ceil(K/32), MW = ceil(M/32).
+std::string build_encoder(const HostTables& t, int K, std::vector<uint32_t>* xt, int* KW, int* MW);
+
 }  // namespace ldpc_b200

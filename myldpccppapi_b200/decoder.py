@@ -138,6 +138,25 @@ class Decoder:
                                               ptr("post"), C.c_void_p(st.cuda_stream)))
         return out
 
+    # -- encode (Coder::forEncoder / Coder::encode on the device) ----------------------
+    def encode_device(self, info):
+        """info: CUDA uint8 tensor [ncw, K/8] (bits LSB-first) -> CUDA uint8 tensor [ncw, N/8] of codewords in
+        the reference's priorCode layout."""
+        import torch
+
+        assert info.is_cuda and info.dtype == torch.uint8 and info.is_contiguous()
+        ncw = info.shape[0]
+        out = torch.empty((ncw, self.N // 8), dtype=torch.uint8, device=info.device)
+        st = torch.cuda.current_stream(info.device)
+        check(self._L.ldpc_b200_encode_device(self._h, info.data_ptr(), ncw, out.data_ptr(), C.c_void_p(st.cuda_stream)))
+        return out
+
+    def encode_host(self, info: np.ndarray) -> np.ndarray:
+        info = np.ascontiguousarray(info, dtype=np.uint8).reshape(-1, self.K // 8)
+        out = np.empty((info.shape[0], self.N // 8), dtype=np.uint8)
+        check(self._L.ldpc_b200_encode_host(self._h, info.ctypes.data, info.shape[0], out.ctypes.data))
+        return out
+
     def decode_host(self, llr: np.ndarray, want_hard: bool = False, want_post: bool = False, out: Optional[dict] = None):
         """llr: host float32 array/tensor [ncw, N] (pinned memory gives full-speed copies).
         Returns numpy arrays {info, iters, hard?, post?}.  Blocking."""

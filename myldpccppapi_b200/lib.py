@@ -51,6 +51,9 @@ SIGNATURES = {
     "ldpc_b200_set_path": (_i, [_vp, _i]),
     "ldpc_b200_set_algorithm": (_i, [_vp, _i]),
     "ldpc_b200_set_layer_height": (_i, [_vp, _i]),
+    "ldpc_b200_encoder_init": (_i, [_vp]),
+    "ldpc_b200_encode_device": (_i, [_vp, _vp, C.c_int64, _vp, _vp]),
+    "ldpc_b200_encode_host": (_i, [_vp, _vp, C.c_int64, _vp]),
     "ldpc_b200_get_info": (_i, [_vp, C.POINTER(Info)]),
     "ldpc_b200_get_csr": (_i, [_vp, _vp, _vp]),
     "ldpc_b200_reserve": (_i, [_vp, _i64]),

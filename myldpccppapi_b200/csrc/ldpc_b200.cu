@@ -312,7 +312,7 @@ struct GrpShape {
 
 bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool sp, GrpShape* out) {
     // G = 8 runs two CTAs per SM (phase-shifted check / variable passes overlap): half the budget each
-    const size_t smem_limit = G == 8 ? (smem_limit_in + 1024) / 2 - 1024 : smem_limit_in;
+    const size_t smem_limit = G == 8 ? (smem_limit_in + 1024) / 2 - 1024 : (G == 4 ? (smem_limit_in + 1024) / 3 - 1024 : smem_limit_in);
     const int SUB = 32 / G, NL = W * SUB;
     GrpShape sh;
     sh.G = G; sh.W = W;
@@ -351,9 +351,20 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool s
 
 bool group_pick(const HostTables& t, size_t smem_limit, bool sp, GrpShape* best) {
     int g_lo = 1, g_hi = 16, w_lo = 8, w_hi = 32;
-    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16 || g == 8) g_lo = g_hi = g; }
+    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16 || g == 8 || g == 4) g_lo = g_hi = g; }
     if (const char* env = std::getenv("LDPC_B200_GRP_WARPS")) { const int w = std::atoi(env); if (w >= 1 && w <= 32) w_lo = w_hi = w; }
     // instantiated: G = 16 (short codes, tables on chip) and G = 1 (one codeword per CTA)
+    if (g_lo == 4) {  // experiment: three CTAs of 4 words per SM (LDPC_B200_GRP_G=4)
+        bool found = false;
+        GrpShape b;
+        for (int W = w_lo; W <= std::min(w_hi, 9); ++W) {
+            GrpShape sh;
+            if (!group_shape(t, 4, W, smem_limit, sp, &sh) || !sh.tab_smem) continue;
+            if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
+        }
+        if (found) { *best = b; return true; }
+        return false;
+    }
     for (int G : {16, 8, 1}) {
         if (G < g_lo || G > g_hi) continue;
         if (G == 16 && g_lo != 16 && !std::getenv("LDPC_B200_GRP_PREFER_16")) {
@@ -762,6 +773,12 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
         return th <= 768 ? launch_group_t<16, 16, true, 768, false>(q, grid, th, sm, stream)
                          : launch_group_t<16, 16, true, 1024, false>(q, grid, th, sm, stream);
     }
+    if (pl.G == 4 && pl.tab_smem && th <= 288) {
+        if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576L72>(pl, q))
+            return launch_group_t<4, 16, true, 288, false, ProfileWimax34B576L72>(q, grid, th, sm, stream);
+        return pl.y_smem ? launch_group_t<4, 16, true, 288, true>(q, grid, th, sm, stream)
+                         : launch_group_t<4, 16, true, 288, false>(q, grid, th, sm, stream);
+    }
     if (pl.G == 8 && pl.tab_smem && th <= 384) {
         if (pl.t16) return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576, true>(q, grid, th, sm, stream);
         if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576>(pl, q))
@@ -1163,7 +1180,7 @@ int make_plan(ldpc_b200_decoder* h) {
             pl.path = LDPC_B200_PATH_GROUP;
             pl.threads = 32 * sh.W;
             pl.smem = sh.smem;
-            pl.ctas = h->sm_count * (sh.G == 8 ? 2 : 1);
+            pl.ctas = h->sm_count * (sh.G == 8 ? 2 : (sh.G == 4 ? 3 : 1));
             pl.cw_per_cta = sh.G;
             pl.W = sh.W; pl.CS = sh.CS; pl.VS = sh.VS; pl.G = sh.G; pl.dmax = sh.dmax; pl.tab_smem = sh.tab_smem;
             pl.cn_stride = sh.cn_stride; pl.vn_stride = sh.vn_stride; pl.r_rows = sh.r_rows;

@@ -717,6 +717,14 @@ struct ProfileWimax34B576 {
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
 };
 
+// The same code dealt over 72 node lanes (G = 4: 9 warps x 8, three CTAs per SM): 2 check slots, 8 variable slots.
+struct ProfileWimax34B576L72 {
+    static constexpr bool kStatic = true;
+    static constexpr int CS = 2, VS = 8;
+    __host__ __device__ static constexpr int cdeg(int) { return 15; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[8] = {6, 6, 6, 3, 3, 3, 3, 2}; return d[i]; }
+};
+
 // Regular (3,6) code with N = 8192 (BASELINE config 3) dealt over 1024 node lanes (G = 1, 32 warps).
 struct ProfileRegular36N8192 {
     static constexpr bool kStatic = true;
@@ -824,7 +832,7 @@ __device__ __forceinline__ uint32_t grp_cn_static(uint32_t tab, const uint32_t* 
 }
 
 template <int G, int DMAX, bool TAB_SMEM, int MAX_THREADS, bool Y_SMEM, class PROF = GenericProfile, bool T16 = false>
-__global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 384 ? 2 : 1)) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
+__global__ void __launch_bounds__(MAX_THREADS, (MAX_THREADS <= 288 ? 3 : (MAX_THREADS <= 384 ? 2 : 1))) ldpc_ms_group_kernel(const __grid_constant__ GroupParams p) {
     constexpr int SUB = 32 / G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_flag[2][32];

@@ -1756,12 +1756,21 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
     const HostTables& t = h->host;
     if (h->reserved == 0) {
-        // default chunk: a few waves of the persistent grid, bounded to ~256 MB of channel values
+        // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the
+        // persistent grid (bounded to ~256 MB of channel values).  On-chip paths: kernels of consecutive chunks run
+        // concurrently and refill each other's tail, so small chunks win -- 3/4 of a wave measured best
+        // (tools/e2e_chunk_sweep.py: 9472 -> 4.69 ms, 1776 -> 4.42 ms per 65,536 words of Test.cpp's code).
         int64_t wave = (int64_t)h->plan.ctas * h->plan.cw_per_cta;
         int64_t chunk = wave * 4;
         const int64_t cap = std::max<int64_t>(wave, ((int64_t)256 << 20) / ((int64_t)t.N * 4) / wave * wave);
         chunk = std::min(chunk, cap);
         chunk = std::min(chunk, (ncw + wave - 1) / wave * wave);
+        const bool workspace = h->algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM &&
+                               (h->plan.path == LDPC_B200_PATH_LANE_GLOBAL || h->plan.path == LDPC_B200_PATH_STREAM);
+        if (!workspace) {
+            const int64_t g = h->plan.cw_per_cta;
+            chunk = std::min(chunk, std::max<int64_t>(g, wave * 3 / 4 / g * g));
+        }
         int rc = ldpc_b200_reserve(h, chunk);
         if (rc) return rc;
     }

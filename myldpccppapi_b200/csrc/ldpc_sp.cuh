@@ -67,13 +67,17 @@ __device__ __forceinline__ uint32_t sp_check(uint32_t tab, uint32_t dummy_hb, ui
         x[j] = (ent[j] != dummy_hb) ? v : 1.0f;
         syn ^= lds_u32(ent[j] + c4);  // hard bit of the row's j-th variable (dummy entry holds 0)
     }
+    // d_j = ((((x_0 x_1) ...) x_{j-1}) x_{j+1}) ... x_{D-1}: the reference's left-to-right product with edge j skipped
+    // (decodeCL.c:31-37).  Its first j factors are the running prefix, shared by all later edges -- same operations in
+    // the same order, D(D-1)/2 + D - 1 multiplies instead of D(D-1).
+    float pre = 1.0f;
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        float d = 1.0f;
+        float d = pre;
 #pragma unroll
-        for (int k = 0; k < D; ++k)
-            if (k != j) d = __fmul_rn(d, x[k]);
+        for (int k = j + 1; k < D; ++k) d = __fmul_rn(d, x[k]);
         sts_f32(rrow + (uint32_t)j * 128u, d);
+        pre = __fmul_rn(pre, x[j]);  // 1 * x_0 = x_0 exactly
     }
     return syn & 1u;
 }
@@ -96,22 +100,24 @@ __device__ __forceinline__ uint32_t sp_variable(uint32_t q, uint32_t dummy_e, fl
     for (int k = 0; k < D; ++k) {
         valid[k] = e[k] != dummy_e;
         const float d = lds_f32(e[k] + c4);
-        r0[k] = valid[k] ? __fdiv_rn(__fadd_rn(1.0f, d), 2.0f) : 1.0f;
-        r1[k] = valid[k] ? __fdiv_rn(__fsub_rn(1.0f, d), 2.0f) : 1.0f;
+        r0[k] = valid[k] ? __fmul_rn(__fadd_rn(1.0f, d), 0.5f) : 1.0f;  // x / 2 == x * 0.5 for every float
+        r1[k] = valid[k] ? __fmul_rn(__fsub_rn(1.0f, d), 0.5f) : 1.0f;
     }
     float t0 = p0, t1 = p1;  // hardDecision, decodeCL.c:64-86
 #pragma unroll
     for (int k = 0; k < D; ++k) { t0 = __fmul_rn(t0, r0[k]); t1 = __fmul_rn(t1, r1[k]); }
     const uint32_t bit = (t0 > t1) ? 0u : ((t0 < t1) ? 1u : prev_bit);
+    float pu0 = p0, pu1 = p1;  // running prefix p * r[0] ... r[k-1], shared like the check products
 #pragma unroll
     for (int k = 0; k < D; ++k) {  // refreshQ, decodeCL.c:43-62
-        float u0 = p0, u1 = p1;
+        float u0 = pu0, u1 = pu1;
 #pragma unroll
-        for (int m = 0; m < D; ++m)
-            if (m != k) { u0 = __fmul_rn(u0, r0[m]); u1 = __fmul_rn(u1, r1[m]); }
+        for (int m = k + 1; m < D; ++m) { u0 = __fmul_rn(u0, r0[m]); u1 = __fmul_rn(u1, r1[m]); }
         const float s = __fadd_rn(u0, u1);
         const float xq = __fsub_rn(__fdiv_rn(u0, s), __fdiv_rn(u1, s));
         if (valid[k] && !frozen) sts_f32(e[k] + c4, xq);
+        pu0 = __fmul_rn(pu0, r0[k]);
+        pu1 = __fmul_rn(pu1, r1[k]);
     }
     return bit;
 }

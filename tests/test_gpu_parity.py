@@ -484,3 +484,16 @@ def test_device_roundtrip_encode_channel_decode(default_code):
         out = dec.decode_device(llr)
         assert torch.equal(out["info"], info), alg
         assert int(out["iters"].max()) < 40
+
+
+def test_coder_shards_over_every_visible_gpu(default_code):
+    """Coder::setDevices ([B200] addition): the codewords of one decode() call are split into contiguous shards,
+    one per GPU, with no collective; results equal the single-GPU ones.  With one visible GPU the same device is
+    listed twice, which exercises the same sharding code (two handles, two host threads)."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    ngpu = torch.cuda.device_count()
+    shards = max(ngpu, 2)
+    kv1, _ = _run_cli("mytest", 54000, 256, 5.5, "MS", 23, 1)
+    kvn, out = _run_cli("mytest", 54000, 256, 5.5, "MS", 23, shards, ngpu)
+    assert kvn["ErrNum"] == kv1["ErrNum"] and kvn["MeanIterations"] == kv1["MeanIterations"], out

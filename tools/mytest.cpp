@@ -16,16 +16,17 @@
 
 int main(int argc, char **argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: %s srcLength batchSize snr_dB SP|MS|CPU|TDMP|TDMPCL|MSCL [seed] [gpus]\n", argv[0]);
+        std::fprintf(stderr, "usage: %s srcLength batchSize snr_dB SP|MS|CPU|TDMP|TDMPCL|MSCL [seed] [shards] [visible_gpus]\n", argv[0]);
         return 2;
     }
     const int z = 24, ldpcN = z * 24, ldpcK = ldpcN / 4 * 3;   // Test.cpp:19-26
     Coder coder(ldpcK, ldpcN, rate_3_4_b);
     srand(argc > 5 ? (unsigned)atoi(argv[5]) : (unsigned)time(0));
     const int gpus = argc > 6 ? atoi(argv[6]) : 1;
+    const int visible = argc > 7 ? atoi(argv[7]) : gpus;  // shards wrap around the visible devices
     if (gpus > 1) {
         std::vector<int> ids(gpus);
-        for (int i = 0; i < gpus; ++i) ids[i] = i;
+        for (int i = 0; i < gpus; ++i) ids[i] = i % (visible > 0 ? visible : 1);
         coder.setDevices(ids.data(), gpus);
     }
     const int srcLength = atoi(argv[1]);

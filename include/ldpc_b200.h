@@ -54,7 +54,7 @@ enum {
 enum {
     LDPC_B200_PATH_LANE_SMEM = 0,  /* 32 codewords per CTA, lane = codeword, state in shared memory */
     LDPC_B200_PATH_LANE_GLOBAL = 1,/* same schedule, state in a CTA-private L2/HBM workspace        */
-    LDPC_B200_PATH_CTA = 2,        /* one codeword (group) per CTA, lane = check / variable         */
+    /* 2 is unassigned */
     LDPC_B200_PATH_GROUP = 4,      /* explicit per-edge messages in shared memory; G codewords per CTA,
                                       32/G graph nodes per warp instruction (G=16 short codes, G=1 N~8k) */
     LDPC_B200_PATH_CLUSTER = 5,    /* long codes: one codeword per 8-CTA thread-block cluster, posteriors and

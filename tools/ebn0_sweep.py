@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--ncw", type=int, default=65536)
     ap.add_argument("--check", type=int, default=512)
     ap.add_argument("--points", default="0,0.5,1,1.5,2,2.5,3,3.5,4")
+    ap.add_argument("--algorithm", default="ms", choices=["ms", "sp", "tdmp"],
+                    help="ms = flooding min-sum (DecodeMS), sp = sum-product (DecodeSP), tdmp = layered min-sum (DecodeTDMP)")
     args = ap.parse_args()
     import torch
     import myldpccppapi_b200 as m
@@ -29,14 +31,24 @@ def main():
 
     N, K, rate = 576, 432, m.rate_3_4_b
     rp, ci, M = m.wimax_csr(K, N, rate)
-    Gp = m.codes.gf2_systematic_encoder(M, N, K, rp, ci).astype(np.float32)
-    dec = m.Decoder(M, N, K, rp, ci, max_iter=40)
+    dec = m.Decoder.wimax(K, N, rate, max_iter=40)
+    dec.set_algorithm({"ms": 0, "sp": 1, "tdmp": 2}[args.algorithm])
     orc = oracle.Oracle(M, N, K, rp, ci, times=40)
+
+    def oracle_decode(y):
+        if args.algorithm == "sp":
+            r = oracle.decode_sp(orc, y)
+        elif args.algorithm == "tdmp":
+            r = oracle.decode_tdmp(orc, y, N // 24)
+        else:
+            r = orc.decode(y, want_post=False, want_hard=False)
+        return r[0], r[1]
+
     rng = np.random.default_rng(2024)
     u = rng.integers(0, 2, (args.ncw, K)).astype(np.uint8)
-    cw = np.concatenate([u, ((u.astype(np.float32) @ Gp) % 2).astype(np.uint8)], axis=1)
-    bits = torch.from_numpy(m.codes.pack_bits(cw)).cuda()
     want = torch.from_numpy(m.codes.pack_bits(u)).cuda()
+    bits = dec.encode_device(want)  # systematic encoder on the device
+    print("algorithm: %s\n" % args.algorithm)
     print("| Eb/N0 dB | sigma | mean iters | cap hits | FER | info BER | ms / %d words | info Gbit/s | oracle match (%d words) | iteration histogram (1,2,3,4,5-8,9-16,17-39,40) |" % (args.ncw, args.check))
     print("|---|---|---|---|---|---|---|---|---|---|")
     for i, e in enumerate(float(x) for x in args.points.split(",")):
@@ -56,7 +68,7 @@ def main():
         wrong_words = int((diff.reshape(args.ncw, -1).max(dim=1).values != 0).sum().item())
         wrong_bits = int(np.unpackbits(diff.cpu().numpy()).sum())
         nchk = min(args.check, args.ncw)
-        ref = orc.decode(llr[:nchk].cpu().numpy(), want_post=False, want_hard=False)
+        ref = oracle_decode(llr[:nchk].cpu().numpy())
         ok = bool(np.array_equal(ref[0], out["info"][:nchk].cpu().numpy()) and np.array_equal(ref[1], it[:nchk]))
         h = [int((it == k).sum()) for k in (1, 2, 3, 4)] + [int(((it >= a) & (it <= b)).sum()) for a, b in ((5, 8), (9, 16), (17, 39))] + [int((it == 40).sum())]
         print("| %.1f | %.4f | %.2f | %.2f%% | %.2e | %.2e | %.3f | %.2f | %s | %s |" % (

@@ -296,12 +296,17 @@ def main() -> None:
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory in, bits out)
     e2e = None
+    numa = None
     if not args.no_e2e:
+        # pinned staging buffers on the NUMA node of this rank's GPU (placement only; affinity restored below)
+        saved_affinity = os.sched_getaffinity(0)
+        numa = m.shard.bind_to_gpu_numa_node(local_rank)
         h_llr = torch.empty((ncw, N), dtype=torch.float32, pin_memory=True)
         h_llr.copy_(llr)
         h_out = {"info": torch.empty((ncw, dec.KB), dtype=torch.uint8, pin_memory=True),
                  "iters": torch.empty((ncw,), dtype=torch.int32, pin_memory=True)}
         torch.cuda.synchronize()
+        os.sched_setaffinity(0, saved_affinity)
         for _ in range(max(1, min(args.warmup, 3))):
             dec.decode_host(h_llr, out=h_out)
         barrier()
@@ -320,6 +325,7 @@ def main() -> None:
                "ms_per_step": dt / args.steps * 1e3, "api": "ldpc_b200_decode_host (pinned host buffers, 3-stream pipeline)"}
         same = bool(torch.equal(h_out["info"], out["info"].cpu()) and torch.equal(h_out["iters"], out["iters"].cpu()))
         e2e["matches_device_path"] = same
+        e2e["host_numa"] = numa
     sampler.stop()
 
     if rank != 0:

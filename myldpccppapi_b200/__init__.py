@@ -12,6 +12,7 @@ from .decoder import (  # noqa: F401
     DecodeCPU, DecodeMS, DecodeSP, DecodeTDMP, DecodeTDMPCL, DecodeMSCL,
 )
 from . import codes  # noqa: F401
-from .shard import shard_range, shard_ranges  # noqa: F401
+from . import shard  # noqa: F401
+from .shard import bind_to_gpu_numa_node, shard_range, shard_ranges  # noqa: F401
 
 __all__ = ["Coder", "Decoder", "synth_llr", "wimax_csr", "edge_tables", "codes", "LdpcError", "load"]

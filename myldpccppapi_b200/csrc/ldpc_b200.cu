@@ -534,7 +534,86 @@ int upload_group_tables(ldpc_b200_decoder* h) {
         const int nvg = (t.N + LN - 1) / LN, ncg = (t.M + LN - 1) / LN;
         uint64_t rng = 0x9E3779B97F4A7C15ull;
         auto rnd = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 32); };
-        // (a) variable lanes
+        // Order of work: (b) first, because it is the hard one (the message order inside a variable is fixed by
+        // the summation order, so a variable group needs, for every k, 32 k-th checks in 32 distinct lanes):
+        //   (b1) swap check lanes until every lane serves each k equally often (otherwise no grouping can work),
+        //   (b2) regroup the variables with targeted swaps: take a variable whose k-th check collides inside its
+        //        group, look for a partner among the variables whose k-th check sits in a lane the group lacks,
+        //        swap if the collision count does not grow.
+        // Then (a) without touching (b): variable lanes inside a group and the group membership of checks that
+        // share a lane are still free.  Only nodes of equal degree trade places (a slot has one degree).
+        const long long effort = std::getenv("LDPC_B200_PLACE_EFFORT") ? std::atoll(std::getenv("LDPC_B200_PLACE_EFFORT")) : 12;
+        const int maxdv = t.max_col_weight;
+        auto kth_check = [&](int v, int k) { return (int)(t.vn_edge[t.col_ptr[v] + k] >> kPosBits); };
+        if (LN == 32 && !keep_order && maxdv <= 16 && effort > 0) {
+            // (b1) lane balance: cnt[k][lane] = number of variables whose k-th check has that lane
+            std::vector<int> clane(t.M);
+            for (int i = 0; i < t.M; ++i) clane[corder[i]] = i % LN;
+            std::vector<int> ck((size_t)t.M * maxdv, 0), cnt((size_t)maxdv * LN, 0), tot(maxdv, 0);
+            for (int v = 0; v < t.N; ++v)
+                for (int k = 0; k < vdegf(v); ++k) { ck[(size_t)kth_check(v, k) * maxdv + k]++; tot[k]++; }
+            for (int c = 0; c < t.M; ++c)
+                for (int k = 0; k < maxdv; ++k) cnt[(size_t)k * LN + clane[c]] += ck[(size_t)c * maxdv + k];
+            auto dev2 = [&](int k, int lane) { const long long d = (long long)cnt[(size_t)k * LN + lane] * LN - tot[k]; return d * d; };
+            for (long long it = 0; it < (long long)t.M * 200; ++it) {
+                const int ra = (int)(rnd() % (uint32_t)t.M), rb = (int)(rnd() % (uint32_t)t.M);
+                const int a = corder[ra], b = corder[rb], la = ra % LN, lb = rb % LN;
+                if (la == lb || cdegf(a) != cdegf(b)) continue;
+                long long before = 0, after = 0;
+                for (int k = 0; k < maxdv; ++k) before += dev2(k, la) + dev2(k, lb);
+                for (int k = 0; k < maxdv; ++k) {
+                    const int d = ck[(size_t)b * maxdv + k] - ck[(size_t)a * maxdv + k];
+                    cnt[(size_t)k * LN + la] += d; cnt[(size_t)k * LN + lb] -= d;
+                }
+                for (int k = 0; k < maxdv; ++k) after += dev2(k, la) + dev2(k, lb);
+                if (after <= before) { std::swap(corder[ra], corder[rb]); clane[a] = lb; clane[b] = la; }
+                else
+                    for (int k = 0; k < maxdv; ++k) {
+                        const int d = ck[(size_t)b * maxdv + k] - ck[(size_t)a * maxdv + k];
+                        cnt[(size_t)k * LN + la] -= d; cnt[(size_t)k * LN + lb] += d;
+                    }
+            }
+            // (b2) variable groups
+            std::vector<std::vector<int>> bylane((size_t)maxdv * LN);  // variables by (k, lane of the k-th check)
+            for (int v = 0; v < t.N; ++v)
+                for (int k = 0; k < vdegf(v); ++k) bylane[(size_t)k * LN + clane[kth_check(v, k)]].push_back(v);
+            std::vector<int> rank_of_var(t.N);
+            for (int r = 0; r < t.N; ++r) rank_of_var[vorder[r]] = r;
+            std::vector<uint8_t> occ((size_t)nvg * maxdv * LN, 0);  // [group][k][lane]
+            auto cell = [&](int g, int k, int lane) -> uint8_t& { return occ[((size_t)g * maxdv + k) * LN + lane]; };
+            for (int v = 0; v < t.N; ++v)
+                for (int k = 0; k < vdegf(v); ++k) cell(rank_of_var[v] / LN, k, clane[kth_check(v, k)])++;
+            auto take = [&](int v, int g) { int d = 0; for (int k = 0; k < vdegf(v); ++k) { uint8_t& x = cell(g, k, clane[kth_check(v, k)]); if (x > 1) --d; --x; } return d; };
+            auto put = [&](int v, int g) { int d = 0; for (int k = 0; k < vdegf(v); ++k) { uint8_t& x = cell(g, k, clane[kth_check(v, k)]); if (x >= 1) ++d; ++x; } return d; };
+            for (long long it = 0; it < (long long)t.N * 100 * effort; ++it) {
+                const int v = (int)(rnd() % (uint32_t)t.N), g = rank_of_var[v] / LN, dv = vdegf(v);
+                int kk = -1;
+                for (int k = 0; k < dv; ++k) if (cell(g, k, clane[kth_check(v, k)]) > 1) { kk = k; break; }
+                if (kk < 0) continue;
+                int miss[32], nm = 0;
+                for (int x = 0; x < LN; ++x) if (cell(g, kk, x) == 0) miss[nm++] = x;
+                if (!nm) continue;
+                int best = -1, bestd = 1 << 30, ties = 0;
+                for (int tr = 0; tr < 24; ++tr) {
+                    const std::vector<int>& lst = bylane[(size_t)kk * LN + miss[rnd() % (uint32_t)nm]];
+                    if (lst.empty()) continue;
+                    const int w = lst[rnd() % (uint32_t)lst.size()], hgrp = rank_of_var[w] / LN;
+                    if (hgrp == g || vdegf(w) != dv) continue;
+                    const int d = take(v, g) + take(w, hgrp) + put(v, hgrp) + put(w, g);
+                    take(v, hgrp); take(w, g); put(v, g); put(w, hgrp);
+                    if (d < bestd) { bestd = d; best = w; ties = 1; }
+                    else if (d == bestd && rnd() % (uint32_t)(++ties) == 0) best = w;
+                }
+                if (best < 0 || bestd > 0 || (bestd == 0 && (rnd() & 3))) continue;
+                const int w = best, hgrp = rank_of_var[w] / LN;
+                take(v, g); take(w, hgrp); put(v, hgrp); put(w, g);
+                const int rv = rank_of_var[v], rw = rank_of_var[w];
+                std::swap(vorder[rv], vorder[rw]);
+                rank_of_var[v] = rw; rank_of_var[w] = rv;
+            }
+            for (int i = 0; i < t.M; ++i) crank_of_chk[corder[i]] = (uint32_t)i;
+        }
+        // (a) variable lanes inside their group, and the group of checks that share a lane
         {
             std::vector<int> cnt((size_t)ncg * LN, 0);  // [check group][bank]
             auto bump = [&](int v, int bank, int dlt, long long& cost) {
@@ -545,30 +624,87 @@ int upload_group_tables(ldpc_b200_decoder* h) {
                     x += dlt;
                 }
             };
+            std::vector<int> lane_of_var(t.N);
+            for (int r = 0; r < t.N; ++r) lane_of_var[vorder[r]] = r % LN;
+            auto bump_chk = [&](int chk, int cg, int dlt, long long& cost) {  // check `chk` joins / leaves check group cg
+                for (int e = t.row_ptr[chk]; e < t.row_ptr[chk + 1]; ++e) {
+                    int& x = cnt[(size_t)cg * LN + lane_of_var[t.col_idx[e]]];
+                    cost += dlt > 0 ? 2 * x + 1 : -(2 * x - 1);
+                    x += dlt;
+                }
+            };
+            std::vector<long long> cg_edges(ncg, 0);  // edges of a check group: its fair share per bank is 1/LN of them
+            for (int r = 0; r < t.M; ++r) cg_edges[r / LN] += cdegf(corder[r]);
             long long cost = 0;
             for (int r = 0; r < t.N; ++r) bump(vorder[r], r % LN, +1, cost);
-            const long long iters = (long long)t.N * 60;
+            const long long iters = (long long)t.N * 60 * std::max<long long>(1, effort / 2);
             for (long long it = 0; it < iters; ++it) {
-                const int vg = (int)(rnd() % (uint32_t)nvg);
-                const int a = vg * LN + (int)(rnd() % LN), b = vg * LN + (int)(rnd() % LN);
-                if (a == b || a >= t.N || b >= t.N) continue;
-                long long d = 0;
-                bump(vorder[a], a % LN, -1, d); bump(vorder[b], b % LN, -1, d);
-                bump(vorder[a], b % LN, +1, d); bump(vorder[b], a % LN, +1, d);
-                if (d <= 0) {
+                if (rnd() & 1) {
+                    // a variable sitting in a bank that one of its check groups sees too often trades lanes with the
+                    // best of a few partners from its own group
+                    const int a = (int)(rnd() % (uint32_t)t.N), va = vorder[a];
+                    bool over = false;
+                    for (int k = t.col_ptr[va]; k < t.col_ptr[va + 1] && !over; ++k) {
+                        const int chk = (int)(t.vn_edge[k] >> kPosBits);
+                        const int cg = (int)crank_of_chk[chk] / LN;
+                        over = cnt[(size_t)cg * LN + a % LN] > (int)((cg_edges[cg] + LN - 1) / LN);
+                    }
+                    if (!over) continue;
+                    int best = -1;
+                    long long bestd = 1;
+                    for (int tr = 0; tr < 6; ++tr) {
+                        const int b = a / LN * LN + (int)(rnd() % LN);
+                        if (b == a || b >= t.N) continue;
+                        long long d = 0;
+                        bump(vorder[a], a % LN, -1, d); bump(vorder[b], b % LN, -1, d);
+                        bump(vorder[a], b % LN, +1, d); bump(vorder[b], a % LN, +1, d);
+                        long long u = 0;
+                        bump(vorder[a], b % LN, -1, u); bump(vorder[b], a % LN, -1, u);
+                        bump(vorder[a], a % LN, +1, u); bump(vorder[b], b % LN, +1, u);
+                        if (d < bestd) { bestd = d; best = b; }
+                    }
+                    if (best < 0 || bestd > 0) continue;
+                    const int b = best;
+                    long long d = 0;
+                    bump(vorder[a], a % LN, -1, d); bump(vorder[b], b % LN, -1, d);
+                    bump(vorder[a], b % LN, +1, d); bump(vorder[b], a % LN, +1, d);
                     std::swap(vorder[a], vorder[b]);
+                    lane_of_var[vorder[a]] = a % LN; lane_of_var[vorder[b]] = b % LN;
                     cost += d;
-                } else {
-                    long long u = 0;
-                    bump(vorder[a], b % LN, -1, u); bump(vorder[b], a % LN, -1, u);
-                    bump(vorder[a], a % LN, +1, u); bump(vorder[b], b % LN, +1, u);
+                } else {  // two checks in the same lane trade groups: (b) is untouched
+                    const int ra = (int)(rnd() % (uint32_t)t.M), a = corder[ra], ga = ra / LN;
+                    bool over = false;  // does this check feed a bank its group sees too often?
+                    for (int e = t.row_ptr[a]; e < t.row_ptr[a + 1] && !over; ++e)
+                        over = cnt[(size_t)ga * LN + lane_of_var[t.col_idx[e]]] > (int)((cg_edges[ga] + LN - 1) / LN);
+                    if (!over) continue;
+                    int best = -1;
+                    long long bestd = 1;
+                    for (int tr = 0; tr < 6; ++tr) {
+                        const int rb = (int)(rnd() % (uint32_t)ncg) * LN + ra % LN;
+                        if (rb == ra || rb >= t.M) continue;
+                        const int b = corder[rb];
+                        if (cdegf(a) != cdegf(b)) continue;
+                        long long d = 0, u = 0;
+                        bump_chk(a, ga, -1, d); bump_chk(b, rb / LN, -1, d);
+                        bump_chk(a, rb / LN, +1, d); bump_chk(b, ga, +1, d);
+                        bump_chk(a, rb / LN, -1, u); bump_chk(b, ga, -1, u);
+                        bump_chk(a, ga, +1, u); bump_chk(b, rb / LN, +1, u);
+                        if (d < bestd) { bestd = d; best = rb; }
+                    }
+                    if (best < 0 || bestd > 0) continue;
+                    const int rb = best, b = corder[rb];
+                    long long d = 0;
+                    bump_chk(a, ga, -1, d); bump_chk(b, rb / LN, -1, d);
+                    bump_chk(a, rb / LN, +1, d); bump_chk(b, ga, +1, d);
+                    std::swap(corder[ra], corder[rb]);
+                    crank_of_chk[a] = (uint32_t)rb; crank_of_chk[b] = (uint32_t)ra;
+                    cost += d;
                 }
             }
             for (int i = 0; i < t.N; ++i) { var_of_pos[i] = (uint32_t)vorder[i]; pos_of_var[vorder[i]] = (uint32_t)i; }
         }
-        // (b) check lanes
-        {
-            int maxdv = t.max_col_weight;
+        // (b) check lanes by plain swaps inside a group -- the fallback when (b1)/(b2) did not run
+        if (!(LN == 32 && !keep_order && maxdv <= 16 && effort > 0)) {
             std::vector<int> cnt((size_t)nvg * maxdv * LN, 0);  // [variable group][k][bank]
             auto bump = [&](int chk, int bank, int dlt, long long& cost) {
                 for (int e = t.row_ptr[chk]; e < t.row_ptr[chk + 1]; ++e) {
@@ -648,6 +784,35 @@ int upload_group_tables(ldpc_b200_decoder* h) {
                 }
             }
         }
+    }
+    if (SUB == 32 && std::getenv("LDPC_B200_DEBUG_PLACEMENT")) {
+        // extra shared-memory wavefronts per iteration caused by bank conflicts in the two gathers
+        long long exA = 0, exB = 0, lbA = 0;
+        const int ncg = (t.M + 31) / 32, nvg = (t.N + 31) / 32;
+        for (int cg = 0; cg < ncg; ++cg) {
+            int cnt[32][32] = {};
+            int maxd = 0;
+            for (int i = 0; i < 32 && cg * 32 + i < t.M; ++i) {
+                const int r = corder[cg * 32 + i];
+                for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) { cnt[slot_of_edge[e]][pos_of_var[t.col_idx[e]] % 32]++; maxd = std::max(maxd, slot_of_edge[e] + 1); }
+            }
+            for (int j = 0; j < maxd; ++j) { int mx = 1; for (int b = 0; b < 32; ++b) mx = std::max(mx, cnt[j][b]); exA += mx - 1; }
+            for (int b = 0; b < 32; ++b) { int tot = 0; for (int j = 0; j < maxd; ++j) tot += cnt[j][b]; lbA += std::max(0, tot - maxd); }
+        }
+        for (int vg = 0; vg < nvg; ++vg) {
+            int cnt[32][32] = {};
+            int maxd = 0;
+            for (int i = 0; i < 32 && vg * 32 + i < t.N; ++i) {
+                const int v = vorder[vg * 32 + i];
+                for (int k = t.col_ptr[v]; k < t.col_ptr[v + 1]; ++k) {
+                    if (k - t.col_ptr[v] >= 32) break;
+                    cnt[k - t.col_ptr[v]][crank_of_chk[t.vn_edge[k] >> kPosBits] % 32]++;
+                    maxd = std::max(maxd, k - t.col_ptr[v] + 1);
+                }
+            }
+            for (int k = 0; k < maxd; ++k) { int mx = 1; for (int b = 0; b < 32; ++b) mx = std::max(mx, cnt[k][b]); exB += mx - 1; }
+        }
+        std::fprintf(stderr, "[ldpc_b200] placement: extra wavefronts per iteration: check-pass gathers %lld (bank imbalance alone: %lld), variable-pass gathers %lld\n", exA, lbA, exB);
     }
     // check pass: T-row byte offset of every edge, [warp][slot][quad][h][4]; padding -> dummy row PD
     std::vector<uint32_t> cn_tab((size_t)W * pl.cn_stride, (uint32_t)PD * G * 4u);

@@ -322,7 +322,7 @@ def main() -> None:
         dt = max_over_ranks(dt)
         e2e = {"value": total_cw * K * args.steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(total_cw) * N * 4, "d2h_bytes_per_step": int(total_cw) * (dec.KB + 4),
-               "ms_per_step": dt / args.steps * 1e3, "api": "ldpc_b200_decode_host (pinned host buffers, 3-stream pipeline)"}
+               "ms_per_step": dt / args.steps * 1e3, "api": "ldpc_b200_decode_host (pinned host buffers; " + ("one persistent launch fed by a copy stream)" if info["path_name"] == "qc" else "3-stream pipeline)")}
         same = bool(torch.equal(h_out["info"], out["info"].cpu()) and torch.equal(h_out["iters"], out["iters"].cpu()))
         e2e["matches_device_path"] = same
         e2e["host_numa"] = numa
@@ -346,7 +346,7 @@ def main() -> None:
     per_gpu_cw_s = ncw / (ms_step * 1e-3)
     b_hbm = 4 * N + (K + 7) // 8 + 1                       # channel values in, info bits + count out
     b_msg = mean_iters * (16 * nnz + 8 * N)                # on-chip message bytes per word
-    onchip = info["path_name"] in ("lane_smem", "lane16", "group", "cluster")
+    onchip = info["path_name"] in ("lane_smem", "lane16", "group", "cluster", "qc")
     roof_smem = {"bound": "smem", "achieved": per_gpu_cw_s * b_msg / 1e9, "peak": smem_gbs.value, "unit": "GB/s",
                  "peak_source": "measured live: ldpc_b200_probe_smem_bandwidth (LDS.128 stream on all SMs)"}
     roof_smem["frac"] = roof_smem["achieved"] / roof_smem["peak"] if roof_smem["peak"] else None
@@ -364,7 +364,7 @@ def main() -> None:
         pass
     roofline = dict(roof_smem if onchip else roof_hbm)
     roofline.update({
-        "kernel": {"group": "ldpc_ms_group_kernel", "cluster": "ldpc_ms_cluster_kernel", "lane16": "ldpc_ms_lane16_kernel",
+        "kernel": {"qc": "ldpc_ms_qc_kernel", "group": "ldpc_ms_group_kernel", "cluster": "ldpc_ms_cluster_kernel", "lane16": "ldpc_ms_lane16_kernel",
                    "lane_smem": "ldpc_ms_lane_kernel<true>", "stream": "ldpc_ms_stream_kernel"}.get(info["path_name"], "ldpc_ms_lane_kernel<false>"),
         "launch_ms": ms_step, "traffic": roof_hbm.get("traffic"),
         "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},

@@ -61,8 +61,11 @@ enum {
                                       messages in distributed shared memory (DSMEM gathers, cluster barriers) */
     LDPC_B200_PATH_STREAM = 6,     /* long codes with check and variable degree <= 8: explicit per-edge messages in a
                                       global workspace, fixed-stride tables, prefetched indices, variable bundles   */
-    LDPC_B200_PATH_LANE16 = 3      /* tuned short-code path: lane = codeword, channel values in
+    LDPC_B200_PATH_LANE16 = 3,     /* tuned short-code path: lane = codeword, channel values in
                                       registers, 16-byte check state and index tables in shared memory */
+    LDPC_B200_PATH_QC = 7          /* quasi-cyclic codes (every code Coder::initCheckMatrix builds): the GROUP
+                                      arithmetic with warp-uniform index tables read from the parameter space
+                                      into uniform registers; cyclic wrap absorbed by padded rows            */
 };
 
 /* Decoding algorithm of a handle (ldpc_b200_set_algorithm). */

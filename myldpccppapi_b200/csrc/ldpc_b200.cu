@@ -19,6 +19,7 @@
 
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
+#include "ldpc_qc.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
 #include "ldpc_stream.cuh"
@@ -106,6 +107,12 @@ struct ldpc_b200_decoder {
     uint32_t* dg_var_of_pos = nullptr;
     uint32_t* dg_pos_of_var = nullptr;
     bool group_ready = false;
+    // QC tables (warp-uniform, one slot of the __constant__ bank)
+    QcParams<QcProfileWimax34B576> qc;
+    QcWarpTab<QcProfileWimax34B576> qc_tab[QcProfileWimax34B576::W];
+    int qc_state = 0;  // 0 = not tried, 1 = tables built and uploaded, -1 = no match / no free slot
+    int qc_slot = -1;
+    size_t qc_smem = 0;
     // CLUSTER tables
     uint32_t* dc_cn_tab = nullptr;
     uint32_t* dc_vn_tab = nullptr;
@@ -149,6 +156,20 @@ struct ldpc_b200_decoder {
     uint8_t* s_hard[kSlots] = {nullptr, nullptr, nullptr};
     int32_t* s_iters[kSlots] = {nullptr, nullptr, nullptr};
     float* s_post[kSlots] = {nullptr, nullptr, nullptr};
+
+    // streamed host pipeline (one persistent launch per batch, input chunks announced through *d_avail)
+    float* st_llr = nullptr;
+    uint8_t* st_info = nullptr;
+    uint8_t* st_hard = nullptr;
+    int32_t* st_iters = nullptr;
+    float* st_post = nullptr;
+    int64_t st_cap = 0;                         // words the st_* buffers hold
+    bool st_has_hard = false, st_has_post = false;
+    unsigned long long* d_avail = nullptr;      // [0] words landed; [1] (as int) timeout status
+    unsigned long long* h_avail_vals = nullptr; // pinned: the values the copy stream writes to *d_avail
+    int64_t h_avail_cap = 0;
+    cudaEvent_t st_event = nullptr;
+    const unsigned long long* cur_avail = nullptr;  // set around a streamed launch (under mu)
 
     int64_t launches = 0;
     std::mutex mu;
@@ -972,6 +993,139 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
     return fail(LDPC_B200_ERR_UNSUPPORTED, "no group kernel instantiated for this shape");
 }
 
+// ---- QC layout (see ldpc_qc.cuh) ---------------------------------------------------------------------
+// Recognises H as a grid of z x z blocks (zero or one cyclically shifted identity each), deals groups of
+// SUB consecutive rows / columns of a block to (slot, warp) in degree order and writes one warp-uniform
+// base per (warp, slot, edge).  Returns false when the code is not of that shape or does not match P.
+template <class P>
+bool qc_build(const HostTables& t, QcParams<P>* out, QcWarpTab<P>* tabs, size_t* smem_out) {
+    constexpr int z = P::Z, G = P::G, SUB = 32 / G, W = P::W;
+    constexpr uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
+    static_assert(z % SUB == 0, "a group of node lanes must not straddle blocks");
+    if (t.M % z || t.N % z) return false;
+    const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
+    if (MB * gpb != P::CS * W || NB * gpb != P::VS * W) return false;
+    struct Blk { int bc, s; };
+    std::vector<std::vector<Blk>> rows(MB);
+    for (int br = 0; br < MB; ++br) {
+        const int r0 = br * z;
+        std::vector<bool> used(NB, false);
+        for (int e = t.row_ptr[r0]; e < t.row_ptr[r0 + 1]; ++e) {
+            const int bc = t.col_idx[e] / z;
+            if (used[bc]) return false;  // two circulants in one block
+            used[bc] = true;
+            rows[br].push_back({bc, t.col_idx[e] % z});
+        }
+        for (int r = 0; r < z; ++r) {
+            if (t.row_ptr[r0 + r + 1] - t.row_ptr[r0 + r] != (int)rows[br].size()) return false;
+            std::vector<int> want;
+            for (const Blk& b : rows[br]) want.push_back(b.bc * z + (r + b.s) % z);
+            std::sort(want.begin(), want.end());
+            for (size_t j = 0; j < want.size(); ++j)
+                if (t.col_idx[t.row_ptr[r0 + r] + (int)j] != want[j]) return false;
+        }
+    }
+    std::vector<int> eb0(MB + 1, 0);  // R block index of (br, 0)
+    for (int br = 0; br < MB; ++br) eb0[br + 1] = eb0[br] + (int)rows[br].size();
+    const uint32_t t_bytes = (uint32_t)NB * (z + SUB) * ROWB, r_bytes = (uint32_t)eb0[MB] * RS;
+    struct Col { int br, j, s; };
+    std::vector<std::vector<Col>> cols(NB);
+    for (int br = 0; br < MB; ++br)
+        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
+    std::vector<int> border(MB), corder(NB);
+    for (int i = 0; i < MB; ++i) border[i] = i;
+    for (int i = 0; i < NB; ++i) corder[i] = i;
+    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cols[a].size() > cols[b].size(); });
+    QcParams<P>& q = *out;
+    std::memset(&q, 0, sizeof(q));
+    std::memset(tabs, 0, sizeof(QcWarpTab<P>) * W);
+    for (int p = 0; p < MB * gpb; ++p) {
+        const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
+        if ((int)rows[br].size() != P::cdeg(slot)) return false;
+        QcWarpTab<P>& tb = tabs[w];
+        tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
+        if (g == gpb - 1) tb.cdup |= 1u << slot;
+        for (int j = 0; j < (int)rows[br].size(); ++j)
+            tb.cn_t[QcLayout<P>::coff(slot) + j] = (uint32_t)(rows[br][j].bc * (z + SUB) + (r0 + rows[br][j].s) % z) * ROWB;
+    }
+    for (int p = 0; p < NB * gpb; ++p) {
+        const int bc = corder[p / gpb], g = p % gpb, slot = p / W, w = p % W, i0 = g * SUB;
+        const int d = (int)cols[bc].size();
+        if (d > P::vdeg(slot)) return false;
+        QcWarpTab<P>& tb = tabs[w];
+        tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
+        tb.var0[slot] = (uint32_t)(bc * z + i0);
+        if (g == 0) tb.vdup |= 1u << slot;
+        for (int k = 0; k < P::vdeg(slot); ++k) {
+            if (k >= d) { tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + r_bytes; continue; }  // zero row
+            const Col& cd = cols[bc][k];  // ascending block row = ascending row: the summation order
+            int m = ((i0 - cd.s) % z + z) % z;
+            if (m > z - SUB) m -= z;      // the group wraps: its first rows are read through the leading pad
+            tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + (uint32_t)(eb0[cd.br] + cd.j) * RS + (uint32_t)(SUB + m) * ROWB;
+        }
+    }
+    // the kernel branches once per pass on "this warp owns wrapped rows": all of a warp's groups or none
+    for (int w = 0; w < W; ++w) {
+        if (tabs[w].cdup != 0u && tabs[w].cdup != (1u << P::CS) - 1u) return false;
+        if (tabs[w].vdup != 0u && tabs[w].vdup != (1u << P::VS) - 1u) return false;
+    }
+    q.N = t.N; q.NB = NB;
+    q.t_bytes = t_bytes; q.r_bytes = r_bytes;
+    *smem_out = (size_t)t_bytes + r_bytes + 128;
+    return true;
+}
+
+// Slots of the __constant__ table bank, per device: which handle owns each.
+constexpr int kQcMaxDevices = 64;
+std::mutex g_qc_mu;
+const void* g_qc_owner[kQcMaxDevices][kQcTabSlots] = {};
+
+int qc_acquire_slot(const void* owner, int device) {
+    if (device < 0 || device >= kQcMaxDevices) return -1;
+    std::lock_guard<std::mutex> lk(g_qc_mu);
+    for (int s = 0; s < kQcTabSlots; ++s)
+        if (!g_qc_owner[device][s]) { g_qc_owner[device][s] = owner; return s; }
+    return -1;
+}
+
+void qc_release_slot(const void* owner, int device, int slot) {
+    if (device < 0 || device >= kQcMaxDevices || slot < 0 || slot >= kQcTabSlots) return;
+    std::lock_guard<std::mutex> lk(g_qc_mu);
+    if (g_qc_owner[device][slot] == owner) g_qc_owner[device][slot] = nullptr;
+}
+
+// Builds the tables, takes a slot and uploads them (current device = the handle's).  false = use another path.
+bool qc_prepare(ldpc_b200_decoder* h) {
+    using P = QcProfileWimax34B576;
+    if (!qc_build<P>(h->host, &h->qc, h->qc_tab, &h->qc_smem)) return false;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return false;
+    const int slot = qc_acquire_slot(h, h->device);
+    if (slot < 0) return false;
+    if (cudaMemcpyToSymbol(g_qc_tab_wimax34b576, h->qc_tab, sizeof(h->qc_tab), (size_t)slot * sizeof(h->qc_tab),
+                           cudaMemcpyHostToDevice) != cudaSuccess) {
+        (void)cudaGetLastError();
+        qc_release_slot(h, h->device, slot);
+        return false;
+    }
+    h->qc_slot = slot;
+    h->qc.tab_slot = slot;
+    h->table_bytes += sizeof(h->qc_tab);
+    return true;
+}
+
+template <class P>
+int launch_qc_t(const QcParams<P>& q, int grid, size_t smem, cudaStream_t stream) {
+    if (const char* env = std::getenv("LDPC_B200_QC_PAD")) smem += (size_t)std::atoi(env);
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (std::getenv("LDPC_B200_QC_CARVEOUT"))
+        CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
+    CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
 // ---- CLUSTER layout (one codeword per 8-CTA cluster, DSMEM gathers; see ldpc_cluster.cuh) ------------
 struct ClShape {
     int W = 32, CS = 0, VS = 0, dmax = 8;
@@ -1335,6 +1489,26 @@ int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* 
 int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
+    {   // quasi-cyclic code matching a compiled profile: warp-uniform tables (min-sum only)
+        using P = QcProfileWimax34B576;
+        const bool want = h->algorithm == LDPC_B200_ALG_MIN_SUM &&
+                          (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !std::getenv("LDPC_B200_NO_QC")));
+        if (want && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
+        const bool fits = want && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
+        if (h->forced_path == LDPC_B200_PATH_QC && !fits)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not match a compiled quasi-cyclic profile (or the algorithm is not min-sum)");
+        if (fits) {
+            pl.path = LDPC_B200_PATH_QC;
+            pl.threads = 32 * P::W;
+            pl.smem = h->qc_smem;
+            pl.ctas = h->sm_count * 2;
+            pl.cw_per_cta = P::G;
+            pl.W = P::W; pl.CS = P::CS; pl.VS = P::VS; pl.G = P::G;
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
+    }
     {   // explicit per-edge messages on chip (G codewords per CTA)
         GrpShape sh;
         const bool fits = group_pick(t, h->smem_optin, h->algorithm == LDPC_B200_ALG_SUM_PRODUCT, &sh);
@@ -1465,7 +1639,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (rc) return rc;
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
-    const int per_group = pl.path == LDPC_B200_PATH_GROUP ? pl.G : kLanes;
+    const int per_group = (pl.path == LDPC_B200_PATH_GROUP || pl.path == LDPC_B200_PATH_QC) ? pl.G : kLanes;
     const int64_t ngroups = (ncw + per_group - 1) / per_group;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
     unsigned long long* ctr64 = h->d_counters + h->counter_next;
@@ -1473,6 +1647,22 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+
+    if (pl.path == LDPC_B200_PATH_QC) {
+        auto& q = h->qc;  // tables filled by qc_build; per-launch fields below
+        q.K = h->K;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter64 = ctr64;
+        q.avail = h->cur_avail;
+        q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
+        rc = launch_qc_t(q, grid, pl.smem, stream);
+        if (rc) return rc;
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
 
     if (pl.path == LDPC_B200_PATH_CLUSTER) {
         rc = upload_cluster_tables(h);
@@ -1705,6 +1895,11 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
         if (guard.ok) {
             cudaDeviceSynchronize();
             free_slots(h);
+            if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
+            cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
+            cudaFree(h->d_avail);
+            if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
+            if (h->st_event) cudaEventDestroy(h->st_event);
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
@@ -1913,6 +2108,88 @@ int ldpc_b200_decode_device(ldpc_b200_handle h, const float* d_llr, int64_t ncw,
     return launch_decode(h, d_llr, ncw, d_info, d_hard, d_iters, d_post, (cudaStream_t)stream);
 }
 
+namespace {
+
+// Host buffers through ONE persistent launch per batch: all input chunks are queued on a copy stream, each
+// followed by an 8-byte write that advances *d_avail; the kernel, launched on a second stream, takes words from
+// its work queue as usual and only waits when it is ahead of the copies.  No kernel boundaries, no tail per chunk,
+// and the device-to-host copy of the bits follows the kernel.  Everything is queued before the launch, so a
+// serialising tool (profiler, CUDA_LAUNCH_BLOCKING) degrades to copy-then-decode instead of deadlocking.
+int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                         int32_t* iters, float* post) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    const HostTables& t = h->host;
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    const int64_t g = h->plan.cw_per_cta;
+    const int64_t batch_cap = std::max<int64_t>(g, (((int64_t)512 << 20) / ((int64_t)t.N * 4)) / g * g);  // <= 512 MB of channel values per launch
+    const int64_t want = std::min(ncw, batch_cap);
+    for (int s = 0; s < 2; ++s)
+        if (!h->streams[s]) CU_TRY(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+    if (!h->st_event) CU_TRY(cudaEventCreateWithFlags(&h->st_event, cudaEventDisableTiming));
+    if (!h->d_avail) CU_TRY(cudaMalloc(&h->d_avail, 2 * sizeof(unsigned long long)));
+    if (h->st_cap < want || (hard && !h->st_has_hard) || (post && !h->st_has_post)) {
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
+        h->st_llr = nullptr; h->st_info = nullptr; h->st_hard = nullptr; h->st_iters = nullptr; h->st_post = nullptr;
+        h->st_cap = 0;
+        const int64_t cap = std::max(want, h->st_cap);
+        h->st_has_hard = h->st_has_hard || hard != nullptr;
+        h->st_has_post = h->st_has_post || post != nullptr;
+        CU_TRY(cudaMalloc(&h->st_llr, sizeof(float) * (size_t)cap * t.N));
+        CU_TRY(cudaMalloc(&h->st_info, (size_t)cap * KB));
+        CU_TRY(cudaMalloc(&h->st_iters, sizeof(int32_t) * (size_t)cap));
+        if (h->st_has_hard) CU_TRY(cudaMalloc(&h->st_hard, (size_t)cap * NB));
+        if (h->st_has_post) CU_TRY(cudaMalloc(&h->st_post, sizeof(float) * (size_t)cap * t.N));
+        h->st_cap = cap;
+    }
+    // input chunks of ~4 MB: the first words arrive after ~0.1 ms, PCIe stays efficient
+    int64_t chunk = std::max<int64_t>(g, (((int64_t)4 << 20) / ((int64_t)t.N * 4)) / g * g);
+    if (const char* env = std::getenv("LDPC_B200_STREAM_CHUNK")) { const long long c = std::atoll(env); if (c >= 1) chunk = (c + g - 1) / g * g; }
+    const int64_t nchunks_max = (want + chunk - 1) / chunk;
+    if (h->h_avail_cap < nchunks_max) {
+        if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
+        h->h_avail_vals = nullptr; h->h_avail_cap = 0;
+        CU_TRY(cudaMallocHost(&h->h_avail_vals, sizeof(unsigned long long) * (size_t)nchunks_max));
+        h->h_avail_cap = nchunks_max;
+    }
+    cudaStream_t cs = h->streams[0], ks = h->streams[1];
+    for (int64_t off = 0; off < ncw; off += batch_cap) {
+        const int64_t n = std::min(batch_cap, ncw - off);
+        // (a later batch reuses the device buffers: its copies wait for the previous batch's kernel and read-back)
+        if (off > 0) { CU_TRY(cudaEventRecord(h->st_event, ks)); CU_TRY(cudaStreamWaitEvent(cs, h->st_event, 0)); CU_TRY(cudaStreamSynchronize(cs)); }
+        CU_TRY(cudaMemsetAsync(h->d_avail, 0, 2 * sizeof(unsigned long long), cs));
+        CU_TRY(cudaEventRecord(h->st_event, cs));
+        CU_TRY(cudaStreamWaitEvent(ks, h->st_event, 0));  // the kernel must not see a stale count
+        int64_t j = 0;
+        for (int64_t c0 = 0; c0 < n; c0 += chunk, ++j) {
+            const int64_t m = std::min(chunk, n - c0);
+            CU_TRY(cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, llr + (size_t)(off + c0) * t.N, sizeof(float) * (size_t)m * t.N,
+                                   cudaMemcpyHostToDevice, cs));
+            h->h_avail_vals[j] = (unsigned long long)(c0 + m);
+            CU_TRY(cudaMemcpyAsync(h->d_avail, h->h_avail_vals + j, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+        }
+        h->cur_avail = h->d_avail;
+        int rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
+                               iters ? h->st_iters : nullptr, post ? h->st_post : nullptr, ks);
+        h->cur_avail = nullptr;
+        if (rc) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); return rc; }
+        if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->st_info, (size_t)n * KB, cudaMemcpyDeviceToHost, ks));
+        if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->st_hard, (size_t)n * NB, cudaMemcpyDeviceToHost, ks));
+        if (iters) CU_TRY(cudaMemcpyAsync(iters + off, h->st_iters, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ks));
+        if (post) CU_TRY(cudaMemcpyAsync(post + (size_t)off * t.N, h->st_post, sizeof(float) * (size_t)n * t.N, cudaMemcpyDeviceToHost, ks));
+        int status = 0;
+        CU_TRY(cudaMemcpyAsync(&status, reinterpret_cast<int*>(h->d_avail + 1), sizeof(int), cudaMemcpyDeviceToHost, ks));
+        CU_TRY(cudaStreamSynchronize(cs));
+        CU_TRY(cudaStreamSynchronize(ks));
+        if (status) return fail(LDPC_B200_ERR_CUDA, "streamed decode: the input copies stalled for more than 4 s");
+    }
+    return LDPC_B200_OK;
+}
+
+}  // namespace
+
 int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
                           int32_t* iters, float* post) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
@@ -1920,6 +2197,9 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     if (ncw == 0) return LDPC_B200_OK;
     if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
     const HostTables& t = h->host;
+    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->planned && h->plan.path == LDPC_B200_PATH_QC && h->reserved == 0 &&
+        !std::getenv("LDPC_B200_NO_STREAMED"))
+        return decode_host_streamed(h, llr, ncw, info, hard, iters, post);
     if (h->reserved == 0) {
         // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the
         // persistent grid (bounded to ~256 MB of channel values).  On-chip paths: kernels of consecutive chunks run

@@ -1,0 +1,381 @@
+// ldpc_qc.cuh -- flooding min-sum for QUASI-CYCLIC codes: the group kernel's arithmetic with
+// warp-uniform index tables.
+//
+// Every code the reference can build is quasi-cyclic (Coder::initCheckMatrix, MyLdpc.cpp:52-109:
+// H is a grid of z x z blocks, each zero or the identity shifted by s: row r of block row br meets
+// column (r + s) mod z of block column bc).  The generic group kernel (ldpc_kernels.cuh) ignores
+// that: it reads one table entry per (node lane, edge), four node lanes per warp instruction, and
+// those lane-varying LDS.128 table reads are 22 % of its shared-memory wavefronts
+// (profiles/r01_j_group_g8_profile_ncu.txt: 5.58 wavefronts per edge-instruction against 4.35 for
+// the data itself).  Here the SUB = 32/G node lanes of a warp instruction take SUB CONSECUTIVE rows
+// (or columns) of one block, so the address of lane (h, c) is
+//       base(warp, slot, edge) + h * G*4 + c * 4  =  base + lane * 4
+// -- one warp-uniform base per edge, read from __constant__ memory into a uniform register
+// (LDCU.64 c[0x3][UR + imm]; no shared-memory wavefront, no vector ALU op) and used directly as
+// `LDS R, [R_lane + UR]`.  A warp access is 128 contiguous bytes: conflict-free by construction.
+// The cyclic wrap is absorbed by padding: every block column of T carries SUB extra rows that
+// repeat its first rows, every R block SUB leading rows that repeat its last rows; the group that
+// owns them stores twice (one group in z/SUB does; the branch is warp-uniform).
+//
+// Layout in shared memory (G codewords per CTA, rows of G floats = 32 B for G = 8):
+//   T [NB][z + SUB][G]     negated posterior, natural column order inside a block column
+//   R [E ][SUB + z][G]     E = number of non-zero blocks; block e = (block row, j) holds the message
+//                          of edge j of every row of that block row, indexed by the ROW
+//   zero row                target of padded variable-pass entries
+// Arithmetic contract, lane refill and outputs are those of ldpc_ms_group_kernel (bit-exact with
+// Coder::decodeCPU, reference MyLdpc.cpp:684-784).
+#pragma once
+#include "ldpc_kernels.cuh"
+
+namespace ldpc_b200 {
+
+// Test.cpp's code (802.16e rate 3/4B, z = 24: N = 576, M = 144), G = 8, 12 warps x 4 node lanes:
+// a slot = 12 groups of 4 rows/columns = two blocks.
+struct QcProfileWimax34B576 {
+    static constexpr int Z = 24, G = 8, W = 12, CS = 3, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 15, 14}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
+};
+
+// Table offsets shared by the host builder and the kernel.  Entries are read two at a time (LDCU.64), so
+// every check slot and every run of variable slots that is processed together starts on an even entry.
+template <class P>
+struct QcLayout {
+    __host__ __device__ static constexpr int coff(int i) { int o = 0; for (int k = 0; k < i; ++k) o += (P::cdeg(k) + 1) & ~1; return o; }
+    // variable slots are processed in runs of NS equal-degree slots (4 for degree <= 3, else 2, else 1)
+    __host__ __device__ static constexpr int vrun(int s0) {
+        const int d = P::vdeg(s0);
+        int n = 1;
+        while (s0 + n < P::VS && P::vdeg(s0 + n) == d) ++n;
+        return (n >= 4 && d <= 3) ? 4 : (n >= 2 ? 2 : 1);
+    }
+    __host__ __device__ static constexpr int voff(int s) {  // s may be P::VS (total)
+        int o = 0, s0 = 0;
+        while (s0 < P::VS) {
+            const int ns = vrun(s0), d = P::vdeg(s0);
+            if (s < s0 + ns) return o + (s - s0) * d;
+            o += (ns * d + 1) & ~1;
+            s0 += ns;
+        }
+        return o;
+    }
+    static constexpr int CE = coff(P::CS), VE = voff(P::VS);
+};
+
+// One warp's tables.  All shared-memory values are byte offsets from the dynamic shared base.
+template <class P>
+struct QcWarpTab {
+    alignas(8) uint32_t cn_t[QcLayout<P>::CE];  // [slot][j]  T rows gathered by edge j of the slot's 4 checks
+    alignas(8) uint32_t vn_r[QcLayout<P>::VE];  // [slot][k]  R rows gathered by the k-th edge (ascending row) of the slot's 4 variables
+    uint32_t cn_r[P::CS];             // own R rows of the slot's checks, edge j at + j * RS
+    uint32_t vn_t[P::VS];             // own T rows of the slot's variables
+    uint32_t var0[P::VS];             // variable index of node lane 0 (node lane h holds var0 + h)
+    uint32_t cdup, vdup;              // non-zero: this warp's groups own wrapped rows -- store the padded copy too
+                                      // (a warp's groups sit at the same place of their blocks: all or none)
+};
+
+// The tables live in __constant__ memory (bank 3), not in the kernel parameters: launches with several KB of
+// parameters neither overlap with each other nor launch quickly (measured: the 3-stream host pipeline lost
+// 47 us per launch).  kQcTabSlots decoders per device can hold tables at once; a handle owns one slot.
+constexpr int kQcTabSlots = 8;
+__constant__ QcWarpTab<QcProfileWimax34B576> g_qc_tab_wimax34b576[kQcTabSlots][QcProfileWimax34B576::W];
+
+template <class P>
+__device__ __forceinline__ const QcWarpTab<P>& qc_tab(int slot, int warp);
+template <>
+__device__ __forceinline__ const QcWarpTab<QcProfileWimax34B576>& qc_tab<QcProfileWimax34B576>(int slot, int warp) {
+    return g_qc_tab_wimax34b576[slot][warp];
+}
+
+template <class P>
+struct QcParams {
+    int tab_slot;                 // which entry of the __constant__ table bank
+    int N, K, NB;                 // NB = N / z block columns
+    uint32_t t_bytes, r_bytes;    // region sizes (T at 0, R at t_bytes, zero row at t_bytes + r_bytes)
+    int max_iter, early_term, refill_wait;
+    const float* __restrict__ llr;
+    long long ncw;
+    uint8_t* info;
+    uint8_t* hard;
+    int32_t* iters;
+    float* post;
+    unsigned long long* counter64;
+    // Streamed input (host-buffer pipeline): words [0, *avail) have landed in `llr`; the copy stream advances
+    // *avail after each chunk while this kernel is already running.  null = everything is there.
+    const unsigned long long* avail;
+    int* status;                  // set to 1 if the wait for input timed out
+};
+
+// Warp 0 waits until the words its lanes just took from the queue have landed (streamed batches).  Every branch
+// is decided by a warp vote, so the warp never diverges here: ptxas keeps treating the table reads of the hot loop
+// as warp-uniform (a divergent spin loop turned every LDCU into a vector LDC + address add and halved the speed).
+// The poll reads through L2 (ld.acquire.gpu); the channel values were never cached by this SM before, so the
+// cp.async that follows sees the DMA's data.  Bounded: a stalled copy stream sets *status instead of hanging.
+__device__ __forceinline__ bool qc_wait_input(const unsigned long long* avail, long long w, bool need, int* status) {
+    unsigned long long t0 = 0ull;
+    for (uint32_t spins = 0;; ++spins) {
+        unsigned long long a;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(avail) : "memory");
+        if (__all_sync(0xffffffffu, !need || a > (unsigned long long)w)) return true;
+        __nanosleep(spins < 64 ? 100 : 1000);
+        if ((spins & 1023u) == 1023u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            if (__any_sync(0xffffffffu, now - t0 > 4000000000ull)) {
+                if (status && (threadIdx.x & 31) == 0) atomicExch(status, 1);
+                return false;
+            }
+        }
+    }
+}
+
+// One check of exact degree D (see grp_check): the T rows come from warp-uniform bases, the R rows are
+// this lane's own column of the block (edge j at + j * RS).  Returns the row's syndrome bit.
+template <int D, uint32_t RS, uint32_t WRAP, bool DUP>
+__device__ __forceinline__ uint32_t qc_check(const uint32_t* __restrict__ tt, uint32_t rrow, uint32_t la) {
+    float tv[D + 1], S[D];
+#pragma unroll
+    for (int j = 0; j < D; j += 2) {  // two warp-uniform bases per LDCU.64
+        const uint2 e = *reinterpret_cast<const uint2*>(tt + j);
+        tv[j] = lds_f32(la + e.x);
+        if (j + 1 < D) tv[j + 1] = lds_f32(la + e.y);
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) S[j] = lds_f32(la + rrow + (uint32_t)j * RS);
+    float m1 = INFINITY, m2 = INFINITY;
+    uint32_t px = 0u, sx = 0u;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
+        const float a = fabsf(S[j]);
+        m2 = fminf(m2, fmaxf(m1, a));
+        m1 = fminf(m1, a);
+    }
+#pragma unroll
+    for (int j = 0; j + 1 < D; j += 2) {
+        px = px ^ __float_as_uint(S[j]) ^ __float_as_uint(S[j + 1]);
+        sx = sx ^ __float_as_uint(tv[j]) ^ __float_as_uint(tv[j + 1]);
+    }
+    if (D & 1) {
+        px ^= __float_as_uint(S[D - 1]);
+        sx ^= __float_as_uint(tv[D - 1]);
+    }
+    // sign(R_j) = parity of the other negative Q's = parity ^ 1 ^ signbit(S_j)   (Q_j < 0  <=>  !signbit(S_j))
+    const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
+    uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
+    uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
+    asm("" : "+r"(m1x), "+r"(m2x));
+    uint32_t rn[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
+        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(rn[j]) : "r"(__float_as_uint(S[j])), "r"(mag));
+        sts_f32(la + rrow + (uint32_t)j * RS, __uint_as_float(rn[j]));
+    }
+    if constexpr (DUP) {  // this group owns the block's last rows, which are also read through the leading pad
+#pragma unroll
+        for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS - WRAP, __uint_as_float(rn[j]));
+    }
+    return ((sx >> 31) ^ (uint32_t)D) & 1u;  // hard bit = !signbit(T)
+}
+
+template <class P, int CS0, bool DUP>
+__device__ __forceinline__ uint32_t qc_cn_static(const QcWarpTab<P>& tb, uint32_t la) {
+    if constexpr (CS0 < P::CS) {
+        constexpr int D = P::cdeg(CS0);
+        constexpr uint32_t RS = (uint32_t)(P::Z + 32 / P::G) * P::G * 4u;
+        constexpr uint32_t WRAP = (uint32_t)P::Z * P::G * 4u;
+        const uint32_t u = qc_check<D, RS, WRAP, DUP>(tb.cn_t + QcLayout<P>::coff(CS0), tb.cn_r[CS0], la);
+        return u | qc_cn_static<P, CS0 + 1, DUP>(tb, la);
+    } else {
+        return 0u;
+    }
+}
+
+// NS variable slots of exact degree D together (independent FADD chains interleaved): T = (-y) - R_1 - R_2 ...
+// in ascending-row order; the new T goes to this lane's own row (and to the trailing pad for the block's first group).
+template <class P, int S0, int D, int NS, bool DUP>
+__device__ __forceinline__ void qc_vn_slots(const QcWarpTab<P>& tb, uint32_t la, const float* yn, bool done) {
+    constexpr uint32_t WRAP = (uint32_t)P::Z * P::G * 4u;
+    constexpr int NE = NS * D;
+    float acc[NS], r[NE + 1];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) acc[i] = yn[S0 + i];
+#pragma unroll
+    for (int e = 0; e < NE; e += 2) {  // entries of the run are contiguous: [slot][k]
+        const uint2 u = *reinterpret_cast<const uint2*>(tb.vn_r + QcLayout<P>::voff(S0) + e);
+        r[e] = lds_f32(la + u.x);
+        if (e + 1 < NE) r[e + 1] = lds_f32(la + u.y);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc[i] = __fsub_rn(acc[i], r[i * D + k]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if (!done) {
+            sts_f32(la + tb.vn_t[S0 + i], acc[i]);
+            if constexpr (DUP) sts_f32(la + tb.vn_t[S0 + i] + WRAP, acc[i]);
+        }
+    }
+}
+
+template <class P, int S0, bool DUP>
+__device__ __forceinline__ void qc_vn_static(const QcWarpTab<P>& tb, uint32_t la, const float* yn, bool done) {
+    if constexpr (S0 < P::VS) {
+        constexpr int NS = QcLayout<P>::vrun(S0);
+        qc_vn_slots<P, S0, P::vdeg(S0), NS, DUP>(tb, la, yn, done);
+        qc_vn_static<P, S0 + NS, DUP>(tb, la, yn, done);
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(P::W * 32, (P::W * 32 <= 288 ? 3 : (P::W * 32 <= 384 ? 2 : 1)))
+ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
+    constexpr int G = P::G, SUB = 32 / G, NL = P::W * SUB, Z = P::Z;
+    constexpr uint32_t ROWB = (uint32_t)G * 4u;              // bytes of one row (G codewords)
+    constexpr uint32_t RS = (uint32_t)(Z + SUB) * ROWB;      // bytes of one padded block
+    constexpr uint32_t WRAP = (uint32_t)Z * ROWB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_flag[2][32];
+    __shared__ long long s_cw[32];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform: the table reads become LDCU
+    const int c = lane & (G - 1), h = lane / G;
+    const QcWarpTab<P>& tb = qc_tab<P>(p.tab_slot, warp);
+    const uint32_t sb = smem_u32(smem_raw);
+    const uint32_t la = sb + (uint32_t)lane * 4u;            // every hot-loop access is [la + uniform (+ imm)]
+    const uint32_t c4 = (uint32_t)c * 4u;
+
+    if (threadIdx.x < 32) sts_f32(sb + p.t_bytes + p.r_bytes + (uint32_t)lane * 4u, 0.0f);  // zero row
+
+    float yn[P::VS];
+#pragma unroll
+    for (int s = 0; s < P::VS; ++s) yn[s] = -1.0f;
+    long long cw = -1;
+    bool live = false, done = false, loading = false;
+    int it = 0, my_iters = 0;
+
+    auto t_addr = [&](int n) -> uint32_t {  // T element of variable n, codeword lane c
+        return sb + (uint32_t)((n / Z) * (Z + SUB) + (n % Z)) * ROWB + c4;
+    };
+    auto emit = [&](bool sel) {
+        // toChar (decodeCL.c:188-199): bit n = !(P > 0) = !signbit(T); node lanes share the bytes
+        if (p.info) {
+            const int KB = (p.K + 7) >> 3;
+            for (int b = warp * SUB + h; b < KB; b += NL) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.K) v |= ((~__float_as_uint(lds_f32(t_addr(n)))) >> 31) << t;
+                }
+                if (sel) p.info[(size_t)cw * KB + b] = (uint8_t)v;
+            }
+        }
+        if (p.hard) {
+            const int NB8 = (p.N + 7) >> 3;
+            for (int b = warp * SUB + h; b < NB8; b += NL) {
+                uint32_t v = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int n = b * 8 + t;
+                    if (n < p.N) v |= ((~__float_as_uint(lds_f32(t_addr(n)))) >> 31) << t;
+                }
+                if (sel) p.hard[(size_t)cw * NB8 + b] = (uint8_t)v;
+            }
+        }
+        if (p.post && sel) {
+            for (int n = warp * SUB + h; n < p.N; n += NL) p.post[(size_t)cw * p.N + n] = -lds_f32(t_addr(n));
+        }
+        if (p.iters && warp == 0 && h == 0 && sel) p.iters[cw] = my_iters;
+    };
+    // fetch the next codeword of the lanes selected by `want`; its channel values travel by cp.async
+    // into this thread's own T elements
+    auto fetch = [&](bool want) {
+        if (warp == 0) {
+            const bool take = h == 0 && want;
+            long long w = take ? (long long)atomicAdd(p.counter64, 1ull) : -1;
+            if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status)) w = p.ncw;  // timed out: give the words up
+            if (take) s_cw[c] = w;
+        }
+        __syncthreads();  // also: every read of the retiring lanes' T (emit) is complete
+        if (want) {
+            live = false; done = false;
+            cw = s_cw[c];
+            if (cw < p.ncw) {
+                loading = true;
+                const float* src = p.llr + (size_t)cw * p.N + h;
+#pragma unroll
+                for (int s = 0; s < P::VS; ++s) {
+                    const uint32_t dst = la + tb.vn_t[s];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + tb.var0[s]) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // lanes whose values have landed start decoding: T = -y (canonical zero), R = 0 (decodeInitMS)
+    auto start_loaded = [&]() {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (loading) {
+#pragma unroll
+            for (int s = 0; s < P::VS; ++s) {
+                const float y = lds_f32(la + tb.vn_t[s]);
+                yn[s] = __fadd_rn(-y, 0.0f);
+                sts_f32(la + tb.vn_t[s], yn[s]);
+                if (tb.vdup) sts_f32(la + tb.vn_t[s] + WRAP, yn[s]);
+            }
+#pragma unroll
+            for (int cs = 0; cs < P::CS; ++cs) {
+                const bool dup = tb.cdup != 0u;
+                for (int j = 0; j < P::cdeg(cs); ++j) {
+                    sts_f32(la + tb.cn_r[cs] + (uint32_t)j * RS, 0.0f);
+                    if (dup) sts_f32(la + tb.cn_r[cs] + (uint32_t)j * RS - WRAP, 0.0f);
+                }
+            }
+            loading = false; live = true; done = false; it = 0;
+        }
+        __syncthreads();
+    };
+
+    if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+    __syncthreads();
+    fetch(true);
+    uint32_t ph = 0;
+    for (;;) {
+        // loop top: start words whose values arrived, retire finished words and refill their lanes
+        // (a warp holds every codeword lane and all threads of a lane agree: the votes are CTA-uniform)
+        if (__any_sync(0xffffffffu, loading)) start_loaded();
+        const bool retire = live && done;
+        if (__any_sync(0xffffffffu, retire)) {
+            emit(retire);
+            fetch(retire);
+            if ((p.refill_wait || !__any_sync(0xffffffffu, live)) && __any_sync(0xffffffffu, loading)) start_loaded();
+        }
+        if (!__any_sync(0xffffffffu, live || loading)) break;
+
+        // check-node pass + syndrome of the previous posterior
+        const uint32_t unsat = tb.cdup ? qc_cn_static<P, 0, true>(tb, la) : qc_cn_static<P, 0, false>(tb, la);  // warp-uniform
+        const bool check = p.early_term && it >= 1 && live && !done;
+        if (check && unsat) s_flag[ph & 1][c] = 1u;  // same-value race, benign
+        __syncthreads();
+        if (check && s_flag[ph & 1][c] == 0u) { done = true; my_iters = it; }
+        if (warp == 0) s_flag[(ph + 1) & 1][lane] = 0u;
+        ++ph;
+
+        // variable-node pass (the posterior of finished / idle lanes is frozen)
+        if (tb.vdup) qc_vn_static<P, 0, true>(tb, la, yn, !(live && !done));  // warp-uniform
+        else qc_vn_static<P, 0, false>(tb, la, yn, !(live && !done));
+        if (live && !done) {
+            ++it;
+            if (it == p.max_iter) { done = true; my_iters = it; }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace ldpc_b200

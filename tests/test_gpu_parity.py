@@ -38,9 +38,9 @@ def test_default_code_parity(default_code, sigma):
     assert_parity(host, ref, c["N"], what="host sigma=%g" % sigma)
 
 
-@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group"), (5, "cluster")])
+@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group"), (5, "cluster"), (7, "qc")])
 def test_default_code_every_kernel_path(default_code, path, name):
-    """Every kernel family (shared-memory lane, global-workspace lane, lane16, group) gives the oracle's bits."""
+    """Every kernel family (shared-memory lane, global-workspace lane, lane16, group, cluster, quasi-cyclic) gives the oracle's bits."""
     import myldpccppapi_b200 as m
     c = default_code
     llr = np.concatenate([awgn_llr(150, c["N"], 0.62, seed=11), awgn_llr(150, c["N"], 0.52, seed=12),

@@ -149,7 +149,7 @@ __device__ __forceinline__ uint32_t qc_check(const uint32_t* __restrict__ tt, ui
     for (int j = 0; j < D; ++j) {
         S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
         const float a = fabsf(S[j]);
-        m2 = fminf(m2, fmaxf(m1, a));
+        m2 = fminf(m2, fmaxf(m1, a));   // (a pair-sort + merge tree needs 2.3 instead of 2.5 ALU ops per edge: measured no faster)
         m1 = fminf(m1, a);
     }
 #pragma unroll

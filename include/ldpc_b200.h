@@ -63,6 +63,8 @@ enum {
                                       global workspace, fixed-stride tables, prefetched indices, variable bundles   */
     LDPC_B200_PATH_LANE16 = 3,     /* tuned short-code path: lane = codeword, channel values in
                                       registers, 16-byte check state and index tables in shared memory */
+    LDPC_B200_PATH_WARP = 8,       /* opt-in, measured alternative: one codeword per CTA, a sub-warp per check with
+                                      shuffle / ballot row reductions, a thread per variable (the textbook mapping) */
     LDPC_B200_PATH_QC = 7          /* quasi-cyclic codes (every code Coder::initCheckMatrix builds): the GROUP
                                       arithmetic with warp-uniform index tables read from the parameter space
                                       into uniform registers; cyclic wrap absorbed by padded rows            */

@@ -20,6 +20,7 @@
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
 #include "ldpc_qc.cuh"
+#include "ldpc_warp.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
 #include "ldpc_stream.cuh"
@@ -113,6 +114,11 @@ struct ldpc_b200_decoder {
     int qc_state = 0;  // 0 = not tried, 1 = tables built and uploaded, -1 = no match / no free slot
     int qc_slot = -1;
     size_t qc_smem = 0;
+    // WARP tables (sub-warp per check)
+    uint32_t* dw_cn_col = nullptr;
+    uint32_t* dw_vn_pos = nullptr;
+    int w_sw = 0;
+    bool warp_ready = false;
     // CLUSTER tables
     uint32_t* dc_cn_tab = nullptr;
     uint32_t* dc_vn_tab = nullptr;
@@ -1126,6 +1132,27 @@ int launch_qc_t(const QcParams<P>& q, int grid, size_t smem, cudaStream_t stream
     return LDPC_B200_OK;
 }
 
+// ---- WARP layout (see ldpc_warp.cuh) ------------------------------------------------------------------
+int warp_sub_width(const HostTables& t) { return t.max_row_weight <= 8 ? 8 : (t.max_row_weight <= 16 ? 16 : (t.max_row_weight <= 32 ? 32 : 0)); }
+
+int upload_warp_tables(ldpc_b200_decoder* h) {
+    if (h->warp_ready) return LDPC_B200_OK;
+    const HostTables& t = h->host;
+    const int SW = warp_sub_width(t);
+    std::vector<uint32_t> cn_col((size_t)t.M * SW, 0xffffffffu), vn_pos((size_t)std::max(t.nnz, 1));
+    for (int r = 0; r < t.M; ++r)
+        for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) cn_col[(size_t)r * SW + (e - t.row_ptr[r])] = (uint32_t)t.col_idx[e];
+    for (int k = 0; k < t.nnz; ++k) vn_pos[k] = (t.vn_edge[k] >> kPosBits) * (uint32_t)SW + (t.vn_edge[k] & ((1u << kPosBits) - 1u));
+    CU_TRY(cudaMalloc(&h->dw_cn_col, cn_col.size() * 4));
+    CU_TRY(cudaMalloc(&h->dw_vn_pos, vn_pos.size() * 4));
+    CU_TRY(cudaMemcpy(h->dw_cn_col, cn_col.data(), cn_col.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->dw_vn_pos, vn_pos.data(), vn_pos.size() * 4, cudaMemcpyHostToDevice));
+    h->table_bytes += (cn_col.size() + vn_pos.size()) * 4;
+    h->w_sw = SW;
+    h->warp_ready = true;
+    return LDPC_B200_OK;
+}
+
 // ---- CLUSTER layout (one codeword per 8-CTA cluster, DSMEM gathers; see ldpc_cluster.cuh) ------------
 struct ClShape {
     int W = 32, CS = 0, VS = 0, dmax = 8;
@@ -1509,6 +1536,21 @@ int make_plan(ldpc_b200_decoder* h) {
             return LDPC_B200_OK;
         }
     }
+    if (h->forced_path == LDPC_B200_PATH_WARP) {  // opt-in: sub-warp per check, shuffle reductions
+        const int SW = warp_sub_width(t);
+        const size_t smem = ((size_t)2 * t.N + (size_t)t.M * SW) * sizeof(float);
+        if (h->algorithm != LDPC_B200_ALG_MIN_SUM || SW == 0 || smem + 1024 > h->smem_optin)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "the warp-per-check path needs min-sum, check degree <= 32 and a codeword that fits one SM's shared memory");
+        pl.path = LDPC_B200_PATH_WARP;
+        pl.threads = std::min(1024, std::max(128, (t.N + 31) / 32 * 32));
+        pl.smem = smem;
+        const size_t per_sm = std::min<size_t>({(h->smem_optin + 1024) / (smem + 1024), (size_t)(2048 / pl.threads), (size_t)16});
+        pl.ctas = h->sm_count * (int)std::max<size_t>(per_sm, 1);
+        pl.cw_per_cta = 1;
+        h->plan = pl;
+        h->planned = true;
+        return LDPC_B200_OK;
+    }
     {   // explicit per-edge messages on chip (G codewords per CTA)
         GrpShape sh;
         const bool fits = group_pick(t, h->smem_optin, h->algorithm == LDPC_B200_ALG_SUM_PRODUCT, &sh);
@@ -1639,7 +1681,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (rc) return rc;
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
-    const int per_group = (pl.path == LDPC_B200_PATH_GROUP || pl.path == LDPC_B200_PATH_QC) ? pl.G : kLanes;
+    const int per_group = (pl.path == LDPC_B200_PATH_GROUP || pl.path == LDPC_B200_PATH_QC) ? pl.G : (pl.path == LDPC_B200_PATH_WARP ? 1 : kLanes);
     const int64_t ngroups = (ncw + per_group - 1) / per_group;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
     unsigned long long* ctr64 = h->d_counters + h->counter_next;
@@ -1647,6 +1689,28 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     h->counter_next = (h->counter_next + 1) % kCounterRing;
     CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
     const int grid = (int)std::min<int64_t>(ngroups, pl.ctas);
+
+    if (pl.path == LDPC_B200_PATH_WARP) {
+        rc = upload_warp_tables(h);
+        if (rc) return rc;
+        WarpParams q;
+        q.cn_col = h->dw_cn_col; q.col_ptr = h->d_col_ptr; q.vn_pos = h->dw_vn_pos;
+        q.M = t.M; q.N = t.N; q.K = h->K; q.SW = h->w_sw;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter64 = ctr64;
+#define WARP_LAUNCH(SWV)                                                                                                        \
+    do {                                                                                                                        \
+        CU_TRY(cudaFuncSetAttribute(ldpc_ms_warp_kernel<SWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));     \
+        ldpc_ms_warp_kernel<SWV><<<grid, pl.threads, pl.smem, stream>>>(q);                                                     \
+    } while (0)
+        if (h->w_sw == 8) WARP_LAUNCH(8); else if (h->w_sw == 16) WARP_LAUNCH(16); else WARP_LAUNCH(32);
+#undef WARP_LAUNCH
+        CU_TRY(cudaGetLastError());
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
 
     if (pl.path == LDPC_B200_PATH_QC) {
         auto& q = h->qc;  // tables filled by qc_build; per-launch fields below
@@ -1907,6 +1971,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dg_cn_tab); cudaFree(h->dg_vn_tab); cudaFree(h->dg_var_of_pos); cudaFree(h->dg_pos_of_var);
             cudaFree(h->d16_cn_tab); cudaFree(h->d16_vn_tab); cudaFree(h->d16_var_of_pos); cudaFree(h->d16_pos_of_var);
             cudaFree(h->dt_cn_tab); cudaFree(h->de_xt);
+            cudaFree(h->dw_cn_col); cudaFree(h->dw_vn_pos);
             cudaFree(h->ds_cn_tab); cudaFree(h->ds_vn_tab); cudaFree(h->ds_var_of_pos); cudaFree(h->ds_pos_of_var);
             cudaFree(h->d_counters); cudaFree(h->d_ws);
             if (h->ws_event) cudaEventDestroy(h->ws_event);

@@ -11,8 +11,8 @@ import re
 from . import _build
 
 OK = 0
-PATH_LANE_SMEM, PATH_LANE_GLOBAL, PATH_LANE16, PATH_GROUP, PATH_CLUSTER, PATH_STREAM, PATH_QC = 0, 1, 3, 4, 5, 6, 7
-PATH_NAMES = {0: "lane_smem", 1: "lane_global", 3: "lane16", 4: "group", 5: "cluster", 6: "stream", 7: "qc"}
+PATH_LANE_SMEM, PATH_LANE_GLOBAL, PATH_LANE16, PATH_GROUP, PATH_CLUSTER, PATH_STREAM, PATH_QC, PATH_WARP = 0, 1, 3, 4, 5, 6, 7, 8
+PATH_NAMES = {0: "lane_smem", 1: "lane_global", 3: "lane16", 4: "group", 5: "cluster", 6: "stream", 7: "qc", 8: "warp"}
 
 
 class LdpcError(RuntimeError):

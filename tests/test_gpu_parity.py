@@ -38,7 +38,7 @@ def test_default_code_parity(default_code, sigma):
     assert_parity(host, ref, c["N"], what="host sigma=%g" % sigma)
 
 
-@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group"), (5, "cluster"), (7, "qc")])
+@pytest.mark.parametrize("path,name", [(0, "lane_smem"), (1, "lane_global"), (3, "lane16"), (4, "group"), (5, "cluster"), (7, "qc"), (8, "warp")])
 def test_default_code_every_kernel_path(default_code, path, name):
     """Every kernel family (shared-memory lane, global-workspace lane, lane16, group, cluster, quasi-cyclic) gives the oracle's bits."""
     import myldpccppapi_b200 as m
@@ -57,7 +57,7 @@ def test_regular_3_6_every_kernel_path():
     M, N, K, rp, ci = m.codes.regular_code()
     llr = awgn_llr(40, N, 0.84, seed=2)
     ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
-    for path, name in [(1, "lane_global"), (4, "group"), (5, "cluster"), (6, "stream")]:
+    for path, name in [(1, "lane_global"), (4, "group"), (5, "cluster"), (6, "stream"), (8, "warp")]:
         dec = m.Decoder(M, N, K, rp, ci)
         dec.set_path(path)
         assert dec.info()["path_name"] == name

@@ -2188,7 +2188,9 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
     const HostTables& t = h->host;
     const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
     const int64_t g = h->plan.cw_per_cta;
-    const int64_t batch_cap = std::max<int64_t>(g, (((int64_t)512 << 20) / ((int64_t)t.N * 4)) / g * g);  // <= 512 MB of channel values per launch
+    int64_t batch_bytes = (int64_t)512 << 20;  // <= 512 MB of channel values per launch
+    if (const char* env = std::getenv("LDPC_B200_STREAM_BATCH_KB")) { const long long kb = std::atoll(env); if (kb >= 1) batch_bytes = kb << 10; }
+    const int64_t batch_cap = std::max<int64_t>(g, (batch_bytes / ((int64_t)t.N * 4)) / g * g);
     const int64_t want = std::min(ncw, batch_cap);
     for (int s = 0; s < 2; ++s)
         if (!h->streams[s]) CU_TRY(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));

@@ -211,6 +211,34 @@ def test_roundtrip_full_batch_properties(default_code):
     assert_parity({k: v.cpu().numpy() for k, v in o2.items()}, ref, N, what="slice")
 
 
+def test_streamed_host_pipeline(default_code, monkeypatch):
+    """Host buffers on the quasi-cyclic path: one persistent launch fed by a copy stream.  Ragged sizes, pageable and
+    pinned inputs, optional outputs asked for only on a later call, several launches per call (small batch cap) and
+    the 3-stream pipeline (LDPC_B200_NO_STREAMED) must all give the oracle's bytes, counts and posteriors."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    c = default_code
+    N = c["N"]
+    ncw = 3001
+    llr = np.concatenate([awgn_llr(1500, N, 0.6, seed=41), awgn_llr(1501, N, 0.5, seed=42)])
+    ref = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr, literal=False)
+    dec = m.Decoder.wimax(c["K"], N, c["rate"])
+    assert dec.info()["path_name"] == "qc"
+    first = dec.decode_host(llr)                                    # pageable input, info + iters only
+    assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
+    assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="streamed, all outputs")
+    pinned = torch.from_numpy(llr).pin_memory().numpy()
+    assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
+    monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # 455 words per launch: 7 launches
+    assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, 7 launches")
+    monkeypatch.setenv("LDPC_B200_STREAM_CHUNK", "8")               # one word group per copy
+    assert_parity(dec.decode_host(pinned[:500], want_hard=True, want_post=True), tuple(r[:500] for r in ref), N, what="streamed, tiny chunks")
+    monkeypatch.delenv("LDPC_B200_STREAM_BATCH_KB"); monkeypatch.delenv("LDPC_B200_STREAM_CHUNK")
+    monkeypatch.setenv("LDPC_B200_NO_STREAMED", "1")
+    assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="3-stream pipeline")
+    assert ncw == llr.shape[0]
+
+
 def test_coder_api_roundtrip(default_code):
     """Test.cpp-shaped run through the Coder mirror: payload -> encode -> test() channel -> decode."""
     import myldpccppapi_b200 as m

@@ -239,7 +239,7 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
     constexpr uint32_t WRAP = (uint32_t)Z * ROWB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_flag[2][32];
-    __shared__ long long s_cw[32];
+    __shared__ long long s_cw[32], s_nxt[32];
 
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform: the table reads become LDCU
@@ -292,12 +292,28 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
         }
         if (p.iters && warp == 0 && h == 0 && sel) p.iters[cw] = my_iters;
     };
-    // fetch the next codeword of the lanes selected by `want`; its channel values travel by cp.async
-    // into this thread's own T elements
+    // warp 0: lanes selected by `want` claim their next word and pull its channel values into L2
+    auto claim = [&](bool want) {
+        long long nn = (h == 0 && want) ? (long long)atomicAdd(p.counter64, 1ull) : p.ncw;
+        if (h == 0 && want) s_nxt[c] = nn;
+        nn = __shfl_sync(0xffffffffu, nn, c);          // node lanes 1..SUB-1 of warp 0 help with the prefetch
+        const bool w2 = __shfl_sync(0xffffffffu, (int)want, c) != 0;
+        const char* base = reinterpret_cast<const char*>(p.llr + (size_t)nn * p.N);
+        const bool pf = w2 && nn < p.ncw;
+        for (int i = 0; i < (p.N * 4 + SUB * 128 - 1) / (SUB * 128); ++i) {  // same trip count in every lane
+            const int off = (i * SUB + h) * 128;
+            if (pf && off < p.N * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+    };
+    // Refill the lanes selected by `want`: each takes the word its lane claimed at the PREVIOUS refill (s_nxt),
+    // whose channel values were prefetched into L2 then, and sends them by cp.async into this thread's own T
+    // elements; after that warp 0 claims the word after it from the queue and starts its L2 prefetch.  The queue's
+    // atomic and the HBM latency are thus off the critical path of a refill (they used to cost ~2 us per event,
+    // which at 3 iterations per word doubled the time of a batch).
     auto fetch = [&](bool want) {
         if (warp == 0) {
             const bool take = h == 0 && want;
-            long long w = take ? (long long)atomicAdd(p.counter64, 1ull) : -1;
+            long long w = take ? s_nxt[c] : -1;
             if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status)) w = p.ncw;  // timed out: give the words up
             if (take) s_cw[c] = w;
         }
@@ -316,6 +332,7 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        if (warp == 0) claim(want);
     };
     // lanes whose values have landed start decoding: T = -y (canonical zero), R = 0 (decodeInitMS)
     auto start_loaded = [&]() {
@@ -342,7 +359,7 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
         __syncthreads();
     };
 
-    if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; }
+    if (warp == 0) { s_flag[0][lane] = 0u; s_flag[1][lane] = 0u; claim(true); }
     __syncthreads();
     fetch(true);
     uint32_t ph = 0;

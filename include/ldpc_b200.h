@@ -66,8 +66,9 @@ enum {
     LDPC_B200_PATH_WARP = 8,       /* opt-in, measured alternative: one codeword per CTA, a sub-warp per check with
                                       shuffle / ballot row reductions, a thread per variable (the textbook mapping) */
     LDPC_B200_PATH_QC = 7          /* quasi-cyclic codes (every code Coder::initCheckMatrix builds): the GROUP
-                                      arithmetic with warp-uniform index tables read from the parameter space
-                                      into uniform registers; cyclic wrap absorbed by padded rows            */
+                                      arithmetic with warp-uniform index tables (constant memory -> uniform
+                                      registers for the compiled profile of Test.cpp's code; shared memory for the
+                                      run-time profile used for z > 24); cyclic wrap absorbed by padded rows     */
 };
 
 /* Decoding algorithm of a handle (ldpc_b200_set_algorithm). */

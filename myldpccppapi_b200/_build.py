@@ -42,7 +42,7 @@ def _stale(target: pathlib.Path, sources) -> bool:
 
 def build_cuda(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> pathlib.Path:
     srcs = [CSRC / "ldpc_b200.cu", CSRC / "ldpc_tables.cpp"]
-    deps = srcs + [CSRC / "ldpc_kernels.cuh", CSRC / "ldpc_cluster.cuh", CSRC / "ldpc_qc.cuh", CSRC / "ldpc_warp.cuh", CSRC / "ldpc_sp.cuh", CSRC / "ldpc_tdmp.cuh", CSRC / "ldpc_stream.cuh", CSRC / "ldpc_encode.cuh", CSRC / "ldpc_tables.h", CSRC / "wimax_tables.h",
+    deps = srcs + [CSRC / "ldpc_kernels.cuh", CSRC / "ldpc_cluster.cuh", CSRC / "ldpc_qc.cuh", CSRC / "ldpc_qcg.cuh", CSRC / "ldpc_warp.cuh", CSRC / "ldpc_sp.cuh", CSRC / "ldpc_tdmp.cuh", CSRC / "ldpc_stream.cuh", CSRC / "ldpc_encode.cuh", CSRC / "ldpc_tables.h", CSRC / "wimax_tables.h",
                    ROOT / "include" / "ldpc_b200.h"]
     if force or _stale(LIB, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-o", str(LIB), *map(str, srcs)]

@@ -20,6 +20,7 @@
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
 #include "ldpc_qc.cuh"
+#include "ldpc_qcg.cuh"
 #include "ldpc_warp.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
@@ -114,6 +115,12 @@ struct ldpc_b200_decoder {
     int qc_state = 0;  // 0 = not tried, 1 = tables built and uploaded, -1 = no match / no free slot
     int qc_slot = -1;
     size_t qc_smem = 0;
+    // QC tables with a run-time profile (ldpc_qcg.cuh)
+    QcgParams qcg;
+    QcgWarpTab qcg_tab[kQcgMaxW];
+    QcgWarpTab* dq_tabs = nullptr;
+    int qcg_state = 0, qcg_G = 0, qcg_ctas_per_sm = 0;
+    size_t qcg_smem = 0;
     // WARP tables (sub-warp per check)
     uint32_t* dw_cn_col = nullptr;
     uint32_t* dw_vn_pos = nullptr;
@@ -1082,7 +1089,108 @@ bool qc_build(const HostTables& t, QcParams<P>* out, QcWarpTab<P>* tabs, size_t*
     return true;
 }
 
-// Slots of the __constant__ table bank, per device: which handle owns each.
+// Block structure of H for block size z: rows[br] = the circulants (block column, shift) of block row br in
+// ascending column order.  false when H is not a grid of z x z blocks that are zero or one shifted identity.
+struct QcBlk { int bc, s; };
+bool qc_blocks(const HostTables& t, int z, std::vector<std::vector<QcBlk>>* rows_out) {
+    if (z < 1 || t.M % z || t.N % z) return false;
+    const int MB = t.M / z, NB = t.N / z;
+    std::vector<std::vector<QcBlk>> rows(MB);
+    for (int br = 0; br < MB; ++br) {
+        const int r0 = br * z;
+        std::vector<bool> used(NB, false);
+        for (int e = t.row_ptr[r0]; e < t.row_ptr[r0 + 1]; ++e) {
+            const int bc = t.col_idx[e] / z;
+            if (used[bc]) return false;
+            used[bc] = true;
+            rows[br].push_back({bc, t.col_idx[e] % z});
+        }
+        std::vector<int> want(rows[br].size());
+        for (int r = 0; r < z; ++r) {
+            if (t.row_ptr[r0 + r + 1] - t.row_ptr[r0 + r] != (int)rows[br].size()) return false;
+            for (size_t j = 0; j < rows[br].size(); ++j) want[j] = rows[br][j].bc * z + (r + rows[br][j].s) % z;
+            std::sort(want.begin(), want.end());
+            for (size_t j = 0; j < want.size(); ++j)
+                if (t.col_idx[t.row_ptr[r0 + r] + (int)j] != want[j]) return false;
+        }
+    }
+    *rows_out = std::move(rows);
+    return true;
+}
+
+// Run-time-profile QC tables for G codewords per CTA (see ldpc_qcg.cuh).  false = this (z, G) does not work.
+bool qcg_build(const HostTables& t, int z, int G, const std::vector<std::vector<QcBlk>>& rows, QcgParams* out, QcgWarpTab* tabs,
+               size_t* smem_out) {
+    const int SUB = 32 / G;
+    if (z % SUB) return false;
+    const uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
+    const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
+    const int cgroups = MB * gpb, vgroups = NB * gpb;
+    int W = 0;
+    for (int w = kQcgMaxW; w >= 4; --w)
+        if (cgroups % w == 0 && vgroups % w == 0) { W = w; break; }
+    if (!W) return false;
+    const int CS = cgroups / W, VS = vgroups / W;
+    if (CS > kQcgMaxCS || VS > kQcgMaxVS) return false;
+    struct Col { int br, j, s; };
+    std::vector<std::vector<Col>> cols(NB);
+    for (int br = 0; br < MB; ++br)
+        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
+    std::vector<int> border(MB), corder(NB);
+    for (int i = 0; i < MB; ++i) border[i] = i;
+    for (int i = 0; i < NB; ++i) corder[i] = i;
+    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cols[a].size() > cols[b].size(); });
+    QcgParams& q = *out;
+    std::memset(&q, 0, sizeof(q));
+    std::memset(tabs, 0, sizeof(QcgWarpTab) * kQcgMaxW);
+    // slot degrees = the largest degree among the slot's groups (groups are in descending degree order)
+    for (int p = 0; p < cgroups; ++p) q.cdeg[p / W] = std::max<uint8_t>(q.cdeg[p / W], (uint8_t)rows[border[p / gpb]].size());
+    for (int p = 0; p < vgroups; ++p) q.vdeg[p / W] = std::max<uint8_t>(q.vdeg[p / W], (uint8_t)cols[corder[p / gpb]].size());
+    int ce = 0, ve = 0;
+    std::vector<int> coff(CS + 1, 0), voff(VS + 1, 0);
+    for (int cs = 0; cs < CS; ++cs) { if (q.cdeg[cs] < 1 || q.cdeg[cs] > kQcgMaxCD) return false; coff[cs] = ce; ce += (q.cdeg[cs] + 3) & ~3; }
+    for (int s = 0; s < VS; ++s) { if (q.vdeg[s] < 1 || q.vdeg[s] > kQcgMaxVD) return false; voff[s] = ve; ve += (q.vdeg[s] + 3) & ~3; }
+    if (ce > kQcgMaxCE || ve > kQcgMaxVE) return false;
+    // R blocks of a block row: as many as the largest slot degree any of its groups is processed with
+    std::vector<int> dpad(MB, 0), eb0(MB + 1, 0);
+    for (int p = 0; p < cgroups; ++p) dpad[border[p / gpb]] = std::max(dpad[border[p / gpb]], (int)q.cdeg[p / W]);
+    for (int br = 0; br < MB; ++br) eb0[br + 1] = eb0[br] + dpad[br];
+    const uint32_t t_bytes = (uint32_t)NB * (z + SUB) * ROWB, r_bytes = (uint32_t)eb0[MB] * RS;
+    const uint32_t zero_row = t_bytes + r_bytes, inf_row = zero_row + 128u;
+    for (int p = 0; p < cgroups; ++p) {
+        const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
+        QcgWarpTab& tb = tabs[w];
+        tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
+        if (g == gpb - 1) tb.cdup |= 1u << slot;
+        for (int j = 0; j < q.cdeg[slot]; ++j)
+            tb.cn_t[coff[slot] + j] = j < (int)rows[br].size()
+                ? (uint32_t)(rows[br][j].bc * (z + SUB) + (r0 + rows[br][j].s) % z) * ROWB
+                : inf_row;  // padded edge: T = -inf is neutral for the minima, the sign parity and the syndrome
+    }
+    for (int p = 0; p < vgroups; ++p) {
+        const int bc = corder[p / gpb], g = p % gpb, slot = p / W, w = p % W, i0 = g * SUB;
+        const int d = (int)cols[bc].size();
+        QcgWarpTab& tb = tabs[w];
+        tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
+        tb.var0[slot] = (uint32_t)(bc * z + i0);
+        if (g == 0) tb.vdup |= 1u << slot;
+        for (int k = 0; k < q.vdeg[slot]; ++k) {
+            if (k >= d) { tb.vn_r[voff[slot] + k] = zero_row; continue; }
+            const Col& cd = cols[bc][k];
+            int m = ((i0 - cd.s) % z + z) % z;
+            if (m > z - SUB) m -= z;
+            tb.vn_r[voff[slot] + k] = t_bytes + (uint32_t)(eb0[cd.br] + cd.j) * RS + (uint32_t)(SUB + m) * ROWB;
+        }
+    }
+    q.N = t.N; q.Z = z; q.W = W; q.CS = CS; q.VS = VS;
+    q.RS = RS; q.WRAP = (uint32_t)z * ROWB;
+    q.t_bytes = t_bytes; q.r_bytes = r_bytes;
+    *smem_out = (size_t)t_bytes + r_bytes + 256 + (size_t)W * sizeof(QcgWarpTab);
+    return true;
+}
+
+// Slots of the __constant__ table banks, per device: which handle owns each.
 constexpr int kQcMaxDevices = 64;
 std::mutex g_qc_mu;
 const void* g_qc_owner[kQcMaxDevices][kQcTabSlots] = {};
@@ -1128,6 +1236,42 @@ int launch_qc_t(const QcParams<P>& q, int grid, size_t smem, cudaStream_t stream
     if (std::getenv("LDPC_B200_QC_CARVEOUT"))
         CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
+    CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+// Run-time-profile QC path: picks G (most codewords per CTA with two CTAs per SM, else one CTA), builds and uploads.
+bool qcg_prepare(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    std::vector<int> zs;
+    if (h->layer_z > 0) zs.push_back(h->layer_z);
+    if (t.N % 24 == 0 && (zs.empty() || zs[0] != t.N / 24)) zs.push_back(t.N / 24);  // 802.16e: 24 block columns
+    for (int z : zs) {
+        std::vector<std::vector<QcBlk>> rows;
+        if (!qc_blocks(t, z, &rows)) continue;
+        for (int per_sm : {2, 1}) {
+            for (int G : {8, 4, 2}) {
+                size_t smem = 0;
+                if (!qcg_build(t, z, G, rows, &h->qcg, h->qcg_tab, &smem)) continue;
+                if ((size_t)per_sm * (smem + 2048) > h->smem_optin + 1024 || smem + 1024 > h->smem_optin) continue;
+                DeviceGuard guard(h->device);
+                if (!guard.ok) return false;
+                if (!h->dq_tabs && cudaMalloc(&h->dq_tabs, sizeof(h->qcg_tab)) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+                if (cudaMemcpy(h->dq_tabs, h->qcg_tab, sizeof(h->qcg_tab), cudaMemcpyHostToDevice) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+                h->qcg.tabs = h->dq_tabs;
+                h->qcg_G = G; h->qcg_ctas_per_sm = per_sm; h->qcg_smem = smem;
+                h->table_bytes += sizeof(h->qcg_tab);
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int G>
+int launch_qcg_t(const QcgParams& q, int grid, size_t smem, cudaStream_t stream) {
+    CU_TRY(cudaFuncSetAttribute(ldpc_ms_qcg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ldpc_ms_qcg_kernel<G><<<grid, q.W * 32, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());
     return LDPC_B200_OK;
 }
@@ -1520,12 +1664,12 @@ int make_plan(ldpc_b200_decoder* h) {
         using P = QcProfileWimax34B576;
         const bool want = h->algorithm == LDPC_B200_ALG_MIN_SUM &&
                           (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !std::getenv("LDPC_B200_NO_QC")));
-        if (want && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
-        const bool fits = want && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
-        if (h->forced_path == LDPC_B200_PATH_QC && !fits)
-            return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not match a compiled quasi-cyclic profile (or the algorithm is not min-sum)");
+        const bool compiled = want && !std::getenv("LDPC_B200_QC_GENERIC");  // (the env var forces the run-time profile: tests)
+        if (compiled && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
+        const bool fits = compiled && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
         if (fits) {
             pl.path = LDPC_B200_PATH_QC;
+            pl.dmax = 1;  // marks the compiled profile
             pl.threads = 32 * P::W;
             pl.smem = h->qc_smem;
             pl.ctas = h->sm_count * 2;
@@ -1535,6 +1679,29 @@ int make_plan(ldpc_b200_decoder* h) {
             h->planned = true;
             return LDPC_B200_OK;
         }
+        // any other quasi-cyclic code: the same kernel with a run-time profile -- when the generic on-chip kernel would
+        // have to run one codeword per CTA (z > 24: measured 1.6-2.2x faster); with 8 or 16 words per CTA the group
+        // kernel is as fast (z = 24 rates: 1.31-1.67 ms against 1.49-1.56 ms per 16,384 words) and stays the choice
+        bool generic = want && !std::getenv("LDPC_B200_NO_QCG");
+        if (generic && h->forced_path < 0 && !std::getenv("LDPC_B200_QC_GENERIC")) {
+            GrpShape sh;
+            if (group_pick(t, h->smem_optin, false, &sh) && sh.G >= 8 && sh.tab_smem) generic = false;
+        }
+        if (generic && h->qcg_state == 0) h->qcg_state = qcg_prepare(h) ? 1 : -1;
+        if (generic && h->qcg_state == 1) {
+            pl.path = LDPC_B200_PATH_QC;
+            pl.threads = 32 * h->qcg.W;
+            pl.smem = h->qcg_smem;
+            pl.ctas = h->sm_count * h->qcg_ctas_per_sm;
+            pl.cw_per_cta = h->qcg_G;
+            pl.W = h->qcg.W; pl.CS = h->qcg.CS; pl.VS = h->qcg.VS; pl.G = h->qcg_G;
+            pl.dmax = 0;  // marks the run-time profile
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
+        if (h->forced_path == LDPC_B200_PATH_QC)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, "code is not quasi-cyclic in a supported shape (or the algorithm is not min-sum)");
     }
     if (h->forced_path == LDPC_B200_PATH_WARP) {  // opt-in: sub-warp per check, shuffle reductions
         const int SW = warp_sub_width(t);
@@ -1708,6 +1875,23 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         if (h->w_sw == 8) WARP_LAUNCH(8); else if (h->w_sw == 16) WARP_LAUNCH(16); else WARP_LAUNCH(32);
 #undef WARP_LAUNCH
         CU_TRY(cudaGetLastError());
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
+
+    if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 0) {
+        QcgParams& q = h->qcg;  // tables filled by qcg_build; per-launch fields below
+        q.K = h->K;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter64 = ctr64;
+        q.avail = h->cur_avail;
+        q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
+        rc = h->qcg_G == 8 ? launch_qcg_t<8>(q, grid, pl.smem, stream)
+           : (h->qcg_G == 4 ? launch_qcg_t<4>(q, grid, pl.smem, stream) : launch_qcg_t<2>(q, grid, pl.smem, stream));
+        if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
     }
@@ -1960,6 +2144,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaDeviceSynchronize();
             free_slots(h);
             if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
+            cudaFree(h->dq_tabs);
             cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
             cudaFree(h->d_avail);
             if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);

@@ -78,6 +78,22 @@ def test_other_wimax_rates(rate, name, num, den):
     assert_parity(_run_device(dec, llr), ref, N, what="rate " + name)
 
 
+@pytest.mark.parametrize("N,rate,name,num,den", [(2304, 0, "1/2", 1, 2), (2304, 4, "3/4B", 3, 4), (2304, 5, "5/6", 5, 6),
+                                                 (576, 0, "1/2", 1, 2), (576, 2, "2/3B", 2, 3), (576, 5, "5/6", 5, 6)])
+def test_largest_and_smallest_wimax_codes(N, rate, name, num, den):
+    """The ends of the reference's code family (z = 96 and z = 24, MyLdpc.cpp:55): whichever kernel path the plan
+    picks for them must give the oracle's bits, counts and posteriors."""
+    import myldpccppapi_b200 as m
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    llr = np.concatenate([awgn_llr(48, N, sigma_from_ebn0(2.0, num / den), seed=7 * rate + N),
+                          awgn_llr(48, N, sigma_from_ebn0(3.5, num / den), seed=7 * rate + N + 1)])
+    ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
+    dec = m.Decoder.wimax(K, N, rate)
+    assert_parity(_run_device(dec, llr), ref, N, what="N=%d rate %s (%s)" % (N, name, dec.info()["path_name"]))
+    assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="host N=%d rate %s" % (N, name))
+
+
 def test_ebn0_sweep_iteration_counts(default_code):
     """BASELINE config 4: Eb/N0 0..4 dB with syndrome early termination, iteration-count parity."""
     import myldpccppapi_b200 as m
@@ -209,6 +225,32 @@ def test_roundtrip_full_batch_properties(default_code):
     o2 = dec.decode_device(llr2, want_hard=True, want_post=True)
     torch.cuda.synchronize()
     assert_parity({k: v.cpu().numpy() for k, v in o2.items()}, ref, N, what="slice")
+
+
+def test_qc_runtime_profile_kernel(default_code, monkeypatch):
+    """The quasi-cyclic kernel with a run-time profile (ldpc_qcg.cuh) on Test.cpp's code (forced: the compiled profile
+    would take it) and on codes with padded slots; bits, counts and posteriors of the oracle, device and host paths."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    N = c["N"]
+    monkeypatch.setenv("LDPC_B200_QC_GENERIC", "1")
+    llr = np.concatenate([awgn_llr(300, N, 0.62, seed=51), awgn_llr(300, N, 0.5, seed=52), awgn_llr(37, N, 1.0, seed=53)])
+    ref = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr, literal=False)
+    dec = m.Decoder.wimax(c["K"], N, c["rate"])
+    inf = dec.info()
+    assert inf["path_name"] == "qc" and inf["codewords_per_cta"] == 8
+    assert_parity(_run_device(dec, llr), ref, N, what="run-time profile")
+    assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="run-time profile, host")
+    monkeypatch.delenv("LDPC_B200_QC_GENERIC")
+    for NN, rate, name, num, den, g in [(1152, 2, "2/3B", 2, 3, 4), (960, 3, "3/4A", 3, 4, 4), (2304, 0, "1/2", 1, 2, 2)]:
+        K = NN * num // den
+        rp, ci, M = oracle.wimax_H(NN, name)
+        y = awgn_llr(96, NN, sigma_from_ebn0(2.5, num / den), seed=NN + rate)
+        r2 = oracle.Oracle(M, NN, K, rp, ci, times=40).decode(y, literal=False)
+        d2 = m.Decoder.wimax(K, NN, rate)
+        i2 = d2.info()
+        assert i2["path_name"] == "qc" and i2["codewords_per_cta"] == g, i2
+        assert_parity(_run_device(d2, y), r2, NN, what="N=%d rate %s" % (NN, name))
 
 
 def test_streamed_host_pipeline(default_code, monkeypatch):

@@ -2453,9 +2453,19 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     if (ncw == 0) return LDPC_B200_OK;
     if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
     const HostTables& t = h->host;
-    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->planned && h->plan.path == LDPC_B200_PATH_QC && h->reserved == 0 &&
-        !std::getenv("LDPC_B200_NO_STREAMED"))
-        return decode_host_streamed(h, llr, ncw, info, hard, iters, post);
+    // (also after ldpc_b200_reserve / Coder::forDecoder(batchSize): the reference's batch size is only its internal
+    // chunking, MyLdpc.cpp:577-616, and kernels of this path do not speed each other up across streams)
+    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->planned && h->plan.path == LDPC_B200_PATH_QC &&
+        !std::getenv("LDPC_B200_NO_STREAMED")) {
+        // pinned (or managed) input only: copies from pageable memory are staged synchronously, so queueing them all
+        // before the launch would serialise copy and decode -- the chunked pipeline below overlaps them instead
+        DeviceGuard guard(h->device);
+        cudaPointerAttributes attr;
+        const bool pinned = guard.ok && cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
+                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        if (!pinned) (void)cudaGetLastError();
+        if (pinned || std::getenv("LDPC_B200_STREAMED_PAGEABLE")) return decode_host_streamed(h, llr, ncw, info, hard, iters, post);
+    }
     if (h->reserved == 0) {
         // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the
         // persistent grid (bounded to ~256 MB of channel values).  On-chip paths: kernels of consecutive chunks run

@@ -266,9 +266,13 @@ def test_streamed_host_pipeline(default_code, monkeypatch):
     ref = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr, literal=False)
     dec = m.Decoder.wimax(c["K"], N, c["rate"])
     assert dec.info()["path_name"] == "qc"
-    first = dec.decode_host(llr)                                    # pageable input, info + iters only
+    first = dec.decode_host(llr)                                    # pageable input: the chunked 3-stream pipeline
+    assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
+    monkeypatch.setenv("LDPC_B200_STREAMED_PAGEABLE", "1")          # ... and the persistent launch fed from pageable memory
+    first = dec.decode_host(llr)                                    # info + iters only
     assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="streamed, all outputs")
+    monkeypatch.delenv("LDPC_B200_STREAMED_PAGEABLE")
     pinned = torch.from_numpy(llr).pin_memory().numpy()
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
     monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # 455 words per launch: 7 launches

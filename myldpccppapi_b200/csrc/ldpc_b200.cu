@@ -110,8 +110,8 @@ struct ldpc_b200_decoder {
     uint32_t* dg_pos_of_var = nullptr;
     bool group_ready = false;
     // QC tables (warp-uniform, one slot of the __constant__ bank)
-    QcParams<QcProfileWimax34B576> qc;
-    QcWarpTab<QcProfileWimax34B576> qc_tab[QcProfileWimax34B576::W];
+    QcParams qc;
+    int qc_kind = -1;  // index into the compiled-profile list (qc_profiles())
     int qc_state = 0;  // 0 = not tried, 1 = tables built and uploaded, -1 = no match / no free slot
     int qc_slot = -1;
     size_t qc_smem = 0;
@@ -1007,88 +1007,9 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
 }
 
 // ---- QC layout (see ldpc_qc.cuh) ---------------------------------------------------------------------
-// Recognises H as a grid of z x z blocks (zero or one cyclically shifted identity each), deals groups of
-// SUB consecutive rows / columns of a block to (slot, warp) in degree order and writes one warp-uniform
-// base per (warp, slot, edge).  Returns false when the code is not of that shape or does not match P.
-template <class P>
-bool qc_build(const HostTables& t, QcParams<P>* out, QcWarpTab<P>* tabs, size_t* smem_out) {
-    constexpr int z = P::Z, G = P::G, SUB = 32 / G, W = P::W;
-    constexpr uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
-    static_assert(z % SUB == 0, "a group of node lanes must not straddle blocks");
-    if (t.M % z || t.N % z) return false;
-    const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
-    if (MB * gpb != P::CS * W || NB * gpb != P::VS * W) return false;
-    struct Blk { int bc, s; };
-    std::vector<std::vector<Blk>> rows(MB);
-    for (int br = 0; br < MB; ++br) {
-        const int r0 = br * z;
-        std::vector<bool> used(NB, false);
-        for (int e = t.row_ptr[r0]; e < t.row_ptr[r0 + 1]; ++e) {
-            const int bc = t.col_idx[e] / z;
-            if (used[bc]) return false;  // two circulants in one block
-            used[bc] = true;
-            rows[br].push_back({bc, t.col_idx[e] % z});
-        }
-        for (int r = 0; r < z; ++r) {
-            if (t.row_ptr[r0 + r + 1] - t.row_ptr[r0 + r] != (int)rows[br].size()) return false;
-            std::vector<int> want;
-            for (const Blk& b : rows[br]) want.push_back(b.bc * z + (r + b.s) % z);
-            std::sort(want.begin(), want.end());
-            for (size_t j = 0; j < want.size(); ++j)
-                if (t.col_idx[t.row_ptr[r0 + r] + (int)j] != want[j]) return false;
-        }
-    }
-    std::vector<int> eb0(MB + 1, 0);  // R block index of (br, 0)
-    for (int br = 0; br < MB; ++br) eb0[br + 1] = eb0[br] + (int)rows[br].size();
-    const uint32_t t_bytes = (uint32_t)NB * (z + SUB) * ROWB, r_bytes = (uint32_t)eb0[MB] * RS;
-    struct Col { int br, j, s; };
-    std::vector<std::vector<Col>> cols(NB);
-    for (int br = 0; br < MB; ++br)
-        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
-    std::vector<int> border(MB), corder(NB);
-    for (int i = 0; i < MB; ++i) border[i] = i;
-    for (int i = 0; i < NB; ++i) corder[i] = i;
-    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
-    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cols[a].size() > cols[b].size(); });
-    QcParams<P>& q = *out;
-    std::memset(&q, 0, sizeof(q));
-    std::memset(tabs, 0, sizeof(QcWarpTab<P>) * W);
-    for (int p = 0; p < MB * gpb; ++p) {
-        const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
-        if ((int)rows[br].size() != P::cdeg(slot)) return false;
-        QcWarpTab<P>& tb = tabs[w];
-        tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
-        if (g == gpb - 1) tb.cdup |= 1u << slot;
-        for (int j = 0; j < (int)rows[br].size(); ++j)
-            tb.cn_t[QcLayout<P>::coff(slot) + j] = (uint32_t)(rows[br][j].bc * (z + SUB) + (r0 + rows[br][j].s) % z) * ROWB;
-    }
-    for (int p = 0; p < NB * gpb; ++p) {
-        const int bc = corder[p / gpb], g = p % gpb, slot = p / W, w = p % W, i0 = g * SUB;
-        const int d = (int)cols[bc].size();
-        if (d > P::vdeg(slot)) return false;
-        QcWarpTab<P>& tb = tabs[w];
-        tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
-        tb.var0[slot] = (uint32_t)(bc * z + i0);
-        if (g == 0) tb.vdup |= 1u << slot;
-        for (int k = 0; k < P::vdeg(slot); ++k) {
-            if (k >= d) { tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + r_bytes; continue; }  // zero row
-            const Col& cd = cols[bc][k];  // ascending block row = ascending row: the summation order
-            int m = ((i0 - cd.s) % z + z) % z;
-            if (m > z - SUB) m -= z;      // the group wraps: its first rows are read through the leading pad
-            tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + (uint32_t)(eb0[cd.br] + cd.j) * RS + (uint32_t)(SUB + m) * ROWB;
-        }
-    }
-    // the kernel branches once per pass on "this warp owns wrapped rows": all of a warp's groups or none
-    for (int w = 0; w < W; ++w) {
-        if (tabs[w].cdup != 0u && tabs[w].cdup != (1u << P::CS) - 1u) return false;
-        if (tabs[w].vdup != 0u && tabs[w].vdup != (1u << P::VS) - 1u) return false;
-    }
-    q.N = t.N; q.NB = NB;
-    q.t_bytes = t_bytes; q.r_bytes = r_bytes;
-    *smem_out = (size_t)t_bytes + r_bytes + 128;
-    return true;
-}
-
+// The QC builders recognise H as a grid of z x z blocks (zero or one cyclically shifted identity each), deal groups
+// of SUB consecutive rows / columns of a block to (slot, warp) in degree order and write one warp-uniform base per
+// (warp, slot, edge).
 // Block structure of H for block size z: rows[br] = the circulants (block column, shift) of block row br in
 // ascending column order.  false when H is not a grid of z x z blocks that are zero or one shifted identity.
 struct QcBlk { int bc, s; };
@@ -1115,6 +1036,74 @@ bool qc_blocks(const HostTables& t, int z, std::vector<std::vector<QcBlk>>* rows
         }
     }
     *rows_out = std::move(rows);
+    return true;
+}
+
+template <class P>
+bool qc_build(const HostTables& t, const std::vector<std::vector<QcBlk>>& rows, QcParams* out, std::vector<unsigned char>* tab_bytes,
+              size_t* smem_out) {
+    constexpr int z = P::Z, G = P::G, SUB = 32 / G, W = P::W;
+    constexpr uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
+    static_assert(z % SUB == 0, "a group of node lanes must not straddle blocks");
+    if (t.M % z || t.N % z) return false;
+    const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
+    if (MB * gpb != P::CS * W || NB * gpb != P::VS * W || (int)rows.size() != MB) return false;
+    struct Col { int br, j, s; };
+    std::vector<std::vector<Col>> cols(NB);
+    for (int br = 0; br < MB; ++br)
+        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
+    std::vector<int> border(MB), corder(NB);
+    for (int i = 0; i < MB; ++i) border[i] = i;
+    for (int i = 0; i < NB; ++i) corder[i] = i;
+    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cols[a].size() > cols[b].size(); });
+    // R blocks of a block row: as many as the degree of the slot(s) its groups are processed with (>= its own)
+    std::vector<int> dpad(MB, 0), eb0(MB + 1, 0);
+    for (int p = 0; p < MB * gpb; ++p) {
+        if ((int)rows[border[p / gpb]].size() > P::cdeg(p / W)) return false;
+        dpad[border[p / gpb]] = std::max(dpad[border[p / gpb]], P::cdeg(p / W));
+    }
+    for (int br = 0; br < MB; ++br) eb0[br + 1] = eb0[br] + dpad[br];
+    const uint32_t t_bytes = (uint32_t)NB * (z + SUB) * ROWB, r_bytes = (uint32_t)eb0[MB] * RS;
+    const uint32_t zero_row = t_bytes + r_bytes, inf_row = zero_row + 128u;
+    QcParams& q = *out;
+    std::memset(&q, 0, sizeof(q));
+    tab_bytes->assign(sizeof(QcWarpTab<P>) * W, 0);
+    QcWarpTab<P>* tabs = reinterpret_cast<QcWarpTab<P>*>(tab_bytes->data());
+    for (int p = 0; p < MB * gpb; ++p) {
+        const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
+        QcWarpTab<P>& tb = tabs[w];
+        tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
+        if (g == gpb - 1) tb.cdup |= 1u << slot;
+        for (int j = 0; j < P::cdeg(slot); ++j)
+            tb.cn_t[QcLayout<P>::coff(slot) + j] = j < (int)rows[br].size()
+                ? (uint32_t)(rows[br][j].bc * (z + SUB) + (r0 + rows[br][j].s) % z) * ROWB
+                : inf_row;  // padded edge: T = -inf is neutral for the minima, the sign parity and the syndrome
+    }
+    for (int p = 0; p < NB * gpb; ++p) {
+        const int bc = corder[p / gpb], g = p % gpb, slot = p / W, w = p % W, i0 = g * SUB;
+        const int d = (int)cols[bc].size();
+        if (d > P::vdeg(slot)) return false;
+        QcWarpTab<P>& tb = tabs[w];
+        tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
+        tb.var0[slot] = (uint32_t)(bc * z + i0);
+        if (g == 0) tb.vdup |= 1u << slot;
+        for (int k = 0; k < P::vdeg(slot); ++k) {
+            if (k >= d) { tb.vn_r[QcLayout<P>::voff(slot) + k] = zero_row; continue; }
+            const Col& cd = cols[bc][k];  // ascending block row = ascending row: the summation order
+            int m = ((i0 - cd.s) % z + z) % z;
+            if (m > z - SUB) m -= z;      // the group wraps: its first rows are read through the leading pad
+            tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + (uint32_t)(eb0[cd.br] + cd.j) * RS + (uint32_t)(SUB + m) * ROWB;
+        }
+    }
+    // the kernel branches once per pass on "this warp owns wrapped rows": all of a warp's groups or none
+    for (int w = 0; w < W; ++w) {
+        if (tabs[w].cdup != 0u && tabs[w].cdup != (1u << P::CS) - 1u) return false;
+        if (tabs[w].vdup != 0u && tabs[w].vdup != (1u << P::VS) - 1u) return false;
+    }
+    q.N = t.N; q.NB = NB;
+    q.t_bytes = t_bytes; q.r_bytes = r_bytes;
+    *smem_out = (size_t)t_bytes + r_bytes + 256;
     return true;
 }
 
@@ -1209,35 +1198,58 @@ void qc_release_slot(const void* owner, int device, int slot) {
     if (g_qc_owner[device][slot] == owner) g_qc_owner[device][slot] = nullptr;
 }
 
-// Builds the tables, takes a slot and uploads them (current device = the handle's).  false = use another path.
-bool qc_prepare(ldpc_b200_decoder* h) {
-    using P = QcProfileWimax34B576;
-    if (!qc_build<P>(h->host, &h->qc, h->qc_tab, &h->qc_smem)) return false;
-    DeviceGuard guard(h->device);
-    if (!guard.ok) return false;
-    const int slot = qc_acquire_slot(h, h->device);
-    if (slot < 0) return false;
-    if (cudaMemcpyToSymbol(g_qc_tab_wimax34b576, h->qc_tab, sizeof(h->qc_tab), (size_t)slot * sizeof(h->qc_tab),
-                           cudaMemcpyHostToDevice) != cudaSuccess) {
-        (void)cudaGetLastError();
-        qc_release_slot(h, h->device, slot);
-        return false;
-    }
-    h->qc_slot = slot;
-    h->qc.tab_slot = slot;
-    h->table_bytes += sizeof(h->qc_tab);
-    return true;
-}
-
+// The compiled profiles: rate x (z, G) for z = 24 / 48 / 96.
 template <class P>
-int launch_qc_t(const QcParams<P>& q, int grid, size_t smem, cudaStream_t stream) {
+int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
     if (const char* env = std::getenv("LDPC_B200_QC_PAD")) smem += (size_t)std::atoi(env);
     CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (std::getenv("LDPC_B200_QC_CARVEOUT"))
-        CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());
     return LDPC_B200_OK;
+}
+
+struct QcProfileEntry {
+    int z, G;
+    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, QcParams*, std::vector<unsigned char>*, size_t*);
+    int (*launch)(const QcParams&, int, size_t, cudaStream_t);
+};
+#define QC_PROFILE(T, Z, G) {Z, G, &qc_build<T<Z, G>>, &launch_qc_t<T<Z, G>>}
+#define QC_PROFILE_SIZES(T) QC_PROFILE(T, 24, 8), QC_PROFILE(T, 48, 4), QC_PROFILE(T, 96, 2)
+const QcProfileEntry kQcProfiles[] = {QC_PROFILE_SIZES(QcProfile34B), QC_PROFILE_SIZES(QcProfile34A), QC_PROFILE_SIZES(QcProfile23B),
+                                      QC_PROFILE_SIZES(QcProfile23A), QC_PROFILE_SIZES(QcProfile12)};
+#undef QC_PROFILE_SIZES
+#undef QC_PROFILE
+
+// Finds the compiled profile the code matches, builds its tables, takes a slot of the constant bank and uploads them
+// (current device = the handle's).  false = use another path.
+bool qc_prepare(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    std::vector<std::vector<QcBlk>> rows;
+    int rows_z = 0;
+    std::vector<unsigned char> tab;
+    for (int k = 0; k < (int)(sizeof(kQcProfiles) / sizeof(kQcProfiles[0])); ++k) {
+        const QcProfileEntry& pe = kQcProfiles[k];
+        if (t.M % pe.z || t.N % pe.z) continue;
+        if (rows_z != pe.z) { rows.clear(); rows_z = pe.z; if (!qc_blocks(t, pe.z, &rows)) rows.clear(); }
+        if (rows.empty()) continue;
+        if (!pe.build(t, rows, &h->qc, &tab, &h->qc_smem)) continue;
+        if (tab.size() > (size_t)kQcBankBytes) continue;
+        DeviceGuard guard(h->device);
+        if (!guard.ok) return false;
+        const int slot = qc_acquire_slot(h, h->device);
+        if (slot < 0) return false;
+        if (cudaMemcpyToSymbol(g_qc_bank, tab.data(), tab.size(), (size_t)slot * kQcBankBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            (void)cudaGetLastError();
+            qc_release_slot(h, h->device, slot);
+            return false;
+        }
+        h->qc_slot = slot;
+        h->qc.tab_slot = slot;
+        h->qc_kind = k;
+        h->table_bytes += tab.size();
+        return true;
+    }
+    return false;
 }
 
 // Run-time-profile QC path: picks G (most codewords per CTA with two CTAs per SM, else one CTA), builds and uploads.
@@ -1661,7 +1673,6 @@ int make_plan(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     Plan pl;
     {   // quasi-cyclic code matching a compiled profile: warp-uniform tables (min-sum only)
-        using P = QcProfileWimax34B576;
         const bool want = h->algorithm == LDPC_B200_ALG_MIN_SUM &&
                           (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !std::getenv("LDPC_B200_NO_QC")));
         const bool compiled = want && !std::getenv("LDPC_B200_QC_GENERIC");  // (the env var forces the run-time profile: tests)
@@ -1670,11 +1681,11 @@ int make_plan(ldpc_b200_decoder* h) {
         if (fits) {
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
-            pl.threads = 32 * P::W;
+            pl.threads = 32 * 12;
             pl.smem = h->qc_smem;
             pl.ctas = h->sm_count * 2;
-            pl.cw_per_cta = P::G;
-            pl.W = P::W; pl.CS = P::CS; pl.VS = P::VS; pl.G = P::G;
+            pl.cw_per_cta = kQcProfiles[h->qc_kind].G;
+            pl.W = 12; pl.G = kQcProfiles[h->qc_kind].G;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;
@@ -1906,7 +1917,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.counter64 = ctr64;
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
-        rc = launch_qc_t(q, grid, pl.smem, stream);
+        rc = kQcProfiles[h->qc_kind].launch(q, grid, pl.smem, stream);
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;

@@ -29,13 +29,41 @@
 
 namespace ldpc_b200 {
 
-// Test.cpp's code (802.16e rate 3/4B, z = 24: N = 576, M = 144), G = 8, 12 warps x 4 node lanes:
-// a slot = 12 groups of 4 rows/columns = two blocks.
-struct QcProfileWimax34B576 {
-    static constexpr int Z = 24, G = 8, W = 12, CS = 3, VS = 12;
+// Compiled profiles.  For z = 24 / 48 / 96 with G = 8 / 4 / 2 codewords per CTA a block has six groups of SUB = 32/G
+// rows, 12 warps take a slot = two blocks, and the slot degrees depend on the 802.16e rate only (seed tables
+// MyLdpc.h:40-102; blocks sorted by degree, a slot's degree = its larger block's, the smaller one is padded).
+// QcProfileWimax34B576 = Test.cpp's code (rate 3/4B, z = 24: N = 576, M = 144).
+template <int Z_, int G_>
+struct QcProfile34B {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 3, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 15, 14}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
 };
+template <int Z_, int G_>
+struct QcProfile34A {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 3, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 14, 14}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 2, 2}; return d[i]; }
+};
+template <int Z_, int G_>
+struct QcProfile23B {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 4, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[4] = {11, 10, 10, 10}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 4, 4, 3, 2, 2, 2}; return d[i]; }
+};
+template <int Z_, int G_>
+struct QcProfile23A {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 4, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[4] = {10, 10, 10, 10}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2, 2}; return d[i]; }
+};
+template <int Z_, int G_>
+struct QcProfile12 {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 6, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[6] = {7, 7, 6, 6, 6, 6}; return d[i]; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 3, 3, 3, 3, 2, 2, 2, 2, 2}; return d[i]; }
+};
+using QcProfileWimax34B576 = QcProfile34B<24, 8>;
 
 // Table offsets shared by the host builder and the kernel.  Entries are read two at a time (LDCU.64), so
 // every check slot and every run of variable slots that is processed together starts on an even entry.
@@ -78,20 +106,19 @@ struct QcWarpTab {
 // parameters neither overlap with each other nor launch quickly (measured: the 3-stream host pipeline lost
 // 47 us per launch).  kQcTabSlots decoders per device can hold tables at once; a handle owns one slot.
 constexpr int kQcTabSlots = 8;
-__constant__ QcWarpTab<QcProfileWimax34B576> g_qc_tab_wimax34b576[kQcTabSlots][QcProfileWimax34B576::W];
+constexpr int kQcBankBytes = 6656;  // per slot: the largest compiled profile's tables (12 warps)
+__constant__ uint4 g_qc_bank[kQcTabSlots][kQcBankBytes / 16];
 
 template <class P>
-__device__ __forceinline__ const QcWarpTab<P>& qc_tab(int slot, int warp);
-template <>
-__device__ __forceinline__ const QcWarpTab<QcProfileWimax34B576>& qc_tab<QcProfileWimax34B576>(int slot, int warp) {
-    return g_qc_tab_wimax34b576[slot][warp];
+__device__ __forceinline__ const QcWarpTab<P>& qc_tab(int slot, int warp) {
+    static_assert(sizeof(QcWarpTab<P>) * P::W <= kQcBankBytes, "profile tables exceed a bank slot");
+    return reinterpret_cast<const QcWarpTab<P>*>(&g_qc_bank[slot][0])[warp];
 }
 
-template <class P>
 struct QcParams {
     int tab_slot;                 // which entry of the __constant__ table bank
     int N, K, NB;                 // NB = N / z block columns
-    uint32_t t_bytes, r_bytes;    // region sizes (T at 0, R at t_bytes, zero row at t_bytes + r_bytes)
+    uint32_t t_bytes, r_bytes;    // region sizes (T at 0, R at t_bytes, then the zero row and the -inf row, 128 B each)
     int max_iter, early_term, refill_wait;
     const float* __restrict__ llr;
     long long ncw;
@@ -232,7 +259,7 @@ __device__ __forceinline__ void qc_vn_static(const QcWarpTab<P>& tb, uint32_t la
 
 template <class P>
 __global__ void __launch_bounds__(P::W * 32, (P::W * 32 <= 288 ? 3 : (P::W * 32 <= 384 ? 2 : 1)))
-ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
+ldpc_ms_qc_kernel(const __grid_constant__ QcParams p) {
     constexpr int G = P::G, SUB = 32 / G, NL = P::W * SUB, Z = P::Z;
     constexpr uint32_t ROWB = (uint32_t)G * 4u;              // bytes of one row (G codewords)
     constexpr uint32_t RS = (uint32_t)(Z + SUB) * ROWB;      // bytes of one padded block
@@ -249,7 +276,10 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams<P> p) {
     const uint32_t la = sb + (uint32_t)lane * 4u;            // every hot-loop access is [la + uniform (+ imm)]
     const uint32_t c4 = (uint32_t)c * 4u;
 
-    if (threadIdx.x < 32) sts_f32(sb + p.t_bytes + p.r_bytes + (uint32_t)lane * 4u, 0.0f);  // zero row
+    if (threadIdx.x < 32) {
+        sts_f32(sb + p.t_bytes + p.r_bytes + (uint32_t)lane * 4u, 0.0f);              // zero row (padded variable-pass entries)
+        sts_f32(sb + p.t_bytes + p.r_bytes + 128u + (uint32_t)lane * 4u, -INFINITY);  // -inf row (padded check-pass entries)
+    }
 
     float yn[P::VS];
 #pragma unroll

@@ -242,7 +242,9 @@ def test_qc_runtime_profile_kernel(default_code, monkeypatch):
     assert_parity(_run_device(dec, llr), ref, N, what="run-time profile")
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="run-time profile, host")
     monkeypatch.delenv("LDPC_B200_QC_GENERIC")
-    for NN, rate, name, num, den, g in [(1152, 2, "2/3B", 2, 3, 4), (960, 3, "3/4A", 3, 4, 4), (2304, 0, "1/2", 1, 2, 2)]:
+    # z = 40 and z = 64 have no compiled profile (run-time profile, G = 4 and 2); z = 48 / 96 take compiled ones (G = 4 / 2)
+    for NN, rate, name, num, den, g in [(960, 3, "3/4A", 3, 4, 4), (1536, 4, "3/4B", 3, 4, 2), (1152, 2, "2/3B", 2, 3, 4),
+                                        (1152, 4, "3/4B", 3, 4, 4), (2304, 0, "1/2", 1, 2, 2), (2304, 1, "2/3A", 2, 3, 2)]:
         K = NN * num // den
         rp, ci, M = oracle.wimax_H(NN, name)
         y = awgn_llr(96, NN, sigma_from_ebn0(2.5, num / den), seed=NN + rate)

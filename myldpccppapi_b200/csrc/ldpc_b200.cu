@@ -1216,7 +1216,7 @@ struct QcProfileEntry {
 #define QC_PROFILE(T, Z, G) {Z, G, &qc_build<T<Z, G>>, &launch_qc_t<T<Z, G>>}
 #define QC_PROFILE_SIZES(T) QC_PROFILE(T, 24, 8), QC_PROFILE(T, 48, 4), QC_PROFILE(T, 96, 2)
 const QcProfileEntry kQcProfiles[] = {QC_PROFILE_SIZES(QcProfile34B), QC_PROFILE_SIZES(QcProfile34A), QC_PROFILE_SIZES(QcProfile23B),
-                                      QC_PROFILE_SIZES(QcProfile23A), QC_PROFILE_SIZES(QcProfile12)};
+                                      QC_PROFILE_SIZES(QcProfile23A), QC_PROFILE_SIZES(QcProfile12), QC_PROFILE_SIZES(QcProfile56)};
 #undef QC_PROFILE_SIZES
 #undef QC_PROFILE
 

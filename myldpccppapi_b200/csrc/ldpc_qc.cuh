@@ -63,6 +63,12 @@ struct QcProfile12 {
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[6] = {7, 7, 6, 6, 6, 6}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 3, 3, 3, 3, 2, 2, 2, 2, 2}; return d[i]; }
 };
+template <int Z_, int G_>
+struct QcProfile56 {
+    static constexpr int Z = Z_, G = G_, W = 12, CS = 2, VS = 12;
+    __host__ __device__ static constexpr int cdeg(int) { return 20; }
+    __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 3, 3, 3, 3, 3, 2}; return d[i]; }
+};
 using QcProfileWimax34B576 = QcProfile34B<24, 8>;
 
 // Table offsets shared by the host builder and the kernel.  Entries are read two at a time (LDCU.64), so

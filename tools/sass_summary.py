@@ -5,7 +5,7 @@ import collections, pathlib, re, subprocess, sys
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 LIB = ROOT / "myldpccppapi_b200" / "libldpc_b200.so"
 WANT = [
-    ("cfg1/2/4 default", r"ldpc_ms_qc_kernel<"),
+    ("cfg1/2/4 default", r"ldpc_ms_qc_kernel<ldpc_b200::QcProfile34B<24, 8>"),
     ("generic on-chip, G=8 static profile", r"ldpc_ms_group_kernel<8, 16, true, 384, false, ldpc_b200::ProfileWimax34B576, false>"),
     ("cfg3 default", r"ldpc_ms_group_kernel<1, 8, false, 1024, false, ldpc_b200::ProfileRegular36N8192, true>"),
     ("cfg5 default", r"ldpc_ms_stream_kernel<1024>"),

@@ -1198,7 +1198,7 @@ void qc_release_slot(const void* owner, int device, int slot) {
     if (g_qc_owner[device][slot] == owner) g_qc_owner[device][slot] = nullptr;
 }
 
-// The compiled profiles: rate x (z, G) for z = 24 / 48 / 96.
+// The compiled profiles: rate x (z, G, W).
 template <class P>
 int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
     if (const char* env = std::getenv("LDPC_B200_QC_PAD")) smem += (size_t)std::atoi(env);
@@ -1209,12 +1209,13 @@ int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
 }
 
 struct QcProfileEntry {
-    int z, G;
+    int z, G, W;
     bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, QcParams*, std::vector<unsigned char>*, size_t*);
     int (*launch)(const QcParams&, int, size_t, cudaStream_t);
 };
-#define QC_PROFILE(T, Z, G) {Z, G, &qc_build<T<Z, G>>, &launch_qc_t<T<Z, G>>}
-#define QC_PROFILE_SIZES(T) QC_PROFILE(T, 24, 8), QC_PROFILE(T, 48, 4), QC_PROFILE(T, 96, 2)
+#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>}
+#define QC_PROFILE_SIZES(T) QC_PROFILE(T, 24, 8, 12), QC_PROFILE(T, 48, 4, 12), QC_PROFILE(T, 96, 2, 12), QC_PROFILE(T, 40, 4, 10), \
+                            QC_PROFILE(T, 80, 2, 10), QC_PROFILE(T, 32, 4, 8), QC_PROFILE(T, 64, 2, 8)
 const QcProfileEntry kQcProfiles[] = {QC_PROFILE_SIZES(QcProfile34B), QC_PROFILE_SIZES(QcProfile34A), QC_PROFILE_SIZES(QcProfile23B),
                                       QC_PROFILE_SIZES(QcProfile23A), QC_PROFILE_SIZES(QcProfile12), QC_PROFILE_SIZES(QcProfile56)};
 #undef QC_PROFILE_SIZES
@@ -1678,14 +1679,16 @@ int make_plan(ldpc_b200_decoder* h) {
         const bool compiled = want && !std::getenv("LDPC_B200_QC_GENERIC");  // (the env var forces the run-time profile: tests)
         if (compiled && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
         const bool fits = compiled && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
+        // (the kernel's launch bounds allow three CTAs per SM up to 288 threads)
+        const int qc_per_sm = fits && kQcProfiles[h->qc_kind].W * 32 <= 288 && 3 * (h->qc_smem + 2048) <= h->smem_optin + 1024 ? 3 : 2;
         if (fits) {
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
-            pl.threads = 32 * 12;
+            pl.threads = 32 * kQcProfiles[h->qc_kind].W;
             pl.smem = h->qc_smem;
-            pl.ctas = h->sm_count * 2;
+            pl.ctas = h->sm_count * qc_per_sm;
             pl.cw_per_cta = kQcProfiles[h->qc_kind].G;
-            pl.W = 12; pl.G = kQcProfiles[h->qc_kind].G;
+            pl.W = kQcProfiles[h->qc_kind].W; pl.G = kQcProfiles[h->qc_kind].G;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;

@@ -29,43 +29,44 @@
 
 namespace ldpc_b200 {
 
-// Compiled profiles.  For z = 24 / 48 / 96 with G = 8 / 4 / 2 codewords per CTA a block has six groups of SUB = 32/G
-// rows, 12 warps take a slot = two blocks, and the slot degrees depend on the 802.16e rate only (seed tables
-// MyLdpc.h:40-102; blocks sorted by degree, a slot's degree = its larger block's, the smaller one is padded).
+// Compiled profiles.  A block has z / SUB groups of SUB = 32/G rows; with W = 2 z / SUB warps a slot = two blocks, and
+// the slot degrees then depend on the 802.16e rate only (seed tables MyLdpc.h:40-102; blocks sorted by degree, a
+// slot's degree = its larger block's, the smaller one is padded).  Instantiated for (z, G, W) = (24, 8, 12),
+// (48, 4, 12), (96, 2, 12), (40, 4, 10), (80, 2, 10), (32, 4, 8), (64, 2, 8).
 // QcProfileWimax34B576 = Test.cpp's code (rate 3/4B, z = 24: N = 576, M = 144).
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile34B {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 3, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 3, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 15, 14}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2}; return d[i]; }
 };
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile34A {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 3, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 3, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[3] = {15, 14, 14}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 2, 2}; return d[i]; }
 };
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile23B {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 4, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 4, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[4] = {11, 10, 10, 10}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 4, 4, 3, 2, 2, 2}; return d[i]; }
 };
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile23A {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 4, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 4, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[4] = {10, 10, 10, 10}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 3, 3, 3, 3, 3, 3, 2, 2, 2}; return d[i]; }
 };
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile12 {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 6, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 6, VS = 12;
     __host__ __device__ static constexpr int cdeg(int i) { constexpr int d[6] = {7, 7, 6, 6, 6, 6}; return d[i]; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {6, 6, 6, 3, 3, 3, 3, 2, 2, 2, 2, 2}; return d[i]; }
 };
-template <int Z_, int G_>
+template <int Z_, int G_, int W_ = 12>
 struct QcProfile56 {
-    static constexpr int Z = Z_, G = G_, W = 12, CS = 2, VS = 12;
+    static constexpr int Z = Z_, G = G_, W = W_, CS = 2, VS = 12;
     __host__ __device__ static constexpr int cdeg(int) { return 20; }
     __host__ __device__ static constexpr int vdeg(int i) { constexpr int d[12] = {4, 4, 4, 4, 4, 4, 3, 3, 3, 3, 3, 2}; return d[i]; }
 };

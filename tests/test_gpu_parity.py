@@ -241,18 +241,23 @@ def test_qc_runtime_profile_kernel(default_code, monkeypatch):
     assert inf["path_name"] == "qc" and inf["codewords_per_cta"] == 8
     assert_parity(_run_device(dec, llr), ref, N, what="run-time profile")
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="run-time profile, host")
-    monkeypatch.delenv("LDPC_B200_QC_GENERIC")
-    # z = 40 and z = 64 have no compiled profile (run-time profile, G = 4 and 2); z = 48 / 96 take compiled ones (G = 4 / 2)
-    for NN, rate, name, num, den, g in [(960, 3, "3/4A", 3, 4, 4), (1536, 4, "3/4B", 3, 4, 2), (1152, 2, "2/3B", 2, 3, 4),
-                                        (1152, 4, "3/4B", 3, 4, 4), (2304, 0, "1/2", 1, 2, 2), (2304, 1, "2/3A", 2, 3, 2)]:
-        K = NN * num // den
-        rp, ci, M = oracle.wimax_H(NN, name)
-        y = awgn_llr(96, NN, sigma_from_ebn0(2.5, num / den), seed=NN + rate)
-        r2 = oracle.Oracle(M, NN, K, rp, ci, times=40).decode(y, literal=False)
-        d2 = m.Decoder.wimax(K, NN, rate)
-        i2 = d2.info()
-        assert i2["path_name"] == "qc" and i2["codewords_per_cta"] == g, i2
-        assert_parity(_run_device(d2, y), r2, NN, what="N=%d rate %s" % (NN, name))
+    # other sizes and rates: first with the run-time profile forced (padded slots, G = 4 and 2), then as planned
+    # (compiled profiles for z = 24, 32, 40, 48, 64, 80, 96; run-time profile or the group kernel for the other z)
+    cases = [(960, 3, "3/4A", 3, 4, 4), (1152, 2, "2/3B", 2, 3, 4), (2304, 0, "1/2", 1, 2, 2), (768, 5, "5/6", 5, 6, 4),
+             (1536, 4, "3/4B", 3, 4, 2), (1920, 1, "2/3A", 2, 3, 2), (2304, 5, "5/6", 5, 6, 2), (1728, 4, "3/4B", 3, 4, None)]
+    for forced in (True, False):
+        if not forced:
+            monkeypatch.delenv("LDPC_B200_QC_GENERIC")
+        for NN, rate, name, num, den, g in cases[:4] if forced else cases:
+            K = NN * num // den
+            rp, ci, M = oracle.wimax_H(NN, name)
+            y = awgn_llr(96, NN, sigma_from_ebn0(2.5, num / den), seed=NN + rate)
+            r2 = oracle.Oracle(M, NN, K, rp, ci, times=40).decode(y, literal=False)
+            d2 = m.Decoder.wimax(K, NN, rate)
+            i2 = d2.info()
+            if g is not None and not (forced and rate == 5):  # (check degree 20 is beyond the run-time profile: other kernels)
+                assert i2["path_name"] == "qc" and i2["codewords_per_cta"] == g, i2
+            assert_parity(_run_device(d2, y), r2, NN, what="N=%d rate %s forced=%s (%s)" % (NN, name, forced, i2["path_name"]))
 
 
 def test_streamed_host_pipeline(default_code, monkeypatch):

@@ -282,6 +282,8 @@ def test_streamed_host_pipeline(default_code, monkeypatch):
     monkeypatch.delenv("LDPC_B200_STREAMED_PAGEABLE")
     pinned = torch.from_numpy(llr).pin_memory().numpy()
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
+    for n in (1, 9):                                                # fewer words than one CTA holds
+        assert_parity(dec.decode_host(pinned[:n], want_hard=True, want_post=True), tuple(r[:n] for r in ref), N, what="streamed, %d words" % n)
     monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # 455 words per launch: 7 launches
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, 7 launches")
     monkeypatch.setenv("LDPC_B200_STREAM_CHUNK", "8")               # one word group per copy

@@ -1201,7 +1201,6 @@ void qc_release_slot(const void* owner, int device, int slot) {
 // The compiled profiles: rate x (z, G, W).
 template <class P>
 int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
-    if (const char* env = std::getenv("LDPC_B200_QC_PAD")) smem += (size_t)std::atoi(env);
     CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
     CU_TRY(cudaGetLastError());

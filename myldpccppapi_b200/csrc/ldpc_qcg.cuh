@@ -50,10 +50,10 @@ struct QcgParams {
     int* status;
 };
 
-// One check of exact degree D; run-time block stride (see qc_check).
+// One check of exact degree D; run-time block stride (see qc_check).  Split into its loads and the rest so that
+// two equal-degree slots can have their loads in flight together.
 template <int D>
-__device__ __forceinline__ uint32_t qcg_check(uint32_t tt, uint32_t rrow, uint32_t la, uint32_t RS, uint32_t WRAP, bool dup) {
-    float tv[D + 3], S[D];
+__device__ __forceinline__ void qcg_check_load(uint32_t tt, uint32_t rrow, uint32_t la, uint32_t RS, float* tv, float* S) {
 #pragma unroll
     for (int j = 0; j < D; j += 4) {  // four warp-uniform bases per broadcast LDS.128
         const uint4 e = lds_u128(tt + (uint32_t)j * 4u);
@@ -64,6 +64,9 @@ __device__ __forceinline__ uint32_t qcg_check(uint32_t tt, uint32_t rrow, uint32
     }
 #pragma unroll
     for (int j = 0; j < D; ++j) S[j] = lds_f32(la + rrow + (uint32_t)j * RS);
+}
+template <int D>
+__device__ __forceinline__ uint32_t qcg_check_finish(uint32_t rrow, uint32_t la, uint32_t RS, uint32_t WRAP, bool dup, const float* tv, float* S) {
     float m1 = INFINITY, m2 = INFINITY;
     uint32_t px = 0u, sx = 0u;
 #pragma unroll
@@ -99,6 +102,22 @@ __device__ __forceinline__ uint32_t qcg_check(uint32_t tt, uint32_t rrow, uint32
     }
     return ((sx >> 31) ^ (uint32_t)D) & 1u;
 }
+template <int D>
+__device__ __forceinline__ uint32_t qcg_check(uint32_t tt, uint32_t rrow, uint32_t la, uint32_t RS, uint32_t WRAP, bool dup) {
+    float tv[D + 3], S[D];
+    qcg_check_load<D>(tt, rrow, la, RS, tv, S);
+    return qcg_check_finish<D>(rrow, la, RS, WRAP, dup, tv, S);
+}
+// Two checks of the same degree (consecutive slots): both sets of loads first.
+template <int D>
+__device__ __forceinline__ uint32_t qcg_check2(uint32_t tt, uint32_t rrow0, uint32_t rrow1, uint32_t la, uint32_t RS, uint32_t WRAP,
+                                                bool dup0, bool dup1) {
+    float tv0[D + 3], S0[D], tv1[D + 3], S1[D];
+    qcg_check_load<D>(tt, rrow0, la, RS, tv0, S0);
+    qcg_check_load<D>(tt + (uint32_t)((D + 3) & ~3) * 4u, rrow1, la, RS, tv1, S1);
+    const uint32_t u0 = qcg_check_finish<D>(rrow0, la, RS, WRAP, dup0, tv0, S0);
+    return u0 | qcg_check_finish<D>(rrow1, la, RS, WRAP, dup1, tv1, S1);
+}
 
 // One variable slot of exact degree D: returns T = (-y) - R_1 - R_2 ... (ascending-row order).
 template <int D>
@@ -115,6 +134,23 @@ __device__ __forceinline__ float qcg_var(uint32_t rr, uint32_t la, float acc) {
 #pragma unroll
     for (int k = 0; k < D; ++k) acc = __fsub_rn(acc, r[k]);
     return acc;
+}
+
+// Two variable slots of the same degree: loads of both first, then the two subtraction chains interleaved.
+template <int D>
+__device__ __forceinline__ void qcg_var2(uint32_t rr, uint32_t la, float& acc0, float& acc1) {
+    float r0[D + 3], r1[D + 3];
+    const uint32_t rr1 = rr + (uint32_t)((D + 3) & ~3) * 4u;
+#pragma unroll
+    for (int k = 0; k < D; k += 4) {
+        const uint4 u = lds_u128(rr + (uint32_t)k * 4u), v = lds_u128(rr1 + (uint32_t)k * 4u);
+        r0[k] = lds_f32(la + u.x); r1[k] = lds_f32(la + v.x);
+        if (k + 1 < D) { r0[k + 1] = lds_f32(la + u.y); r1[k + 1] = lds_f32(la + v.y); }
+        if (k + 2 < D) { r0[k + 2] = lds_f32(la + u.z); r1[k + 2] = lds_f32(la + v.z); }
+        if (k + 3 < D) { r0[k + 3] = lds_f32(la + u.w); r1[k + 3] = lds_f32(la + v.w); }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) { acc0 = __fsub_rn(acc0, r0[k]); acc1 = __fsub_rn(acc1, r1[k]); }
 }
 
 template <int G>
@@ -165,6 +201,20 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
             const int d = p.cdeg[cs];
             const bool dup = (cdup_bits >> cs) & 1u;
             const uint32_t rrow = tab_u32(kOffCnR + (uint32_t)cs * 4u);
+            const uint32_t step = (uint32_t)((d + 3) & ~3) * 4u;
+            if (d <= 8 && cs + 1 < CS && p.cdeg[cs + 1] == d) {  // two slots of a low degree: loads of both in flight
+                const bool dup1 = (cdup_bits >> (cs + 1)) & 1u;
+                const uint32_t rrow1 = tab_u32(kOffCnR + (uint32_t)(cs + 1) * 4u);
+#define QCG_CASE2(D) case D: unsat |= qcg_check2<D>(tt, rrow, rrow1, la, RS, WRAP, dup, dup1); break;
+                switch (d) {
+                    QCG_CASE2(1) QCG_CASE2(2) QCG_CASE2(3) QCG_CASE2(4) QCG_CASE2(5) QCG_CASE2(6) QCG_CASE2(7) QCG_CASE2(8)
+                    default: break;
+                }
+#undef QCG_CASE2
+                tt += 2u * step;
+                ++cs;
+                continue;
+            }
 #define QCG_CASE(D) case D: unsat |= qcg_check<D>(tt, rrow, la, RS, WRAP, dup); break;
             switch (d) {
                 QCG_CASE(1) QCG_CASE(2) QCG_CASE(3) QCG_CASE(4) QCG_CASE(5) QCG_CASE(6) QCG_CASE(7) QCG_CASE(8)
@@ -172,34 +222,58 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
                 default: break;
             }
 #undef QCG_CASE
-            tt += (uint32_t)((d + 3) & ~3) * 4u;
+            tt += step;
         }
         return unsat;
     };
     auto vn_pass = [&](bool frozen) {
         uint32_t rr = tsm + kOffVnR;
+        auto store_t = [&](int s, float acc) {
+            if (!frozen) {
+                const uint32_t ta = la + tab_u32(kOffVnT + (uint32_t)s * 4u);
+                sts_f32(ta, acc);
+                if ((vdup_bits >> s) & 1u) sts_f32(ta + WRAP, acc);
+            }
+        };
+        auto one = [&](int s, int d, float acc) {
+            switch (d) {
+                case 1: acc = qcg_var<1>(rr, la, acc); break;
+                case 2: acc = qcg_var<2>(rr, la, acc); break;
+                case 3: acc = qcg_var<3>(rr, la, acc); break;
+                case 4: acc = qcg_var<4>(rr, la, acc); break;
+                case 5: acc = qcg_var<5>(rr, la, acc); break;
+                case 6: acc = qcg_var<6>(rr, la, acc); break;
+                case 7: acc = qcg_var<7>(rr, la, acc); break;
+                case 8: acc = qcg_var<8>(rr, la, acc); break;
+                default: break;
+            }
+            store_t(s, acc);
+            rr += (uint32_t)((d + 3) & ~3) * 4u;
+        };
 #pragma unroll
-        for (int s = 0; s < kQcgMaxVS; ++s) {
+        for (int s = 0; s < kQcgMaxVS; s += 2) {  // slots in pairs: equal degrees (the common case) share one straight-line block
             if (s < VS) {
-                const int d = p.vdeg[s];
-                float acc = yn[s];
-                switch (d) {
-                    case 1: acc = qcg_var<1>(rr, la, acc); break;
-                    case 2: acc = qcg_var<2>(rr, la, acc); break;
-                    case 3: acc = qcg_var<3>(rr, la, acc); break;
-                    case 4: acc = qcg_var<4>(rr, la, acc); break;
-                    case 5: acc = qcg_var<5>(rr, la, acc); break;
-                    case 6: acc = qcg_var<6>(rr, la, acc); break;
-                    case 7: acc = qcg_var<7>(rr, la, acc); break;
-                    case 8: acc = qcg_var<8>(rr, la, acc); break;
-                    default: break;
+                const int d0 = p.vdeg[s];
+                if (s + 1 < VS && p.vdeg[s + 1] == d0) {
+                    float a0 = yn[s], a1 = yn[s + 1];
+                    switch (d0) {
+                        case 1: qcg_var2<1>(rr, la, a0, a1); break;
+                        case 2: qcg_var2<2>(rr, la, a0, a1); break;
+                        case 3: qcg_var2<3>(rr, la, a0, a1); break;
+                        case 4: qcg_var2<4>(rr, la, a0, a1); break;
+                        case 5: qcg_var2<5>(rr, la, a0, a1); break;
+                        case 6: qcg_var2<6>(rr, la, a0, a1); break;
+                        case 7: qcg_var2<7>(rr, la, a0, a1); break;
+                        case 8: qcg_var2<8>(rr, la, a0, a1); break;
+                        default: break;
+                    }
+                    store_t(s, a0);
+                    store_t(s + 1, a1);
+                    rr += 2u * (uint32_t)((d0 + 3) & ~3) * 4u;
+                } else {
+                    one(s, d0, yn[s]);
+                    if (s + 1 < VS) one(s + 1, p.vdeg[s + 1], yn[s + 1]);
                 }
-                if (!frozen) {
-                    const uint32_t ta = la + tab_u32(kOffVnT + (uint32_t)s * 4u);
-                    sts_f32(ta, acc);
-                    if ((vdup_bits >> s) & 1u) sts_f32(ta + WRAP, acc);
-                }
-                rr += (uint32_t)((d + 3) & ~3) * 4u;
             }
         }
     };

@@ -1115,12 +1115,18 @@ bool qcg_build(const HostTables& t, int z, int G, const std::vector<std::vector<
     const uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
     const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
     const int cgroups = MB * gpb, vgroups = NB * gpb;
+    // warps per CTA: the count that leaves the fewest empty (warp, slot) places -- groups need not divide evenly, the
+    // last slot of some warps stays empty
     int W = 0;
-    for (int w = kQcgMaxW; w >= 4; --w)
-        if (cgroups % w == 0 && vgroups % w == 0) { W = w; break; }
+    double best_u = 0.0;
+    for (int w = kQcgMaxW; w >= 4; --w) {
+        const int cs = (cgroups + w - 1) / w, vs = (vgroups + w - 1) / w;
+        if (cs > kQcgMaxCS || vs > kQcgMaxVS) continue;
+        const double u = (0.6 * cgroups / (double)(cs * w) + 0.4 * vgroups / (double)(vs * w)) * (0.9 + 0.1 * w / kQcgMaxW);
+        if (u > best_u + 1e-9) { best_u = u; W = w; }
+    }
     if (!W) return false;
-    const int CS = cgroups / W, VS = vgroups / W;
-    if (CS > kQcgMaxCS || VS > kQcgMaxVS) return false;
+    const int CS = (cgroups + W - 1) / W, VS = (vgroups + W - 1) / W;
     struct Col { int br, j, s; };
     std::vector<std::vector<Col>> cols(NB);
     for (int br = 0; br < MB; ++br)
@@ -1151,6 +1157,7 @@ bool qcg_build(const HostTables& t, int z, int G, const std::vector<std::vector<
         const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
         QcgWarpTab& tb = tabs[w];
         tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
+        tb.cact |= 1u << slot;
         if (g == gpb - 1) tb.cdup |= 1u << slot;
         for (int j = 0; j < q.cdeg[slot]; ++j)
             tb.cn_t[coff[slot] + j] = j < (int)rows[br].size()
@@ -1163,6 +1170,7 @@ bool qcg_build(const HostTables& t, int z, int G, const std::vector<std::vector<
         QcgWarpTab& tb = tabs[w];
         tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
         tb.var0[slot] = (uint32_t)(bc * z + i0);
+        tb.vact |= 1u << slot;
         if (g == 0) tb.vdup |= 1u << slot;
         for (int k = 0; k < q.vdeg[slot]; ++k) {
             if (k >= d) { tb.vn_r[voff[slot] + k] = zero_row; continue; }

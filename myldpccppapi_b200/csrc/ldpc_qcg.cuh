@@ -17,8 +17,8 @@ namespace ldpc_b200 {
 constexpr int kQcgMaxW = 12;    // warps per CTA (two CTAs of <= 384 threads per SM: 80 registers)
 constexpr int kQcgMaxCS = 12;   // check slots per thread
 constexpr int kQcgMaxVS = 16;   // variable slots per thread (channel values in registers)
-constexpr int kQcgMaxCE = 64;   // table entries per warp (sum of even-padded slot degrees)
-constexpr int kQcgMaxVE = 64;
+constexpr int kQcgMaxCE = 96;   // table entries per warp (sum of the slot degrees, each padded to a multiple of 4)
+constexpr int kQcgMaxVE = 96;
 constexpr int kQcgMaxCD = 16;   // check degree instantiated
 constexpr int kQcgMaxVD = 8;    // variable degree instantiated
 
@@ -29,6 +29,7 @@ struct QcgWarpTab {
     uint32_t vn_t[kQcgMaxVS];             // own T rows of the slot's variables
     uint32_t var0[kQcgMaxVS];             // variable index of node lane 0
     uint32_t cdup, vdup;                  // bit s: the slot's group owns wrapped rows
+    uint32_t cact, vact;                  // bit s: the slot holds a real group (the last slot of some warps is empty)
 };
 
 struct QcgParams {
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
     constexpr uint32_t kOffCnR = (uint32_t)offsetof(QcgWarpTab, cn_r), kOffVnT = (uint32_t)offsetof(QcgWarpTab, vn_t);
     constexpr uint32_t kOffVar0 = (uint32_t)offsetof(QcgWarpTab, var0);
     const uint32_t cdup_bits = tab_u32((uint32_t)offsetof(QcgWarpTab, cdup)), vdup_bits = tab_u32((uint32_t)offsetof(QcgWarpTab, vdup));
+    const uint32_t cact_bits = tab_u32((uint32_t)offsetof(QcgWarpTab, cact)), vact_bits = tab_u32((uint32_t)offsetof(QcgWarpTab, vact));
     const uint32_t la = sb + (uint32_t)lane * 4u;
     const uint32_t c4 = (uint32_t)c * 4u;
     const int NL = p.W * SUB, Z = p.Z, CS = p.CS, VS = p.VS;
@@ -202,7 +204,8 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
             const bool dup = (cdup_bits >> cs) & 1u;
             const uint32_t rrow = tab_u32(kOffCnR + (uint32_t)cs * 4u);
             const uint32_t step = (uint32_t)((d + 3) & ~3) * 4u;
-            if (d <= 8 && cs + 1 < CS && p.cdeg[cs + 1] == d) {  // two slots of a low degree: loads of both in flight
+            if (!((cact_bits >> cs) & 1u)) { tt += step; continue; }  // empty slot of this warp (warp-uniform)
+            if (d <= 8 && cs + 1 < CS && p.cdeg[cs + 1] == d && ((cact_bits >> (cs + 1)) & 1u)) {  // two slots of a low degree: loads of both in flight
                 const bool dup1 = (cdup_bits >> (cs + 1)) & 1u;
                 const uint32_t rrow1 = tab_u32(kOffCnR + (uint32_t)(cs + 1) * 4u);
 #define QCG_CASE2(D) case D: unsat |= qcg_check2<D>(tt, rrow, rrow1, la, RS, WRAP, dup, dup1); break;
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
             }
         };
         auto one = [&](int s, int d, float acc) {
+            if (!((vact_bits >> s) & 1u)) { rr += (uint32_t)((d + 3) & ~3) * 4u; return; }  // empty slot of this warp
             switch (d) {
                 case 1: acc = qcg_var<1>(rr, la, acc); break;
                 case 2: acc = qcg_var<2>(rr, la, acc); break;
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
         for (int s = 0; s < kQcgMaxVS; s += 2) {  // slots in pairs: equal degrees (the common case) share one straight-line block
             if (s < VS) {
                 const int d0 = p.vdeg[s];
-                if (s + 1 < VS && p.vdeg[s + 1] == d0) {
+                if (s + 1 < VS && p.vdeg[s + 1] == d0 && ((vact_bits >> (s + 1)) & 1u)) {  // (slot s + 1 real => slot s real)
                     float a0 = yn[s], a1 = yn[s + 1];
                     switch (d0) {
                         case 1: qcg_var2<1>(rr, la, a0, a1); break;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
                 const float* src = p.llr + (size_t)cw * p.N + h;
 #pragma unroll
                 for (int s = 0; s < kQcgMaxVS; ++s) {
-                    if (s < VS) {
+                    if (s < VS && ((vact_bits >> s) & 1u)) {
                         const uint32_t dst = la + tab_u32(kOffVnT + (uint32_t)s * 4u);
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + tab_u32(kOffVar0 + (uint32_t)s * 4u)) : "memory");
                     }
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
         if (loading) {
 #pragma unroll
             for (int s = 0; s < kQcgMaxVS; ++s) {
-                if (s < VS) {
+                if (s < VS && ((vact_bits >> s) & 1u)) {
                     const uint32_t ta = la + tab_u32(kOffVnT + (uint32_t)s * 4u);
                     const float y = lds_f32(ta);
                     yn[s] = __fadd_rn(-y, 0.0f);
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
                 }
             }
             for (int cs = 0; cs < CS; ++cs) {
+                if (!((cact_bits >> cs) & 1u)) continue;
                 const bool dup = (cdup_bits >> cs) & 1u;
                 const uint32_t rrow = la + tab_u32(kOffCnR + (uint32_t)cs * 4u);
                 for (int j = 0; j < p.cdeg[cs]; ++j) {

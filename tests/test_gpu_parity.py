@@ -244,7 +244,9 @@ def test_qc_runtime_profile_kernel(default_code, monkeypatch):
     # other sizes and rates: first with the run-time profile forced (padded slots, G = 4 and 2), then as planned
     # (compiled profiles for z = 24, 32, 40, 48, 64, 80, 96; run-time profile or the group kernel for the other z)
     cases = [(960, 3, "3/4A", 3, 4, 4), (1152, 2, "2/3B", 2, 3, 4), (2304, 0, "1/2", 1, 2, 2), (768, 5, "5/6", 5, 6, 4),
-             (1536, 4, "3/4B", 3, 4, 2), (1920, 1, "2/3A", 2, 3, 2), (2304, 5, "5/6", 5, 6, 2), (1728, 4, "3/4B", 3, 4, None)]
+             (1536, 4, "3/4B", 3, 4, 2), (1920, 1, "2/3A", 2, 3, 2), (2304, 5, "5/6", 5, 6, 2),
+             # block sizes whose groups do not divide evenly over the warps (empty slots): z = 72, 56, 36, 92
+             (1728, 4, "3/4B", 3, 4, None), (1344, 0, "1/2", 1, 2, None), (864, 3, "3/4A", 3, 4, None), (2208, 2, "2/3B", 2, 3, None)]
     for forced in (True, False):
         if not forced:
             monkeypatch.delenv("LDPC_B200_QC_GENERIC")

@@ -21,7 +21,7 @@
 //   T [NB][z + SUB][G]     negated posterior, natural column order inside a block column
 //   R [E ][SUB + z][G]     E = number of non-zero blocks; block e = (block row, j) holds the message
 //                          of edge j of every row of that block row, indexed by the ROW
-//   zero row                target of padded variable-pass entries
+//   zero row, -inf row      targets of padded variable-pass / check-pass entries (slots whose two blocks differ in degree)
 // Arithmetic contract, lane refill and outputs are those of ldpc_ms_group_kernel (bit-exact with
 // Coder::decodeCPU, reference MyLdpc.cpp:684-784).
 #pragma once

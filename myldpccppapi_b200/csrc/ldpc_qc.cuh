@@ -82,7 +82,7 @@ struct QcLayout {
         const int d = P::vdeg(s0);
         int n = 1;
         while (s0 + n < P::VS && P::vdeg(s0 + n) == d) ++n;
-        return (n >= 4 && d <= 3) ? 4 : (n >= 2 ? 2 : 1);
+        return (n >= 4 && d <= 6) ? 4 : (n >= 2 ? 2 : 1);
     }
     __host__ __device__ static constexpr int voff(int s) {  // s may be P::VS (total)
         int o = 0, s0 = 0;

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -183,6 +185,11 @@ struct ldpc_b200_decoder {
     int64_t h_avail_cap = 0;
     cudaEvent_t st_event = nullptr;
     const unsigned long long* cur_avail = nullptr;  // set around a streamed launch (under mu)
+    // pageable input: ring of pinned staging buffers filled by host threads
+    static constexpr int kStageSlots = 8;
+    float* st_pin[kStageSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t st_pin_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t st_pin_bytes = 0;
 
     int64_t launches = 0;
     std::mutex mu;
@@ -2168,6 +2175,10 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dq_tabs);
             cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
             cudaFree(h->d_avail);
+            for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
+                if (h->st_pin[i]) cudaFreeHost(h->st_pin[i]);
+                if (h->st_pin_ev[i]) cudaEventDestroy(h->st_pin_ev[i]);
+            }
             if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
             if (h->st_event) cudaEventDestroy(h->st_event);
             for (int s = 0; s < kSlots; ++s)
@@ -2386,8 +2397,15 @@ namespace {
 // its work queue as usual and only waits when it is ahead of the copies.  No kernel boundaries, no tail per chunk,
 // and the device-to-host copy of the bits follows the kernel.  Everything is queued before the launch, so a
 // serialising tool (profiler, CUDA_LAUNCH_BLOCKING) degrades to copy-then-decode instead of deadlocking.
+//
+// staged = true (pageable input): the driver would stage such copies synchronously at ~7.5 GB/s; instead four host
+// threads copy the chunks into a ring of pinned buffers and queue the DMA of each (in chunk order), while the kernel
+// -- launched first in this mode -- already decodes.  If nothing can feed the kernel (a tool that serialises kernel
+// launches and blocks the other threads' API calls), its 4 s bound expires and the caller falls back to the chunked
+// pipeline: returns kStreamedRetry.
+constexpr int kStreamedRetry = 1;
 int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                         int32_t* iters, float* post) {
+                         int32_t* iters, float* post, bool staged) {
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
@@ -2424,6 +2442,22 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
     auto words_of = [&](int64_t bytes) { return std::max<int64_t>(g, (bytes / ((int64_t)t.N * 4)) / g * g); };
     int64_t chunk0 = words_of((int64_t)1 << 20), chunk_max = words_of((int64_t)4 << 20);
     if (const char* env = std::getenv("LDPC_B200_STREAM_CHUNK")) { const long long c = std::atoll(env); if (c >= 1) chunk0 = chunk_max = (c + g - 1) / g * g; }
+    if (staged) {
+        chunk0 = chunk_max;  // fixed-size chunks = ring slots
+        const size_t need = sizeof(float) * (size_t)chunk_max * t.N;
+        if (h->st_pin_bytes < need) {
+            CU_TRY(cudaDeviceSynchronize());
+            for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
+                if (h->st_pin[i]) { cudaFreeHost(h->st_pin[i]); h->st_pin[i] = nullptr; }
+            }
+            h->st_pin_bytes = 0;
+            for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
+                CU_TRY(cudaMallocHost(&h->st_pin[i], need));
+                if (!h->st_pin_ev[i]) CU_TRY(cudaEventCreateWithFlags(&h->st_pin_ev[i], cudaEventDisableTiming));
+            }
+            h->st_pin_bytes = need;
+        }
+    }
     const int64_t nchunks_max = (want + chunk_max - 1) / chunk_max + 8;
     if (h->h_avail_cap < nchunks_max) {
         if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
@@ -2439,18 +2473,61 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
         CU_TRY(cudaMemsetAsync(h->d_avail, 0, 2 * sizeof(unsigned long long), cs));
         CU_TRY(cudaEventRecord(h->st_event, cs));
         CU_TRY(cudaStreamWaitEvent(ks, h->st_event, 0));  // the kernel must not see a stale count
-        int64_t j = 0, chunk = chunk0;
-        for (int64_t c0 = 0; c0 < n; c0 += chunk, chunk = std::min(chunk * 2, chunk_max), ++j) {
-            const int64_t m = std::min(chunk, n - c0);
-            CU_TRY(cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, llr + (size_t)(off + c0) * t.N, sizeof(float) * (size_t)m * t.N,
-                                   cudaMemcpyHostToDevice, cs));
-            h->h_avail_vals[j] = (unsigned long long)(c0 + m);
-            CU_TRY(cudaMemcpyAsync(h->d_avail, h->h_avail_vals + j, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
-        }
-        h->cur_avail = h->d_avail;
-        int rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
+        int rc = LDPC_B200_OK;
+        if (!staged) {
+            int64_t j = 0, chunk = chunk0;
+            for (int64_t c0 = 0; c0 < n; c0 += chunk, chunk = std::min(chunk * 2, chunk_max), ++j) {
+                const int64_t m = std::min(chunk, n - c0);
+                CU_TRY(cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, llr + (size_t)(off + c0) * t.N, sizeof(float) * (size_t)m * t.N,
+                                       cudaMemcpyHostToDevice, cs));
+                h->h_avail_vals[j] = (unsigned long long)(c0 + m);
+                CU_TRY(cudaMemcpyAsync(h->d_avail, h->h_avail_vals + j, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
+            }
+            h->cur_avail = h->d_avail;
+            rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
                                iters ? h->st_iters : nullptr, post ? h->st_post : nullptr, ks);
-        h->cur_avail = nullptr;
+            h->cur_avail = nullptr;
+        } else {
+            h->cur_avail = h->d_avail;
+            rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
+                               iters ? h->st_iters : nullptr, post ? h->st_post : nullptr, ks);
+            h->cur_avail = nullptr;
+            if (rc == LDPC_B200_OK) {
+                constexpr int S = ldpc_b200_decoder::kStageSlots;
+                const int64_t cw = chunk_max, nch = (n + cw - 1) / cw;
+                std::atomic<int64_t> next_chunk{0}, next_enq{0};
+                std::atomic<int> err{0};
+                const float* src = llr + (size_t)off * t.N;
+                auto work = [&]() {
+                    if (cudaSetDevice(h->device) != cudaSuccess) { err.store(1); return; }
+                    for (;;) {
+                        const int64_t j = next_chunk.fetch_add(1);
+                        if (j >= nch || err.load()) break;
+                        const int slot = (int)(j % S);
+                        if (j >= S) {  // the slot's previous chunk must have been queued and its DMA finished
+                            while (next_enq.load() <= j - S && !err.load()) std::this_thread::yield();
+                            if (err.load()) break;
+                            if (cudaEventSynchronize(h->st_pin_ev[slot]) != cudaSuccess) { err.store(1); break; }
+                        }
+                        const int64_t c0 = j * cw, m = std::min(cw, n - c0);
+                        std::memcpy(h->st_pin[slot], src + (size_t)c0 * t.N, sizeof(float) * (size_t)m * t.N);
+                        while (next_enq.load() != j && !err.load()) std::this_thread::yield();  // queue in chunk order
+                        if (err.load()) break;
+                        h->h_avail_vals[j] = (unsigned long long)(c0 + m);
+                        if (cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, h->st_pin[slot], sizeof(float) * (size_t)m * t.N, cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+                            cudaMemcpyAsync(h->d_avail, h->h_avail_vals + j, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs) != cudaSuccess ||
+                            cudaEventRecord(h->st_pin_ev[slot], cs) != cudaSuccess) { err.store(1); break; }
+                        next_enq.store(j + 1);
+                    }
+                };
+                const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>({4, nch, (int64_t)std::max(1u, std::thread::hardware_concurrency())}));
+                std::vector<std::thread> pool;
+                for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
+                work();
+                for (auto& th : pool) th.join();
+                if (err.load()) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); return fail(LDPC_B200_ERR_CUDA, std::string("staged input copy: ") + cudaGetErrorString(cudaGetLastError())); }
+            }
+        }
         if (rc) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); return rc; }
         if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->st_info, (size_t)n * KB, cudaMemcpyDeviceToHost, ks));
         if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->st_hard, (size_t)n * NB, cudaMemcpyDeviceToHost, ks));
@@ -2460,6 +2537,7 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
         CU_TRY(cudaMemcpyAsync(&status, reinterpret_cast<int*>(h->d_avail + 1), sizeof(int), cudaMemcpyDeviceToHost, ks));
         CU_TRY(cudaStreamSynchronize(cs));
         CU_TRY(cudaStreamSynchronize(ks));
+        if (status && staged) return kStreamedRetry;
         if (status) return fail(LDPC_B200_ERR_CUDA, "streamed decode: the input copies stalled for more than 4 s");
     }
     return LDPC_B200_OK;
@@ -2485,7 +2563,14 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
         const bool pinned = guard.ok && cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
                             (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
         if (!pinned) (void)cudaGetLastError();
-        if (pinned || std::getenv("LDPC_B200_STREAMED_PAGEABLE")) return decode_host_streamed(h, llr, ncw, info, hard, iters, post);
+        if (pinned || std::getenv("LDPC_B200_STREAMED_PAGEABLE")) return decode_host_streamed(h, llr, ncw, info, hard, iters, post, false);
+        // pageable input staged by host threads through pinned buffers under the running kernel: opt-in
+        // (LDPC_B200_STAGED_MIN_KB = smallest input that takes it).  Measured through Test.cpp's flow (one decode of
+        // 65,536 words from malloc'd memory, first call): 38 ms against 20 ms for the chunked pipeline below.
+        if (const char* env = std::getenv("LDPC_B200_STAGED_MIN_KB"); env && (int64_t)ncw * t.N * 4 >= ((int64_t)std::atoll(env) << 10)) {
+            const int rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, true);
+            if (rc != kStreamedRetry) return rc;
+        }
     }
     if (h->reserved == 0) {
         // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the

@@ -277,6 +277,13 @@ def test_streamed_host_pipeline(default_code, monkeypatch):
     assert dec.info()["path_name"] == "qc"
     first = dec.decode_host(llr)                                    # pageable input: the chunked 3-stream pipeline
     assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
+    monkeypatch.setenv("LDPC_B200_STAGED_MIN_KB", "0")              # ... staged by host threads through pinned buffers
+    assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="staged pageable input")
+    monkeypatch.setenv("LDPC_B200_STREAM_CHUNK", "8")               # 376 chunks through the ring of 8 staging buffers
+    assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="staged, tiny chunks")
+    monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # several launches
+    assert_parity(dec.decode_host(llr[:1000], want_hard=True, want_post=True), tuple(r[:1000] for r in ref), N, what="staged, batches")
+    monkeypatch.delenv("LDPC_B200_STREAM_CHUNK"); monkeypatch.delenv("LDPC_B200_STREAM_BATCH_KB"); monkeypatch.delenv("LDPC_B200_STAGED_MIN_KB")
     monkeypatch.setenv("LDPC_B200_STREAMED_PAGEABLE", "1")          # ... and the persistent launch fed from pageable memory
     first = dec.decode_host(llr)                                    # info + iters only
     assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])

@@ -124,6 +124,14 @@ int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm);     /* LDPC_B200
 int ldpc_b200_set_layer_height(ldpc_b200_handle h, int z);
 /* Force a kernel path (LDPC_B200_PATH_*) or -1 for automatic choice. */
 int ldpc_b200_set_path(ldpc_b200_handle h, int path);
+/* Experiment switches of the host-buffer pipeline.  Every switch is seeded ONCE, in
+ * ldpc_b200_create, from the environment variable LDPC_B200_<NAME>; nothing on the decode path reads the
+ * environment.  The ones below can be changed per handle afterwards (the kernel-choice switches shape the
+ * plan made at create time and are refused here with LDPC_B200_ERR_UNSUPPORTED):
+ *   "refill_wait", "no_streamed", "streamed_pageable", "no_staged", "staged_min_kb", "stream_chunk",
+ *   "stream_batch_kb", "wait_timeout_ms" (bound of the persistent kernel's wait for streamed input; when it
+ *   expires the call is rerun through the chunked pipeline).                                                */
+int ldpc_b200_set_option(ldpc_b200_handle h, const char *name, long long value);
 int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info *info);
 
 /* Copy the CSR of H back (for Coder::checkMatrix); arrays sized M+1 and nnz. */

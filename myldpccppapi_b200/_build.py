@@ -22,8 +22,18 @@ NVCC_FLAGS = [
     "--fmad=false",            # never contract a*b+c: the posterior must round after every add
     "--ftz=false", "--prec-div=true", "--prec-sqrt=true",
     "-Xcompiler", "-fPIC,-O2,-fno-fast-math",
-    "-shared", "-cudart", "shared",
 ]
+
+OBJ = ROOT / "build" / "obj"   # git-ignored; objects are an implementation detail of this script
+
+# One translation unit per kernel family so nvcc builds them in parallel (the compiled quasi-cyclic profiles: one per
+# 802.16e rate).  (source, object name, extra defines)
+QC_RATES = [("34B", "QcProfile34B"), ("34A", "QcProfile34A"), ("23B", "QcProfile23B"),
+            ("23A", "QcProfile23A"), ("12", "QcProfile12"), ("56", "QcProfile56")]
+UNITS = [("ldpc_b200.cu", "ldpc_b200", []), ("ldpc_tables.cpp", "ldpc_tables", []),
+         ("k_group.cu", "k_group", []), ("k_qcg.cu", "k_qcg", []), ("k_sp.cu", "k_sp", []),
+         ("k_tdmp.cu", "k_tdmp", []), ("k_misc.cu", "k_misc", [])]
+UNITS += [("k_qc.cu", "k_qc_" + tag, ["-DLDPC_QC_RATE=" + prof, "-DLDPC_QC_RATE_FN=qc_profiles_" + tag]) for tag, prof in QC_RATES]
 
 
 def _nvcc() -> str:
@@ -40,20 +50,52 @@ def _stale(target: pathlib.Path, sources) -> bool:
     return any(pathlib.Path(s).stat().st_mtime > t for s in sources)
 
 
-def build_cuda(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> pathlib.Path:
-    srcs = [CSRC / "ldpc_b200.cu", CSRC / "ldpc_tables.cpp"]
-    deps = srcs + [CSRC / "ldpc_kernels.cuh", CSRC / "ldpc_cluster.cuh", CSRC / "ldpc_qc.cuh", CSRC / "ldpc_qcg.cuh", CSRC / "ldpc_warp.cuh", CSRC / "ldpc_sp.cuh", CSRC / "ldpc_tdmp.cuh", CSRC / "ldpc_stream.cuh", CSRC / "ldpc_encode.cuh", CSRC / "ldpc_tables.h", CSRC / "wimax_tables.h",
-                   ROOT / "include" / "ldpc_b200.h"]
-    if force or _stale(LIB, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-o", str(LIB), *map(str, srcs)]
-        if ptxas_info:
-            cmd += ["-Xptxas", "-v"]
+def _headers():
+    return sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "ldpc_b200.h"]
+
+
+def build_cuda(force: bool = False, verbose: bool = False, ptxas_info: bool = False, only=None) -> pathlib.Path:
+    """nvcc -c every unit that is older than its source or any header (in parallel), then link."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    hdrs = _headers()
+    if not (force or only or ptxas_info) and not _stale(LIB, [CSRC / src for src, _, _ in UNITS] + hdrs):
+        return LIB  # the shipped library is current (the objects need not exist: build/ does not travel to the GPU box)
+    OBJ.mkdir(parents=True, exist_ok=True)
+    jobs = []
+    for src, name, defs in UNITS:
+        obj = OBJ / (name + ".o")
+        if only and name not in only and obj.exists():
+            continue
+        if force or _stale(obj, [CSRC / src] + hdrs):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-split-compile", "2", "-I", str(ROOT / "include"), *defs, "-c", str(CSRC / src), "-o", str(obj)]
+            if ptxas_info:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append((name, cmd))
+
+    def run(job):
+        name, cmd = job
         r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode or ptxas_info:
+        return name, cmd, r
+
+    if jobs:
+        workers = max(1, min(len(jobs), (os.cpu_count() or 4)))
+        with ThreadPoolExecutor(workers) as ex:
+            for name, cmd, r in ex.map(run, jobs):
+                if verbose or r.returncode or ptxas_info:
+                    print(" ".join(cmd))
+                    print(r.stdout, r.stderr)
+                if r.returncode:
+                    raise RuntimeError("nvcc failed for " + name)
+    objs = [OBJ / (name + ".o") for _, name, _ in UNITS]
+    if jobs or force or _stale(LIB, objs):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", str(LIB), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
             print(" ".join(cmd))
             print(r.stdout, r.stderr)
         if r.returncode:
-            raise RuntimeError("nvcc failed for libldpc_b200.so")
+            raise RuntimeError("link failed for libldpc_b200.so")
     return LIB
 
 

@@ -1,0 +1,76 @@
+// k_misc.cu -- instantiations of the alternative / fallback kernels: sub-warp per check (ldpc_warp.cuh), one codeword
+// per 8-CTA cluster (ldpc_cluster.cuh), lane = codeword with compressed check state (ldpc_kernels.cuh: lane16) and the
+// long-code kernel with its messages in a global workspace (ldpc_stream.cuh).
+#include <algorithm>
+
+#include "ldpc_launch.h"
+#include "ldpc_kernels.cuh"
+#include "ldpc_cluster.cuh"
+#include "ldpc_stream.cuh"
+#include "ldpc_warp.cuh"
+
+namespace ldpc_b200 {
+namespace {
+template <int SW>
+int launch_warp_t(const WarpParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_warp_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ldpc_ms_warp_kernel<SW><<<grid, threads, smem, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+template <int DMAX>
+int launch_cluster_t(const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_cluster_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(kClusterSize);
+    int maxc = 0;
+    e = cudaOccupancyMaxActiveClusters(&maxc, ldpc_ms_cluster_kernel<DMAX>, &cfg);
+    if (e != cudaSuccess) return (int)e;
+    if (maxc < 1) return kNoCluster;
+    cfg.gridDim = dim3(kClusterSize * std::min(maxc, nclusters_wanted));
+    return (int)cudaLaunchKernelEx(&cfg, ldpc_ms_cluster_kernel<DMAX>, q);
+}
+
+template <int MAXT>
+int launch_lane16_t(const Lane16Params& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_lane16_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ldpc_ms_lane16_kernel<MAXT><<<grid, threads, smem, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+}  // namespace
+
+int k_launch_warp(int sw, const WarpParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    switch (sw) {
+        case 8: return launch_warp_t<8>(q, grid, threads, smem, stream);
+        case 16: return launch_warp_t<16>(q, grid, threads, smem, stream);
+        case 32: return launch_warp_t<32>(q, grid, threads, smem, stream);
+    }
+    return kNoKernel;
+}
+
+int k_launch_cluster(int dmax, const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream) {
+    return dmax == 8 ? launch_cluster_t<8>(q, nclusters_wanted, threads, smem, stream)
+                     : launch_cluster_t<16>(q, nclusters_wanted, threads, smem, stream);
+}
+
+int k_launch_lane16(const Lane16Params& q, int grid, int threads, size_t smem, cudaStream_t stream) {
+    return threads <= 768 ? launch_lane16_t<768>(q, grid, threads, smem, stream) : launch_lane16_t<1024>(q, grid, threads, smem, stream);
+}
+
+int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream) {
+    if (threads <= 512) ldpc_ms_stream_kernel<512><<<grid, threads, 0, stream>>>(q);
+    else if (threads <= 768) ldpc_ms_stream_kernel<768><<<grid, threads, 0, stream>>>(q);
+    else ldpc_ms_stream_kernel<1024><<<grid, threads, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+}  // namespace ldpc_b200

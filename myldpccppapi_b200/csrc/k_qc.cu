@@ -1,0 +1,41 @@
+// k_qc.cu -- the compiled quasi-cyclic profiles of ONE 802.16e rate (ldpc_qc.cuh), built once per rate:
+//   nvcc -DLDPC_QC_RATE=QcProfile34B -DLDPC_QC_RATE_FN=qc_profiles_34B ...
+// Each unit owns its copy of the __constant__ table bank; `upload` is how the host logic reaches it.
+#include "ldpc_qc_host.h"
+
+#ifndef LDPC_QC_RATE
+#error "compile with -DLDPC_QC_RATE=<profile template> -DLDPC_QC_RATE_FN=<table function>"
+#endif
+
+namespace ldpc_b200 {
+namespace {
+
+template <class P>
+int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int upload_bank(int slot, const void* tab, size_t bytes) {
+    if (slot < 0 || slot >= kQcTabSlots || bytes > (size_t)kQcBankBytes) return (int)cudaErrorInvalidValue;
+    return (int)cudaMemcpyToSymbol(g_qc_bank, tab, bytes, (size_t)slot * kQcBankBytes, cudaMemcpyHostToDevice);
+}
+
+#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank}
+const QcProfileEntry kTable[] = {
+    QC_PROFILE(LDPC_QC_RATE, 24, 8, 12), QC_PROFILE(LDPC_QC_RATE, 48, 4, 12), QC_PROFILE(LDPC_QC_RATE, 96, 2, 12),
+    QC_PROFILE(LDPC_QC_RATE, 40, 4, 10), QC_PROFILE(LDPC_QC_RATE, 80, 2, 10),
+    QC_PROFILE(LDPC_QC_RATE, 32, 4, 8),  QC_PROFILE(LDPC_QC_RATE, 64, 2, 8),
+};
+#undef QC_PROFILE
+
+}  // namespace
+
+const QcProfileEntry* LDPC_QC_RATE_FN(int* n) {
+    *n = (int)(sizeof(kTable) / sizeof(kTable[0]));
+    return kTable;
+}
+
+}  // namespace ldpc_b200

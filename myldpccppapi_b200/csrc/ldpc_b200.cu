@@ -29,6 +29,7 @@
 #include "ldpc_stream.cuh"
 #include "ldpc_encode.cuh"
 #include "ldpc_tables.h"
+#include "ldpc_launch.h"
 
 using namespace ldpc_b200;
 
@@ -52,6 +53,54 @@ int fail(int code, const std::string& msg) {
 
 constexpr int kSlots = 3;          // rotating streams of the host-buffer pipeline
 constexpr int kCounterRing = 256;  // one work-queue head per in-flight launch
+
+// Experiment switches.  Seeded ONCE per handle from the LDPC_B200_* environment variables in
+// ldpc_b200_create; the host-pipeline ones can be changed afterwards with ldpc_b200_set_option.  Nothing on the
+// decode path calls getenv.
+struct Options {
+    // kernel choice: read when a plan is made
+    bool no_qc = false, no_qcg = false, qc_generic = false;
+    bool grp_no_profile = false, grp_no_ysmem = false, grp_prefer_16 = false, grp_t16 = false, grp_no_t16 = false;
+    bool debug_placement = false;
+    int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0;
+    long long place_effort = 12;
+    // launch / host pipeline: read per call
+    int refill_wait = 1;              // measured: profiles/r01_refill_sweep.txt
+    bool no_streamed = false, streamed_pageable = false, no_staged = false;
+    long long staged_min_kb = 8 << 10;  // pageable input of 8 MB or more is staged by host threads
+    long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
+    long long stream_batch_kb = 0;    // channel values per launch (0 = default)
+    long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
+};
+
+struct OptionName { const char* name; int kind; size_t off; };  // kind 0 bool, 1 int, 2 long long
+#define OPT(n, k) {#n, k, offsetof(Options, n)}
+const OptionName kOptionNames[] = {
+    OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
+    OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(place_effort, 2), OPT(refill_wait, 1), OPT(no_streamed, 0),
+    OPT(streamed_pageable, 0), OPT(no_staged, 0), OPT(staged_min_kb, 2), OPT(stream_chunk, 2), OPT(stream_batch_kb, 2),
+    OPT(wait_timeout_ms, 2),
+};
+#undef OPT
+constexpr int kFirstRuntimeOption = 15;  // refill_wait and everything after it may change after create
+
+void option_store(Options* o, const OptionName& n, long long v) {
+    char* p = reinterpret_cast<char*>(o) + n.off;
+    if (n.kind == 0) *reinterpret_cast<bool*>(p) = v != 0;
+    else if (n.kind == 1) *reinterpret_cast<int*>(p) = (int)v;
+    else *reinterpret_cast<long long*>(p) = v;
+}
+
+Options options_from_env() {
+    Options o;
+    for (const OptionName& n : kOptionNames) {
+        std::string env = "LDPC_B200_";
+        for (const char* c = n.name; *c; ++c) env += (char)std::toupper((unsigned char)*c);
+        if (const char* v = std::getenv(env.c_str())) option_store(&o, n, n.kind == 0 ? 1 : std::atoll(v));
+    }
+    return o;
+}
 
 struct Plan {
     int path = LDPC_B200_PATH_LANE_SMEM;
@@ -90,6 +139,8 @@ struct ldpc_b200_decoder {
     size_t smem_optin = 0;
     int forced_path = -1;
     int algorithm = LDPC_B200_ALG_MIN_SUM;
+    int plan_alg = -1;  // the flooding algorithm `plan` (and the group tables) were built for
+    Options opt;
     bool tables_keep_edge_order = false;  // group tables were built in CSR edge order (needed by sum-product)
     Plan plan;
     bool planned = false;
@@ -181,6 +232,7 @@ struct ldpc_b200_decoder {
     int64_t st_cap = 0;                         // words the st_* buffers hold
     bool st_has_hard = false, st_has_post = false;
     unsigned long long* d_avail = nullptr;      // [0] words landed; [1] (as int) timeout status
+    int* h_status = nullptr;                    // pinned: the kernel's timeout status, read back after each batch
     unsigned long long* h_avail_vals = nullptr; // pinned: the values the copy stream writes to *d_avail
     int64_t h_avail_cap = 0;
     cudaEvent_t st_event = nullptr;
@@ -254,15 +306,12 @@ L16Shape lane16_shape(const HostTables& t, int W) {
     return sh;
 }
 
-bool lane16_pick(const HostTables& t, size_t smem_limit, L16Shape* best) {
+bool lane16_pick(const HostTables& t, size_t smem_limit, const Options& opt, L16Shape* best) {
     if (t.max_row_weight > 32 || t.max_row_weight < 1 || t.nnz < 1) return false;
     bool found = false;
     double best_cost = 0.0;
     int w_lo = 8, w_hi = 32;
-    if (const char* env = std::getenv("LDPC_B200_L16_WARPS")) {  // tuning aid: pin the warp count
-        const int w = std::atoi(env);
-        if (w >= 1 && w <= 32) w_lo = w_hi = w;
-    }
+    if (opt.l16_warps >= 1 && opt.l16_warps <= 32) w_lo = w_hi = opt.l16_warps;  // tuning aid: pin the warp count
     for (int W = w_lo; W <= w_hi; ++W) {
         L16Shape sh = lane16_shape(t, W);
         if (sh.VS > kL16MaxVS || sh.CS > kL16MaxCS) continue;
@@ -351,7 +400,7 @@ struct GrpShape {
     double cost = 0.0;
 };
 
-bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool sp, GrpShape* out) {
+bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool sp, const Options& opt, GrpShape* out) {
     // G = 8 runs two CTAs per SM (phase-shifted check / variable passes overlap): half the budget each
     const size_t smem_limit = G == 8 ? (smem_limit_in + 1024) / 2 - 1024 : (G == 4 ? (smem_limit_in + 1024) / 3 - 1024 : smem_limit_in);
     const int SUB = 32 / G, NL = W * SUB;
@@ -381,7 +430,7 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool s
     sh.tab_smem = core + tabs + 512 <= smem_limit;
     sh.smem = core + (sh.tab_smem ? tabs : 0);
     // channel values on chip too when they fit (dynamic slot loop, two slots in flight)
-    sh.y_smem = !sp && t.max_col_weight <= 12 && sh.smem + tbytes + 512 <= smem_limit && !std::getenv("LDPC_B200_GRP_NO_YSMEM");
+    sh.y_smem = !sp && t.max_col_weight <= 12 && sh.smem + tbytes + 512 <= smem_limit && !opt.grp_no_ysmem;
     if (sh.y_smem) sh.smem += tbytes;
     // issue-slot proxy of the padded work, as for LANE16
     sh.cost = (14.0 * rrows + 4.0 * ventries + 12.0 * sh.CS + 6.0 * sh.VS) * NL / (0.97 + 0.03 * W / 32.0);
@@ -390,17 +439,17 @@ bool group_shape(const HostTables& t, int G, int W, size_t smem_limit_in, bool s
     return true;
 }
 
-bool group_pick(const HostTables& t, size_t smem_limit, bool sp, GrpShape* best) {
+bool group_pick(const HostTables& t, size_t smem_limit, bool sp, const Options& opt, GrpShape* best) {
     int g_lo = 1, g_hi = 16, w_lo = 8, w_hi = 32;
-    if (const char* env = std::getenv("LDPC_B200_GRP_G")) { const int g = std::atoi(env); if (g == 1 || g == 16 || g == 8 || g == 4) g_lo = g_hi = g; }
-    if (const char* env = std::getenv("LDPC_B200_GRP_WARPS")) { const int w = std::atoi(env); if (w >= 1 && w <= 32) w_lo = w_hi = w; }
+    if (opt.grp_g == 1 || opt.grp_g == 16 || opt.grp_g == 8 || opt.grp_g == 4) g_lo = g_hi = opt.grp_g;
+    if (opt.grp_warps >= 1 && opt.grp_warps <= 32) w_lo = w_hi = opt.grp_warps;
     // instantiated: G = 16 (short codes, tables on chip) and G = 1 (one codeword per CTA)
     if (g_lo == 4) {  // experiment: three CTAs of 4 words per SM (LDPC_B200_GRP_G=4)
         bool found = false;
         GrpShape b;
         for (int W = w_lo; W <= std::min(w_hi, 9); ++W) {
             GrpShape sh;
-            if (!group_shape(t, 4, W, smem_limit, sp, &sh) || !sh.tab_smem) continue;
+            if (!group_shape(t, 4, W, smem_limit, sp, opt, &sh) || !sh.tab_smem) continue;
             if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
         }
         if (found) { *best = b; return true; }
@@ -408,13 +457,13 @@ bool group_pick(const HostTables& t, size_t smem_limit, bool sp, GrpShape* best)
     }
     for (int G : {16, 8, 1}) {
         if (G < g_lo || G > g_hi) continue;
-        if (G == 16 && g_lo != 16 && !std::getenv("LDPC_B200_GRP_PREFER_16")) {
+        if (G == 16 && g_lo != 16 && !opt.grp_prefer_16) {
             // measured (profiles/): two phase-shifted CTAs of 8 words beat one CTA of 16 -- try G = 8 first
             bool found8 = false;
             GrpShape b8;
             for (int W = w_lo; W <= std::min(w_hi, 12); ++W) {
                 GrpShape sh;
-                if (!group_shape(t, 8, W, smem_limit, sp, &sh) || !sh.tab_smem) continue;
+                if (!group_shape(t, 8, W, smem_limit, sp, opt, &sh) || !sh.tab_smem) continue;
                 if (!found8 || sh.cost < b8.cost - 1e-9 || (std::abs(sh.cost - b8.cost) <= 1e-9 && W > b8.W)) { found8 = true; b8 = sh; }
             }
             if (found8) { *best = b8; return true; }
@@ -424,7 +473,7 @@ bool group_pick(const HostTables& t, size_t smem_limit, bool sp, GrpShape* best)
         GrpShape b;
         for (int W = w_lo; W <= w_hi; ++W) {
             GrpShape sh;
-            if (!group_shape(t, G, W, smem_limit, sp, &sh)) continue;
+            if (!group_shape(t, G, W, smem_limit, sp, opt, &sh)) continue;
             if (G == 16 && !sh.tab_smem) continue;
             if (G == 8 && (!sh.tab_smem || W > 12)) continue;
             if (!found || sh.cost < b.cost - 1e-9 || (std::abs(sh.cost - b.cost) <= 1e-9 && W > b.W)) { found = true; b = sh; }
@@ -469,7 +518,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     std::vector<int> slot_of_edge(t.nnz);
     for (int r = 0; r < t.M; ++r)
         for (int e = t.row_ptr[r]; e < t.row_ptr[r + 1]; ++e) slot_of_edge[e] = e - t.row_ptr[r];
-    const bool keep_order = h->algorithm == LDPC_B200_ALG_SUM_PRODUCT;  // products are taken in CSR edge order
+    const bool keep_order = h->plan_alg == LDPC_B200_ALG_SUM_PRODUCT;  // products are taken in CSR edge order
     h->tables_keep_edge_order = keep_order;
     if (SUB == 2 || SUB == 4) {
         // Lanes of one warp instruction touch SUB different rows; a row occupies 32/SUB banks chosen by
@@ -583,7 +632,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
         //        swap if the collision count does not grow.
         // Then (a) without touching (b): variable lanes inside a group and the group membership of checks that
         // share a lane are still free.  Only nodes of equal degree trade places (a slot has one degree).
-        const long long effort = std::getenv("LDPC_B200_PLACE_EFFORT") ? std::atoll(std::getenv("LDPC_B200_PLACE_EFFORT")) : 12;
+        const long long effort = h->opt.place_effort;
         const int maxdv = t.max_col_weight;
         auto kth_check = [&](int v, int k) { return (int)(t.vn_edge[t.col_ptr[v] + k] >> kPosBits); };
         if (LN == 32 && !keep_order && maxdv <= 16 && effort > 0) {
@@ -826,7 +875,7 @@ int upload_group_tables(ldpc_b200_decoder* h) {
             }
         }
     }
-    if (SUB == 32 && std::getenv("LDPC_B200_DEBUG_PLACEMENT")) {
+    if (SUB == 32 && h->opt.debug_placement) {
         // extra shared-memory wavefronts per iteration caused by bank conflicts in the two gathers
         long long exA = 0, exB = 0, lbA = 0;
         const int ncg = (t.M + 31) / 32, nvg = (t.N + 31) / 32;
@@ -897,9 +946,9 @@ int upload_group_tables(ldpc_b200_decoder* h) {
             return true;
         };
         bool match = false;
-        if (!keep_order && !std::getenv("LDPC_B200_GRP_NO_PROFILE")) {
-            if (G == 8 && pl.tab_smem && !pl.y_smem && std::getenv("LDPC_B200_GRP_T16")) match = prof_match(ProfileWimax34B576{});
-            if (G == 1 && !pl.tab_smem && !std::getenv("LDPC_B200_GRP_NO_T16")) match = prof_match(ProfileRegular36N8192{});
+        if (!keep_order && !h->opt.grp_no_profile) {
+            if (G == 8 && pl.tab_smem && !pl.y_smem && h->opt.grp_t16) match = prof_match(ProfileWimax34B576{});
+            if (G == 1 && !pl.tab_smem && !h->opt.grp_no_t16) match = prof_match(ProfileRegular36N8192{});
         }
         if (match) {
             std::vector<int> ooff(CS + 1, 0), vbyte(VS + 1, 0);
@@ -952,65 +1001,20 @@ int upload_group_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int G, int DMAX, bool TAB, int MAXT, bool YS, class PROF = GenericProfile, bool T16 = false>
-int launch_group_t(const GroupParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_group_kernel<G, DMAX, TAB, MAXT, YS, PROF, T16><<<grid, threads, smem, stream>>>(q);
-    CU_TRY(cudaGetLastError());
-    return LDPC_B200_OK;
+// 0 / cudaError_t / kNoKernel from a launcher in k_*.cu  ->  C-ABI status
+int launch_status(int rc, const char* what) {
+    if (rc == 0) return LDPC_B200_OK;
+    if (rc == kNoKernel) return fail(LDPC_B200_ERR_UNSUPPORTED, std::string("no ") + what + " kernel instantiated for this shape");
+    if (rc == kNoCluster) return fail(LDPC_B200_ERR_UNSUPPORTED, "no 8-CTA cluster of this size can be resident");
+    return fail(LDPC_B200_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorName((cudaError_t)rc) + " (" + cudaGetErrorString((cudaError_t)rc) + ")");
 }
 
-template <class P>
-bool profile_matches(const Plan& pl, const GroupParams& q) {
-    if (pl.CS != P::CS || pl.VS != P::VS) return false;
-    for (int i = 0; i < P::CS; ++i) if (q.cdeg[i] != P::cdeg(i)) return false;
-    for (int i = 0; i < P::VS; ++i) if (q.vdeg[i] != P::vdeg(i)) return false;
-    return true;
-}
-
-int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t stream) {
-    const int th = pl.threads;
-    const size_t sm = pl.smem;
-    if (pl.G == 16 && pl.tab_smem) {
-        if (pl.dmax == 8) return pl.y_smem ? launch_group_t<16, 8, true, 1024, true>(q, grid, th, sm, stream)
-                                           : launch_group_t<16, 8, true, 1024, false>(q, grid, th, sm, stream);
-        if (pl.y_smem) return th <= 768 ? launch_group_t<16, 16, true, 768, true>(q, grid, th, sm, stream)
-                                        : launch_group_t<16, 16, true, 1024, true>(q, grid, th, sm, stream);
-        return th <= 768 ? launch_group_t<16, 16, true, 768, false>(q, grid, th, sm, stream)
-                         : launch_group_t<16, 16, true, 1024, false>(q, grid, th, sm, stream);
-    }
-    if (pl.G == 4 && pl.tab_smem && th <= 288) {
-        if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576L72>(pl, q))
-            return launch_group_t<4, 16, true, 288, false, ProfileWimax34B576L72>(q, grid, th, sm, stream);
-        return pl.y_smem ? launch_group_t<4, 16, true, 288, true>(q, grid, th, sm, stream)
-                         : launch_group_t<4, 16, true, 288, false>(q, grid, th, sm, stream);
-    }
-    if (pl.G == 8 && pl.tab_smem && th <= 384) {
-        if (pl.t16) return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576, true>(q, grid, th, sm, stream);
-        if (!pl.y_smem && !std::getenv("LDPC_B200_GRP_NO_PROFILE") && profile_matches<ProfileWimax34B576>(pl, q))
-            return launch_group_t<8, 16, true, 384, false, ProfileWimax34B576>(q, grid, th, sm, stream);
-        if (pl.dmax == 8) return pl.y_smem ? launch_group_t<8, 8, true, 384, true>(q, grid, th, sm, stream)
-                                           : launch_group_t<8, 8, true, 384, false>(q, grid, th, sm, stream);
-        return pl.y_smem ? launch_group_t<8, 16, true, 384, true>(q, grid, th, sm, stream)
-                         : launch_group_t<8, 16, true, 384, false>(q, grid, th, sm, stream);
-    }
-    if (pl.G == 1 && !pl.tab_smem && pl.dmax == 8 && !std::getenv("LDPC_B200_GRP_NO_PROFILE") &&
-        profile_matches<ProfileRegular36N8192>(pl, q))
-        return pl.t16 ? launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192, true>(q, grid, th, sm, stream)
-                      : launch_group_t<1, 8, false, 1024, false, ProfileRegular36N8192>(q, grid, th, sm, stream);
-    if (pl.G == 1 && pl.y_smem) {
-        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, true>(q, grid, th, sm, stream)
-                                             : launch_group_t<1, 16, true, 1024, true>(q, grid, th, sm, stream);
-        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024, true>(q, grid, th, sm, stream)
-                            : launch_group_t<1, 16, false, 1024, true>(q, grid, th, sm, stream);
-    }
-    if (pl.G == 1) {
-        if (pl.tab_smem) return pl.dmax == 8 ? launch_group_t<1, 8, true, 1024, false>(q, grid, th, sm, stream)
-                                             : launch_group_t<1, 16, true, 1024, false>(q, grid, th, sm, stream);
-        return pl.dmax == 8 ? launch_group_t<1, 8, false, 1024, false>(q, grid, th, sm, stream)
-                            : launch_group_t<1, 16, false, 1024, false>(q, grid, th, sm, stream);
-    }
-    return fail(LDPC_B200_ERR_UNSUPPORTED, "no group kernel instantiated for this shape");
+int launch_group(const Plan& pl, const GroupParams& q, int grid, bool allow_profile, cudaStream_t stream) {
+    GroupSel sel;
+    sel.G = pl.G; sel.dmax = pl.dmax; sel.threads = pl.threads; sel.CS = pl.CS; sel.VS = pl.VS;
+    sel.tab_smem = pl.tab_smem; sel.y_smem = pl.y_smem; sel.t16 = pl.t16;
+    sel.allow_profile = allow_profile;
+    return launch_status(k_launch_group(sel, q, grid, pl.smem, stream), "group");
 }
 
 // ---- QC layout (see ldpc_qc.cuh) ---------------------------------------------------------------------
@@ -1019,7 +1023,6 @@ int launch_group(const Plan& pl, const GroupParams& q, int grid, cudaStream_t st
 // (warp, slot, edge).
 // Block structure of H for block size z: rows[br] = the circulants (block column, shift) of block row br in
 // ascending column order.  false when H is not a grid of z x z blocks that are zero or one shifted identity.
-struct QcBlk { int bc, s; };
 bool qc_blocks(const HostTables& t, int z, std::vector<std::vector<QcBlk>>* rows_out) {
     if (z < 1 || t.M % z || t.N % z) return false;
     const int MB = t.M / z, NB = t.N / z;
@@ -1043,74 +1046,6 @@ bool qc_blocks(const HostTables& t, int z, std::vector<std::vector<QcBlk>>* rows
         }
     }
     *rows_out = std::move(rows);
-    return true;
-}
-
-template <class P>
-bool qc_build(const HostTables& t, const std::vector<std::vector<QcBlk>>& rows, QcParams* out, std::vector<unsigned char>* tab_bytes,
-              size_t* smem_out) {
-    constexpr int z = P::Z, G = P::G, SUB = 32 / G, W = P::W;
-    constexpr uint32_t ROWB = (uint32_t)G * 4u, RS = (uint32_t)(z + SUB) * ROWB;
-    static_assert(z % SUB == 0, "a group of node lanes must not straddle blocks");
-    if (t.M % z || t.N % z) return false;
-    const int MB = t.M / z, NB = t.N / z, gpb = z / SUB;
-    if (MB * gpb != P::CS * W || NB * gpb != P::VS * W || (int)rows.size() != MB) return false;
-    struct Col { int br, j, s; };
-    std::vector<std::vector<Col>> cols(NB);
-    for (int br = 0; br < MB; ++br)
-        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
-    std::vector<int> border(MB), corder(NB);
-    for (int i = 0; i < MB; ++i) border[i] = i;
-    for (int i = 0; i < NB; ++i) corder[i] = i;
-    std::stable_sort(border.begin(), border.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
-    std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return cols[a].size() > cols[b].size(); });
-    // R blocks of a block row: as many as the degree of the slot(s) its groups are processed with (>= its own)
-    std::vector<int> dpad(MB, 0), eb0(MB + 1, 0);
-    for (int p = 0; p < MB * gpb; ++p) {
-        if ((int)rows[border[p / gpb]].size() > P::cdeg(p / W)) return false;
-        dpad[border[p / gpb]] = std::max(dpad[border[p / gpb]], P::cdeg(p / W));
-    }
-    for (int br = 0; br < MB; ++br) eb0[br + 1] = eb0[br] + dpad[br];
-    const uint32_t t_bytes = (uint32_t)NB * (z + SUB) * ROWB, r_bytes = (uint32_t)eb0[MB] * RS;
-    const uint32_t zero_row = t_bytes + r_bytes, inf_row = zero_row + 128u;
-    QcParams& q = *out;
-    std::memset(&q, 0, sizeof(q));
-    tab_bytes->assign(sizeof(QcWarpTab<P>) * W, 0);
-    QcWarpTab<P>* tabs = reinterpret_cast<QcWarpTab<P>*>(tab_bytes->data());
-    for (int p = 0; p < MB * gpb; ++p) {
-        const int br = border[p / gpb], g = p % gpb, slot = p / W, w = p % W, r0 = g * SUB;
-        QcWarpTab<P>& tb = tabs[w];
-        tb.cn_r[slot] = t_bytes + (uint32_t)eb0[br] * RS + (uint32_t)(SUB + r0) * ROWB;
-        if (g == gpb - 1) tb.cdup |= 1u << slot;
-        for (int j = 0; j < P::cdeg(slot); ++j)
-            tb.cn_t[QcLayout<P>::coff(slot) + j] = j < (int)rows[br].size()
-                ? (uint32_t)(rows[br][j].bc * (z + SUB) + (r0 + rows[br][j].s) % z) * ROWB
-                : inf_row;  // padded edge: T = -inf is neutral for the minima, the sign parity and the syndrome
-    }
-    for (int p = 0; p < NB * gpb; ++p) {
-        const int bc = corder[p / gpb], g = p % gpb, slot = p / W, w = p % W, i0 = g * SUB;
-        const int d = (int)cols[bc].size();
-        if (d > P::vdeg(slot)) return false;
-        QcWarpTab<P>& tb = tabs[w];
-        tb.vn_t[slot] = (uint32_t)(bc * (z + SUB) + i0) * ROWB;
-        tb.var0[slot] = (uint32_t)(bc * z + i0);
-        if (g == 0) tb.vdup |= 1u << slot;
-        for (int k = 0; k < P::vdeg(slot); ++k) {
-            if (k >= d) { tb.vn_r[QcLayout<P>::voff(slot) + k] = zero_row; continue; }
-            const Col& cd = cols[bc][k];  // ascending block row = ascending row: the summation order
-            int m = ((i0 - cd.s) % z + z) % z;
-            if (m > z - SUB) m -= z;      // the group wraps: its first rows are read through the leading pad
-            tb.vn_r[QcLayout<P>::voff(slot) + k] = t_bytes + (uint32_t)(eb0[cd.br] + cd.j) * RS + (uint32_t)(SUB + m) * ROWB;
-        }
-    }
-    // the kernel branches once per pass on "this warp owns wrapped rows": all of a warp's groups or none
-    for (int w = 0; w < W; ++w) {
-        if (tabs[w].cdup != 0u && tabs[w].cdup != (1u << P::CS) - 1u) return false;
-        if (tabs[w].vdup != 0u && tabs[w].vdup != (1u << P::VS) - 1u) return false;
-    }
-    q.N = t.N; q.NB = NB;
-    q.t_bytes = t_bytes; q.r_bytes = r_bytes;
-    *smem_out = (size_t)t_bytes + r_bytes + 256;
     return true;
 }
 
@@ -1213,27 +1148,19 @@ void qc_release_slot(const void* owner, int device, int slot) {
     if (g_qc_owner[device][slot] == owner) g_qc_owner[device][slot] = nullptr;
 }
 
-// The compiled profiles: rate x (z, G, W).
-template <class P>
-int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_qc_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_qc_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
-    CU_TRY(cudaGetLastError());
-    return LDPC_B200_OK;
+// The compiled profiles: rate x (z, G, W), one table per translation unit (k_qc.cu built once per rate).
+const std::vector<QcProfileEntry>& qc_profiles() {
+    static const std::vector<QcProfileEntry> all = [] {
+        std::vector<QcProfileEntry> v;
+        for (auto fn : {&qc_profiles_34B, &qc_profiles_34A, &qc_profiles_23B, &qc_profiles_23A, &qc_profiles_12, &qc_profiles_56}) {
+            int n = 0;
+            const QcProfileEntry* e = fn(&n);
+            v.insert(v.end(), e, e + n);
+        }
+        return v;
+    }();
+    return all;
 }
-
-struct QcProfileEntry {
-    int z, G, W;
-    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, QcParams*, std::vector<unsigned char>*, size_t*);
-    int (*launch)(const QcParams&, int, size_t, cudaStream_t);
-};
-#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>}
-#define QC_PROFILE_SIZES(T) QC_PROFILE(T, 24, 8, 12), QC_PROFILE(T, 48, 4, 12), QC_PROFILE(T, 96, 2, 12), QC_PROFILE(T, 40, 4, 10), \
-                            QC_PROFILE(T, 80, 2, 10), QC_PROFILE(T, 32, 4, 8), QC_PROFILE(T, 64, 2, 8)
-const QcProfileEntry kQcProfiles[] = {QC_PROFILE_SIZES(QcProfile34B), QC_PROFILE_SIZES(QcProfile34A), QC_PROFILE_SIZES(QcProfile23B),
-                                      QC_PROFILE_SIZES(QcProfile23A), QC_PROFILE_SIZES(QcProfile12), QC_PROFILE_SIZES(QcProfile56)};
-#undef QC_PROFILE_SIZES
-#undef QC_PROFILE
 
 // Finds the compiled profile the code matches, builds its tables, takes a slot of the constant bank and uploads them
 // (current device = the handle's).  false = use another path.
@@ -1242,8 +1169,9 @@ bool qc_prepare(ldpc_b200_decoder* h) {
     std::vector<std::vector<QcBlk>> rows;
     int rows_z = 0;
     std::vector<unsigned char> tab;
-    for (int k = 0; k < (int)(sizeof(kQcProfiles) / sizeof(kQcProfiles[0])); ++k) {
-        const QcProfileEntry& pe = kQcProfiles[k];
+    const std::vector<QcProfileEntry>& profiles = qc_profiles();
+    for (int k = 0; k < (int)profiles.size(); ++k) {
+        const QcProfileEntry& pe = profiles[k];
         if (t.M % pe.z || t.N % pe.z) continue;
         if (rows_z != pe.z) { rows.clear(); rows_z = pe.z; if (!qc_blocks(t, pe.z, &rows)) rows.clear(); }
         if (rows.empty()) continue;
@@ -1253,7 +1181,7 @@ bool qc_prepare(ldpc_b200_decoder* h) {
         if (!guard.ok) return false;
         const int slot = qc_acquire_slot(h, h->device);
         if (slot < 0) return false;
-        if (cudaMemcpyToSymbol(g_qc_bank, tab.data(), tab.size(), (size_t)slot * kQcBankBytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (pe.upload(slot, tab.data(), tab.size()) != 0) {
             (void)cudaGetLastError();
             qc_release_slot(h, h->device, slot);
             return false;
@@ -1293,14 +1221,6 @@ bool qcg_prepare(ldpc_b200_decoder* h) {
         }
     }
     return false;
-}
-
-template <int G>
-int launch_qcg_t(const QcgParams& q, int grid, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_qcg_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_ms_qcg_kernel<G><<<grid, q.W * 32, smem, stream>>>(q);
-    CU_TRY(cudaGetLastError());
-    return LDPC_B200_OK;
 }
 
 // ---- WARP layout (see ldpc_warp.cuh) ------------------------------------------------------------------
@@ -1484,26 +1404,6 @@ int upload_cluster_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int DMAX>
-int launch_cluster_t(const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_ms_cluster_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cfg.gridDim = dim3(kClusterSize);
-    int maxc = 0;
-    CU_TRY(cudaOccupancyMaxActiveClusters(&maxc, ldpc_ms_cluster_kernel<DMAX>, &cfg));
-    if (maxc < 1) return fail(LDPC_B200_ERR_UNSUPPORTED, "no 8-CTA cluster of this size can be resident");
-    cfg.gridDim = dim3(kClusterSize * std::min(maxc, nclusters_wanted));
-    CU_TRY(cudaLaunchKernelEx(&cfg, ldpc_ms_cluster_kernel<DMAX>, q));
-    return LDPC_B200_OK;
-}
-
 // ---- STREAM layout (see ldpc_stream.cuh) --------------------------------------------------------------
 struct StreamShape { int np = 0, nb8 = 0, nb4 = 0, nb2 = 0; };
 
@@ -1581,8 +1481,7 @@ int tdmp_plan(ldpc_b200_decoder* h) {
                 seen[t.col_idx[e]] = r / z;
             }
     }
-    int force_g = 0;
-    if (const char* env = std::getenv("LDPC_B200_TDMP_G")) force_g = std::atoi(env);
+    const int force_g = h->opt.tdmp_g;
     for (int G : {4, 8, 16}) {
         if (force_g && G != force_g) continue;
         const int SUB = 32 / G;
@@ -1645,14 +1544,6 @@ int upload_tdmp_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
-template <int G, int MAXT>
-int launch_tdmp_t(const TdmpParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
-    CU_TRY(cudaFuncSetAttribute(ldpc_tdmp_group_kernel<G, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ldpc_tdmp_group_kernel<G, MAXT><<<grid, threads, smem, stream>>>(q);
-    CU_TRY(cudaGetLastError());
-    return LDPC_B200_OK;
-}
-
 int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard, int32_t* d_iters,
                 float* d_post, cudaStream_t stream) {
     int rc = upload_tdmp_tables(h);
@@ -1673,36 +1564,32 @@ int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* 
     std::memcpy(q.ldeg, pl.ldeg, sizeof(q.ldeg));
     const int64_t ngroups = (ncw + pl.G - 1) / pl.G;
     const int grid = (int)std::min<int64_t>(ngroups, (int64_t)h->sm_count * pl.ctas_per_sm);
-    const bool big = pl.threads > 384;
-    switch (pl.G) {
-        case 4: rc = big ? launch_tdmp_t<4, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<4, 384>(q, grid, pl.threads, pl.smem, stream); break;
-        case 8: rc = big ? launch_tdmp_t<8, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<8, 384>(q, grid, pl.threads, pl.smem, stream); break;
-        default: rc = big ? launch_tdmp_t<16, 1024>(q, grid, pl.threads, pl.smem, stream) : launch_tdmp_t<16, 384>(q, grid, pl.threads, pl.smem, stream); break;
-    }
+    rc = launch_status(k_launch_tdmp(pl.G, q, grid, pl.threads, pl.smem, stream), "layered");
     if (rc) return rc;
     h->launches += 1;
     return LDPC_B200_OK;
 }
 
-int make_plan(ldpc_b200_decoder* h) {
+// Plans the FLOODING decoder for `flood_alg` (min-sum or sum-product); the layered decoder has its own plan (tdmp_plan).
+int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
     const HostTables& t = h->host;
     Plan pl;
     {   // quasi-cyclic code matching a compiled profile: warp-uniform tables (min-sum only)
-        const bool want = h->algorithm == LDPC_B200_ALG_MIN_SUM &&
-                          (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !std::getenv("LDPC_B200_NO_QC")));
-        const bool compiled = want && !std::getenv("LDPC_B200_QC_GENERIC");  // (the env var forces the run-time profile: tests)
+        const bool want = flood_alg == LDPC_B200_ALG_MIN_SUM &&
+                          (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !h->opt.no_qc));
+        const bool compiled = want && !h->opt.qc_generic;  // (the switch forces the run-time profile: tests)
         if (compiled && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
         const bool fits = compiled && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
         // (the kernel's launch bounds allow three CTAs per SM up to 288 threads)
-        const int qc_per_sm = fits && kQcProfiles[h->qc_kind].W * 32 <= 288 && 3 * (h->qc_smem + 2048) <= h->smem_optin + 1024 ? 3 : 2;
+        const int qc_per_sm = fits && qc_profiles()[h->qc_kind].W * 32 <= 288 && 3 * (h->qc_smem + 2048) <= h->smem_optin + 1024 ? 3 : 2;
         if (fits) {
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
-            pl.threads = 32 * kQcProfiles[h->qc_kind].W;
+            pl.threads = 32 * qc_profiles()[h->qc_kind].W;
             pl.smem = h->qc_smem;
             pl.ctas = h->sm_count * qc_per_sm;
-            pl.cw_per_cta = kQcProfiles[h->qc_kind].G;
-            pl.W = kQcProfiles[h->qc_kind].W; pl.G = kQcProfiles[h->qc_kind].G;
+            pl.cw_per_cta = qc_profiles()[h->qc_kind].G;
+            pl.W = qc_profiles()[h->qc_kind].W; pl.G = qc_profiles()[h->qc_kind].G;
             h->plan = pl;
             h->planned = true;
             return LDPC_B200_OK;
@@ -1710,10 +1597,10 @@ int make_plan(ldpc_b200_decoder* h) {
         // any other quasi-cyclic code: the same kernel with a run-time profile -- when the generic on-chip kernel would
         // have to run one codeword per CTA (z > 24: measured 1.6-2.2x faster); with 8 or 16 words per CTA the group
         // kernel is as fast (z = 24 rates: 1.31-1.67 ms against 1.49-1.56 ms per 16,384 words) and stays the choice
-        bool generic = want && !std::getenv("LDPC_B200_NO_QCG");
-        if (generic && h->forced_path < 0 && !std::getenv("LDPC_B200_QC_GENERIC")) {
+        bool generic = want && !h->opt.no_qcg;
+        if (generic && h->forced_path < 0 && !h->opt.qc_generic) {
             GrpShape sh;
-            if (group_pick(t, h->smem_optin, false, &sh) && sh.G >= 8 && sh.tab_smem) generic = false;
+            if (group_pick(t, h->smem_optin, false, h->opt, &sh) && sh.G >= 8 && sh.tab_smem) generic = false;
         }
         if (generic && h->qcg_state == 0) h->qcg_state = qcg_prepare(h) ? 1 : -1;
         if (generic && h->qcg_state == 1) {
@@ -1734,7 +1621,7 @@ int make_plan(ldpc_b200_decoder* h) {
     if (h->forced_path == LDPC_B200_PATH_WARP) {  // opt-in: sub-warp per check, shuffle reductions
         const int SW = warp_sub_width(t);
         const size_t smem = ((size_t)2 * t.N + (size_t)t.M * SW) * sizeof(float);
-        if (h->algorithm != LDPC_B200_ALG_MIN_SUM || SW == 0 || smem + 1024 > h->smem_optin)
+        if (flood_alg != LDPC_B200_ALG_MIN_SUM || SW == 0 || smem + 1024 > h->smem_optin)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "the warp-per-check path needs min-sum, check degree <= 32 and a codeword that fits one SM's shared memory");
         pl.path = LDPC_B200_PATH_WARP;
         pl.threads = std::min(1024, std::max(128, (t.N + 31) / 32 * 32));
@@ -1748,7 +1635,7 @@ int make_plan(ldpc_b200_decoder* h) {
     }
     {   // explicit per-edge messages on chip (G codewords per CTA)
         GrpShape sh;
-        const bool fits = group_pick(t, h->smem_optin, h->algorithm == LDPC_B200_ALG_SUM_PRODUCT, &sh);
+        const bool fits = group_pick(t, h->smem_optin, flood_alg == LDPC_B200_ALG_SUM_PRODUCT, h->opt, &sh);
         if (h->forced_path == LDPC_B200_PATH_GROUP && !fits)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the group shared-memory path");
         if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_GROUP) && fits) {
@@ -1768,7 +1655,7 @@ int make_plan(ldpc_b200_decoder* h) {
     }
     {   // tuned short-code path: channel values in registers, 16-byte check state, tables in smem
         L16Shape sh;
-        const bool fits = (uint64_t)t.M * 512u < (1ull << 31) && lane16_pick(t, h->smem_optin, &sh);
+        const bool fits = (uint64_t)t.M * 512u < (1ull << 31) && lane16_pick(t, h->smem_optin, h->opt, &sh);
         if (h->forced_path == LDPC_B200_PATH_LANE16 && !fits)
             return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the lane16 shared-memory path");
         if ((h->forced_path < 0 || h->forced_path == LDPC_B200_PATH_LANE16) && fits) {
@@ -1831,7 +1718,7 @@ int make_plan(ldpc_b200_decoder* h) {
     } else if (path == LDPC_B200_PATH_STREAM) {
         pl.path = path;
         pl.threads = 1024;
-        if (const char* env = std::getenv("LDPC_B200_STREAM_THREADS")) { const int th = std::atoi(env); if (th >= 32 && th <= 1024 && th % 32 == 0) pl.threads = th; }
+        { const int th = h->opt.stream_threads; if (th >= 32 && th <= 1024 && th % 32 == 0) pl.threads = th; }
         pl.smem = 0;
         pl.ctas = h->sm_count;
         pl.ws_stride = ((size_t)2 * stream_shape(t).np + (size_t)8 * t.M) * kLanes;
@@ -1841,6 +1728,13 @@ int make_plan(ldpc_b200_decoder* h) {
     h->plan = pl;
     h->planned = true;
     return LDPC_B200_OK;
+}
+
+int make_plan(ldpc_b200_decoder* h) {
+    const int flood_alg = h->algorithm == LDPC_B200_ALG_SUM_PRODUCT ? LDPC_B200_ALG_SUM_PRODUCT : LDPC_B200_ALG_MIN_SUM;
+    const int rc = make_plan_for(h, flood_alg);
+    if (rc == LDPC_B200_OK) h->plan_alg = flood_alg;
+    return rc;
 }
 
 int ensure_workspace(ldpc_b200_decoder* h) {
@@ -1895,14 +1789,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter64 = ctr64;
-#define WARP_LAUNCH(SWV)                                                                                                        \
-    do {                                                                                                                        \
-        CU_TRY(cudaFuncSetAttribute(ldpc_ms_warp_kernel<SWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));     \
-        ldpc_ms_warp_kernel<SWV><<<grid, pl.threads, pl.smem, stream>>>(q);                                                     \
-    } while (0)
-        if (h->w_sw == 8) WARP_LAUNCH(8); else if (h->w_sw == 16) WARP_LAUNCH(16); else WARP_LAUNCH(32);
-#undef WARP_LAUNCH
-        CU_TRY(cudaGetLastError());
+        rc = launch_status(k_launch_warp(h->w_sw, q, grid, pl.threads, pl.smem, stream), "warp-per-check");
         h->launches += 1;
         return LDPC_B200_OK;
     }
@@ -1911,14 +1798,14 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         QcgParams& q = h->qcg;  // tables filled by qcg_build; per-launch fields below
         q.K = h->K;
         q.max_iter = h->max_iter; q.early_term = h->early;
-        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;
+        q.refill_wait = h->opt.refill_wait;
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter64 = ctr64;
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
-        rc = h->qcg_G == 8 ? launch_qcg_t<8>(q, grid, pl.smem, stream)
-           : (h->qcg_G == 4 ? launch_qcg_t<4>(q, grid, pl.smem, stream) : launch_qcg_t<2>(q, grid, pl.smem, stream));
+        q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
+        rc = launch_status(k_launch_qcg(h->qcg_G, q, grid, pl.smem, stream), "quasi-cyclic (run-time profile)");
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
@@ -1928,13 +1815,14 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         auto& q = h->qc;  // tables filled by qc_build; per-launch fields below
         q.K = h->K;
         q.max_iter = h->max_iter; q.early_term = h->early;
-        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;
+        q.refill_wait = h->opt.refill_wait;
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter64 = ctr64;
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
-        rc = kQcProfiles[h->qc_kind].launch(q, grid, pl.smem, stream);
+        q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
+        rc = launch_status(qc_profiles()[h->qc_kind].launch(q, grid, pl.smem, stream), "quasi-cyclic");
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
@@ -1954,8 +1842,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
         std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
         const int want = (int)std::min<int64_t>(ncw, 1 << 20);
-        rc = pl.dmax == 8 ? launch_cluster_t<8>(q, want, pl.threads, pl.smem, stream)
-                          : launch_cluster_t<16>(q, want, pl.threads, pl.smem, stream);
+        rc = launch_status(k_launch_cluster(pl.dmax, q, want, pl.threads, pl.smem, stream), "cluster");
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
@@ -1973,7 +1860,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.llr = d_llr; q.ncw = ncw;
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter = ctr; q.counter64 = ctr64; q.ngroups = (int)ngroups;
-        q.refill_wait = std::getenv("LDPC_B200_REFILL_WAIT") ? std::atoi(std::getenv("LDPC_B200_REFILL_WAIT")) : 1;  // measured: profiles/r01_refill_sweep.txt
+        q.refill_wait = h->opt.refill_wait;
         std::memcpy(q.vdeg, h->g_vdeg, sizeof(q.vdeg));
         std::memcpy(q.cdeg, h->g_cdeg, sizeof(q.cdeg));
         q.n_vclass = 0;
@@ -1987,21 +1874,12 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
             if (!pl.tab_smem || pl.t16 || (pl.G != 8 && pl.G != 16) || t.max_col_weight > 8 || t.max_row_weight > 20)
                 return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product needs the on-chip group layout (short codes, variable degree <= 8, check degree <= 20)");
             if (d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
-            if (pl.G == 8) {
-                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<8, 20, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                ldpc_sp_group_kernel<8, 20, 384><<<grid, pl.threads, pl.smem, stream>>>(q);
-            } else if (pl.threads <= 768) {
-                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<16, 20, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                ldpc_sp_group_kernel<16, 20, 768><<<grid, pl.threads, pl.smem, stream>>>(q);
-            } else {
-                CU_TRY(cudaFuncSetAttribute(ldpc_sp_group_kernel<16, 20, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-                ldpc_sp_group_kernel<16, 20, 1024><<<grid, pl.threads, pl.smem, stream>>>(q);
-            }
-            CU_TRY(cudaGetLastError());
+            rc = launch_status(k_launch_sp(pl.G, pl.threads, q, grid, pl.smem, stream), "sum-product");
+            if (rc) return rc;
             h->launches += 1;
             return LDPC_B200_OK;
         }
-        rc = launch_group(pl, q, grid, stream);
+        rc = launch_group(pl, q, grid, !h->opt.grp_no_profile, stream);
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
@@ -2023,14 +1901,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.counter = ctr; q.ngroups = (int)ngroups;
         std::memcpy(q.vdeg, h->l16_vdeg, sizeof(q.vdeg));
         std::memcpy(q.cdeg, h->l16_cdeg, sizeof(q.cdeg));
-        if (pl.threads <= 768) {
-            CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-            ldpc_ms_lane16_kernel<768><<<grid, pl.threads, pl.smem, stream>>>(q);
-        } else {
-            CU_TRY(cudaFuncSetAttribute(ldpc_ms_lane16_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-            ldpc_ms_lane16_kernel<1024><<<grid, pl.threads, pl.smem, stream>>>(q);
-        }
-        CU_TRY(cudaGetLastError());
+        rc = launch_status(k_launch_lane16(q, grid, pl.threads, pl.smem, stream), "lane16");
+        if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
     }
@@ -2049,10 +1921,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.counter = ctr; q.ngroups = (int)ngroups;
         // the workspace is shared by every launch of this handle: serialise launches on it
         if (h->ws_event_valid) CU_TRY(cudaStreamWaitEvent(stream, h->ws_event, 0));
-        if (pl.threads <= 512) ldpc_ms_stream_kernel<512><<<grid, pl.threads, 0, stream>>>(q);
-        else if (pl.threads <= 768) ldpc_ms_stream_kernel<768><<<grid, pl.threads, 0, stream>>>(q);
-        else ldpc_ms_stream_kernel<1024><<<grid, pl.threads, 0, stream>>>(q);
-        CU_TRY(cudaGetLastError());
+        rc = launch_status(k_launch_stream(q, grid, pl.threads, stream), "stream");
+        if (rc) return rc;
         CU_TRY(cudaEventRecord(h->ws_event, stream));
         h->ws_event_valid = true;
         h->launches += 1;
@@ -2108,6 +1978,7 @@ int ldpc_b200_create(ldpc_b200_handle* out, int M, int N, int K, const int32_t* 
     }
     h->K = K;
     h->device = device;
+    h->opt = options_from_env();  // the only place the experiment switches are read from the environment
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -2180,6 +2051,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
                 if (h->st_pin_ev[i]) cudaEventDestroy(h->st_pin_ev[i]);
             }
             if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
+            if (h->h_status) cudaFreeHost(h->h_status);
             if (h->st_event) cudaEventDestroy(h->st_event);
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
@@ -2201,12 +2073,14 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
 int ldpc_b200_set_max_iter(ldpc_b200_handle h, int max_iter) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
     if (max_iter < 1 || max_iter > 65535) return fail(LDPC_B200_ERR_ARG, "max_iter must be in 1..65535");
+    std::lock_guard<std::mutex> lk(h->mu);
     h->max_iter = max_iter;
     return LDPC_B200_OK;
 }
 
 int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
     h->early = on ? 1 : 0;
     return LDPC_B200_OK;
 }
@@ -2229,9 +2103,9 @@ int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
     }
     const int prev = h->algorithm;
     h->algorithm = algorithm;
-    if (prev == LDPC_B200_ALG_LAYERED_MIN_SUM && algorithm == LDPC_B200_ALG_MIN_SUM && !h->tables_keep_edge_order) return LDPC_B200_OK;
-    // the two flooding kernels want different group layouts (sum-product multiplies in CSR edge order and admits
-    // check degree 20; min-sum reorders edges for bank placement): drop the tables and plan again
+    // the plan and the group tables were built for one flooding algorithm (sum-product multiplies in CSR edge order and
+    // admits check degree 20; min-sum reorders edges for bank placement): keep them only if that is the one asked for
+    if (h->planned && h->plan_alg == algorithm) return LDPC_B200_OK;
     if (h->group_ready) {
         DeviceGuard guard(h->device);
         if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
@@ -2240,7 +2114,28 @@ int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
         h->dg_cn_tab = h->dg_vn_tab = h->dg_var_of_pos = h->dg_pos_of_var = nullptr;
         h->group_ready = false;
     }
-    return make_plan(h);
+    const int rc = make_plan(h);
+    if (rc) {  // leave the handle as it was
+        const std::string keep = g_err;
+        h->algorithm = prev;
+        (void)make_plan(h);
+        g_err = keep;
+    }
+    return rc;
+}
+
+int ldpc_b200_set_option(ldpc_b200_handle h, const char* name, long long value) {
+    if (!h || !name) return fail(LDPC_B200_ERR_ARG, "null argument");
+    const int n = (int)(sizeof(kOptionNames) / sizeof(kOptionNames[0]));
+    for (int i = 0; i < n; ++i) {
+        if (std::strcmp(kOptionNames[i].name, name) != 0) continue;
+        if (i < kFirstRuntimeOption)
+            return fail(LDPC_B200_ERR_UNSUPPORTED, std::string("option '") + name + "' shapes the plan: set LDPC_B200_<NAME> before ldpc_b200_create");
+        std::lock_guard<std::mutex> lk(h->mu);
+        option_store(&h->opt, kOptionNames[i], value);
+        return LDPC_B200_OK;
+    }
+    return fail(LDPC_B200_ERR_ARG, std::string("unknown option '") + name + "'");
 }
 
 int ldpc_b200_set_layer_height(ldpc_b200_handle h, int z) {
@@ -2357,10 +2252,11 @@ int ldpc_b200_get_csr(ldpc_b200_handle h, int32_t* row_ptr, int32_t* col_idx) {
     return LDPC_B200_OK;
 }
 
-int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch) {
-    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
-    if (batch < 1) return fail(LDPC_B200_ERR_ARG, "batch must be positive");
-    std::lock_guard<std::mutex> lk(h->mu);
+}  // extern "C"
+
+namespace {
+// (h->mu held)
+int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
     if (batch <= h->reserved) return LDPC_B200_OK;
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
@@ -2384,7 +2280,8 @@ int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch) {
         const int64_t g = h->plan.cw_per_cta;
         const int64_t chunk = std::max<int64_t>(g, ((((int64_t)4 << 20)) / ((int64_t)t.N * 4)) / g * g);
         const size_t need = sizeof(float) * (size_t)chunk * t.N;
-        if (h->st_pin_bytes < need && !std::getenv("LDPC_B200_NO_STAGED")) {
+        if (!h->h_status) CU_TRY(cudaMallocHost(&h->h_status, sizeof(int)));
+        if (h->st_pin_bytes < need && !h->opt.no_staged) {
             for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
                 if (h->st_pin[i]) { cudaFreeHost(h->st_pin[i]); h->st_pin[i] = nullptr; }
             }
@@ -2397,6 +2294,16 @@ int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch) {
         }
     }
     return LDPC_B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (batch < 1) return fail(LDPC_B200_ERR_ARG, "batch must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return reserve_locked(h, batch);
 }
 
 int ldpc_b200_decode_device(ldpc_b200_handle h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
@@ -2424,28 +2331,27 @@ namespace {
 // launches and blocks the other threads' API calls), its 4 s bound expires and the caller falls back to the chunked
 // pipeline: returns kStreamedRetry.
 constexpr int kStreamedRetry = 1;
-int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                         int32_t* iters, float* post, bool staged) {
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->device);
-    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+// (h->mu held, current device = the handle's; the caller drains the streams when this returns non-zero)
+int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                              int32_t* iters, float* post, bool staged) {
     const HostTables& t = h->host;
     const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
     const int64_t g = h->plan.cw_per_cta;
     int64_t batch_bytes = (int64_t)512 << 20;  // <= 512 MB of channel values per launch
-    if (const char* env = std::getenv("LDPC_B200_STREAM_BATCH_KB")) { const long long kb = std::atoll(env); if (kb >= 1) batch_bytes = kb << 10; }
+    if (h->opt.stream_batch_kb >= 1) batch_bytes = h->opt.stream_batch_kb << 10;
     const int64_t batch_cap = std::max<int64_t>(g, (batch_bytes / ((int64_t)t.N * 4)) / g * g);
     const int64_t want = std::min(ncw, batch_cap);
     for (int s = 0; s < 2; ++s)
         if (!h->streams[s]) CU_TRY(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
     if (!h->st_event) CU_TRY(cudaEventCreateWithFlags(&h->st_event, cudaEventDisableTiming));
     if (!h->d_avail) CU_TRY(cudaMalloc(&h->d_avail, 2 * sizeof(unsigned long long)));
+    if (!h->h_status) CU_TRY(cudaMallocHost(&h->h_status, sizeof(int)));
     if (h->st_cap < want || (hard && !h->st_has_hard) || (post && !h->st_has_post)) {
         CU_TRY(cudaDeviceSynchronize());
         cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
         h->st_llr = nullptr; h->st_info = nullptr; h->st_hard = nullptr; h->st_iters = nullptr; h->st_post = nullptr;
+        const int64_t cap = std::max(want, h->st_cap);  // never shrink: alternating call sizes must not reallocate
         h->st_cap = 0;
-        const int64_t cap = std::max(want, h->st_cap);
         h->st_has_hard = h->st_has_hard || hard != nullptr;
         h->st_has_post = h->st_has_post || post != nullptr;
         CU_TRY(cudaMalloc(&h->st_llr, sizeof(float) * (size_t)cap * t.N));
@@ -2461,7 +2367,7 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
     // 4.08 ms with 4 MB chunks, 4.11 with 8 MB, 4.27 with 16 MB).
     auto words_of = [&](int64_t bytes) { return std::max<int64_t>(g, (bytes / ((int64_t)t.N * 4)) / g * g); };
     int64_t chunk0 = words_of((int64_t)1 << 20), chunk_max = words_of((int64_t)4 << 20);
-    if (const char* env = std::getenv("LDPC_B200_STREAM_CHUNK")) { const long long c = std::atoll(env); if (c >= 1) chunk0 = chunk_max = (c + g - 1) / g * g; }
+    if (h->opt.stream_chunk >= 1) chunk0 = chunk_max = (h->opt.stream_chunk + g - 1) / g * g;
     if (staged) {
         chunk0 = chunk_max;  // fixed-size chunks = ring slots
         const size_t need = sizeof(float) * (size_t)chunk_max * t.N;
@@ -2545,77 +2451,42 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
                 for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
                 work();
                 for (auto& th : pool) th.join();
-                if (err.load()) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); return fail(LDPC_B200_ERR_CUDA, std::string("staged input copy: ") + cudaGetErrorString(cudaGetLastError())); }
+                if (err.load()) return fail(LDPC_B200_ERR_CUDA, std::string("staged input copy: ") + cudaGetErrorString(cudaGetLastError()));
             }
         }
-        if (rc) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); return rc; }
+        if (rc) return rc;
         if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->st_info, (size_t)n * KB, cudaMemcpyDeviceToHost, ks));
         if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->st_hard, (size_t)n * NB, cudaMemcpyDeviceToHost, ks));
         if (iters) CU_TRY(cudaMemcpyAsync(iters + off, h->st_iters, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ks));
         if (post) CU_TRY(cudaMemcpyAsync(post + (size_t)off * t.N, h->st_post, sizeof(float) * (size_t)n * t.N, cudaMemcpyDeviceToHost, ks));
-        int status = 0;
-        CU_TRY(cudaMemcpyAsync(&status, reinterpret_cast<int*>(h->d_avail + 1), sizeof(int), cudaMemcpyDeviceToHost, ks));
+        *h->h_status = 0;
+        CU_TRY(cudaMemcpyAsync(h->h_status, reinterpret_cast<int*>(h->d_avail + 1), sizeof(int), cudaMemcpyDeviceToHost, ks));
         CU_TRY(cudaStreamSynchronize(cs));
         CU_TRY(cudaStreamSynchronize(ks));
-        if (status && staged) return kStreamedRetry;
-        if (status) return fail(LDPC_B200_ERR_CUDA, "streamed decode: the input copies stalled for more than 4 s");
+        // the kernel gave up waiting for its input (a tool that serialises launches, a copy engine busy elsewhere,
+        // time-slicing): nothing is wrong with the data -- the caller reruns the call through the chunked pipeline
+        if (*h->h_status) return kStreamedRetry;
     }
     return LDPC_B200_OK;
 }
 
-}  // namespace
+int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                         int32_t* iters, float* post, bool staged) {
+    const int rc = decode_host_streamed_body(h, llr, ncw, info, hard, iters, post, staged);
+    if (rc != LDPC_B200_OK) {  // no copy into the caller's buffers may still be in flight when an error returns
+        const std::string keep = g_err;
+        for (int s = 0; s < 2; ++s) if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
+        (void)cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
 
-int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                          int32_t* iters, float* post) {
-    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
-    if (ncw < 0) return fail(LDPC_B200_ERR_ARG, "ncw must be >= 0");
-    if (ncw == 0) return LDPC_B200_OK;
-    if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
+// The chunked 3-stream pipeline: H2D, kernel and D2H of consecutive chunks overlap across kSlots streams.
+// (h->mu held, current device = the handle's)
+int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                             int32_t* iters, float* post) {
     const HostTables& t = h->host;
-    // (also after ldpc_b200_reserve / Coder::forDecoder(batchSize): the reference's batch size is only its internal
-    // chunking, MyLdpc.cpp:577-616, and kernels of this path do not speed each other up across streams)
-    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->planned && h->plan.path == LDPC_B200_PATH_QC &&
-        !std::getenv("LDPC_B200_NO_STREAMED")) {
-        // pinned (or managed) input only: copies from pageable memory are staged synchronously, so queueing them all
-        // before the launch would serialise copy and decode -- the chunked pipeline below overlaps them instead
-        DeviceGuard guard(h->device);
-        cudaPointerAttributes attr;
-        const bool pinned = guard.ok && cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
-                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
-        if (!pinned) (void)cudaGetLastError();
-        if (pinned || std::getenv("LDPC_B200_STREAMED_PAGEABLE")) return decode_host_streamed(h, llr, ncw, info, hard, iters, post, false);
-        // pageable input of some size: four host threads stage it through pinned buffers under the running kernel.
-        // Repeated decodes of 65,536 words from malloc'd memory: 4.8-6.1 ms against 21.6 ms for the chunked pipeline
-        // below (the driver stages pageable copies itself at ~7.5 GB/s); the first call pays the allocations either way.
-        int64_t staged_min = (int64_t)8 << 20;
-        if (const char* env = std::getenv("LDPC_B200_STAGED_MIN_KB")) staged_min = (int64_t)std::atoll(env) << 10;
-        if ((int64_t)ncw * t.N * 4 >= staged_min && !std::getenv("LDPC_B200_NO_STAGED")) {
-            const int rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, true);
-            if (rc != kStreamedRetry) return rc;
-        }
-    }
-    if (h->reserved == 0) {
-        // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the
-        // persistent grid (bounded to ~256 MB of channel values).  On-chip paths: kernels of consecutive chunks run
-        // concurrently and refill each other's tail, so small chunks win -- 3/4 of a wave measured best
-        // (tools/e2e_chunk_sweep.py: 9472 -> 4.69 ms, 1776 -> 4.42 ms per 65,536 words of Test.cpp's code).
-        int64_t wave = (int64_t)h->plan.ctas * h->plan.cw_per_cta;
-        int64_t chunk = wave * 4;
-        const int64_t cap = std::max<int64_t>(wave, ((int64_t)256 << 20) / ((int64_t)t.N * 4) / wave * wave);
-        chunk = std::min(chunk, cap);
-        chunk = std::min(chunk, (ncw + wave - 1) / wave * wave);
-        const bool workspace = h->algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM &&
-                               (h->plan.path == LDPC_B200_PATH_LANE_GLOBAL || h->plan.path == LDPC_B200_PATH_STREAM);
-        if (!workspace) {
-            const int64_t g = h->plan.cw_per_cta;
-            chunk = std::min(chunk, std::max<int64_t>(g, wave * 3 / 4 / g * g));
-        }
-        int rc = ldpc_b200_reserve(h, chunk);
-        if (rc) return rc;
-    }
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard guard(h->device);
-    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
     const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
     const int64_t chunk = h->reserved;
     if (post) {
@@ -2638,6 +2509,69 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     }
     for (int s = 0; s < kSlots; ++s) CU_TRY(cudaStreamSynchronize(h->streams[s]));
     return LDPC_B200_OK;
+}
+
+}  // namespace
+
+int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                          int32_t* iters, float* post) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (ncw < 0) return fail(LDPC_B200_ERR_ARG, "ncw must be >= 0");
+    if (ncw == 0) return LDPC_B200_OK;
+    if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
+    std::lock_guard<std::mutex> lk(h->mu);  // one lock for the whole call: plan, reservation and buffers stay put
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    const HostTables& t = h->host;
+    // (also after ldpc_b200_reserve / Coder::forDecoder(batchSize): the reference's batch size is only its internal
+    // chunking, MyLdpc.cpp:577-616, and kernels of this path do not speed each other up across streams)
+    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->planned && h->plan.path == LDPC_B200_PATH_QC && !h->opt.no_streamed) {
+        // pinned (or managed) input: every chunk copy is queued before the launch.  Copies from pageable memory are
+        // staged synchronously by the driver, so queueing them all first would serialise copy and decode.
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
+                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        if (!pinned) (void)cudaGetLastError();
+        int rc = kStreamedRetry;
+        if (pinned || h->opt.streamed_pageable) {
+            rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, false);
+        } else if ((int64_t)ncw * t.N * 4 >= (h->opt.staged_min_kb << 10) && !h->opt.no_staged) {
+            // pageable input of some size: four host threads stage it through pinned buffers under the running kernel.
+            // Repeated decodes of 65,536 words from malloc'd memory: 4.8-6.1 ms against 21.6 ms for the chunked
+            // pipeline below (the driver stages pageable copies itself at ~7.5 GB/s).
+            rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, true);
+        }
+        if (rc != kStreamedRetry) return rc;
+        // kStreamedRetry: the persistent kernel's bounded wait for input expired (or the mode does not apply);
+        // every output is rewritten by the chunked pipeline below
+    }
+    if (h->reserved == 0) {
+        // default chunk.  Global-workspace paths: launches serialise on the workspace, so whole waves of the
+        // persistent grid (bounded to ~256 MB of channel values).  On-chip paths: kernels of consecutive chunks run
+        // concurrently and refill each other's tail, so small chunks win -- 3/4 of a wave measured best
+        // (tools/e2e_chunk_sweep.py: 9472 -> 4.69 ms, 1776 -> 4.42 ms per 65,536 words of Test.cpp's code).
+        int64_t wave = (int64_t)h->plan.ctas * h->plan.cw_per_cta;
+        int64_t chunk = wave * 4;
+        const int64_t cap = std::max<int64_t>(wave, ((int64_t)256 << 20) / ((int64_t)t.N * 4) / wave * wave);
+        chunk = std::min(chunk, cap);
+        chunk = std::min(chunk, (ncw + wave - 1) / wave * wave);
+        const bool workspace = h->algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM &&
+                               (h->plan.path == LDPC_B200_PATH_LANE_GLOBAL || h->plan.path == LDPC_B200_PATH_STREAM);
+        if (!workspace) {
+            const int64_t g = h->plan.cw_per_cta;
+            chunk = std::min(chunk, std::max<int64_t>(g, wave * 3 / 4 / g * g));
+        }
+        int rc = reserve_locked(h, chunk);
+        if (rc) return rc;
+    }
+    const int rc = decode_host_chunked_body(h, llr, ncw, info, hard, iters, post);
+    if (rc != LDPC_B200_OK) {  // drain the streams: no copy into the caller's buffers may outlive an error return
+        const std::string keep = g_err;
+        for (int s = 0; s < kSlots; ++s) if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
+        (void)cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
 }
 
 int ldpc_b200_synth_llr(float* d_llr, int64_t ncw, int N, float sigma, uint64_t seed, const uint8_t* d_bits, int device,

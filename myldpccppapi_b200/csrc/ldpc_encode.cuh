@@ -24,7 +24,7 @@ struct EncodeParams {
     long long ncw;
 };
 
-__global__ void __launch_bounds__(256) ldpc_encode_kernel(const EncodeParams p) {
+static __global__ void __launch_bounds__(256) ldpc_encode_kernel(const EncodeParams p) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;

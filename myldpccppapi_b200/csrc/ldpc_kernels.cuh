@@ -1160,7 +1160,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     return x ^ (x >> 31);
 }
 
-__global__ void __launch_bounds__(256) ldpc_synth_llr_kernel(float* __restrict__ out, long long total, int N,
+static __global__ void __launch_bounds__(256) ldpc_synth_llr_kernel(float* __restrict__ out, long long total, int N,
                                                              float sigma, uint64_t seed,
                                                              const uint8_t* __restrict__ bits, long long first_index) {
     const int NB = (N + 7) >> 3;
@@ -1185,7 +1185,7 @@ __global__ void __launch_bounds__(256) ldpc_synth_llr_kernel(float* __restrict__
 // thread streams conflict-free 16-byte loads from a 128 KB tile.  Bytes moved per launch =
 // gridDim.x * blockDim.x * 16 * 8 * loops.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) ldpc_smem_probe_kernel(uint32_t* __restrict__ sink, int loops) {
+static __global__ void __launch_bounds__(1024, 1) ldpc_smem_probe_kernel(uint32_t* __restrict__ sink, int loops) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4* buf = reinterpret_cast<uint4*>(smem_raw);
     for (int i = threadIdx.x; i < 8192; i += blockDim.x) buf[i] = make_uint4(i, i * 3, i * 5, i * 7);

@@ -1,0 +1,64 @@
+// ldpc_launch.h -- internal seam between the host logic (ldpc_b200.cu) and the translation units that
+// instantiate the sm_100a kernels (k_*.cu).  One unit per kernel family (and one per 802.16e rate for the
+// compiled quasi-cyclic profiles) so that nvcc builds them in parallel; nothing here is part of the C-ABI.
+//
+// Every launcher returns 0 on success, a cudaError_t (> 0) when the runtime refused, or kNoKernel when no
+// instantiation matches the requested shape (the caller turns that into LDPC_B200_ERR_UNSUPPORTED).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "ldpc_tables.h"
+
+namespace ldpc_b200 {
+
+constexpr int kNoKernel = -1;
+constexpr int kNoCluster = -2;  // cluster kernel: no 8-CTA cluster of this size can be resident
+
+struct GroupParams;
+struct Lane16Params;
+struct StreamParams;
+struct WarpParams;
+struct ClusterParams;
+struct QcParams;
+struct QcgParams;
+struct TdmpParams;
+
+// Which ldpc_ms_group_kernel instantiation a plan asks for (ldpc_b200.cu: Plan).
+struct GroupSel {
+    int G, dmax, threads, CS, VS;
+    bool tab_smem, y_smem, t16, allow_profile;
+};
+int k_launch_group(const GroupSel& sel, const GroupParams& q, int grid, size_t smem, cudaStream_t stream);
+int k_launch_sp(int G, int threads, const GroupParams& q, int grid, size_t smem, cudaStream_t stream);
+int k_launch_tdmp(int G, const TdmpParams& q, int grid, int threads, size_t smem, cudaStream_t stream);
+int k_launch_qcg(int G, const QcgParams& q, int grid, size_t smem, cudaStream_t stream);
+int k_launch_warp(int sw, const WarpParams& q, int grid, int threads, size_t smem, cudaStream_t stream);
+int k_launch_cluster(int dmax, const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream);
+int k_launch_lane16(const Lane16Params& q, int grid, int threads, size_t smem, cudaStream_t stream);
+int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream);
+
+// Quasi-cyclic block structure of H for block size z: rows[br] = the circulants (block column, shift) of block
+// row br in ascending column order.
+struct QcBlk { int bc, s; };
+
+// A compiled quasi-cyclic profile (ldpc_qc.cuh): rate x (z, G, W).  `upload` writes a handle's tables into slot
+// `slot` of the __constant__ bank of the translation unit that holds the kernel.
+struct QcProfileEntry {
+    int z, G, W;
+    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, QcParams*, std::vector<unsigned char>*, size_t*);
+    int (*launch)(const QcParams&, int grid, size_t smem, cudaStream_t stream);
+    int (*upload)(int slot, const void* tab, size_t bytes);
+};
+// one table per 802.16e rate (k_qc.cu compiled with -DLDPC_QC_RATE=...)
+const QcProfileEntry* qc_profiles_34B(int* n);
+const QcProfileEntry* qc_profiles_34A(int* n);
+const QcProfileEntry* qc_profiles_23B(int* n);
+const QcProfileEntry* qc_profiles_23A(int* n);
+const QcProfileEntry* qc_profiles_12(int* n);
+const QcProfileEntry* qc_profiles_56(int* n);
+
+}  // namespace ldpc_b200

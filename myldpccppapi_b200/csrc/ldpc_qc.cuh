@@ -114,7 +114,9 @@ struct QcWarpTab {
 // 47 us per launch).  kQcTabSlots decoders per device can hold tables at once; a handle owns one slot.
 constexpr int kQcTabSlots = 8;
 constexpr int kQcBankBytes = 6656;  // per slot: the largest compiled profile's tables (12 warps)
-__constant__ uint4 g_qc_bank[kQcTabSlots][kQcBankBytes / 16];
+// (static: the library is built from several translation units, one per 802.16e rate for these kernels -- each
+// has its own bank; a handle's tables are uploaded through the unit that holds its profile.)
+static __constant__ uint4 g_qc_bank[kQcTabSlots][kQcBankBytes / 16];
 
 template <class P>
 __device__ __forceinline__ const QcWarpTab<P>& qc_tab(int slot, int warp) {
@@ -138,6 +140,7 @@ struct QcParams {
     // *avail after each chunk while this kernel is already running.  null = everything is there.
     const unsigned long long* avail;
     int* status;                  // set to 1 if the wait for input timed out
+    unsigned long long wait_ns;   // bound of that wait (ldpc_b200_set_option "wait_timeout_ms")
 };
 
 // Warp 0 waits until the words its lanes just took from the queue have landed (streamed batches).  Every branch
@@ -145,7 +148,8 @@ struct QcParams {
 // as warp-uniform (a divergent spin loop turned every LDCU into a vector LDC + address add and halved the speed).
 // The poll reads through L2 (ld.acquire.gpu); the channel values were never cached by this SM before, so the
 // cp.async that follows sees the DMA's data.  Bounded: a stalled copy stream sets *status instead of hanging.
-__device__ __forceinline__ bool qc_wait_input(const unsigned long long* avail, long long w, bool need, int* status) {
+__device__ __forceinline__ bool qc_wait_input(const unsigned long long* avail, long long w, bool need, int* status,
+                                              unsigned long long wait_ns) {
     unsigned long long t0 = 0ull;
     for (uint32_t spins = 0;; ++spins) {
         unsigned long long a;
@@ -153,10 +157,14 @@ __device__ __forceinline__ bool qc_wait_input(const unsigned long long* avail, l
         if (__all_sync(0xffffffffu, !need || a > (unsigned long long)w)) return true;
         __nanosleep(spins < 64 ? 100 : 1000);
         if ((spins & 1023u) == 1023u) {
+            // once one lane group anywhere has timed out the whole launch is given up: do not wait a second time
+            int st = 0;
+            if (status) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(st) : "l"(status) : "memory");
+            if (__any_sync(0xffffffffu, st != 0)) return false;
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0ull) t0 = now;
-            if (__any_sync(0xffffffffu, now - t0 > 4000000000ull)) {
+            if (__any_sync(0xffffffffu, now - t0 > wait_ns)) {
                 if (status && (threadIdx.x & 31) == 0) atomicExch(status, 1);
                 return false;
             }
@@ -351,7 +359,7 @@ ldpc_ms_qc_kernel(const __grid_constant__ QcParams p) {
         if (warp == 0) {
             const bool take = h == 0 && want;
             long long w = take ? s_nxt[c] : -1;
-            if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status)) w = p.ncw;  // timed out: give the words up
+            if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status, p.wait_ns)) w = p.ncw;  // timed out: give the words up
             if (take) s_cw[c] = w;
         }
         __syncthreads();  // also: every read of the retiring lanes' T (emit) is complete

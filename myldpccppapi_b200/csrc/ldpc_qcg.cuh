@@ -49,6 +49,7 @@ struct QcgParams {
     unsigned long long* counter64;
     const unsigned long long* avail;
     int* status;
+    unsigned long long wait_ns;
 };
 
 // One check of exact degree D; run-time block stride (see qc_check).  Split into its loads and the rest so that
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kQcgMaxW * 32, 2) ldpc_ms_qcg_kernel(const __g
         if (warp == 0) {
             const bool take = h == 0 && want;
             long long w = take ? s_nxt[c] : -1;
-            if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status)) w = p.ncw;
+            if (p.avail && !qc_wait_input(p.avail, w, take && w < p.ncw, p.status, p.wait_ns)) w = p.ncw;
             if (take) s_cw[c] = w;
         }
         __syncthreads();  // also: every read of the retiring lanes' T (emit) is complete

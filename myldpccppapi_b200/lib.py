@@ -51,6 +51,7 @@ SIGNATURES = {
     "ldpc_b200_set_path": (_i, [_vp, _i]),
     "ldpc_b200_set_algorithm": (_i, [_vp, _i]),
     "ldpc_b200_set_layer_height": (_i, [_vp, _i]),
+    "ldpc_b200_set_option": (_i, [_vp, C.c_char_p, C.c_longlong]),
     "ldpc_b200_encoder_init": (_i, [_vp]),
     "ldpc_b200_encode_device": (_i, [_vp, _vp, C.c_int64, _vp, _vp]),
     "ldpc_b200_encode_host": (_i, [_vp, _vp, C.c_int64, _vp]),

@@ -98,6 +98,10 @@ class Decoder:
     def set_path(self, path: int) -> None:
         check(self._L.ldpc_b200_set_path(self._h, path))
 
+    def set_option(self, name: str, value: int) -> None:
+        """Host-pipeline experiment switch (ldpc_b200_set_option), e.g. "stream_chunk", "no_streamed"."""
+        check(self._L.ldpc_b200_set_option(self._h, name.encode(), int(value)))
+
     def reserve(self, batch: int) -> None:
         check(self._L.ldpc_b200_reserve(self._h, batch))
 
@@ -178,10 +182,20 @@ class Decoder:
 
 def _as_host_array(x, dtype):
     if hasattr(x, "data_ptr"):  # torch CPU tensor (possibly pinned)
+        import torch
+
         if x.is_cuda:
             raise ValueError("expected a host tensor")
+        want = {np.float32: torch.float32, np.uint8: torch.uint8}[dtype]
+        if x.dtype != want:
+            raise ValueError("expected a %s tensor, got %s" % (want, x.dtype))
         return x.contiguous()
-    return np.ascontiguousarray(x, dtype=dtype)
+    a = np.asarray(x)
+    if a.dtype != dtype:
+        if a.dtype.kind != np.dtype(dtype).kind:
+            raise ValueError("expected %s data, got %s" % (np.dtype(dtype), a.dtype))
+        a = a.astype(dtype)  # float64 -> float32 etc.: an explicit, rounding conversion
+    return np.ascontiguousarray(a)
 
 
 def _numel(x) -> int:

@@ -59,6 +59,9 @@ def lib() -> C.CDLL:
         L.oracle_decode_tdmp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_decode_tdmp_batch.restype = C.c_int
+        L.oracle_decode_fused_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_decode_fused_batch.restype = C.c_int
         L.oracle_tdmp_layering_ok.argtypes = [C.c_void_p, C.c_int]
         L.oracle_tdmp_layering_ok.restype = C.c_int
         L.oracle_sp_expf.argtypes = [C.c_float]
@@ -166,6 +169,27 @@ def decode_tdmp(o: "Oracle", llr: np.ndarray, z: int, threads: int = 0):
     post = np.zeros((ncw, o.N), dtype=np.float32)
     rc = L.oracle_decode_tdmp_batch(o._t, o.K, o.times, int(z), y.ctypes.data, ncw, info.ctypes.data,
                                     iters.ctypes.data, hard.ctypes.data, post.ctypes.data, threads)
+    if rc:
+        raise ValueError("layers of %d rows are not column-disjoint" % z)
+    return info, iters, hard, post
+
+
+def decode_fused(o: "Oracle", llr: np.ndarray, z: int, layered: bool, times: int | None = None, threads: int = 0):
+    """The reference's fused OpenCL kernels restated (see ldpc_oracle.h): decodeOnceMS (layered=False, cap 120 in the
+    reference) or decodeOnceTDMP (layered=True, cap 40).  Returns (info, iters, hard, post)."""
+    L = lib()
+    y = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, o.N)
+    ncw = y.shape[0]
+    if threads <= 0:
+        threads = os.cpu_count() or 1
+    if times is None:
+        times = 40 if layered else 120  # decodeCL.c:344, 479
+    info = np.zeros((ncw, (o.K + 7) // 8), dtype=np.uint8)
+    iters = np.zeros(ncw, dtype=np.int32)
+    hard = np.zeros((ncw, o.N), dtype=np.uint8)
+    post = np.zeros((ncw, o.N), dtype=np.float32)
+    rc = L.oracle_decode_fused_batch(o._t, o.K, int(times), int(z), 1 if layered else 0, y.ctypes.data, ncw,
+                                     info.ctypes.data, iters.ctypes.data, hard.ctypes.data, post.ctypes.data, threads)
     if rc:
         raise ValueError("layers of %d rows are not column-disjoint" % z)
     return info, iters, hard, post

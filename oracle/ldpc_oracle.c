@@ -610,6 +610,120 @@ int oracle_decode_tdmp_batch(const oracle_tables *t, int K, int times, int z, co
     return 0;
 }
 
+
+/* ---- the two FUSED OpenCL kernels restated (decodeCL.c:307-426 decodeOnceTDMP, :432-567 decodeOnceMS) -----------
+ * Both keep, per check row, the sign of every Q in lR and multiply it by  a * (second minimum for the edge that holds
+ * the minimum, else the minimum)  where  a = sign(product of all Q of the row)  (a float product, taken in row order;
+ * an exact zero or an underflowed product makes every message of the row zero, an overflow to inf keeps the sign, and
+ * inf * 0 gives NaN -> sign 0).  The minimum search is  `if (t <= b) {c = b; b = t; ind = num;} else if (t > b && t <= c) c = t;`
+ * from b = 1000, c = 1001 (decodeCL.c:346-365, 481-500), the hard decision is  bit = (lP < 0)  (:386, :541) -- a
+ * zero posterior decodes as 0, where decodeCPU says 1 -- and the iteration caps are the literals 40 and 120 (:344, :479).
+ * mode 0 = decodeOnceMS (flooding: all rows from the previous posterior, then lP = y + sum of lR in ascending row order,
+ * :517-537); mode 1 = decodeOnceTDMP (layered: rows of one block row, lP = Q, then lP += lR, :346-380).
+ * Pinned against the executed kernels (oracle/_ref/libmyldpc_refcl.so) in tests/test_oracle_vs_refcl.py.           */
+static float cl_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : (x == 0.0f ? x : 0.0f)); }
+
+typedef struct {
+    const oracle_tables *t;
+    int K, times, z, mode;
+    const float *llr;
+    int64_t b0, b1;
+    uint8_t *info, *hard;
+    int32_t *iters;
+    float *post;
+} fjob_t;
+
+/* one check row: Q from lP and the old lR, new lR in place; layered mode also rewrites lP (decodeCL.c:346-380) */
+static void fused_row(const oracle_tables *t, int row, float *lP, float *lR, int layered) {
+    const int e0 = t->hRowRange[row], e1 = t->hRowRange[row + 1];
+    float a = 1, b = 1000, c = 1001;
+    int bInd = -1;
+    for (int e = e0; e < e1; ++e) {
+        float tmp = lP[t->hCols[e]] - lR[e];
+        lR[e] = cl_sign(tmp);
+        a *= tmp;
+        if (layered) lP[t->hCols[e]] = tmp;
+        tmp = fabsf(tmp);
+        if (tmp <= b) { c = b; b = tmp; bInd = e; }
+        else if (tmp > b && tmp <= c) { c = tmp; }
+    }
+    a = cl_sign(a);
+    for (int e = e0; e < e1; ++e) {
+        if (e == bInd) lR[e] *= a * c;
+        else lR[e] *= a * b;
+    }
+    if (layered)
+        for (int e = e0; e < e1; ++e) lP[t->hCols[e]] += lR[e];
+}
+
+static void *fjob_run(void *arg) {
+    fjob_t *j = (fjob_t *)arg;
+    const oracle_tables *t = j->t;
+    const int nonZeros = t->nnz, ldpcN = t->N, ldpcM = t->M, K = j->K, KB = (K + 7) / 8, z = j->z;
+    float *lR = (float *)malloc(sizeof(float) * (size_t)nonZeros), *lP = (float *)malloc(sizeof(float) * (size_t)ldpcN);
+    unsigned char *src = (unsigned char *)malloc((size_t)ldpcN);
+    for (int64_t b = j->b0; b < j->b1; ++b) {
+        const float *codes = j->llr + (size_t)b * ldpcN;
+        for (int n = 0; n < ldpcN; ++n) lP[n] = codes[n];
+        for (int e = 0; e < nonZeros; ++e) lR[e] = 0;
+        int time = 0;
+        while (1) {
+            if (j->mode == 1) {
+                for (int layer = 0; layer < ldpcM / z; ++layer)
+                    for (int r = layer * z; r < (layer + 1) * z; ++r) fused_row(t, r, lP, lR, 1);
+            } else {
+                for (int r = 0; r < ldpcM; ++r) fused_row(t, r, lP, lR, 0);
+                for (int n = 0; n < ldpcN; ++n) { /* decodeCL.c:517-537: ascending seed row = ascending edge id */
+                    float tmp = codes[n];
+                    for (int ptr = t->hColFirstPtr[n]; ptr != -1; ptr = t->hColNextPtr[ptr]) tmp += lR[ptr];
+                    lP[n] = tmp;
+                }
+            }
+            for (int n = 0; n < ldpcN; ++n) src[n] = lP[n] < 0;
+            unsigned char flag = 0;
+            for (int row = 0; row < ldpcM && !flag; ++row) {
+                unsigned char result = 0;
+                for (int e = t->hRowRange[row]; e < t->hRowRange[row + 1]; ++e) result ^= src[t->hCols[e]];
+                if (result) flag = 1;
+            }
+            ++time;
+            if (!flag) break;
+            if (time == j->times) break;
+        }
+        if (j->info) {
+            uint8_t *o = j->info + (size_t)b * KB;
+            memset(o, 0, (size_t)KB);
+            for (int i = 0; i < K; ++i)
+                if (src[i]) o[i >> 3] |= (uint8_t)(1u << (i & 7));
+        }
+        if (j->iters) j->iters[b] = time;
+        if (j->hard) memcpy(j->hard + (size_t)b * ldpcN, src, (size_t)ldpcN);
+        if (j->post) memcpy(j->post + (size_t)b * ldpcN, lP, sizeof(float) * (size_t)ldpcN);
+    }
+    free(lR); free(lP); free(src);
+    return NULL;
+}
+
+int oracle_decode_fused_batch(const oracle_tables *t, int K, int times, int z, int mode, const float *llr, int64_t ncw,
+                              uint8_t *info, int32_t *iters, uint8_t *hard, float *post, int nthreads) {
+    if (mode == 1 && !oracle_tdmp_layering_ok(t, z)) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if ((int64_t)nthreads > ncw) nthreads = ncw > 0 ? (int)ncw : 1;
+    fjob_t jobs[256];
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; ++i) {
+        fjob_t *j = &jobs[i];
+        j->t = t; j->K = K; j->times = times; j->z = z; j->mode = mode; j->llr = llr;
+        j->b0 = ncw * i / nthreads; j->b1 = ncw * (i + 1) / nthreads;
+        j->info = info; j->iters = iters; j->hard = hard; j->post = post;
+    }
+    if (nthreads == 1) { fjob_run(&jobs[0]); return 0; }
+    for (int i = 0; i < nthreads; ++i) pthread_create(&th[i], NULL, fjob_run, &jobs[i]);
+    for (int i = 0; i < nthreads; ++i) pthread_join(th[i], NULL);
+    return 0;
+}
+
 /* reference MyLdpc.cpp:1063-1072: bit (LSB first) 1 -> -1.0, 0 -> +1.0 */
 void oracle_bpsk(const uint8_t *bytes, int nbytes, float *out) {
     for (int charOffset = 0; charOffset < nbytes; ++charOffset) {

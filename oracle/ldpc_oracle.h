@@ -10,7 +10,10 @@
  * unseeded).  The pin is oracle/_ref: the reference's own MyLdpc.cpp compiled unmodified
  * against container-only shims (see oracle/Makefile, oracle/shim/), whose decodeCPU output
  * is compared with this restatement in tests/test_oracle_vs_ref.py, plus committed golden
- * fixtures generated from it (tests/golden/).
+ * fixtures generated from it (tests/golden/).  The sum-product, layered and fused-kernel
+ * restatements are pinned the same way against oracle/_ref/libmyldpc_refcl.so, which also compiles
+ * the reference's decodeCL.c unmodified and executes its kernels on the CPU
+ * (tests/test_oracle_vs_refcl.py).
  */
 #ifndef LDPC_ORACLE_H_
 #define LDPC_ORACLE_H_
@@ -76,8 +79,11 @@ int oracle_decode_batch(const oracle_tables *t, int K, int times, const float *l
  *   refreshQ  t0 = prior0 * prod_{others} r0, t1 likewise (column-list order); q0 = t0/(t0+t1), q1 = t1/(t0+t1)
  * `exp` is an OpenCL built-in in the reference (implementation-defined rounding, no canonical value):
  * oracle and CUDA kernel both use oracle_sp_expf / the identical device routine, a fixed sequence of
- * IEEE fp32 operations, so the two sides can be compared bit for bit.  There is no CPU sum-product in the
- * reference to pin this restatement against: parity for DecodeSP is GPU == this oracle ("unpinned").  */
+ * IEEE fp32 operations, so the two sides can be compared bit for bit.
+ * PINNED: the reference's own decodeOnceSP host loop driving its own kernels (oracle/_ref/libmyldpc_refcl.so,
+ * exp supplied by oracle_sp_expf, every other operation the reference's) gives the bytes and the per-word
+ * iteration counts of this restatement for all six rates, saturating inputs included
+ * (tests/test_oracle_vs_refcl.py::test_reference_opencl_sum_product_*).                                  */
 float oracle_sp_expf(float x);
 int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float *llr, int64_t ncw,
                            uint8_t *info, int32_t *iters, uint8_t *hard, float *post0, float *post1,
@@ -91,16 +97,30 @@ int oracle_decode_sp_batch(const oracle_tables *t, int K, int times, const float
  * (clamp 1000, as decodeCPU),  lPostP = lQ + lR;  after the last layer a hard decision
  * (>0 -> 0, <0 -> 1, ==0 keeps the previous bit; bits start at 0 here, the reference's buffer is
  * uninitialised), the syndrome check, ++time, stop if clean or time == times.
- * As shipped the reference's host loop cannot produce this (it sizes a layer with
- * hRowRange[blockRow + z] instead of hRowRange[(blockRow+1)*z], MyLdpc.cpp:907,958; lQ is indexed
- * without the layer offset in refreshPostPTDMP, decodeCL.c:258; decodeInitTDMP seeds only the first N
- * edges), and it exists only as OpenCL kernels: there is nothing to run, so this restatement follows
- * the kernels' arithmetic with the layer bookkeeping repaired.  Parity for DecodeTDMP is
- * GPU == this oracle ("unpinned").  Returns -1 if some column appears twice inside a layer (the
- * reference's per-edge threads would race there).                                                     */
+ * PINNED where the reference's own loop is sound: decodeOnceTDMP sizes layer b as
+ * hRowRange[b + z] - hRowRange[b] (MyLdpc.cpp:907,958; b is a BLOCK row index), which is the layer's edge count
+ * exactly when all rows have one weight -- rates 2/3A and 5/6.  There the reference's own host loop and kernels,
+ * executed on the CPU (oracle/_ref/libmyldpc_refcl.so), give the bytes and per-word iteration counts of this
+ * restatement.  For mixed row weights (rates 1/2, 2/3B, 3/4A, 3/4B) the shipped loop launches the wrong number
+ * of work-items from the second layer on and its output is no longer a layered schedule
+ * (tests/test_oracle_vs_refcl.py::test_reference_host_looped_tdmp_*); this restatement uses the true layer
+ * boundaries hRowRange[(b+1) z] there.  (lQ is layer-relative in all four kernels, decodeCL.c:232-258,284-292, and
+ * decodeInitTDMP's first N entries cover the first layer: those two are consistent, not defects.)
+ * Returns -1 if some column appears twice inside a layer (the reference's per-edge threads would race there).  */
 int oracle_tdmp_layering_ok(const oracle_tables *t, int z);
 int oracle_decode_tdmp_batch(const oracle_tables *t, int K, int times, int z, const float *llr, int64_t ncw,
                              uint8_t *info, int32_t *iters, uint8_t *hard, float *post, int nthreads);
+
+/* ---- the fused one-kernel decoders (DecodeMSCL / DecodeTDMPCL) ------------------------------------------------
+ * Literal restatement of decodeOnceMS (mode 0, decodeCL.c:432-567) and decodeOnceTDMP (mode 1, decodeCL.c:307-426):
+ * the min-sum / layered min-sum schedules with those kernels' own arithmetic -- message sign through the float
+ * PRODUCT of the row's Q (a zero or an underflow zeroes the whole row), min search from (1000, 1001), hard decision
+ * bit = (P < 0), caps passed in `times` (the kernels hard-code 120 and 40).  Per-word iteration counts and the
+ * final posterior are exposed (the kernels keep them private).  Pinned bit for bit against the kernels themselves,
+ * executed by oracle/shim/cl_exec.h (tests/test_oracle_vs_refcl.py).  On inputs that never produce an exact-zero
+ * message or posterior the results equal oracle_decode_batch (mode 0) / oracle_decode_tdmp_batch (mode 1).     */
+int oracle_decode_fused_batch(const oracle_tables *t, int K, int times, int z, int mode, const float *llr, int64_t ncw,
+                              uint8_t *info, int32_t *iters, uint8_t *hard, float *post, int nthreads);
 
 /* Restates Coder::test's bit->BPSK map (reference MyLdpc.cpp:1061-1072), noise supplied by
  * the caller (the reference's rand()-based Box-Muller is unseeded).                      */

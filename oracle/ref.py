@@ -2,8 +2,10 @@
 
 ctypes door into oracle/_ref/libmyldpc_ref*.so: the reference's own MyLdpc.cpp compiled
 unmodified (oracle/Makefile) against container-only Eigen / OpenCL stand-ins (oracle/shim/).
-Only Coder's host paths are meaningful there: initCheckMatrix, forDecoder's edge tables,
-decode(..., DecodeCPU), forEncoder/encode, test.  Prebuilt files travel to the GPU box;
+In libmyldpc_ref{,_O2}.so only Coder's host paths are meaningful: initCheckMatrix, forDecoder's edge tables,
+decode(..., DecodeCPU), forEncoder/encode, test.  libmyldpc_refcl.so (opt="cl") additionally compiles the
+reference's decodeCL.c unmodified and EXECUTES its OpenCL decode variants on the CPU (oracle/shim/cl_exec.h,
+cl_kernels.cpp): RefCoder.decode_cl.  Prebuilt files travel to the GPU box;
 /root/reference itself is never read at run time.
 """
 from __future__ import annotations
@@ -19,7 +21,7 @@ _LIBS = {}
 
 
 def _path(opt: str) -> pathlib.Path:
-    return _HERE / "_ref" / ("libmyldpc_ref.so" if opt == "O0" else "libmyldpc_ref_O2.so")
+    return _HERE / "_ref" / {"O0": "libmyldpc_ref.so", "O2": "libmyldpc_ref_O2.so", "cl": "libmyldpc_refcl.so"}[opt]
 
 
 def available(opt: str = "O0") -> bool:
@@ -44,6 +46,11 @@ def lib(opt: str = "O0") -> C.CDLL:
         L.ref_csr.argtypes = [vp, vp, vp]
         L.ref_edge_tables.argtypes = [vp] * 8
         L.ref_test.argtypes = [vp, vp, vp, i, C.c_float]
+        L.ref_addDecodeType.argtypes = [vp, i]
+        L.ref_decode.argtypes = [vp, vp, vp, i, i, vp, i]
+        L.ref_stepTime.argtypes = [vp, i]
+        L.ref_stepTime.restype = C.c_double
+        L.ref_z.argtypes = [vp]
         _LIBS[opt] = L
     return _LIBS[opt]
 
@@ -98,6 +105,29 @@ class RefCoder:
         out = np.zeros(src_length + 1, dtype=np.uint8)  # the reference may touch srcCode[srcLength]
         self.L.ref_decode_cpu(self.h, y.ctypes.data, out.ctypes.data, src_length)
         return out[:src_length]
+
+    def decode_cl(self, post_code: np.ndarray, src_length: int, de_type: int, batch: int = 1):
+        """Coder::decode(postCode, srcCode, srcLength, deType) for the reference's OpenCL variants
+        (DecodeMS=1, DecodeSP=2, DecodeTDMP=3, DecodeTDMPCL=4, DecodeMSCL=5), executed on the CPU by
+        oracle/shim/cl_exec.h -- needs opt="cl".  Follows Test.cpp's call order: forDecoder(batch),
+        addDecodeType(deType), decode.  Returns (srcCode[:srcLength], times) where times holds the "Time="
+        value the reference printed for every chunk of `batch` words (batch = 1: its per-word iteration counts;
+        empty for the two fused kernels, which print nothing)."""
+        assert self.L is lib("cl"), "decode_cl needs RefCoder(..., opt='cl')"
+        if not self._dec or getattr(self, "_batch", None) != batch:
+            assert not self._dec, "forDecoder was already called with another batch size"
+            self.L.ref_forDecoder(self.h, batch)
+            self._dec, self._batch, self._types = True, batch, set()
+        if de_type not in self._types:
+            self.L.ref_addDecodeType(self.h, de_type)
+            self._types.add(de_type)
+        y = np.ascontiguousarray(post_code, dtype=np.float32).reshape(-1)
+        assert y.size >= self.L.ref_getPostCodeLength(self.h, src_length)
+        out = np.zeros(src_length + 1, dtype=np.uint8)
+        nchunks = (self.L.ref_getCodeSize(self.h, src_length) + batch - 1) // batch
+        times = np.zeros(nchunks + 1, dtype=np.int32)
+        n = self.L.ref_decode(self.h, y.ctypes.data, out.ctypes.data, src_length, de_type, times.ctypes.data, times.size)
+        return out[:src_length], times[:min(n, nchunks)]
 
     def encode(self, src: np.ndarray) -> np.ndarray:
         """Coder::encode -> priorCode bytes (getPriorCodeLength(srcLength))."""

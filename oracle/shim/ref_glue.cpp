@@ -10,6 +10,13 @@
 #undef private
 
 #include <cstring>
+#include <iostream>
+#include <sstream>
+#include <string>
+
+// The container's g++ wrapper links libstdc++ statically; a dlopen'ed library then carries its own std::cout, which
+// nobody initialises unless an ios_base::Init object is constructed in it (Python has no C++ runtime of its own).
+static std::ios_base::Init s_ios_init;
 
 extern "C" {
 
@@ -21,6 +28,27 @@ void ref_set_times(void *c, int times) { static_cast<Coder *>(c)->times = times;
 int ref_decode_cpu(void *c, float *post, char *src, int srcLength) {
     return static_cast<Coder *>(c)->decode(post, src, srcLength, DecodeCPU);
 }
+// The OpenCL decode variants (meaningful only in libmyldpc_refcl.so, where oracle/shim/cl_exec.h executes the
+// reference's kernels; in the inert-shim builds they return without decoding).  The reference prints the number
+// of iterations of every chunk it decodes ("Time=", MyLdpc.cpp:838,966,1048): std::cout is captured during the
+// call and the numbers are returned in times_out (one per chunk of batchSize words; with forDecoder(1) that is
+// the reference's own per-codeword iteration count).  Returns the number of "Time=" lines seen.
+int ref_addDecodeType(void *c, int type) { return static_cast<Coder *>(c)->addDecodeType((enum decodeType)type); }
+int ref_decode(void *c, float *post, char *src, int srcLength, int type, int *times_out, int times_cap) {
+    std::ostringstream cap;
+    std::streambuf *old = std::cout.rdbuf(cap.rdbuf());
+    static_cast<Coder *>(c)->decode(post, src, srcLength, (enum decodeType)type);
+    std::cout.rdbuf(old);
+    const std::string text = cap.str();
+    int n = 0;
+    for (size_t pos = 0; (pos = text.find("Time=", pos)) != std::string::npos; pos += 5) {
+        if (times_out && n < times_cap) times_out[n] = std::atoi(text.c_str() + pos + 5);
+        ++n;
+    }
+    return n;
+}
+double ref_stepTime(void *c, int i) { return (i >= 0 && i < 10) ? static_cast<Coder *>(c)->stepTime[i] : -1.0; }
+int ref_z(void *c) { return static_cast<Coder *>(c)->z; }
 int ref_encode(void *c, char *src, char *prior, int srcLength) { return static_cast<Coder *>(c)->encode(src, prior, srcLength); }
 int ref_getCodeSize(void *c, int srcLength) { return static_cast<Coder *>(c)->getCodeSize(srcLength); }
 int ref_getPostCodeLength(void *c, int srcLength) { return static_cast<Coder *>(c)->getPostCodeLength(srcLength); }

@@ -262,10 +262,10 @@ def test_qc_runtime_profile_kernel(default_code, monkeypatch):
             assert_parity(_run_device(d2, y), r2, NN, what="N=%d rate %s forced=%s (%s)" % (NN, name, forced, i2["path_name"]))
 
 
-def test_streamed_host_pipeline(default_code, monkeypatch):
+def test_streamed_host_pipeline(default_code):
     """Host buffers on the quasi-cyclic path: one persistent launch fed by a copy stream.  Ragged sizes, pageable and
     pinned inputs, optional outputs asked for only on a later call, several launches per call (small batch cap) and
-    the 3-stream pipeline (LDPC_B200_NO_STREAMED) must all give the oracle's bytes, counts and posteriors."""
+    the 3-stream pipeline (option no_streamed) must all give the oracle's bytes, counts and posteriors."""
     import myldpccppapi_b200 as m
     torch = _torch()
     c = default_code
@@ -277,28 +277,28 @@ def test_streamed_host_pipeline(default_code, monkeypatch):
     assert dec.info()["path_name"] == "qc"
     first = dec.decode_host(llr)                                    # pageable input: the chunked 3-stream pipeline
     assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
-    monkeypatch.setenv("LDPC_B200_STAGED_MIN_KB", "0")              # ... staged by host threads through pinned buffers
+    dec.set_option("staged_min_kb", 0)              # ... staged by host threads through pinned buffers
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="staged pageable input")
-    monkeypatch.setenv("LDPC_B200_STREAM_CHUNK", "8")               # 376 chunks through the ring of 8 staging buffers
+    dec.set_option("stream_chunk", 8)               # 376 chunks through the ring of 8 staging buffers
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="staged, tiny chunks")
-    monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # several launches
+    dec.set_option("stream_batch_kb", 1024)         # several launches
     assert_parity(dec.decode_host(llr[:1000], want_hard=True, want_post=True), tuple(r[:1000] for r in ref), N, what="staged, batches")
-    monkeypatch.delenv("LDPC_B200_STREAM_CHUNK"); monkeypatch.delenv("LDPC_B200_STREAM_BATCH_KB"); monkeypatch.delenv("LDPC_B200_STAGED_MIN_KB")
-    monkeypatch.setenv("LDPC_B200_STREAMED_PAGEABLE", "1")          # ... and the persistent launch fed from pageable memory
+    dec.set_option("stream_chunk", 0); dec.set_option("stream_batch_kb", 0); dec.set_option("staged_min_kb", 8192)
+    dec.set_option("streamed_pageable", 1)          # ... and the persistent launch fed from pageable memory
     first = dec.decode_host(llr)                                    # info + iters only
     assert np.array_equal(first["info"], ref[0]) and np.array_equal(first["iters"], ref[1])
     assert_parity(dec.decode_host(llr, want_hard=True, want_post=True), ref, N, what="streamed, all outputs")
-    monkeypatch.delenv("LDPC_B200_STREAMED_PAGEABLE")
+    dec.set_option("streamed_pageable", 0)
     pinned = torch.from_numpy(llr).pin_memory().numpy()
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
     for n in (1, 9):                                                # fewer words than one CTA holds
         assert_parity(dec.decode_host(pinned[:n], want_hard=True, want_post=True), tuple(r[:n] for r in ref), N, what="streamed, %d words" % n)
-    monkeypatch.setenv("LDPC_B200_STREAM_BATCH_KB", "1024")         # 455 words per launch: 7 launches
+    dec.set_option("stream_batch_kb", 1024)         # 455 words per launch: 7 launches
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, 7 launches")
-    monkeypatch.setenv("LDPC_B200_STREAM_CHUNK", "8")               # one word group per copy
+    dec.set_option("stream_chunk", 8)               # one word group per copy
     assert_parity(dec.decode_host(pinned[:500], want_hard=True, want_post=True), tuple(r[:500] for r in ref), N, what="streamed, tiny chunks")
-    monkeypatch.delenv("LDPC_B200_STREAM_BATCH_KB"); monkeypatch.delenv("LDPC_B200_STREAM_CHUNK")
-    monkeypatch.setenv("LDPC_B200_NO_STREAMED", "1")
+    dec.set_option("stream_batch_kb", 0); dec.set_option("stream_chunk", 0)
+    dec.set_option("no_streamed", 1)
     assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="3-stream pipeline")
     assert ncw == llr.shape[0]
 

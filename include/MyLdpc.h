@@ -8,7 +8,8 @@
 // fall back to min-sum, reported through lastError()); DecodeTDMP and DecodeTDMPCL select the layered
 // min-sum kernel (the schedule decodeOnceTDMP intends, MyLdpc.cpp:889-976 / decodeCL.c:203-292, with the
 // same fallback); DecodeCPU, DecodeMS and DecodeMSCL run flooding min-sum with the semantics of the
-// reference's Coder::decodeCPU (MyLdpc.cpp:684-784).  There is no CPU decode path in
+// reference's Coder::decodeCPU (MyLdpc.cpp:684-784) -- DecodeMSCL with the iteration cap 120 that the reference's
+// fused kernel hard-codes (decodeCL.c:479) unless setMaxIter() was called.  There is no CPU decode path in
 // this library, DecodeCPU included.
 //
 //   reference                         here
@@ -111,9 +112,19 @@ public:
     int setMaxIter(int times);                       // the reference fixes times = 40 (MyLdpc.cpp:24)
     int setDevices(const int *deviceIds, int count); // shard codewords over these GPUs (before forDecoder)
     int setEarlyTermination(bool on);
+    // DecodeSP / DecodeTDMP / DecodeTDMPCL need their kernel's layout to hold the code.  Default (false): a code that
+    // does not fit is decoded with flooding min-sum instead, decode() returns 0 and lastAlgorithm() tells; strict
+    // (true): decode() returns LDPC_B200_ERR_UNSUPPORTED (-3) and writes nothing.
+    int setStrictDecodeType(bool strict);
+    int lastAlgorithm() const;                       // LDPC_B200_ALG_* the last decode() actually ran (-1: none yet)
     const int *lastIterations() const;               // per-codeword iteration counts of the last decode()
     int lastCodeSize() const;
     const char *lastError() const;
+    // Time of the last decode() by phase, in seconds (the reference keeps clock() sums per kernel in stepTime[],
+    // MyLdpc.cpp:26-28, 987-1056; the phases of a fused decoder are different): [0] whole call, wall clock;
+    // [1] host->device copies, [2] kernels, [3] device->host copies (CUDA events on the busiest device; the three
+    // overlap, so they do not add up to [0]).  Returns the number of entries written (<= n).
+    int lastStepTimes(double *seconds, int n) const;
     Coder(const Coder &) = delete;
     Coder &operator=(const Coder &) = delete;
 

@@ -187,6 +187,19 @@ int ldpc_b200_edge_tables(int M, int N, const int32_t *row_ptr, const int32_t *c
  * reports the achieved GB/s (the denominator of the on-chip roofline in bench.py).       */
 int ldpc_b200_probe_smem_bandwidth(int device, double *gbytes_per_s);
 
+/* Run-time phase timers of ldpc_b200_decode_host, accumulated since creation / the last reset (the reference keeps
+ * clock() sums per kernel launch in Coder::stepTime[], MyLdpc.cpp:26-28, 987-1056; here the iterations are fused into
+ * one kernel, so the phases a caller can see are the copies and the kernel).  CUDA events on the handle's streams:
+ * h2d_s = host->device copies of the channel values, kernel_s = decode kernels (on the streamed path the kernel
+ * runs under the copies and its time includes waiting for them), d2h_s = read-back of the results; wall_s = host
+ * wall clock of the calls.  The three device phases overlap, so they do not add up to wall_s.                       */
+typedef struct ldpc_b200_timing {
+    int64_t calls, codewords;
+    double wall_s, h2d_s, kernel_s, d2h_s;
+} ldpc_b200_timing;
+int ldpc_b200_get_timing(ldpc_b200_handle h, ldpc_b200_timing *out);
+int ldpc_b200_reset_timing(ldpc_b200_handle h);
+
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ldpc_b200_launch_count(ldpc_b200_handle h);
 

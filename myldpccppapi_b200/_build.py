@@ -103,7 +103,7 @@ def build_coder(force: bool = False, verbose: bool = False) -> pathlib.Path:
     src = CSRC / "mycoder.cpp"
     if not src.exists():
         return CODER_LIB
-    deps = [src, ROOT / "include" / "MyLdpc.h", ROOT / "include" / "ldpc_b200.h"]
+    deps = [src, ROOT / "include" / "MyLdpc.h", ROOT / "include" / "MyLdpc_c.h", ROOT / "include" / "ldpc_b200.h"]
     if force or _stale(CODER_LIB, deps) or _stale(CODER_LIB, [LIB]):
         cxx = shutil.which("g++") or "g++"
         cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-I", str(ROOT / "include"), str(src),

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <new>
@@ -244,6 +245,10 @@ struct ldpc_b200_decoder {
     size_t st_pin_bytes = 0;
 
     int64_t launches = 0;
+    // run-time phase timers of the host-buffer decode (ldpc_b200_get_timing): CUDA events around the copies and the
+    // kernels, accumulated per call -- what the reference keeps in stepTime[] (MyLdpc.cpp:26-28, 987-1056)
+    ldpc_b200_timing timing{};
+    std::vector<cudaEvent_t> tev;  // timing events, created on demand
     std::mutex mu;
 };
 
@@ -2053,6 +2058,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
             if (h->h_status) cudaFreeHost(h->h_status);
             if (h->st_event) cudaEventDestroy(h->st_event);
+            for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
@@ -2255,6 +2261,44 @@ int ldpc_b200_get_csr(ldpc_b200_handle h, int32_t* row_ptr, int32_t* col_idx) {
 }  // extern "C"
 
 namespace {
+// n timing-enabled events of the handle (created on demand); false if the runtime refuses
+bool timing_events(ldpc_b200_decoder* h, size_t n) {
+    while (h->tev.size() < n) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+        h->tev.push_back(e);
+    }
+    return true;
+}
+double event_seconds(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { (void)cudaGetLastError(); return 0.0; }
+    return (double)ms * 1e-3;
+}
+
+// Device buffers of the streamed host pipeline for up to `want` words per launch (grown, never shrunk).
+// (h->mu held, current device = the handle's)
+int ensure_streamed_buffers(ldpc_b200_decoder* h, int64_t want, bool hard, bool post) {
+    const HostTables& t = h->host;
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    if (h->st_cap < want || (hard && !h->st_has_hard) || (post && !h->st_has_post)) {
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
+        h->st_llr = nullptr; h->st_info = nullptr; h->st_hard = nullptr; h->st_iters = nullptr; h->st_post = nullptr;
+        const int64_t cap = std::max(want, h->st_cap);  // never shrink: alternating call sizes must not reallocate
+        h->st_cap = 0;
+        h->st_has_hard = h->st_has_hard || hard;
+        h->st_has_post = h->st_has_post || post;
+        CU_TRY(cudaMalloc(&h->st_llr, sizeof(float) * (size_t)cap * t.N));
+        CU_TRY(cudaMalloc(&h->st_info, (size_t)cap * KB));
+        CU_TRY(cudaMalloc(&h->st_iters, sizeof(int32_t) * (size_t)cap));
+        if (h->st_has_hard) CU_TRY(cudaMalloc(&h->st_hard, (size_t)cap * NB));
+        if (h->st_has_post) CU_TRY(cudaMalloc(&h->st_post, sizeof(float) * (size_t)cap * t.N));
+        h->st_cap = cap;
+    }
+    return LDPC_B200_OK;
+}
+
 // (h->mu held)
 int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
     if (batch <= h->reserved) return LDPC_B200_OK;
@@ -2281,6 +2325,24 @@ int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
         const int64_t chunk = std::max<int64_t>(g, ((((int64_t)4 << 20)) / ((int64_t)t.N * 4)) / g * g);
         const size_t need = sizeof(float) * (size_t)chunk * t.N;
         if (!h->h_status) CU_TRY(cudaMallocHost(&h->h_status, sizeof(int)));
+        for (int s = 0; s < 2; ++s)
+            if (!h->streams[s]) CU_TRY(cudaStreamCreateWithFlags(&h->streams[s], cudaStreamNonBlocking));
+        {   // the launch buffers for a call of `batch` words (what the reference allocates in addDecodeType,
+            // MyLdpc.cpp:387-437): the first decode() then costs what the tenth does
+            int64_t batch_bytes = (int64_t)512 << 20;
+            if (h->opt.stream_batch_kb >= 1) batch_bytes = h->opt.stream_batch_kb << 10;
+            const int64_t batch_cap = std::max<int64_t>(g, (batch_bytes / ((int64_t)t.N * 4)) / g * g);
+            const int rc = ensure_streamed_buffers(h, std::min(batch, batch_cap), false, false);
+            if (rc) return rc;
+            const int64_t nchunks_max = (std::min(batch, batch_cap) + chunk - 1) / chunk + 8;
+            if (h->h_avail_cap < nchunks_max) {
+                if (h->h_avail_vals) cudaFreeHost(h->h_avail_vals);
+                h->h_avail_vals = nullptr; h->h_avail_cap = 0;
+                CU_TRY(cudaMallocHost(&h->h_avail_vals, sizeof(unsigned long long) * (size_t)nchunks_max));
+                h->h_avail_cap = nchunks_max;
+            }
+            (void)timing_events(h, 5);
+        }
         if (h->st_pin_bytes < need && !h->opt.no_staged) {
             for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
                 if (h->st_pin[i]) { cudaFreeHost(h->st_pin[i]); h->st_pin[i] = nullptr; }
@@ -2346,21 +2408,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
     if (!h->st_event) CU_TRY(cudaEventCreateWithFlags(&h->st_event, cudaEventDisableTiming));
     if (!h->d_avail) CU_TRY(cudaMalloc(&h->d_avail, 2 * sizeof(unsigned long long)));
     if (!h->h_status) CU_TRY(cudaMallocHost(&h->h_status, sizeof(int)));
-    if (h->st_cap < want || (hard && !h->st_has_hard) || (post && !h->st_has_post)) {
-        CU_TRY(cudaDeviceSynchronize());
-        cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
-        h->st_llr = nullptr; h->st_info = nullptr; h->st_hard = nullptr; h->st_iters = nullptr; h->st_post = nullptr;
-        const int64_t cap = std::max(want, h->st_cap);  // never shrink: alternating call sizes must not reallocate
-        h->st_cap = 0;
-        h->st_has_hard = h->st_has_hard || hard != nullptr;
-        h->st_has_post = h->st_has_post || post != nullptr;
-        CU_TRY(cudaMalloc(&h->st_llr, sizeof(float) * (size_t)cap * t.N));
-        CU_TRY(cudaMalloc(&h->st_info, (size_t)cap * KB));
-        CU_TRY(cudaMalloc(&h->st_iters, sizeof(int32_t) * (size_t)cap));
-        if (h->st_has_hard) CU_TRY(cudaMalloc(&h->st_hard, (size_t)cap * NB));
-        if (h->st_has_post) CU_TRY(cudaMalloc(&h->st_post, sizeof(float) * (size_t)cap * t.N));
-        h->st_cap = cap;
-    }
+    { const int rc = ensure_streamed_buffers(h, want, hard != nullptr, post != nullptr); if (rc) return rc; }
     // input chunks of ~1 MB, 2 MB, then ~4 MB: the first words land after a few tens of microseconds and PCIe stays
     // efficient.  Larger chunks lose: the kernel consumes words in order at 70 % of the PCIe rate, so it keeps
     // running into the end of the announced range and waits for a whole chunk (measured, cfg2 end to end:
@@ -2392,6 +2440,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
         h->h_avail_cap = nchunks_max;
     }
     cudaStream_t cs = h->streams[0], ks = h->streams[1];
+    const bool timed = timing_events(h, 5);  // [0] copies start, [1] copies end, [2] kernel start, [3] kernel end, [4] read-back end
     for (int64_t off = 0; off < ncw; off += batch_cap) {
         const int64_t n = std::min(batch_cap, ncw - off);
         // (a later batch reuses the device buffers: its copies wait for the previous batch's kernel and read-back)
@@ -2399,6 +2448,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
         CU_TRY(cudaMemsetAsync(h->d_avail, 0, 2 * sizeof(unsigned long long), cs));
         CU_TRY(cudaEventRecord(h->st_event, cs));
         CU_TRY(cudaStreamWaitEvent(ks, h->st_event, 0));  // the kernel must not see a stale count
+        if (timed) { CU_TRY(cudaEventRecord(h->tev[0], cs)); CU_TRY(cudaEventRecord(h->tev[2], ks)); }
         int rc = LDPC_B200_OK;
         if (!staged) {
             int64_t j = 0, chunk = chunk0;
@@ -2455,14 +2505,21 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
             }
         }
         if (rc) return rc;
+        if (timed) { CU_TRY(cudaEventRecord(h->tev[1], cs)); CU_TRY(cudaEventRecord(h->tev[3], ks)); }
         if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->st_info, (size_t)n * KB, cudaMemcpyDeviceToHost, ks));
         if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->st_hard, (size_t)n * NB, cudaMemcpyDeviceToHost, ks));
         if (iters) CU_TRY(cudaMemcpyAsync(iters + off, h->st_iters, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ks));
         if (post) CU_TRY(cudaMemcpyAsync(post + (size_t)off * t.N, h->st_post, sizeof(float) * (size_t)n * t.N, cudaMemcpyDeviceToHost, ks));
         *h->h_status = 0;
         CU_TRY(cudaMemcpyAsync(h->h_status, reinterpret_cast<int*>(h->d_avail + 1), sizeof(int), cudaMemcpyDeviceToHost, ks));
+        if (timed) CU_TRY(cudaEventRecord(h->tev[4], ks));
         CU_TRY(cudaStreamSynchronize(cs));
         CU_TRY(cudaStreamSynchronize(ks));
+        if (timed) {
+            h->timing.h2d_s += event_seconds(h->tev[0], h->tev[1]);
+            h->timing.kernel_s += event_seconds(h->tev[2], h->tev[3]);  // (waits for streamed input included)
+            h->timing.d2h_s += event_seconds(h->tev[3], h->tev[4]);
+        }
         // the kernel gave up waiting for its input (a tool that serialises launches, a copy engine busy elsewhere,
         // time-slicing): nothing is wrong with the data -- the caller reruns the call through the chunked pipeline
         if (*h->h_status) return kStreamedRetry;
@@ -2493,21 +2550,39 @@ int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw
         for (int s = 0; s < kSlots; ++s)
             if (!h->s_post[s]) CU_TRY(cudaMalloc(&h->s_post[s], sizeof(float) * (size_t)chunk * t.N));
     }
+    // phase timers: four events per chunk for the first kTimedChunks chunks (a sample when there are more)
+    constexpr int64_t kTimedChunks = 64;
+    const int64_t nchunks = (ncw + chunk - 1) / chunk, ntimed = std::min(nchunks, kTimedChunks);
+    const bool timed = timing_events(h, (size_t)(4 * ntimed));
     int slot = 0;
-    for (int64_t off = 0; off < ncw; off += chunk, slot = (slot + 1) % kSlots) {
+    int64_t ci = 0;
+    for (int64_t off = 0; off < ncw; off += chunk, slot = (slot + 1) % kSlots, ++ci) {
         const int64_t n = std::min(chunk, ncw - off);
         cudaStream_t st = h->streams[slot];
+        const bool tc = timed && ci < ntimed;
+        if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci], st));
         CU_TRY(cudaMemcpyAsync(h->s_llr[slot], llr + (size_t)off * t.N, sizeof(float) * (size_t)n * t.N,
                                cudaMemcpyHostToDevice, st));
+        if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci + 1], st));
         int rc = launch_decode(h, h->s_llr[slot], n, info ? h->s_info[slot] : nullptr, hard ? h->s_hard[slot] : nullptr,
                                iters ? h->s_iters[slot] : nullptr, post ? h->s_post[slot] : nullptr, st);
         if (rc) return rc;
+        if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci + 2], st));
         if (info) CU_TRY(cudaMemcpyAsync(info + (size_t)off * KB, h->s_info[slot], (size_t)n * KB, cudaMemcpyDeviceToHost, st));
         if (hard) CU_TRY(cudaMemcpyAsync(hard + (size_t)off * NB, h->s_hard[slot], (size_t)n * NB, cudaMemcpyDeviceToHost, st));
         if (iters) CU_TRY(cudaMemcpyAsync(iters + off, h->s_iters[slot], sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
         if (post) CU_TRY(cudaMemcpyAsync(post + (size_t)off * t.N, h->s_post[slot], sizeof(float) * (size_t)n * t.N, cudaMemcpyDeviceToHost, st));
+        if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci + 3], st));
     }
     for (int s = 0; s < kSlots; ++s) CU_TRY(cudaStreamSynchronize(h->streams[s]));
+    if (timed) {  // per-stream sums (chunks on different streams overlap), scaled up when only a sample was timed
+        const double scale = (double)nchunks / (double)ntimed;
+        for (int64_t c = 0; c < ntimed; ++c) {
+            h->timing.h2d_s += scale * event_seconds(h->tev[4 * c], h->tev[4 * c + 1]);
+            h->timing.kernel_s += scale * event_seconds(h->tev[4 * c + 1], h->tev[4 * c + 2]);
+            h->timing.d2h_s += scale * event_seconds(h->tev[4 * c + 2], h->tev[4 * c + 3]);
+        }
+    }
     return LDPC_B200_OK;
 }
 
@@ -2522,6 +2597,13 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     std::lock_guard<std::mutex> lk(h->mu);  // one lock for the whole call: plan, reservation and buffers stay put
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    struct WallTimer {  // accumulates the call into the handle's phase timers on every exit path
+        ldpc_b200_decoder* h; int64_t n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~WallTimer() {
+            h->timing.wall_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            h->timing.calls += 1; h->timing.codewords += n;
+        }
+    } wall_timer{h, ncw};
     const HostTables& t = h->host;
     // (also after ldpc_b200_reserve / Coder::forDecoder(batchSize): the reference's batch size is only its internal
     // chunking, MyLdpc.cpp:577-616, and kernels of this path do not speed each other up across streams)
@@ -2591,6 +2673,20 @@ int ldpc_b200_synth_llr(float* d_llr, int64_t ncw, int N, float sigma, uint64_t 
 }
 
 int64_t ldpc_b200_launch_count(ldpc_b200_handle h) { return h ? h->launches : 0; }
+
+int ldpc_b200_get_timing(ldpc_b200_handle h, ldpc_b200_timing* out) {
+    if (!h || !out) return fail(LDPC_B200_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = h->timing;
+    return LDPC_B200_OK;
+}
+
+int ldpc_b200_reset_timing(ldpc_b200_handle h) {
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->timing = ldpc_b200_timing{};
+    return LDPC_B200_OK;
+}
 
 int ldpc_b200_probe_smem_bandwidth(int device, double* gbytes_per_s) {
     if (!gbytes_per_s) return fail(LDPC_B200_ERR_ARG, "null argument");

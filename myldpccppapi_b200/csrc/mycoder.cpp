@@ -6,6 +6,7 @@
 #include "MyLdpc.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -17,6 +18,10 @@ struct Coder::Impl {
     int K = 0, N = 0, M = 0;
     int rate = -1;       // rate_type, or -1 for a CSR-constructed code
     int times = 40;      // reference MyLdpc.cpp:24
+    int timesMSCL = 120; // the cap decodeOnceMS hard-codes (decodeCL.c:479); setMaxIter() overrides both
+    bool strict = false; // setStrictDecodeType
+    int lastAlg = -1;
+    double stepTimes[4] = {0, 0, 0, 0};
     int batchSize = 0;
     bool early = true;
     std::vector<int> devices{0};
@@ -79,6 +84,7 @@ Coder::~Coder() {
 int Coder::setMaxIter(int times) {
     if (times < 1) return LDPC_B200_ERR_ARG;
     impl->times = times;
+    impl->timesMSCL = times;
     for (ldpc_b200_handle h : impl->handles)
         if (ldpc_b200_set_max_iter(h, times) != LDPC_B200_OK) return impl->fail(LDPC_B200_ERR_ARG);
     return LDPC_SUCCESS;
@@ -98,6 +104,20 @@ int Coder::setDevices(const int *deviceIds, int count) {
     }
     impl->devices.assign(deviceIds, deviceIds + count);
     return LDPC_SUCCESS;
+}
+
+int Coder::setStrictDecodeType(bool strict) {
+    impl->strict = strict;
+    return LDPC_SUCCESS;
+}
+
+int Coder::lastAlgorithm() const { return impl->lastAlg; }
+
+int Coder::lastStepTimes(double *seconds, int n) const {
+    if (!seconds || n < 1) return 0;
+    const int m = n < 4 ? n : 4;
+    for (int i = 0; i < m; ++i) seconds[i] = impl->stepTimes[i];
+    return m;
 }
 
 const int *Coder::lastIterations() const { return impl->iters.data(); }
@@ -164,11 +184,20 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
     int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT
               : (deType == DecodeTDMP || deType == DecodeTDMPCL) ? LDPC_B200_ALG_LAYERED_MIN_SUM
                                                                  : LDPC_B200_ALG_MIN_SUM;
+    // DecodeMSCL: the reference's fused kernel iterates up to 120 times whatever Coder::times says (decodeCL.c:479)
+    const int cap = deType == DecodeMSCL ? impl->timesMSCL : impl->times;
     const char *fallback_note = "requested decodeType does not fit its on-chip layout for this code, decoded with flooding min-sum";
     bool fell_back = false;
-    for (ldpc_b200_handle h : impl->handles)
+    for (ldpc_b200_handle h : impl->handles) {
+        ldpc_b200_set_max_iter(h, cap);
         if (ldpc_b200_set_algorithm(h, alg) != LDPC_B200_OK) fell_back = true;
+    }
     if (fell_back) {
+        if (impl->strict) {
+            impl->fail(LDPC_B200_ERR_UNSUPPORTED);
+            for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, LDPC_B200_ALG_MIN_SUM);
+            return LDPC_B200_ERR_UNSUPPORTED;
+        }
         alg = LDPC_B200_ALG_MIN_SUM;
         for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, alg);
     }
@@ -177,6 +206,8 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
     impl->lastCodeSize = codeSize;
     std::vector<int> rcs(G, LDPC_B200_OK);
     std::vector<std::string> msgs(G);
+    for (ldpc_b200_handle h : impl->handles) ldpc_b200_reset_timing(h);
+    const auto wall0 = std::chrono::steady_clock::now();
     auto work = [&](int g) {
         // contiguous shard [b, e) of the codewords for device g: no data-path collective
         const int64_t b = (int64_t)codeSize * g / G, e = (int64_t)codeSize * (g + 1) / G;
@@ -185,27 +216,33 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
                                        impl->info.data() + (size_t)b * KB, nullptr, impl->iters.data() + b, nullptr);
         if (rcs[g] != LDPC_B200_OK) msgs[g] = ldpc_b200_last_error();
     };
-    if (G == 1) {
-        work(0);
-    } else {
+    auto run_all = [&]() {
+        if (G == 1) { work(0); return; }
         std::vector<std::thread> th;
         for (int g = 0; g < G; ++g) th.emplace_back(work, g);
         for (auto &t : th) t.join();
-    }
+    };
+    run_all();
     bool unsupported = false;
     for (int g = 0; g < G; ++g)
         if (rcs[g] == LDPC_B200_ERR_UNSUPPORTED && alg != LDPC_B200_ALG_MIN_SUM) unsupported = true;
-    if (unsupported) {  // the kernel of this decodeType cannot hold the code: decode with min-sum instead, and say so
+    if (unsupported && !impl->strict) {  // the kernel of this decodeType cannot hold the code: decode with min-sum instead, and say so
         fell_back = true;
+        alg = LDPC_B200_ALG_MIN_SUM;
         for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, LDPC_B200_ALG_MIN_SUM);
         std::fill(rcs.begin(), rcs.end(), LDPC_B200_OK);
-        if (G == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int g = 0; g < G; ++g) th.emplace_back(work, g);
-            for (auto &t : th) t.join();
-        }
+        run_all();
     }
+    impl->stepTimes[0] = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    impl->stepTimes[1] = impl->stepTimes[2] = impl->stepTimes[3] = 0.0;
+    for (ldpc_b200_handle h : impl->handles) {  // the busiest device per phase
+        ldpc_b200_timing tm;
+        if (ldpc_b200_get_timing(h, &tm) != LDPC_B200_OK) continue;
+        impl->stepTimes[1] = std::max(impl->stepTimes[1], tm.h2d_s);
+        impl->stepTimes[2] = std::max(impl->stepTimes[2], tm.kernel_s);
+        impl->stepTimes[3] = std::max(impl->stepTimes[3], tm.d2h_s);
+    }
+    impl->lastAlg = alg;
     if (fell_back) impl->err = fallback_note;
     for (int g = 0; g < G; ++g)
         if (rcs[g] != LDPC_B200_OK) {
@@ -321,4 +358,47 @@ char *load_program_source(const char *filename) {
     source[got] = '\0';
     std::fclose(fh);
     return source;
+}
+
+// ---- C doorway (include/MyLdpc_c.h): the same Coder for callers without a C++ compiler -- the Python binding in
+// myldpccppapi_b200/decoder.py and the parity tests use it, so that the class above is the ONE implementation.
+#include "MyLdpc_c.h"
+
+extern "C" {
+myldpc_coder *myldpc_coder_new(int ldpcK, int ldpcN, int rate) { return reinterpret_cast<myldpc_coder *>(new Coder(ldpcK, ldpcN, (enum rate_type)rate)); }
+myldpc_coder *myldpc_coder_new_csr(int ldpcM, int ldpcN, int ldpcK, const int *rowPtr, const int *colIdx) {
+    return reinterpret_cast<myldpc_coder *>(new Coder(ldpcM, ldpcN, ldpcK, rowPtr, colIdx));
+}
+void myldpc_coder_free(myldpc_coder *c) { delete reinterpret_cast<Coder *>(c); }
+#define CODER(c) reinterpret_cast<Coder *>(c)
+int myldpc_forEncoder(myldpc_coder *c) { return CODER(c)->forEncoder(); }
+int myldpc_forDecoder(myldpc_coder *c, int batchSize) { return CODER(c)->forDecoder(batchSize); }
+int myldpc_addDecodeType(myldpc_coder *c, int deType) { return CODER(c)->addDecodeType((enum decodeType)deType); }
+int myldpc_encode(myldpc_coder *c, char *srcCode, char *priorCode, int srcLength) { return CODER(c)->encode(srcCode, priorCode, srcLength); }
+int myldpc_decode(myldpc_coder *c, float *postCode, char *srcCode, int srcLength, int deType) {
+    return CODER(c)->decode(postCode, srcCode, srcLength, (enum decodeType)deType);
+}
+int myldpc_test(myldpc_coder *c, char *priorCode, float *postCode, int priorCodeLength, float sd) { return CODER(c)->test(priorCode, postCode, priorCodeLength, sd); }
+int myldpc_getPriorCodeLength(myldpc_coder *c, int srcLength) { return CODER(c)->getPriorCodeLength(srcLength); }
+int myldpc_getPostCodeLength(myldpc_coder *c, int srcLength) { return CODER(c)->getPostCodeLength(srcLength); }
+int myldpc_getCodeSize(myldpc_coder *c, int srcLength) { return CODER(c)->getCodeSize(srcLength); }
+int myldpc_checkMatrix(myldpc_coder *c, int *rows, int *cols, int *nnz, int *rowPtr, int *colIdx) {
+    const CheckMatrixCSR &m = CODER(c)->checkMatrix;
+    if (rows) *rows = m.rows();
+    if (cols) *cols = m.cols();
+    if (nnz) *nnz = m.nonZeros();
+    if (rowPtr) std::memcpy(rowPtr, m.outerIndexPtr(), sizeof(int) * (size_t)(m.rows() + 1));
+    if (colIdx) std::memcpy(colIdx, m.innerIndexPtr(), sizeof(int) * (size_t)m.nonZeros());
+    return LDPC_SUCCESS;
+}
+int myldpc_setMaxIter(myldpc_coder *c, int times) { return CODER(c)->setMaxIter(times); }
+int myldpc_setDevices(myldpc_coder *c, const int *deviceIds, int count) { return CODER(c)->setDevices(deviceIds, count); }
+int myldpc_setEarlyTermination(myldpc_coder *c, int on) { return CODER(c)->setEarlyTermination(on != 0); }
+int myldpc_setStrictDecodeType(myldpc_coder *c, int strict) { return CODER(c)->setStrictDecodeType(strict != 0); }
+int myldpc_lastAlgorithm(myldpc_coder *c) { return CODER(c)->lastAlgorithm(); }
+const int *myldpc_lastIterations(myldpc_coder *c) { return CODER(c)->lastIterations(); }
+int myldpc_lastCodeSize(myldpc_coder *c) { return CODER(c)->lastCodeSize(); }
+const char *myldpc_lastError(myldpc_coder *c) { return CODER(c)->lastError(); }
+int myldpc_lastStepTimes(myldpc_coder *c, double *seconds, int n) { return CODER(c)->lastStepTimes(seconds, n); }
+#undef CODER
 }

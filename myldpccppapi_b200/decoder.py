@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 from . import lib as _lib
-from .lib import Info, LdpcError, check
+from .lib import Info, LdpcError, Timing, check
 
 # enum rate_type / decodeType, reference MyLdpc.h:33-39
 rate_1_2, rate_2_3_a, rate_2_3_b, rate_3_4_a, rate_3_4_b, rate_5_6 = range(6)
@@ -109,6 +109,15 @@ class Decoder:
         inf = Info()
         check(self._L.ldpc_b200_get_info(self._h, C.byref(inf)))
         return inf.asdict()
+
+    def timing(self, reset: bool = False) -> dict:
+        """Phase timers of decode_host accumulated so far (ldpc_b200_get_timing): calls, codewords, wall_s, h2d_s,
+        kernel_s, d2h_s."""
+        t = Timing()
+        check(self._L.ldpc_b200_get_timing(self._h, C.byref(t)))
+        if reset:
+            check(self._L.ldpc_b200_reset_timing(self._h))
+        return t.asdict()
 
     @property
     def launches(self) -> int:
@@ -222,96 +231,141 @@ def synth_llr(ncw: int, N: int, sigma: float, seed: int, device: int = 0, bits=N
 
 
 class Coder:
-    """Python mirror of the reference's `class Coder` decode interface (MyLdpc.h:104-129).
+    """ctypes binding of the drop-in C++ `class Coder` (include/MyLdpc.h, libmyldpc_b200.so) through its C doorway
+    include/MyLdpc_c.h -- same method names, argument meaning and return values as the reference's Coder
+    (MyLdpc.h:104-129).  There is ONE implementation of the Coder logic (csrc/mycoder.cpp); this class only marshals.
 
     coder = Coder(ldpcK, ldpcN, rate); coder.forDecoder(batchSize); coder.addDecodeType(DecodeMS)
-    coder.decode(postCode, srcCode, srcLength, DecodeMS)
+    coder.decode(postCode, srcCode, srcLength, DecodeMS)      # -> 0 like the reference
 
-    Every decodeType is served by the CUDA min-sum decoder with Coder::decodeCPU's semantics
-    (DecodeCPU included: there is no CPU path in this package).  Returns 0 like the reference.
-    Additive: from_csr() for arbitrary H, setMaxIter(), lastIterations.
+    DecodeSP runs the sum-product kernel, DecodeTDMP / DecodeTDMPCL the layered kernel, DecodeCPU / DecodeMS /
+    DecodeMSCL flooding min-sum with Coder::decodeCPU's semantics (DecodeMSCL with the reference kernel's cap of 120);
+    there is no CPU path.  Additive: from_csr(), setMaxIter(), setDevices(), setStrictDecodeType(), lastIterations,
+    lastAlgorithm, lastStepTimes.
     """
 
-    def __init__(self, ldpcK: int, ldpcN: int, rate: int, device: int = 0):
-        self.ldpcK, self.ldpcN, self.ldpcM, self.rate = ldpcK, ldpcN, ldpcN - ldpcK, rate
+    def __init__(self, ldpcK: int, ldpcN: int, rate: int, device: int = 0, _csr=None):
+        self._L = _lib.load_coder()
+        self.ldpcK, self.ldpcN = int(ldpcK), int(ldpcN)
+        if _csr is None:
+            self.ldpcM, self.rate = self.ldpcN - self.ldpcK, int(rate)
+            self._c = self._L.myldpc_coder_new(self.ldpcK, self.ldpcN, self.rate)
+        else:
+            M, rp, ci = _csr
+            self.ldpcM, self.rate = int(M), None
+            rp = np.ascontiguousarray(rp, dtype=np.int32)
+            ci = np.ascontiguousarray(ci, dtype=np.int32)
+            self._c = self._L.myldpc_coder_new_csr(self.ldpcM, self.ldpcN, self.ldpcK, rp.ctypes.data, ci.ctypes.data)
+        if not self._c:
+            raise LdpcError(-4, "Coder construction failed")
         self.device = device
-        self.times = 40  # reference MyLdpc.cpp:24
-        self.row_ptr, self.col_idx, M = wimax_csr(ldpcK, ldpcN, rate)
-        assert M == self.ldpcM
-        self._z = ldpcN // 24  # rows per layer of the layered decoder = z, reference MyLdpc.cpp:22
-        self.batchSize = 0
-        self._dec: Optional[Decoder] = None
+        if device != 0:
+            self.setDevices([device])
         self.lastIterations = None
 
     @classmethod
     def from_csr(cls, M: int, N: int, K: int, row_ptr, col_idx, device: int = 0) -> "Coder":
-        self = cls.__new__(cls)
-        self.ldpcK, self.ldpcN, self.ldpcM, self.rate = K, N, M, None
-        self.device = device
-        self.times = 40
-        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
-        self.col_idx = np.ascontiguousarray(col_idx, dtype=np.int32)
-        self._z = 0
-        self.batchSize = 0
-        self._dec = None
-        self.lastIterations = None
-        return self
+        return cls(K, N, -1, device=device, _csr=(M, row_ptr, col_idx))
 
-    # reference MyLdpc.cpp:167-305
+    def close(self) -> None:
+        if getattr(self, "_c", None):
+            self._L.myldpc_coder_free(self._c)
+            self._c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc != 0:
+            raise LdpcError(rc, self.lastError())
+        return rc
+
+    @property
+    def checkMatrix(self):
+        """(row_ptr, col_idx) of the public member checkMatrix (MyLdpc.h:128)."""
+        rows, cols, nnz = C.c_int(), C.c_int(), C.c_int()
+        self._L.myldpc_checkMatrix(self._c, C.byref(rows), C.byref(cols), C.byref(nnz), None, None)
+        rp = np.zeros(rows.value + 1, dtype=np.int32)
+        ci = np.zeros(nnz.value, dtype=np.int32)
+        self._L.myldpc_checkMatrix(self._c, None, None, None, rp.ctypes.data, ci.ctypes.data)
+        return rp, ci
+
+    # reference MyLdpc.cpp:137-165 / :167-305 / :307-552
+    def forEncoder(self) -> int:
+        return self._check(self._L.myldpc_forEncoder(self._c))
+
     def forDecoder(self, batchSize: int) -> int:
-        self.batchSize = int(batchSize)
-        self._dec = Decoder(self.ldpcM, self.ldpcN, self.ldpcK, self.row_ptr, self.col_idx, device=self.device,
-                            max_iter=self.times)
-        if self._z:
-            self._dec.set_layer_height(self._z)  # z, reference MyLdpc.cpp:22
-        return 0
+        return self._check(self._L.myldpc_forDecoder(self._c, int(batchSize)))
 
-    # reference MyLdpc.cpp:307-552
     def addDecodeType(self, deType: int) -> int:
-        if self._dec is None:
-            raise LdpcError(-1, "forDecoder must be called before addDecodeType")
-        if self.batchSize > 0:
-            self._dec.reserve(self.batchSize)
-        return 0
+        return self._check(self._L.myldpc_addDecodeType(self._c, int(deType)))
 
-    def setMaxIter(self, times: int) -> None:
-        self.times = int(times)
-        if self._dec is not None:
-            self._dec.set_max_iter(self.times)
+    # [B200] additive
+    def setMaxIter(self, times: int) -> int:
+        return self._check(self._L.myldpc_setMaxIter(self._c, int(times)))
+
+    def setDevices(self, devices) -> int:
+        d = np.ascontiguousarray(list(devices), dtype=np.int32)
+        return self._check(self._L.myldpc_setDevices(self._c, d.ctypes.data, d.size))
+
+    def setEarlyTermination(self, on: bool) -> int:
+        return self._check(self._L.myldpc_setEarlyTermination(self._c, 1 if on else 0))
+
+    def setStrictDecodeType(self, strict: bool) -> int:
+        return self._check(self._L.myldpc_setStrictDecodeType(self._c, 1 if strict else 0))
+
+    @property
+    def lastAlgorithm(self) -> int:
+        return int(self._L.myldpc_lastAlgorithm(self._c))
+
+    def lastError(self) -> str:
+        return (self._L.myldpc_lastError(self._c) or b"").decode("utf-8", "replace")
+
+    def lastStepTimes(self) -> dict:
+        t = (C.c_double * 4)()
+        n = self._L.myldpc_lastStepTimes(self._c, t, 4)
+        return dict(zip(("wall_s", "h2d_s", "kernel_s", "d2h_s"), list(t)[:n]))
 
     # reference MyLdpc.cpp:620-631
     def getCodeSize(self, srcLength: int) -> int:
-        return (srcLength + (self.ldpcK // 8) - 1) // (self.ldpcK // 8)
+        return int(self._L.myldpc_getCodeSize(self._c, int(srcLength)))
 
     def getPostCodeLength(self, srcLength: int) -> int:
-        return self.getCodeSize(srcLength) * self.ldpcN
+        return int(self._L.myldpc_getPostCodeLength(self._c, int(srcLength)))
 
     def getPriorCodeLength(self, srcLength: int) -> int:
-        return self.getCodeSize(srcLength) * (self.ldpcN // 8)
+        return int(self._L.myldpc_getPriorCodeLength(self._c, int(srcLength)))
+
+    # reference MyLdpc.cpp:554-569
+    def encode(self, srcCode, priorCode, srcLength: int) -> int:
+        src = np.ascontiguousarray(srcCode, dtype=np.uint8)
+        if priorCode.dtype != np.uint8 or priorCode.size < self.getPriorCodeLength(srcLength):
+            raise ValueError("priorCode must be a uint8 array of getPriorCodeLength(srcLength) bytes")
+        return self._check(self._L.myldpc_encode(self._c, src.ctypes.data, priorCode.ctypes.data, int(srcLength)))
+
+    # reference MyLdpc.cpp:1061-1078 (rand()-based Box-Muller: seed it with libc srand)
+    def test(self, priorCode, postCode, priorCodeLength: int, sd: float) -> int:
+        pr = np.ascontiguousarray(priorCode, dtype=np.uint8)
+        if postCode.dtype != np.float32 or postCode.size < 8 * priorCodeLength:
+            raise ValueError("postCode must be a float32 array of 8 * priorCodeLength values")
+        return self._check(self._L.myldpc_test(self._c, pr.ctypes.data, postCode.ctypes.data, int(priorCodeLength), float(sd)))
 
     # reference MyLdpc.cpp:571-618 (+ :684-784 for the semantics)
     def decode(self, postCode, srcCode, srcLength: int, deType: int = DecodeMS) -> int:
-        if self._dec is None:
-            raise LdpcError(-1, "forDecoder must be called before decode")
-        codeSize = self.getCodeSize(srcLength)
+        """postCode: host float32 array / CPU tensor of getPostCodeLength(srcLength) values; srcCode: writable uint8
+        buffer of at least srcLength bytes.  Returns 0, or raises LdpcError with the C++ Coder's code and message."""
         y = _as_host_array(postCode, np.float32)
-        if _numel(y) < codeSize * self.ldpcN:
+        if _numel(y) < self.getPostCodeLength(srcLength):
             raise ValueError("postCode shorter than getPostCodeLength(srcLength)")
-        yy = y.reshape(-1)[: codeSize * self.ldpcN]
-        # DecodeSP -> sum-product kernel, DecodeTDMP / DecodeTDMPCL -> layered min-sum kernel, where the code
-        # fits them; otherwise (and for DecodeCPU / DecodeMS / DecodeMSCL) flooding min-sum with
-        # Coder::decodeCPU semantics
-        alg = {DecodeSP: 1, DecodeTDMP: 2, DecodeTDMPCL: 2}.get(deType, 0)
-        try:
-            self._dec.set_algorithm(alg)
-            res = self._dec.decode_host(yy)
-        except LdpcError as e:
-            if alg == 0 or e.code != -3:
-                raise
-            self._dec.set_algorithm(0)
-            res = self._dec.decode_host(yy)
-        flat = res["info"].reshape(-1)[:srcLength]
         dst = np.frombuffer(srcCode, dtype=np.uint8) if not isinstance(srcCode, np.ndarray) else srcCode.view(np.uint8)
-        dst[:srcLength] = flat
-        self.lastIterations = res["iters"]
+        if dst.size < srcLength or not dst.flags.c_contiguous:
+            raise ValueError("srcCode must be a contiguous buffer of at least srcLength bytes")
+        rc = self._L.myldpc_decode(self._c, _host_ptr(y), dst.ctypes.data, int(srcLength), int(deType))
+        if rc != 0:
+            raise LdpcError(rc, self.lastError())
+        n = int(self._L.myldpc_lastCodeSize(self._c))
+        self.lastIterations = np.ctypeslib.as_array(self._L.myldpc_lastIterations(self._c), shape=(n,)).copy()
         return 0

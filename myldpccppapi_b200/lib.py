@@ -38,6 +38,14 @@ class Info(C.Structure):
         return d
 
 
+class Timing(C.Structure):
+    _fields_ = [("calls", C.c_int64), ("codewords", C.c_int64), ("wall_s", C.c_double), ("h2d_s", C.c_double),
+                ("kernel_s", C.c_double), ("d2h_s", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _vp, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
 _pi = C.POINTER(C.c_int)
 
@@ -65,6 +73,8 @@ SIGNATURES = {
     "ldpc_b200_edge_tables": (_i, [_i, _i, _vp, _vp, _vp, _vp, _pi, _pi]),
     "ldpc_b200_probe_smem_bandwidth": (_i, [_i, C.POINTER(C.c_double)]),
     "ldpc_b200_launch_count": (_i64, [_vp]),
+    "ldpc_b200_get_timing": (_i, [_vp, C.POINTER(Timing)]),
+    "ldpc_b200_reset_timing": (_i, [_vp]),
     "ldpc_b200_last_error": (C.c_char_p, []),
     "ldpc_b200_version": (C.c_char_p, []),
 }
@@ -93,6 +103,58 @@ def load() -> C.CDLL:
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+# name -> (restype, argtypes) of include/MyLdpc_c.h (libmyldpc_b200.so)
+_pint = C.POINTER(C.c_int)
+CODER_SIGNATURES = {
+    "myldpc_coder_new": (_vp, [_i, _i, _i]),
+    "myldpc_coder_new_csr": (_vp, [_i, _i, _i, _vp, _vp]),
+    "myldpc_coder_free": (None, [_vp]),
+    "myldpc_forEncoder": (_i, [_vp]),
+    "myldpc_forDecoder": (_i, [_vp, _i]),
+    "myldpc_addDecodeType": (_i, [_vp, _i]),
+    "myldpc_encode": (_i, [_vp, _vp, _vp, _i]),
+    "myldpc_decode": (_i, [_vp, _vp, _vp, _i, _i]),
+    "myldpc_test": (_i, [_vp, _vp, _vp, _i, _f]),
+    "myldpc_getPriorCodeLength": (_i, [_vp, _i]),
+    "myldpc_getPostCodeLength": (_i, [_vp, _i]),
+    "myldpc_getCodeSize": (_i, [_vp, _i]),
+    "myldpc_checkMatrix": (_i, [_vp, _pint, _pint, _pint, _vp, _vp]),
+    "myldpc_setMaxIter": (_i, [_vp, _i]),
+    "myldpc_setDevices": (_i, [_vp, _vp, _i]),
+    "myldpc_setEarlyTermination": (_i, [_vp, _i]),
+    "myldpc_setStrictDecodeType": (_i, [_vp, _i]),
+    "myldpc_lastAlgorithm": (_i, [_vp]),
+    "myldpc_lastIterations": (C.POINTER(C.c_int32), [_vp]),
+    "myldpc_lastCodeSize": (_i, [_vp]),
+    "myldpc_lastError": (C.c_char_p, [_vp]),
+    "myldpc_lastStepTimes": (_i, [_vp, C.POINTER(C.c_double), _i]),
+}
+_CODER_LIB = None
+
+
+def coder_header_symbols() -> list[str]:
+    text = (_build.ROOT / "include" / "MyLdpc_c.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(myldpc_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def load_coder() -> C.CDLL:
+    """Load (building if needed) libmyldpc_b200.so, the drop-in C++ Coder, through its C doorway."""
+    global _CODER_LIB
+    if _CODER_LIB is None:
+        load()
+        so = _build.build_coder()
+        if not so.exists():
+            raise RuntimeError("libmyldpc_b200.so is missing and could not be built")
+        L = C.CDLL(str(so))
+        for name, (res, args) in CODER_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _CODER_LIB = L
+    return _CODER_LIB
 
 
 def check(rc: int) -> None:

@@ -19,6 +19,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), "libldpc_b200.so does not export " + n
     assert set(names) == set(lib.SIGNATURES), "lib.py signatures out of sync with include/ldpc_b200.h"
     assert b"sm_100a" in L.ldpc_b200_version()
+    # the drop-in C++ Coder's C doorway (include/MyLdpc_c.h, libmyldpc_b200.so)
+    LC = lib.load_coder()
+    cnames = lib.coder_header_symbols()
+    assert len(cnames) >= 20
+    for n in cnames:
+        assert hasattr(LC, n), "libmyldpc_b200.so does not export " + n
+    assert set(cnames) == set(lib.CODER_SIGNATURES), "lib.py signatures out of sync with include/MyLdpc_c.h"
 
 
 def test_library_is_sm_100a_only():

@@ -68,7 +68,7 @@ def build_cuda(force: bool = False, verbose: bool = False, ptxas_info: bool = Fa
         if only and name not in only and obj.exists():
             continue
         if force or _stale(obj, [CSRC / src] + hdrs):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-split-compile", "2", "-I", str(ROOT / "include"), *defs, "-c", str(CSRC / src), "-o", str(obj)]
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), *defs, "-c", str(CSRC / src), "-o", str(obj)]
             if ptxas_info:
                 cmd += ["-Xptxas", "-v"]
             jobs.append((name, cmd))

@@ -244,6 +244,7 @@ def main() -> None:
     ap.add_argument("--max-iter", type=int, default=None, help="override the workload's iteration cap")
     ap.add_argument("--path", type=int, default=-1, help="force a kernel path (see ldpc_b200.h)")
     ap.add_argument("--algorithm", type=int, default=0, help="0 min-sum, 1 sum-product, 2 layered (LDPC_B200_ALG_*)")
+    ap.add_argument("--option", action="append", default=[], help="name=value for ldpc_b200_set_option (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline only: no sustained / workloads / plugin / setdevices legs")
@@ -372,6 +373,9 @@ def main() -> None:
             dec.set_path(forced_path)
         if alg:
             dec.set_algorithm(alg)
+        for kv in args.option:
+            name, _, val = kv.partition("=")
+            dec.set_option(name, int(val))
         info = dec.info()
         llr = m.synth_llr(ncw, N, sigma, seed=0x4C445043 + rank, device=local_rank)  # every rank: its own seeded shard
         out = {}

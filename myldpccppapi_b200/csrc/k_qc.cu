@@ -18,16 +18,40 @@ int launch_qc_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+template <class P>
+int launch_qc_ring_t(const QcParams& q, int grid, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_qc_ring_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ldpc_ms_qc_ring_kernel<P><<<grid, P::W * 32, smem, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+// resident CTAs per SM of the ring kernel with `smem` bytes of dynamic shared memory (0 if it cannot launch)
+template <class P>
+int ring_ctas_per_sm(size_t smem) {
+    if (cudaFuncSetAttribute(ldpc_ms_qc_ring_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ldpc_ms_qc_ring_kernel<P>, P::W * 32, smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
 int upload_bank(int slot, const void* tab, size_t bytes) {
     if (slot < 0 || slot >= kQcTabSlots || bytes > (size_t)kQcBankBytes) return (int)cudaErrorInvalidValue;
     return (int)cudaMemcpyToSymbol(g_qc_bank, tab, bytes, (size_t)slot * kQcBankBytes, cudaMemcpyHostToDevice);
 }
 
-#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank}
+#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank, &launch_qc_ring_t<T<Z, G, W>>, &ring_ctas_per_sm<T<Z, G, W>>}
 const QcProfileEntry kTable[] = {
     QC_PROFILE(LDPC_QC_RATE, 24, 8, 12), QC_PROFILE(LDPC_QC_RATE, 48, 4, 12), QC_PROFILE(LDPC_QC_RATE, 96, 2, 12),
     QC_PROFILE(LDPC_QC_RATE, 40, 4, 10), QC_PROFILE(LDPC_QC_RATE, 80, 2, 10),
     QC_PROFILE(LDPC_QC_RATE, 32, 4, 8),  QC_PROFILE(LDPC_QC_RATE, 64, 2, 8),
+    QC_PROFILE(LDPC_QC_RATE, 24, 4, 6),  // experiment (option qc_prefer_g = 4): half-size CTAs, three per SM
 };
 #undef QC_PROFILE
 

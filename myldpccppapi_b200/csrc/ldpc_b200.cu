@@ -60,10 +60,10 @@ constexpr int kCounterRing = 256;  // one work-queue head per in-flight launch
 // decode path calls getenv.
 struct Options {
     // kernel choice: read when a plan is made
-    bool no_qc = false, no_qcg = false, qc_generic = false;
+    bool no_qc = false, no_qcg = false, qc_generic = false, qc_ring = false;
     bool grp_no_profile = false, grp_no_ysmem = false, grp_prefer_16 = false, grp_t16 = false, grp_no_t16 = false;
     bool debug_placement = false;
-    int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0;
+    int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0, qc_prefer_g = 0;
     long long place_effort = 12;
     // launch / host pipeline: read per call
     int refill_wait = 1;              // measured: profiles/r01_refill_sweep.txt
@@ -77,14 +77,14 @@ struct Options {
 struct OptionName { const char* name; int kind; size_t off; };  // kind 0 bool, 1 int, 2 long long
 #define OPT(n, k) {#n, k, offsetof(Options, n)}
 const OptionName kOptionNames[] = {
-    OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
+    OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
-    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(place_effort, 2), OPT(refill_wait, 1), OPT(no_streamed, 0),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2), OPT(refill_wait, 1), OPT(no_streamed, 0),
     OPT(streamed_pageable, 0), OPT(no_staged, 0), OPT(staged_min_kb, 2), OPT(stream_chunk, 2), OPT(stream_batch_kb, 2),
     OPT(wait_timeout_ms, 2),
 };
 #undef OPT
-constexpr int kFirstRuntimeOption = 15;  // refill_wait and everything after it may change after create
+constexpr int kFirstRuntimeOption = 17;  // refill_wait and everything after it may change after create
 
 void option_store(Options* o, const OptionName& n, long long v) {
     char* p = reinterpret_cast<char*>(o) + n.off;
@@ -169,6 +169,8 @@ struct ldpc_b200_decoder {
     int qc_state = 0;  // 0 = not tried, 1 = tables built and uploaded, -1 = no match / no free slot
     int qc_slot = -1;
     size_t qc_smem = 0;
+    size_t qc_ring_smem = 0;  // dynamic shared memory of the ring kernel (0: not usable for this profile)
+    int qc_ring_per_sm = 0;
     // QC tables with a run-time profile (ldpc_qcg.cuh)
     QcgParams qcg;
     QcgWarpTab qcg_tab[kQcgMaxW];
@@ -1178,6 +1180,7 @@ bool qc_prepare(ldpc_b200_decoder* h) {
     for (int k = 0; k < (int)profiles.size(); ++k) {
         const QcProfileEntry& pe = profiles[k];
         if (t.M % pe.z || t.N % pe.z) continue;
+        if (h->opt.qc_prefer_g ? pe.G != h->opt.qc_prefer_g : (pe.z == 24 && pe.G == 4)) continue;  // (24, 4, 6) only on request
         if (rows_z != pe.z) { rows.clear(); rows_z = pe.z; if (!qc_blocks(t, pe.z, &rows)) rows.clear(); }
         if (rows.empty()) continue;
         if (!pe.build(t, rows, &h->qc, &tab, &h->qc_smem)) continue;
@@ -1588,6 +1591,19 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
         // (the kernel's launch bounds allow three CTAs per SM up to 288 threads)
         const int qc_per_sm = fits && qc_profiles()[h->qc_kind].W * 32 <= 288 && 3 * (h->qc_smem + 2048) <= h->smem_optin + 1024 ? 3 : 2;
         if (fits) {
+            // the ring kernel (refill off the critical path) needs a staging ring of G/2 codewords on top: used when as
+            // many CTAs stay resident
+            const QcProfileEntry& pe = qc_profiles()[h->qc_kind];
+            const uint32_t ring_off = (uint32_t)((h->qc_smem + 127) & ~(size_t)127);
+            const uint32_t ring_bytes = (uint32_t)std::max(1, pe.G / 2) * (uint32_t)t.N * 4u;
+            h->qc.ring_off = ring_off;
+            h->qc_ring_smem = 0;
+            if (h->opt.qc_ring) {  // opt-in: measured slower than the loop-top refill (profiles/r02_ring_kernel.md)
+                DeviceGuard guard(h->device);
+                const size_t need = (size_t)ring_off + ring_bytes;
+                const int n = guard.ok ? pe.ring_ctas_per_sm(need) : 0;
+                if (n >= qc_per_sm) { h->qc_ring_smem = need; h->qc_ring_per_sm = n; }
+            }
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
             pl.threads = 32 * qc_profiles()[h->qc_kind].W;
@@ -1827,7 +1843,11 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
-        rc = launch_status(qc_profiles()[h->qc_kind].launch(q, grid, pl.smem, stream), "quasi-cyclic");
+        // ring kernel unless its bulk copies cannot be used (channel values not 16-byte aligned)
+        if (h->qc_ring_smem && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0)
+            rc = launch_status(qc_profiles()[h->qc_kind].launch_ring(q, grid, h->qc_ring_smem, stream), "quasi-cyclic (ring)");
+        else
+            rc = launch_status(qc_profiles()[h->qc_kind].launch(q, grid, pl.smem, stream), "quasi-cyclic");
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;

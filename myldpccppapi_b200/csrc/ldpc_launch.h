@@ -52,6 +52,10 @@ struct QcProfileEntry {
     bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, QcParams*, std::vector<unsigned char>*, size_t*);
     int (*launch)(const QcParams&, int grid, size_t smem, cudaStream_t stream);
     int (*upload)(int slot, const void* tab, size_t bytes);
+    // the same profile with the refill off the critical path (ldpc_ms_qc_ring_kernel): needs extra shared memory for
+    // the staging ring and the hard-bit table; ring_ctas_per_sm = resident CTAs with that much (current device)
+    int (*launch_ring)(const QcParams&, int grid, size_t smem, cudaStream_t stream);
+    int (*ring_ctas_per_sm)(size_t smem);
 };
 // one table per 802.16e rate (k_qc.cu compiled with -DLDPC_QC_RATE=...)
 const QcProfileEntry* qc_profiles_34B(int* n);

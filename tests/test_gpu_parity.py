@@ -262,6 +262,40 @@ def test_qc_runtime_profile_kernel(default_code, monkeypatch):
             assert_parity(_run_device(d2, y), r2, NN, what="N=%d rate %s forced=%s (%s)" % (NN, name, forced, i2["path_name"]))
 
 
+@pytest.mark.parametrize("env", [{"LDPC_B200_QC_RING": "1"}, {"LDPC_B200_QC_PREFER_G": "4"}, {"LDPC_B200_QC_RING": "1", "LDPC_B200_QC_PREFER_G": "4"}])
+def test_qc_alternative_kernels(default_code, monkeypatch, env):
+    """The opt-in variants of the quasi-cyclic path (profiles/r02_ring_kernel.md): the ring kernel (codewords staged by
+    bulk asynchronous copies behind mbarriers, refill off the loop top) and the half-size-CTA profile (24, 4, 6).  Bits,
+    counts and posteriors of the oracle on the device path, the streamed host path and tiny batches."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    c = default_code
+    N = c["N"]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)   # plan-time switches: read once, at create
+    llr = np.concatenate([awgn_llr(900, N, 0.62, seed=61), awgn_llr(1200, N, 0.5, seed=62), awgn_llr(301, N, 1.0, seed=63)])
+    ref = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40).decode(llr, literal=False)
+    dec = m.Decoder.wimax(c["K"], N, c["rate"])
+    inf = dec.info()
+    assert inf["path_name"] == "qc" and inf["codewords_per_cta"] == (4 if "LDPC_B200_QC_PREFER_G" in env else 8)
+    assert_parity(_run_device(dec, llr), ref, N, what="device")
+    pinned = torch.from_numpy(llr).pin_memory().numpy()
+    assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
+    dec.set_option("stream_chunk", 8)
+    assert_parity(dec.decode_host(pinned[:700], want_hard=True, want_post=True), tuple(r[:700] for r in ref), N, what="streamed, tiny chunks")
+    dec.set_option("stream_chunk", 0)
+    for n in (1, 5, 9, 2401):
+        assert_parity(_run_device(dec, llr[:n]), tuple(r[:n] for r in ref), N, what="%d words" % n)
+    dec.set_early_termination(False)
+    dec.set_max_iter(7)
+    ref7 = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=7).decode(llr[:500], literal=False)
+    out = _run_device(dec, llr[:500])
+    assert np.array_equal(out["iters"], np.full(500, 7))
+    # without early termination every word runs the cap: bits are those of the capped oracle for the words it did not stop early
+    late = ref7[1] == 7
+    assert np.array_equal(out["info"][late], ref7[0][late])
+
+
 def test_streamed_host_pipeline(default_code):
     """Host buffers on the quasi-cyclic path: one persistent launch fed by a copy stream.  Ragged sizes, pageable and
     pinned inputs, optional outputs asked for only on a later call, several launches per call (small batch cap) and

@@ -1,0 +1,13 @@
+#!/usr/bin/env python3
+"""One-screen summary of a bench.py JSON line (tools/bench_summary.py file.json)."""
+import json, sys
+d = json.load(open(sys.argv[1]))
+print("headline: %.3f Gbit/s  %.3f ms/step  frac %.3f  clocks %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["clocks"]))
+if d.get("sustained"): print("sustained: %.3f Gbit/s over %.2f s  %s" % (d["sustained"]["value"], d["sustained"]["seconds"], d["sustained"]["clocks"]))
+if d.get("e2e"): e = d["e2e"]; print("e2e: %.3f Gbit/s %.3f ms  phases %s  h2d/gpu %s  per-rank ms %s" % (e["value"], e["ms_per_step"], {k: round(v, 3) for k, v in e["phase_ms_per_step"].items()}, e["h2d_gbs_per_gpu"], e.get("ms_per_step_per_rank")))
+if d.get("e2e_plugin"): p = d["e2e_plugin"]; print("plugin: %.3f Gbit/s %.3f ms  first %.2f ms  setup %.1f ms  match %s" % (p["value"], p["ms_per_step"], p["first_call_ms"], p["setup_ms"], p["bytes_match_device_path"]))
+for k, v in (d.get("workloads") or {}).items():
+    if "error" in v: print(k, "ERROR", v["error"]); continue
+    print("%s: %.3f Gbit/s  %.3f ms  iters %.2f  frac %.3f (%s)  %s  oracle %s" % (k, v["value"], v["ms_per_step"], v["mean_iterations"], v["roofline"]["frac"], v["roofline"]["bound"], v["clocks"], v["gpu_matches_oracle_all_ranks"]))
+print("parity_all_ranks:", d.get("parity_all_ranks", {}).get("ok"), " setdevices:", d.get("setdevices"))
+print("cpu_baseline:", d.get("cpu_baseline"))

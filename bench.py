@@ -274,6 +274,9 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    # CPU-side barrier (gloo) for the leg in which rank 0 alone drives every GPU: ranks parked in an NCCL barrier would
+    # keep a spinning kernel on the very GPUs rank 0 is timing
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -535,7 +538,8 @@ def main() -> None:
     # ---- one process, all N GPUs through Coder::setDevices (rank 0 drives; the other ranks wait)
     setdev = None
     if world > 1 and not (args.no_extras or args.no_e2e) and args.workload in ("cfg1", "cfg2", "cfg4") and args.algorithm == 0:
-        barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             try:
                 tot = ncw * world
@@ -563,7 +567,7 @@ def main() -> None:
                 coder.close()
             except Exception as e:
                 setdev = {"error": "%s: %s" % (type(e).__name__, e)}
-        barrier()
+        dist.barrier(group=cpu_group)
     sampler.stop()
 
     if rank != 0:

@@ -1,6 +1,7 @@
 // k_misc.cu -- instantiations of the alternative / fallback kernels: sub-warp per check (ldpc_warp.cuh), one codeword
 // per 8-CTA cluster (ldpc_cluster.cuh), lane = codeword with compressed check state (ldpc_kernels.cuh: lane16) and the
-// long-code kernel with its messages in a global workspace (ldpc_stream.cuh).
+// long-code kernel with its messages in a global workspace (ldpc_stream.cuh); sum-product and layered min-sum for codes
+// of any size (ldpc_big.cuh).
 #include <algorithm>
 
 #include "ldpc_launch.h"
@@ -8,6 +9,8 @@
 #include "ldpc_cluster.cuh"
 #include "ldpc_stream.cuh"
 #include "ldpc_warp.cuh"
+#define LDPC_B200_BIG_KERNELS
+#include "ldpc_big.cuh"
 
 namespace ldpc_b200 {
 namespace {
@@ -65,6 +68,16 @@ int k_launch_cluster(int dmax, const ClusterParams& q, int nclusters_wanted, int
 
 int k_launch_lane16(const Lane16Params& q, int grid, int threads, size_t smem, cudaStream_t stream) {
     return threads <= 768 ? launch_lane16_t<768>(q, grid, threads, smem, stream) : launch_lane16_t<1024>(q, grid, threads, smem, stream);
+}
+
+int k_launch_sp_big(const BigParams& q, int grid, cudaStream_t stream) {
+    ldpc_sp_big_kernel<<<grid, 512, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream) {
+    ldpc_tdmp_big_kernel<<<grid, 512, 0, stream>>>(q);
+    return (int)cudaGetLastError();
 }
 
 int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream) {

@@ -27,6 +27,7 @@
 #include "ldpc_warp.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
+#include "ldpc_big.cuh"
 #include "ldpc_stream.cuh"
 #include "ldpc_encode.cuh"
 #include "ldpc_tables.h"
@@ -62,7 +63,7 @@ struct Options {
     // kernel choice: read when a plan is made
     bool no_qc = false, no_qcg = false, qc_generic = false, qc_ring = false;
     bool grp_no_profile = false, grp_no_ysmem = false, grp_prefer_16 = false, grp_t16 = false, grp_no_t16 = false;
-    bool debug_placement = false;
+    bool debug_placement = false, sp_big = false;  // sp_big: sum-product through the any-size kernel even where the on-chip one fits (tests)
     int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0, qc_prefer_g = 0;
     long long place_effort = 12;
     // launch / host pipeline: read per call
@@ -78,13 +79,13 @@ struct OptionName { const char* name; int kind; size_t off; };  // kind 0 bool, 
 #define OPT(n, k) {#n, k, offsetof(Options, n)}
 const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
-    OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
+    OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2), OPT(refill_wait, 1), OPT(no_streamed, 0),
     OPT(streamed_pageable, 0), OPT(no_staged, 0), OPT(staged_min_kb, 2), OPT(stream_chunk, 2), OPT(stream_batch_kb, 2),
     OPT(wait_timeout_ms, 2),
 };
 #undef OPT
-constexpr int kFirstRuntimeOption = 17;  // refill_wait and everything after it may change after create
+constexpr int kFirstRuntimeOption = 18;  // refill_wait and everything after it may change after create
 
 void option_store(Options* o, const OptionName& n, long long v) {
     char* p = reinterpret_cast<char*>(o) + n.off;
@@ -204,6 +205,10 @@ struct ldpc_b200_decoder {
     TdmpPlan tdmp;
     uint32_t* dt_cn_tab = nullptr;
     bool tdmp_ready = false;
+    bool tdmp_big = false;       // the code does not fit the on-chip layered layout: ldpc_tdmp_big_kernel
+    // sum-product / layered decoding of codes of any size (ldpc_big.cuh): CTA-private global workspace
+    float* d_ws_big = nullptr;
+    size_t ws_big_bytes = 0;
     uint8_t g_vdeg[kGrpMaxVS] = {0};
     uint8_t g_cdeg[kGrpMaxCS] = {0};
     int l16_vn_stride = 0;
@@ -1479,8 +1484,7 @@ int tdmp_plan(ldpc_b200_decoder* h) {
     if (z < 1) return fail(LDPC_B200_ERR_UNSUPPORTED, "layered decoding needs the layer height (ldpc_b200_set_layer_height)");
     if (t.M % z || t.N % z) return fail(LDPC_B200_ERR_UNSUPPORTED, "layer height must divide M and N");
     const int L = t.M / z, VS = t.N / z;
-    if (L > kTdmpMaxLayers || VS > 32 || t.max_row_weight > 20)
-        return fail(LDPC_B200_ERR_UNSUPPORTED, "layered decoding: at most 16 layers, N <= 32 z, check degree <= 20");
+    h->tdmp_big = false;
     {   // no column may appear twice inside a layer (the rows of a layer are updated concurrently)
         std::vector<int> seen(t.N, -1);
         for (int r = 0; r < t.M; ++r)
@@ -1490,7 +1494,9 @@ int tdmp_plan(ldpc_b200_decoder* h) {
             }
     }
     const int force_g = h->opt.tdmp_g;
+    const bool onchip_shape = L <= kTdmpMaxLayers && VS <= 32 && t.max_row_weight <= 20 && force_g != 32;  // (tdmp_g = 32 forces the any-size kernel: tests)
     for (int G : {4, 8, 16}) {
+        if (!onchip_shape) break;
         if (force_g && G != force_g) continue;
         const int SUB = 32 / G;
         if (z % SUB) continue;
@@ -1520,7 +1526,12 @@ int tdmp_plan(ldpc_b200_decoder* h) {
         const int warps = pl.ctas_per_sm * pl.W, bw = best.ok ? best.ctas_per_sm * best.W : -1;
         if (!best.ok || warps > bw || (warps == bw && pl.ctas_per_sm > best.ctas_per_sm)) best = pl;
     }
-    if (!best.ok) return fail(LDPC_B200_ERR_UNSUPPORTED, "code does not fit the layered shared-memory layout");
+    if (!best.ok) {  // does not fit on chip: the any-size kernel (messages in a global workspace) takes it
+        h->tdmp_big = true;
+        h->tdmp = TdmpPlan{};
+        h->tdmp.z = z;
+        return LDPC_B200_OK;
+    }
     h->tdmp = best;
     return LDPC_B200_OK;
 }
@@ -1552,8 +1563,48 @@ int upload_tdmp_tables(ldpc_b200_decoder* h) {
     return LDPC_B200_OK;
 }
 
+// Sum-product (layered = false) or layered min-sum of a code of any size: 32 codewords per CTA, lane = codeword, every
+// message in a CTA-private slice of a global workspace (ldpc_big.cuh).
+int launch_big(ldpc_b200_decoder* h, bool layered, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
+               int32_t* d_iters, float* d_post, cudaStream_t stream) {
+    const HostTables& t = h->host;
+    if (!layered && d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
+    const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
+    if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
+    const int grid = (int)std::min<int64_t>(ngroups, h->sm_count);
+    const size_t stride = layered ? ((size_t)t.N + t.nnz) * kLanes + (size_t)t.N + 32
+                                  : ((size_t)2 * t.nnz + (size_t)2 * t.N) * kLanes + (size_t)t.N + 32;
+    const size_t need = stride * sizeof(float) * (size_t)h->sm_count;
+    if (h->ws_big_bytes < need) {
+        CU_TRY(cudaDeviceSynchronize());
+        if (h->d_ws_big) { cudaFree(h->d_ws_big); h->d_ws_big = nullptr; h->ws_big_bytes = 0; }
+        CU_TRY(cudaMalloc(&h->d_ws_big, need));
+        h->ws_big_bytes = need;
+    }
+    unsigned long long* ctr64 = h->d_counters + h->counter_next;
+    h->counter_next = (h->counter_next + 1) % kCounterRing;
+    CU_TRY(cudaMemsetAsync(ctr64, 0, sizeof(unsigned long long), stream));
+    BigParams q;
+    q.row_ptr = h->d_row_ptr; q.cn_col = h->d_cn_col; q.col_ptr = h->d_col_ptr; q.vn_edge = h->d_vn_edge;
+    q.M = t.M; q.N = t.N; q.K = h->K; q.nnz = t.nnz;
+    q.max_iter = h->max_iter; q.early_term = h->early; q.z = h->layer_z;
+    q.llr = d_llr; q.ncw = ncw;
+    q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+    q.ws = h->d_ws_big; q.ws_stride = stride;
+    q.counter = reinterpret_cast<unsigned int*>(ctr64); q.ngroups = (int)ngroups;
+    // the workspace is shared by every launch of this handle: serialise launches on it
+    if (h->ws_event_valid) CU_TRY(cudaStreamWaitEvent(stream, h->ws_event, 0));
+    int rc = launch_status(layered ? k_launch_tdmp_big(q, grid, stream) : k_launch_sp_big(q, grid, stream), layered ? "layered (any size)" : "sum-product (any size)");
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(h->ws_event, stream));
+    h->ws_event_valid = true;
+    h->launches += 1;
+    return LDPC_B200_OK;
+}
+
 int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard, int32_t* d_iters,
                 float* d_post, cudaStream_t stream) {
+    if (h->tdmp_big) return launch_big(h, true, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     int rc = upload_tdmp_tables(h);
     if (rc) return rc;
     const HostTables& t = h->host;
@@ -1787,10 +1838,17 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         int rc = make_plan(h);
         if (rc) return rc;
     }
-    int rc = ensure_workspace(h);
-    if (rc) return rc;
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
+    if (h->algorithm == LDPC_B200_ALG_SUM_PRODUCT) {
+        // the on-chip kernel takes short codes (group layout with 8 or 16 words per CTA, variable degree <= 8, check degree
+        // <= 20); every other code goes to the any-size kernel -- DecodeSP never decodes with another algorithm
+        const bool onchip = pl.path == LDPC_B200_PATH_GROUP && pl.tab_smem && !pl.t16 && (pl.G == 8 || pl.G == 16) &&
+                            t.max_col_weight <= 8 && t.max_row_weight <= 20 && !h->opt.sp_big;
+        if (!onchip) return launch_big(h, false, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
+    }
+    int rc = ensure_workspace(h);
+    if (rc) return rc;
     const int per_group = (pl.path == LDPC_B200_PATH_GROUP || pl.path == LDPC_B200_PATH_QC) ? pl.G : (pl.path == LDPC_B200_PATH_WARP ? 1 : kLanes);
     const int64_t ngroups = (ncw + per_group - 1) / per_group;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
@@ -2088,7 +2146,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaFree(h->dt_cn_tab); cudaFree(h->de_xt);
             cudaFree(h->dw_cn_col); cudaFree(h->dw_vn_pos);
             cudaFree(h->ds_cn_tab); cudaFree(h->ds_vn_tab); cudaFree(h->ds_var_of_pos); cudaFree(h->ds_pos_of_var);
-            cudaFree(h->d_counters); cudaFree(h->d_ws);
+            cudaFree(h->d_counters); cudaFree(h->d_ws); cudaFree(h->d_ws_big);
             if (h->ws_event) cudaEventDestroy(h->ws_event);
         }
     }

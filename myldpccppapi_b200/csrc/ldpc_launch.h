@@ -26,6 +26,7 @@ struct ClusterParams;
 struct QcParams;
 struct QcgParams;
 struct TdmpParams;
+struct BigParams;
 
 // Which ldpc_ms_group_kernel instantiation a plan asks for (ldpc_b200.cu: Plan).
 struct GroupSel {
@@ -40,6 +41,8 @@ int k_launch_warp(int sw, const WarpParams& q, int grid, int threads, size_t sme
 int k_launch_cluster(int dmax, const ClusterParams& q, int nclusters_wanted, int threads, size_t smem, cudaStream_t stream);
 int k_launch_lane16(const Lane16Params& q, int grid, int threads, size_t smem, cudaStream_t stream);
 int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream);
+int k_launch_sp_big(const BigParams& q, int grid, cudaStream_t stream);    // any size, messages in a global workspace
+int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream);
 
 // Quasi-cyclic block structure of H for block size z: rows[br] = the circulants (block column, shift) of block
 // row br in ascending column order.

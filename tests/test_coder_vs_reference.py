@@ -113,7 +113,8 @@ def test_fused_min_sum_kernel_bytes_equal_the_reference(rate):
 
 
 def test_strict_decode_type_and_fallback_query():
-    """A code that does not fit the sum-product / layered layouts: by default decoded with flooding min-sum and
+    """DecodeSP on a code that does not fit the on-chip layout runs the any-size sum-product kernel (no fallback).
+    DecodeTDMP on a code without a layer structure cannot be layered: by default it is decoded with flooding min-sum and
     lastAlgorithm says so; strict mode returns LDPC_B200_ERR_UNSUPPORTED instead."""
     import myldpccppapi_b200 as m
     M, N, K, rp, ci = m.codes.regular_code()
@@ -122,13 +123,18 @@ def test_strict_decode_type_and_fallback_query():
     c.forDecoder(4)
     c.addDecodeType(SP)
     out = np.zeros(4 * K // 8 + 1, dtype=np.uint8)
+    o = oracle.Oracle(M, N, K, rp, ci, times=40)
     assert c.decode(y.reshape(-1), out, 4 * K // 8, SP) == 0
+    assert c.lastAlgorithm == 1
+    sp = oracle.decode_sp(o, y)
+    assert np.array_equal(out[:-1], sp[0].reshape(-1)) and np.array_equal(c.lastIterations, sp[1])
+    assert c.decode(y.reshape(-1), out, 4 * K // 8, TDMP) == 0
     assert c.lastAlgorithm == 0 and "min-sum" in c.lastError()
-    want = oracle.Oracle(M, N, K, rp, ci, times=40).decode(y, literal=False)[0]
+    want = o.decode(y, literal=False)[0]
     assert np.array_equal(out[:-1], want.reshape(-1))
     c.setStrictDecodeType(True)
     with pytest.raises(m.LdpcError) as e:
-        c.decode(y.reshape(-1), out, 4 * K // 8, SP)
+        c.decode(y.reshape(-1), out, 4 * K // 8, TDMP)
     assert e.value.code == -3
     assert c.decode(y.reshape(-1), out, 4 * K // 8, MS) == 0 and c.lastAlgorithm == 0
 

@@ -296,6 +296,68 @@ def test_qc_alternative_kernels(default_code, monkeypatch, env):
     assert np.array_equal(out["info"][late], ref7[0][late])
 
 
+@pytest.mark.parametrize("N,rate,name,num,den", [(1152, 4, "3/4B", 3, 4), (1632, 0, "1/2", 1, 2), (2304, 5, "5/6", 5, 6), (1824, 1, "2/3A", 2, 3)])
+def test_any_size_sum_product_and_layered_kernels(N, rate, name, num, den):
+    """The reference's kernels have no size limit (decodeCL.c:25-62, 203-292).  Codes beyond the on-chip layouts --
+    most of the reference's own family -- run ldpc_sp_big_kernel / ldpc_tdmp_big_kernel (messages in a global workspace):
+    bits and iteration counts of the sum-product oracle; bits, counts and posteriors of the layered oracle."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    y = np.concatenate([awgn_llr(20, N, sigma_from_ebn0(e, num / den), seed=N + i) for i, e in enumerate((1.5, 2.5, 4.0))])
+    y = y[:53]  # a ragged last group of 32
+    o = oracle.Oracle(M, N, K, rp, ci, times=40)
+    dec = m.Decoder.wimax(K, N, rate)
+    dec.set_algorithm(1)
+    out = dec.decode_device(torch.from_numpy(y).cuda(), want_hard=True)
+    torch.cuda.synchronize()
+    sp = oracle.decode_sp(o, y)
+    assert np.array_equal(out["iters"].cpu().numpy(), sp[1]) and np.array_equal(out["info"].cpu().numpy(), sp[0])
+    assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(sp[2], axis=1, bitorder="little"))
+    host = dec.decode_host(y)
+    assert np.array_equal(host["iters"], sp[1]) and np.array_equal(host["info"], sp[0])
+    dec.set_algorithm(2)
+    td = oracle.decode_tdmp(o, y, N // 24)
+    assert_parity(_run_device(dec, y), td, N, what="layered, N=%d" % N)
+    dec.set_max_iter(3)
+    td3 = oracle.decode_tdmp(oracle.Oracle(M, N, K, rp, ci, times=3), y, N // 24)
+    assert_parity(_run_device(dec, y), td3, N, what="layered cap 3, N=%d" % N)
+
+
+def test_any_size_kernels_equal_the_on_chip_ones(default_code, monkeypatch):
+    """Test.cpp's code through the any-size kernels (forced) gives what the on-chip kernels give: one contract, two layouts."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    N = c["N"]
+    y = np.concatenate([awgn_llr(100, N, 0.62, seed=71), awgn_llr(100, N, 0.5, seed=72), awgn_llr(41, N, 0.9, seed=73)])
+    o = oracle.Oracle(c["M"], N, c["K"], c["row_ptr"], c["col_idx"], times=40)
+    monkeypatch.setenv("LDPC_B200_SP_BIG", "1")
+    monkeypatch.setenv("LDPC_B200_TDMP_G", "32")
+    dec = m.Decoder.wimax(c["K"], N, c["rate"])
+    dec.set_algorithm(1)
+    sp = oracle.decode_sp(o, y)
+    out = _run_device_nopost(dec, y)
+    assert np.array_equal(out["iters"], sp[1]) and np.array_equal(out["info"], sp[0])
+    dec.set_algorithm(2)
+    assert_parity(_run_device(dec, y), oracle.decode_tdmp(o, y, 24), N, what="layered, any-size kernel")
+    # long synthetic codes: the regular (3,6) code has no layer structure, sum-product runs
+    M2, N2, K2, rp2, ci2 = m.codes.regular_code()
+    y2 = awgn_llr(5, N2, 0.75, seed=9)
+    d2 = m.Decoder(M2, N2, K2, rp2, ci2)
+    d2.set_algorithm(1)
+    sp2 = oracle.decode_sp(oracle.Oracle(M2, N2, K2, rp2, ci2, times=40), y2)
+    o2 = _run_device_nopost(d2, y2)
+    assert np.array_equal(o2["iters"], sp2[1]) and np.array_equal(o2["info"], sp2[0])
+
+
+def _run_device_nopost(dec, llr_np):
+    torch = _torch()
+    out = dec.decode_device(torch.from_numpy(llr_np).cuda(), want_hard=True)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
 def test_streamed_host_pipeline(default_code):
     """Host buffers on the quasi-cyclic path: one persistent launch fed by a copy stream.  Ragged sizes, pageable and
     pinned inputs, optional outputs asked for only on a later call, several launches per call (small batch cap) and
@@ -479,13 +541,14 @@ def test_sum_product_other_rates_and_caps():
             assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(hard, axis=1, bitorder="little")), (name, cap)
 
 
-def test_sum_product_unsupported_on_long_codes():
+def test_sum_product_has_no_posterior_output():
+    """(the reference's sum-product keeps probabilities, not a posterior LLR: the one output DecodeSP cannot give)"""
     import myldpccppapi_b200 as m
     M, N, K, rp, ci = m.codes.regular_code()
     dec = m.Decoder(M, N, K, rp, ci)
     dec.set_algorithm(1)
     with pytest.raises(m.LdpcError) as e:
-        dec.decode_device(_torch().zeros((4, N), dtype=_torch().float32, device="cuda"))
+        dec.decode_device(_torch().zeros((4, N), dtype=_torch().float32, device="cuda"), want_post=True)
     assert e.value.code == -3
 
 

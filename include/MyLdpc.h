@@ -116,6 +116,11 @@ public:
     // does not fit is decoded with flooding min-sum instead, decode() returns 0 and lastAlgorithm() tells; strict
     // (true): decode() returns LDPC_B200_ERR_UNSUPPORTED (-3) and writes nothing.
     int setStrictDecodeType(bool strict);
+    // DecodeMSCL / DecodeTDMPCL: by default the fast flooding / layered kernels (the reference kernels' caps, 120 / 40,
+    // and schedules; results differ from the reference's fused OpenCL kernels only where a message or posterior is
+    // EXACTLY zero).  true: reproduce those kernels' arithmetic exactly (sign through the product of the row's Q,
+    // bit = (P < 0); decodeCL.c:307-567) with the any-size kernel -- byte-identical to the reference, slower.
+    int setFusedKernelArithmetic(bool exact);
     int lastAlgorithm() const;                       // LDPC_B200_ALG_* the last decode() actually ran (-1: none yet)
     const int *lastIterations() const;               // per-codeword iteration counts of the last decode()
     int lastCodeSize() const;

@@ -75,14 +75,23 @@ enum {
 enum {
     LDPC_B200_ALG_MIN_SUM = 0,     /* Coder::decodeCPU / DecodeMS semantics (default)                    */
     LDPC_B200_ALG_SUM_PRODUCT = 1, /* DecodeSP: probability-domain sum-product of decodeCL.c:3-108 under
-                                      decodeOnceSP (MyLdpc.cpp:977-1059); short codes (on-chip group layout,
-                                      variable degree <= 8, check degree <= 20); no posterior output   */
-    LDPC_B200_ALG_LAYERED_MIN_SUM = 2 /* DecodeTDMP: layered min-sum, the schedule decodeOnceTDMP intends
+                                      decodeOnceSP (MyLdpc.cpp:977-1059); on-chip kernel for short codes (group
+                                      layout, variable degree <= 8, check degree <= 20), the any-size kernel
+                                      (global workspace) otherwise; no posterior output                 */
+    LDPC_B200_ALG_LAYERED_MIN_SUM = 2, /* DecodeTDMP: layered min-sum, the schedule decodeOnceTDMP intends
                                       (MyLdpc.cpp:889-976, decodeCL.c:203-292): layers of z consecutive rows,
                                       Q = P - R, R = min-sum, P = Q + R per layer, then hard decision
                                       (P == 0 keeps the bit) and syndrome.  Needs the layer height
                                       (known for ldpc_b200_create_wimax, else ldpc_b200_set_layer_height),
-                                      column-disjoint layers, <= 16 layers, N <= 32 z, on-chip layout     */
+                                      column-disjoint layers; on-chip kernel for <= 16 layers, N <= 32 z that fit
+                                      shared memory, the any-size kernel (global workspace) otherwise        */
+    LDPC_B200_ALG_FUSED_MIN_SUM = 3,  /* DecodeMSCL with the ARITHMETIC of the reference's fused kernel decodeOnceMS
+                                      (decodeCL.c:432-567) reproduced exactly: message sign through the float
+                                      product of the row's Q (a zero, an underflow or inf*0 zeroes the row), minimum
+                                      search from (1000, 1001), bit = (P < 0).  Differs from MIN_SUM only on such
+                                      corner events.  Any-size kernel (global workspace): exact, not fast.
+                                      The kernel's cap is 120: set it with ldpc_b200_set_max_iter.          */
+    LDPC_B200_ALG_FUSED_LAYERED = 4   /* DecodeTDMPCL likewise (decodeOnceTDMP, decodeCL.c:307-426; cap 40)   */
 };
 
 typedef struct ldpc_b200_info {

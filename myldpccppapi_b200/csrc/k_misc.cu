@@ -80,6 +80,11 @@ int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
+int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream) {
+    ldpc_fused_big_kernel<<<grid, 512, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
 int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream) {
     if (threads <= 512) ldpc_ms_stream_kernel<512><<<grid, threads, 0, stream>>>(q);
     else if (threads <= 768) ldpc_ms_stream_kernel<768><<<grid, threads, 0, stream>>>(q);

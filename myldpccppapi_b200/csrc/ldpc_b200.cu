@@ -1565,10 +1565,26 @@ int upload_tdmp_tables(ldpc_b200_decoder* h) {
 
 // Sum-product (layered = false) or layered min-sum of a code of any size: 32 codewords per CTA, lane = codeword, every
 // message in a CTA-private slice of a global workspace (ldpc_big.cuh).
-int launch_big(ldpc_b200_decoder* h, bool layered, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
+// does the handle's current algorithm run an any-size kernel (global workspace, launches serialise on it)?
+bool uses_big_kernel(const ldpc_b200_decoder* h) {
+    const Plan& pl = h->plan;
+    const HostTables& t = h->host;
+    switch (h->algorithm) {
+        case LDPC_B200_ALG_FUSED_MIN_SUM: case LDPC_B200_ALG_FUSED_LAYERED: return true;
+        case LDPC_B200_ALG_LAYERED_MIN_SUM: return h->tdmp_big;
+        case LDPC_B200_ALG_SUM_PRODUCT:
+            return !(pl.path == LDPC_B200_PATH_GROUP && pl.tab_smem && !pl.t16 && (pl.G == 8 || pl.G == 16) &&
+                     t.max_col_weight <= 8 && t.max_row_weight <= 20 && !h->opt.sp_big);
+        default: return false;
+    }
+}
+
+enum BigKind { kBigSumProduct, kBigLayered, kBigFusedFlooding, kBigFusedLayered };
+int launch_big(ldpc_b200_decoder* h, BigKind kind, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard,
                int32_t* d_iters, float* d_post, cudaStream_t stream) {
     const HostTables& t = h->host;
-    if (!layered && d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
+    const bool layered = kind != kBigSumProduct;  // (workspace shape: P + R + bits; sum-product keeps four arrays)
+    if (kind == kBigSumProduct && d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
     const int64_t ngroups = (ncw + kLanes - 1) / kLanes;
     if (ngroups > 0x7fffffff) return fail(LDPC_B200_ERR_ARG, "too many codewords in one call");
     const int grid = (int)std::min<int64_t>(ngroups, h->sm_count);
@@ -1588,13 +1604,16 @@ int launch_big(ldpc_b200_decoder* h, bool layered, const float* d_llr, int64_t n
     q.row_ptr = h->d_row_ptr; q.cn_col = h->d_cn_col; q.col_ptr = h->d_col_ptr; q.vn_edge = h->d_vn_edge;
     q.M = t.M; q.N = t.N; q.K = h->K; q.nnz = t.nnz;
     q.max_iter = h->max_iter; q.early_term = h->early; q.z = h->layer_z;
+    q.fused_layered = kind == kBigFusedLayered ? 1 : 0;
     q.llr = d_llr; q.ncw = ncw;
     q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
     q.ws = h->d_ws_big; q.ws_stride = stride;
     q.counter = reinterpret_cast<unsigned int*>(ctr64); q.ngroups = (int)ngroups;
     // the workspace is shared by every launch of this handle: serialise launches on it
     if (h->ws_event_valid) CU_TRY(cudaStreamWaitEvent(stream, h->ws_event, 0));
-    int rc = launch_status(layered ? k_launch_tdmp_big(q, grid, stream) : k_launch_sp_big(q, grid, stream), layered ? "layered (any size)" : "sum-product (any size)");
+    int rc = kind == kBigSumProduct ? launch_status(k_launch_sp_big(q, grid, stream), "sum-product (any size)")
+           : kind == kBigLayered    ? launch_status(k_launch_tdmp_big(q, grid, stream), "layered (any size)")
+                                    : launch_status(k_launch_fused_big(q, grid, stream), "fused-kernel arithmetic");
     if (rc) return rc;
     CU_TRY(cudaEventRecord(h->ws_event, stream));
     h->ws_event_valid = true;
@@ -1604,7 +1623,7 @@ int launch_big(ldpc_b200_decoder* h, bool layered, const float* d_llr, int64_t n
 
 int launch_tdmp(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t* d_info, uint8_t* d_hard, int32_t* d_iters,
                 float* d_post, cudaStream_t stream) {
-    if (h->tdmp_big) return launch_big(h, true, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
+    if (h->tdmp_big) return launch_big(h, kBigLayered, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     int rc = upload_tdmp_tables(h);
     if (rc) return rc;
     const HostTables& t = h->host;
@@ -1834,6 +1853,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
                   int32_t* d_iters, float* d_post, cudaStream_t stream) {
     if (ncw == 0) return LDPC_B200_OK;
     if (h->algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM) return launch_tdmp(h, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
+    if (h->algorithm == LDPC_B200_ALG_FUSED_MIN_SUM) return launch_big(h, kBigFusedFlooding, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
+    if (h->algorithm == LDPC_B200_ALG_FUSED_LAYERED) return launch_big(h, kBigFusedLayered, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     if (!h->planned) {
         int rc = make_plan(h);
         if (rc) return rc;
@@ -1843,9 +1864,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (h->algorithm == LDPC_B200_ALG_SUM_PRODUCT) {
         // the on-chip kernel takes short codes (group layout with 8 or 16 words per CTA, variable degree <= 8, check degree
         // <= 20); every other code goes to the any-size kernel -- DecodeSP never decodes with another algorithm
-        const bool onchip = pl.path == LDPC_B200_PATH_GROUP && pl.tab_smem && !pl.t16 && (pl.G == 8 || pl.G == 16) &&
-                            t.max_col_weight <= 8 && t.max_row_weight <= 20 && !h->opt.sp_big;
-        if (!onchip) return launch_big(h, false, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
+        if (uses_big_kernel(h)) return launch_big(h, kBigSumProduct, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     }
     int rc = ensure_workspace(h);
     if (rc) return rc;
@@ -2171,11 +2190,15 @@ int ldpc_b200_set_early_termination(ldpc_b200_handle h, int on) {
 
 int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
     if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
-    if (algorithm != LDPC_B200_ALG_MIN_SUM && algorithm != LDPC_B200_ALG_SUM_PRODUCT && algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM)
+    if (algorithm < LDPC_B200_ALG_MIN_SUM || algorithm > LDPC_B200_ALG_FUSED_LAYERED)
         return fail(LDPC_B200_ERR_ARG, "unknown algorithm");
     std::lock_guard<std::mutex> lk(h->mu);
     if (algorithm == h->algorithm) return LDPC_B200_OK;
-    if (algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM) {
+    if (algorithm == LDPC_B200_ALG_FUSED_MIN_SUM) {  // any-size kernel, its own workspace: nothing to plan
+        h->algorithm = algorithm;
+        return LDPC_B200_OK;
+    }
+    if (algorithm == LDPC_B200_ALG_LAYERED_MIN_SUM || algorithm == LDPC_B200_ALG_FUSED_LAYERED) {
         // its own layout and tables; nothing of the flooding plan changes.  Fails here (not at the first decode)
         // when the code cannot be layered, so a caller can fall back.
         if (!h->tdmp_ready) {
@@ -2715,8 +2738,9 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
         const int64_t cap = std::max<int64_t>(wave, ((int64_t)256 << 20) / ((int64_t)t.N * 4) / wave * wave);
         chunk = std::min(chunk, cap);
         chunk = std::min(chunk, (ncw + wave - 1) / wave * wave);
-        const bool workspace = h->algorithm != LDPC_B200_ALG_LAYERED_MIN_SUM &&
-                               (h->plan.path == LDPC_B200_PATH_LANE_GLOBAL || h->plan.path == LDPC_B200_PATH_STREAM);
+        const bool workspace = uses_big_kernel(h) ||
+                               (h->algorithm == LDPC_B200_ALG_MIN_SUM && (h->plan.path == LDPC_B200_PATH_LANE_GLOBAL || h->plan.path == LDPC_B200_PATH_STREAM));
+        if (uses_big_kernel(h)) { wave = (int64_t)h->sm_count * kLanes; chunk = std::min(wave * 4, (ncw + wave - 1) / wave * wave); }
         if (!workspace) {
             const int64_t g = h->plan.cw_per_cta;
             chunk = std::min(chunk, std::max<int64_t>(g, wave * 3 / 4 / g * g));

@@ -27,6 +27,7 @@ struct BigParams {
     const uint32_t* __restrict__ vn_edge;  // [nnz] (check << 5) | position, per variable in ascending row order
     int M, N, K, nnz, max_iter, early_term;
     int z;                                 // layered: rows per layer
+    int fused_layered;                     // fused-kernel arithmetic: 1 = decodeOnceTDMP (layered), 0 = decodeOnceMS (flooding)
     const float* __restrict__ llr;
     long long ncw;
     uint8_t* info;
@@ -287,6 +288,125 @@ __global__ void __launch_bounds__(512, 1) ldpc_tdmp_big_kernel(const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's two FUSED OpenCL kernels with their own arithmetic, reproduced exactly (DecodeMSCL -> decodeOnceMS,
+// decodeCL.c:432-567; DecodeTDMPCL -> decodeOnceTDMP, decodeCL.c:307-426).  They differ from decodeCPU / the layered
+// schedule in corner cases only: the message sign comes from the float PRODUCT of the row's Q (an exact zero, an
+// underflow or inf * 0 zeroes every message of the row), the minimum search starts from (1000, 1001) with `<=`, the hard
+// decision is bit = (P < 0), and the caps are the literals 120 / 40 (passed in max_iter).  Operation for operation the
+// test checker.s literal restatement of those kernels, which is pinned against the executed kernels themselves.
+// Workspace: P[N], R[nnz], HB[N].
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cl_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : (x == 0.0f ? x : 0.0f)); }
+
+__device__ __forceinline__ void fused_row(const BigParams& p, float* P, float* R, int r, int lane, bool layered, bool active) {
+    const int e0 = p.row_ptr[r], d = p.row_ptr[r + 1] - e0;
+    float a = 1.0f, b = 1000.0f, c = 1001.0f;
+    int bInd = -1;
+    float sg[kBigMaxDeg];
+    uint32_t col[kBigMaxDeg];
+#pragma unroll
+    for (int j = 0; j < kBigMaxDeg; ++j) {
+        if (j < d) {
+            col[j] = p.cn_col[e0 + j];
+            float tmp = __fsub_rn(P[(size_t)col[j] * 32 + lane], R[(size_t)(e0 + j) * 32 + lane]);
+            sg[j] = cl_sign(tmp);
+            a = __fmul_rn(a, tmp);
+            if (layered && active) P[(size_t)col[j] * 32 + lane] = tmp;
+            tmp = fabsf(tmp);
+            if (tmp <= b) { c = b; b = tmp; bInd = j; }
+            else if (tmp > b && tmp <= c) { c = tmp; }
+        }
+    }
+    a = cl_sign(a);
+    const float ac = __fmul_rn(a, c), ab = __fmul_rn(a, b);
+#pragma unroll
+    for (int j = 0; j < kBigMaxDeg; ++j) {
+        if (j < d) {
+            const float rn = __fmul_rn(sg[j], j == bInd ? ac : ab);
+            if (active) {
+                R[(size_t)(e0 + j) * 32 + lane] = rn;
+                if (layered) P[(size_t)col[j] * 32 + lane] = __fadd_rn(P[(size_t)col[j] * 32 + lane], rn);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) ldpc_fused_big_kernel(const __grid_constant__ BigParams p) {
+    __shared__ uint32_t s_unsat;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const bool layered = p.fused_layered != 0;
+    float* P = p.ws + (size_t)blockIdx.x * p.ws_stride;
+    float* R = P + (size_t)p.N * 32;
+    uint32_t* HB = reinterpret_cast<uint32_t*>(R + (size_t)p.nnz * 32);
+    for (;;) {
+        __shared__ int s_group;
+        __syncthreads();
+        if (threadIdx.x == 0) s_group = (int)atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const int g = s_group;
+        if (g >= p.ngroups) break;
+        const long long cw = (long long)g * 32 + lane;
+        const bool valid = cw < p.ncw;
+        const float* y = p.llr + (size_t)(valid ? cw : 0) * p.N;
+        for (int n = warp; n < p.N; n += nwarps) {
+            P[(size_t)n * 32 + lane] = y[n];
+            if (lane == 0) HB[n] = 0u;
+        }
+        for (int e = warp; e < p.nnz; e += nwarps) R[(size_t)e * 32 + lane] = 0.0f;
+        bool live = valid, done = !valid;
+        int it = 0, my_iters = 0;
+        if (threadIdx.x == 0) s_unsat = 0u;
+        __syncthreads();
+        for (;;) {
+            const bool active = live && !done;
+            if (layered) {
+                for (int r0 = 0; r0 < p.M; r0 += p.z) {
+                    for (int r = r0 + warp; r < r0 + p.z; r += nwarps) fused_row(p, P, R, r, lane, true, active);
+                    __syncthreads();
+                }
+            } else {
+                for (int r = warp; r < p.M; r += nwarps) fused_row(p, P, R, r, lane, false, active);
+                __syncthreads();
+                for (int n = warp; n < p.N; n += nwarps) {  // decodeCL.c:517-537: lP = y + the column's lR in ascending row order
+                    float t = y[n];
+                    for (int k = p.col_ptr[n]; k < p.col_ptr[n + 1]; ++k) t = __fadd_rn(t, R[(size_t)big_edge(p, p.vn_edge[k]) * 32 + lane]);
+                    if (active) P[(size_t)n * 32 + lane] = t;
+                }
+                __syncthreads();
+            }
+            for (int n = warp; n < p.N; n += nwarps) {  // srcBool = lP < 0 (decodeCL.c:386, 541)
+                const uint32_t one = __ballot_sync(0xffffffffu, P[(size_t)n * 32 + lane] < 0.0f);
+                const uint32_t frozen = __ballot_sync(0xffffffffu, !active);
+                if (lane == 0) HB[n] = (HB[n] & frozen) | (one & ~frozen);
+            }
+            __syncthreads();
+            uint32_t un = 0u;
+            for (int r = warp; r < p.M; r += nwarps) {
+                uint32_t xw = 0u;
+                for (int e = p.row_ptr[r] + lane; e < p.row_ptr[r + 1]; e += 32) xw ^= HB[p.cn_col[e]];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) xw ^= __shfl_xor_sync(0xffffffffu, xw, o);
+                un |= xw;
+            }
+            if (lane == 0 && un) atomicOr(&s_unsat, un);
+            __syncthreads();
+            const uint32_t unsat = s_unsat;
+            if (active) {
+                ++it;
+                if ((p.early_term && !((unsat >> lane) & 1u)) || it == p.max_iter) { done = true; my_iters = it; }
+            }
+            const bool all_done = __all_sync(0xffffffffu, done);
+            __syncthreads();
+            if (threadIdx.x == 0) s_unsat = 0u;
+            if (all_done) break;
+        }
+        if (p.post && valid)
+            for (int n = warp; n < p.N; n += nwarps) p.post[(size_t)cw * p.N + n] = P[(size_t)n * 32 + lane];
+        big_emit(p, HB, cw, valid, my_iters, lane, warp, nwarps);
+    }
+}
 #endif  // LDPC_B200_BIG_KERNELS
 
 }  // namespace ldpc_b200

@@ -43,6 +43,7 @@ int k_launch_lane16(const Lane16Params& q, int grid, int threads, size_t smem, c
 int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t stream);
 int k_launch_sp_big(const BigParams& q, int grid, cudaStream_t stream);    // any size, messages in a global workspace
 int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream);
+int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream);  // the reference's fused kernels, their arithmetic
 
 // Quasi-cyclic block structure of H for block size z: rows[br] = the circulants (block column, shift) of block
 // row br in ascending column order.

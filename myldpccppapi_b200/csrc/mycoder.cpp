@@ -20,6 +20,7 @@ struct Coder::Impl {
     int times = 40;      // reference MyLdpc.cpp:24
     int timesMSCL = 120; // the cap decodeOnceMS hard-codes (decodeCL.c:479); setMaxIter() overrides both
     bool strict = false; // setStrictDecodeType
+    bool fusedExact = false;  // setFusedKernelArithmetic
     int lastAlg = -1;
     double stepTimes[4] = {0, 0, 0, 0};
     int batchSize = 0;
@@ -111,6 +112,11 @@ int Coder::setStrictDecodeType(bool strict) {
     return LDPC_SUCCESS;
 }
 
+int Coder::setFusedKernelArithmetic(bool exact) {
+    impl->fusedExact = exact;
+    return LDPC_SUCCESS;
+}
+
 int Coder::lastAlgorithm() const { return impl->lastAlg; }
 
 int Coder::lastStepTimes(double *seconds, int n) const {
@@ -184,6 +190,8 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
     int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT
               : (deType == DecodeTDMP || deType == DecodeTDMPCL) ? LDPC_B200_ALG_LAYERED_MIN_SUM
                                                                  : LDPC_B200_ALG_MIN_SUM;
+    if (impl->fusedExact && deType == DecodeMSCL) alg = LDPC_B200_ALG_FUSED_MIN_SUM;      // decodeOnceMS's own arithmetic
+    if (impl->fusedExact && deType == DecodeTDMPCL) alg = LDPC_B200_ALG_FUSED_LAYERED;    // decodeOnceTDMP's own arithmetic
     // DecodeMSCL: the reference's fused kernel iterates up to 120 times whatever Coder::times says (decodeCL.c:479)
     const int cap = deType == DecodeMSCL ? impl->timesMSCL : impl->times;
     const char *fallback_note = "requested decodeType does not fit its on-chip layout for this code, decoded with flooding min-sum";
@@ -395,6 +403,7 @@ int myldpc_setMaxIter(myldpc_coder *c, int times) { return CODER(c)->setMaxIter(
 int myldpc_setDevices(myldpc_coder *c, const int *deviceIds, int count) { return CODER(c)->setDevices(deviceIds, count); }
 int myldpc_setEarlyTermination(myldpc_coder *c, int on) { return CODER(c)->setEarlyTermination(on != 0); }
 int myldpc_setStrictDecodeType(myldpc_coder *c, int strict) { return CODER(c)->setStrictDecodeType(strict != 0); }
+int myldpc_setFusedKernelArithmetic(myldpc_coder *c, int exact) { return CODER(c)->setFusedKernelArithmetic(exact != 0); }
 int myldpc_lastAlgorithm(myldpc_coder *c) { return CODER(c)->lastAlgorithm(); }
 const int *myldpc_lastIterations(myldpc_coder *c) { return CODER(c)->lastIterations(); }
 int myldpc_lastCodeSize(myldpc_coder *c) { return CODER(c)->lastCodeSize(); }

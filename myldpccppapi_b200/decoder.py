@@ -88,7 +88,8 @@ class Decoder:
         check(self._L.ldpc_b200_set_early_termination(self._h, 1 if on else 0))
 
     def set_algorithm(self, alg: int) -> None:
-        """0 = min-sum (default), 1 = probability-domain sum-product (DecodeSP), 2 = layered min-sum (DecodeTDMP)."""
+        """0 = min-sum (default), 1 = probability-domain sum-product (DecodeSP), 2 = layered min-sum (DecodeTDMP),
+        3 / 4 = the reference's fused kernels decodeOnceMS / decodeOnceTDMP with their own arithmetic (exact, any-size kernel)."""
         check(self._L.ldpc_b200_set_algorithm(self._h, alg))
 
     def set_layer_height(self, z: int) -> None:
@@ -316,6 +317,9 @@ class Coder:
 
     def setStrictDecodeType(self, strict: bool) -> int:
         return self._check(self._L.myldpc_setStrictDecodeType(self._c, 1 if strict else 0))
+
+    def setFusedKernelArithmetic(self, exact: bool) -> int:
+        return self._check(self._L.myldpc_setFusedKernelArithmetic(self._c, 1 if exact else 0))
 
     @property
     def lastAlgorithm(self) -> int:

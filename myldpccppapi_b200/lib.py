@@ -125,6 +125,7 @@ CODER_SIGNATURES = {
     "myldpc_setDevices": (_i, [_vp, _vp, _i]),
     "myldpc_setEarlyTermination": (_i, [_vp, _i]),
     "myldpc_setStrictDecodeType": (_i, [_vp, _i]),
+    "myldpc_setFusedKernelArithmetic": (_i, [_vp, _i]),
     "myldpc_lastAlgorithm": (_i, [_vp]),
     "myldpc_lastIterations": (C.POINTER(C.c_int32), [_vp]),
     "myldpc_lastCodeSize": (_i, [_vp]),

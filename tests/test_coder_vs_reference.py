@@ -112,6 +112,33 @@ def test_fused_min_sum_kernel_bytes_equal_the_reference(rate):
     assert np.array_equal(np.minimum(iters, 40), it40)
 
 
+@pytest.mark.parametrize("rate,N", [(0, 576), (2, 576), (3, 576), (4, 576), (5, 576), (4, 1152), (1, 2304)])
+@pytest.mark.parametrize("de_type", [TDMPCL, MSCL])
+def test_fused_kernel_arithmetic_is_byte_identical_on_request(rate, N, de_type):
+    """setFusedKernelArithmetic(true): every word -- zero messages, zero posteriors and erased inputs included -- carries
+    the bytes of the reference's fused OpenCL kernel executed work-group by work-group.  (Rate 2/3A only at z = 96: for
+    other z the reference's fused kernels expand a different matrix than Coder::initCheckMatrix.)"""
+    import myldpccppapi_b200 as m
+    ncw = 12 if N > 1152 else 30
+    K, y = _inputs(N, rate, ncw, seed=1200 + rate, ebn0s=(1.2, 2.4, 3.6))
+    y[0, ::11] = 0.0
+    y[1, 5::13] = -0.0
+    kb = K // 8
+    c = m.Coder(K, N, rate)
+    c.setFusedKernelArithmetic(True)
+    c.forDecoder(ncw)
+    c.addDecodeType(de_type)
+    out = np.zeros(ncw * kb + 1, dtype=np.uint8)
+    assert c.decode(y.reshape(-1), out, ncw * kb, de_type) == 0
+    assert c.lastAlgorithm == (4 if de_type == TDMPCL else 3)
+    want, _ = ref.RefCoder(K, N, rate, opt="cl").decode_cl(y, ncw * kb, de_type, batch=6)
+    assert np.array_equal(out[:-1], want)
+    _, name, num, den = RATES[rate]
+    rp, ci, M = oracle.wimax_H(N, name)
+    fused = oracle.decode_fused(oracle.Oracle(M, N, K, rp, ci), y, N // 24, layered=(de_type == TDMPCL))
+    assert np.array_equal(c.lastIterations, fused[1])
+
+
 def test_strict_decode_type_and_fallback_query():
     """DecodeSP on a code that does not fit the on-chip layout runs the any-size sum-product kernel (no fallback).
     DecodeTDMP on a code without a layer structure cannot be layered: by default it is decoded with flooding min-sum and

@@ -473,7 +473,26 @@ def main() -> None:
                "h2d_gbs_per_gpu": [round(v, 2) for v in gather(h2d_rank)],
                "h2d_gbs_aggregate": round(sum_over_ranks(ncw * N * 4 * args.steps) / dt / 1e9, 2),
                "ms_per_step_per_rank": [round(v / args.steps * 1e3, 3) for v in gather(dt_rank)]}
-        del h_llr
+        # the host's copy ceiling: the same pinned buffer copied to the device by every rank at once, nothing else running
+        d_tmp = torch.empty_like(h_llr, device=dev)
+        for _ in range(2):
+            d_tmp.copy_(h_llr, non_blocking=True)
+        barrier()
+        torch.cuda.synchronize()
+        cev0, cev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cev0.record()
+        for _ in range(10):
+            d_tmp.copy_(h_llr, non_blocking=True)
+        cev1.record()
+        torch.cuda.synchronize()
+        barrier()
+        ceil_rank = ncw * N * 4 * 10 / (cev0.elapsed_time(cev1) * 1e-3) / 1e9
+        ceil = gather(ceil_rank)
+        e2e["h2d_ceiling_gbs_per_gpu"] = [round(v, 2) for v in ceil]
+        e2e["h2d_ceiling_note"] = ("plain cudaMemcpyAsync of the same pinned buffer on all %d ranks at once: what the host can feed; "
+                                   "the end-to-end step cannot be shorter than bytes / this rate" % world)
+        e2e["h2d_bound_ms_per_step"] = round(max(ncw * N * 4 / (v * 1e9) for v in ceil) * 1e3, 3)
+        del h_llr, d_tmp
 
     # ---- the call a user of the reference makes: Coder::decode of the drop-in C++ class, malloc'd buffers
     plugin = None
@@ -501,7 +520,29 @@ def main() -> None:
         dt_p = max_over_ranks(time.perf_counter() - t0)
         sampler.region(False)
         barrier()
+        # the same buffer page-locked on first sight (Coder::setRegisterHostBuffers): no staging copy on the host afterwards
+        coder2 = m.Coder(K, N, m.rate_3_4_b, device=local_rank)
+        coder2.setMaxIter(cap)
+        coder2.setRegisterHostBuffers(True)
+        coder2.forDecoder(ncw)
+        coder2.addDecodeType(m.DecodeMS)
+        barrier()
+        t0 = time.perf_counter()
+        coder2.decode(post, src, src_len, m.DecodeMS)
+        first_reg_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps_p):
+            coder2.decode(post, src, src_len, m.DecodeMS)
+        dt_r = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        registered = {"api": "the same call after Coder::setRegisterHostBuffers(true): the malloc'd postCode is page-locked at the first decode",
+                      "value": total_cw * K * steps_p / dt_r / 1e9, "unit": UNIT, "ms_per_step": dt_r / steps_p * 1e3,
+                      "first_call_ms": first_reg_s * 1e3,
+                      "bytes_match_device_path": bool(np.array_equal(src[:src_len], out["info"].cpu().numpy().reshape(-1)))}
+        coder2.close()
         plugin = {"api": "Coder::decode(postCode, srcCode, srcLength, DecodeMS) of libmyldpc_b200.so, malloc'd host buffers, setup (forDecoder + addDecodeType) outside the timed region as in Test.cpp",
+                  "registered": registered,
                   "value": total_cw * K * steps_p / dt_p / 1e9, "unit": UNIT, "ms_per_step": dt_p / steps_p * 1e3, "steps": steps_p,
                   "first_call_ms": first_s * 1e3, "setup_ms": setup_s * 1e3,
                   "phase_ms_last_call": {k: v * 1e3 for k, v in coder.lastStepTimes().items()},

@@ -121,6 +121,10 @@ public:
     // EXACTLY zero).  true: reproduce those kernels' arithmetic exactly (sign through the product of the row's Q,
     // bit = (P < 0); decodeCL.c:307-567) with the any-size kernel -- byte-identical to the reference, slower.
     int setFusedKernelArithmetic(bool exact);
+    // true: page-lock (cudaHostRegister) a malloc'd postCode buffer the first time decode() sees it and keep it so until
+    // the Coder is destroyed -- the caller promises not to free it before.  Repeated decodes out of one buffer (Test.cpp's
+    // loop) then cost what pinned memory costs; default false (pageable input is staged through pinned buffers).
+    int setRegisterHostBuffers(bool on);
     int lastAlgorithm() const;                       // LDPC_B200_ALG_* the last decode() actually ran (-1: none yet)
     const int *lastIterations() const;               // per-codeword iteration counts of the last decode()
     int lastCodeSize() const;

@@ -36,6 +36,7 @@ int myldpc_setDevices(myldpc_coder *c, const int *deviceIds, int count);
 int myldpc_setEarlyTermination(myldpc_coder *c, int on);
 int myldpc_setStrictDecodeType(myldpc_coder *c, int strict);
 int myldpc_setFusedKernelArithmetic(myldpc_coder *c, int exact);
+int myldpc_setRegisterHostBuffers(myldpc_coder *c, int on);
 int myldpc_lastAlgorithm(myldpc_coder *c);
 const int *myldpc_lastIterations(myldpc_coder *c);
 int myldpc_lastCodeSize(myldpc_coder *c);

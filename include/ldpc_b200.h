@@ -139,7 +139,9 @@ int ldpc_b200_set_path(ldpc_b200_handle h, int path);
  * plan made at create time and are refused here with LDPC_B200_ERR_UNSUPPORTED):
  *   "refill_wait", "no_streamed", "streamed_pageable", "no_staged", "staged_min_kb", "stream_chunk",
  *   "stream_batch_kb", "wait_timeout_ms" (bound of the persistent kernel's wait for streamed input; when it
- *   expires the call is rerun through the chunked pipeline).                                                */
+ *   expires the call is rerun through the chunked pipeline), "register_host" (page-lock a pageable input buffer
+ *   with cudaHostRegister the first time it is seen and keep it so until ldpc_b200_destroy: the caller promises
+ *   not to free it before; repeated decodes out of one malloc'd buffer then run at pinned-memory speed).        */
 int ldpc_b200_set_option(ldpc_b200_handle h, const char *name, long long value);
 int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info *info);
 
@@ -208,6 +210,11 @@ typedef struct ldpc_b200_timing {
 } ldpc_b200_timing;
 int ldpc_b200_get_timing(ldpc_b200_handle h, ldpc_b200_timing *out);
 int ldpc_b200_reset_timing(ldpc_b200_handle h);
+
+/* Page-locked host memory for callers without the CUDA headers (the drop-in Coder keeps its result staging in it, so
+ * that the device-to-host copies of a decode are true DMA).  NULL / an error code when the runtime refuses.          */
+void *ldpc_b200_host_alloc(size_t bytes);
+int ldpc_b200_host_free(void *p);
 
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches). */
 int64_t ldpc_b200_launch_count(ldpc_b200_handle h);

@@ -69,23 +69,25 @@ struct Options {
     // launch / host pipeline: read per call
     int refill_wait = 1;              // measured: profiles/r01_refill_sweep.txt
     bool no_streamed = false, streamed_pageable = false, no_staged = false;
+    bool register_host = false;       // page-lock a pageable input buffer on first sight (cudaHostRegister) and keep it registered
     long long staged_min_kb = 8 << 10;  // pageable input of 8 MB or more is staged by host threads
     long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
     long long stream_batch_kb = 0;    // channel values per launch (0 = default)
     long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
 };
 
-struct OptionName { const char* name; int kind; size_t off; };  // kind 0 bool, 1 int, 2 long long
-#define OPT(n, k) {#n, k, offsetof(Options, n)}
+struct OptionName { const char* name; int kind; size_t off; bool runtime; };  // kind 0 bool, 1 int, 2 long long
+#define OPT(n, k) {#n, k, offsetof(Options, n), false}   // shapes the plan: environment only, read at create
+#define OPTR(n, k) {#n, k, offsetof(Options, n), true}   // may change afterwards (ldpc_b200_set_option)
 const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
-    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2), OPT(refill_wait, 1), OPT(no_streamed, 0),
-    OPT(streamed_pageable, 0), OPT(no_staged, 0), OPT(staged_min_kb, 2), OPT(stream_chunk, 2), OPT(stream_batch_kb, 2),
-    OPT(wait_timeout_ms, 2),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
+    OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
+    OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
 };
 #undef OPT
-constexpr int kFirstRuntimeOption = 18;  // refill_wait and everything after it may change after create
+#undef OPTR
 
 void option_store(Options* o, const OptionName& n, long long v) {
     char* p = reinterpret_cast<char*>(o) + n.off;
@@ -254,6 +256,8 @@ struct ldpc_b200_decoder {
     int64_t launches = 0;
     // run-time phase timers of the host-buffer decode (ldpc_b200_get_timing): CUDA events around the copies and the
     // kernels, accumulated per call -- what the reference keeps in stepTime[] (MyLdpc.cpp:26-28, 987-1056)
+    // option register_host: input ranges this handle page-locked (released in destroy)
+    std::vector<std::pair<const void*, size_t>> registered;
     ldpc_b200_timing timing{};
     std::vector<cudaEvent_t> tev;  // timing events, created on demand
     std::mutex mu;
@@ -2156,6 +2160,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             if (h->h_status) cudaFreeHost(h->h_status);
             if (h->st_event) cudaEventDestroy(h->st_event);
             for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+            for (auto& r : h->registered) cudaHostUnregister(const_cast<void*>(r.first));
             for (int s = 0; s < kSlots; ++s)
                 if (h->streams[s]) cudaStreamDestroy(h->streams[s]);
             cudaFree(h->d_row_ptr); cudaFree(h->d_cn_col); cudaFree(h->d_col_ptr); cudaFree(h->d_vn_edge);
@@ -2236,7 +2241,7 @@ int ldpc_b200_set_option(ldpc_b200_handle h, const char* name, long long value) 
     const int n = (int)(sizeof(kOptionNames) / sizeof(kOptionNames[0]));
     for (int i = 0; i < n; ++i) {
         if (std::strcmp(kOptionNames[i].name, name) != 0) continue;
-        if (i < kFirstRuntimeOption)
+        if (!kOptionNames[i].runtime)
             return fail(LDPC_B200_ERR_UNSUPPORTED, std::string("option '") + name + "' shapes the plan: set LDPC_B200_<NAME> before ldpc_b200_create");
         std::lock_guard<std::mutex> lk(h->mu);
         option_store(&h->opt, kOptionNames[i], value);
@@ -2712,9 +2717,21 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
         // pinned (or managed) input: every chunk copy is queued before the launch.  Copies from pageable memory are
         // staged synchronously by the driver, so queueing them all first would serialise copy and decode.
         cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
-                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        bool pinned = cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
+                      (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
         if (!pinned) (void)cudaGetLastError();
+        if (!pinned && h->opt.register_host) {
+            // the caller promised that the buffer outlives the handle (or is decoded from again): page-lock it once, then
+            // every call DMAs straight out of it -- no staging copy on the host (a malloc'd postCode decoded repeatedly,
+            // as in Test.cpp's loop, then costs what a pinned one does)
+            const size_t bytes = sizeof(float) * (size_t)ncw * t.N;
+            if (cudaHostRegister(const_cast<float*>(llr), bytes, cudaHostRegisterDefault) == cudaSuccess) {
+                h->registered.emplace_back(llr, bytes);
+                pinned = true;
+            } else {
+                (void)cudaGetLastError();  // (overlaps an older registration, or the driver refused: staged path below)
+            }
+        }
         int rc = kStreamedRetry;
         if (pinned || h->opt.streamed_pageable) {
             rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, false);
@@ -2771,6 +2788,20 @@ int ldpc_b200_synth_llr(float* d_llr, int64_t ncw, int N, float sigma, uint64_t 
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
     ldpc_synth_llr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_llr, total, N, sigma, seed, d_bits, 0);
     CU_TRY(cudaGetLastError());
+    return LDPC_B200_OK;
+}
+
+void* ldpc_b200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(LDPC_B200_ERR_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+int ldpc_b200_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) return fail(LDPC_B200_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(cudaGetLastError()));
     return LDPC_B200_OK;
 }
 

@@ -21,14 +21,18 @@ struct Coder::Impl {
     int timesMSCL = 120; // the cap decodeOnceMS hard-codes (decodeCL.c:479); setMaxIter() overrides both
     bool strict = false; // setStrictDecodeType
     bool fusedExact = false;  // setFusedKernelArithmetic
+    bool registerHost = false;  // setRegisterHostBuffers
     int lastAlg = -1;
     double stepTimes[4] = {0, 0, 0, 0};
     int batchSize = 0;
     bool early = true;
     std::vector<int> devices{0};
     std::vector<ldpc_b200_handle> handles;
-    std::vector<int32_t> iters;
-    std::vector<uint8_t> info;
+    // result staging of decode(): page-locked when the runtime grants it (true DMA for the read-back), grown on demand
+    int32_t *iters = nullptr;
+    uint8_t *info = nullptr;
+    size_t itersCap = 0, infoCap = 0;
+    bool itersPinned = false, infoPinned = false;
     int lastCodeSize = 0;
     std::string err;
     // systematic encoder: parity = X u over GF(2); X stored row-wise, 64 info bits per word
@@ -39,6 +43,22 @@ struct Coder::Impl {
     int fail(int code) {
         err = ldpc_b200_last_error();
         return code;
+    }
+    template <class T>
+    static bool grow(T *&p, size_t &cap, bool &pinned, size_t n) {
+        if (n <= cap) return true;
+        if (p) { if (pinned) ldpc_b200_host_free(p); else std::free(p); p = nullptr; cap = 0; }
+        void *q = ldpc_b200_host_alloc(n * sizeof(T));
+        pinned = q != nullptr;
+        if (!q) q = std::malloc(n * sizeof(T));
+        if (!q) return false;
+        p = static_cast<T *>(q);
+        cap = n;
+        return true;
+    }
+    void freeStaging() {
+        if (iters) { if (itersPinned) ldpc_b200_host_free(iters); else std::free(iters); iters = nullptr; itersCap = 0; }
+        if (info) { if (infoPinned) ldpc_b200_host_free(info); else std::free(info); info = nullptr; infoCap = 0; }
     }
     void destroyHandles() {
         for (ldpc_b200_handle h : handles) ldpc_b200_destroy(h);
@@ -78,6 +98,7 @@ Coder::Coder(int ldpcM, int ldpcN, int ldpcK, const int *rowPtr, const int *colI
 
 Coder::~Coder() {
     impl->destroyHandles();
+    impl->freeStaging();
     delete impl;
 }
 
@@ -117,6 +138,12 @@ int Coder::setFusedKernelArithmetic(bool exact) {
     return LDPC_SUCCESS;
 }
 
+int Coder::setRegisterHostBuffers(bool on) {
+    impl->registerHost = on;
+    for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_option(h, "register_host", on ? 1 : 0);
+    return LDPC_SUCCESS;
+}
+
 int Coder::lastAlgorithm() const { return impl->lastAlg; }
 
 int Coder::lastStepTimes(double *seconds, int n) const {
@@ -126,7 +153,7 @@ int Coder::lastStepTimes(double *seconds, int n) const {
     return m;
 }
 
-const int *Coder::lastIterations() const { return impl->iters.data(); }
+const int *Coder::lastIterations() const { return impl->iters; }
 int Coder::lastCodeSize() const { return impl->lastCodeSize; }
 const char *Coder::lastError() const { return impl->err.c_str(); }
 
@@ -145,6 +172,7 @@ int Coder::forDecoder(int batchSize) {
         }
         ldpc_b200_set_max_iter(h, impl->times);
         ldpc_b200_set_early_termination(h, impl->early ? 1 : 0);
+        ldpc_b200_set_option(h, "register_host", impl->registerHost ? 1 : 0);
         if (impl->rate >= 0) ldpc_b200_set_layer_height(h, impl->N / 24);  // z, reference MyLdpc.cpp:22
         impl->handles.push_back(h);
     }
@@ -162,6 +190,10 @@ int Coder::addDecodeType(enum decodeType deType) {
             int rc = ldpc_b200_reserve(h, impl->batchSize);
             if (rc != LDPC_B200_OK) return impl->fail(rc);
         }
+    if (impl->batchSize > 0) {  // result staging for a call of batchSize words: the first decode() allocates nothing
+        Impl::grow(impl->iters, impl->itersCap, impl->itersPinned, (size_t)impl->batchSize);
+        Impl::grow(impl->info, impl->infoCap, impl->infoPinned, (size_t)impl->batchSize * ((impl->K + 7) / 8));
+    }
     return LDPC_SUCCESS;
 }
 
@@ -209,8 +241,11 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
         alg = LDPC_B200_ALG_MIN_SUM;
         for (ldpc_b200_handle h : impl->handles) ldpc_b200_set_algorithm(h, alg);
     }
-    impl->iters.assign(codeSize, 0);
-    impl->info.assign((size_t)codeSize * KB, 0);
+    if (!Impl::grow(impl->iters, impl->itersCap, impl->itersPinned, (size_t)codeSize) ||
+        !Impl::grow(impl->info, impl->infoCap, impl->infoPinned, (size_t)codeSize * KB)) {
+        impl->err = "out of host memory";
+        return LDPC_B200_ERR_NOMEM;
+    }
     impl->lastCodeSize = codeSize;
     std::vector<int> rcs(G, LDPC_B200_OK);
     std::vector<std::string> msgs(G);
@@ -221,7 +256,7 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
         const int64_t b = (int64_t)codeSize * g / G, e = (int64_t)codeSize * (g + 1) / G;
         if (e <= b) return;
         rcs[g] = ldpc_b200_decode_host(impl->handles[g], postCode + (size_t)b * impl->N, e - b,
-                                       impl->info.data() + (size_t)b * KB, nullptr, impl->iters.data() + b, nullptr);
+                                       impl->info + (size_t)b * KB, nullptr, impl->iters + b, nullptr);
         if (rcs[g] != LDPC_B200_OK) msgs[g] = ldpc_b200_last_error();
     };
     auto run_all = [&]() {
@@ -258,7 +293,7 @@ int Coder::decode(float *postCode, char *srcCode, int srcLength, enum decodeType
             return rcs[g];
         }
     // the stream holds the first srcLength bytes (the last codeword may be partly padding)
-    std::memcpy(srcCode, impl->info.data(), std::min<size_t>((size_t)srcLength, impl->info.size()));
+    std::memcpy(srcCode, impl->info, std::min<size_t>((size_t)srcLength, (size_t)codeSize * KB));
     return LDPC_SUCCESS;
 }
 
@@ -404,6 +439,7 @@ int myldpc_setDevices(myldpc_coder *c, const int *deviceIds, int count) { return
 int myldpc_setEarlyTermination(myldpc_coder *c, int on) { return CODER(c)->setEarlyTermination(on != 0); }
 int myldpc_setStrictDecodeType(myldpc_coder *c, int strict) { return CODER(c)->setStrictDecodeType(strict != 0); }
 int myldpc_setFusedKernelArithmetic(myldpc_coder *c, int exact) { return CODER(c)->setFusedKernelArithmetic(exact != 0); }
+int myldpc_setRegisterHostBuffers(myldpc_coder *c, int on) { return CODER(c)->setRegisterHostBuffers(on != 0); }
 int myldpc_lastAlgorithm(myldpc_coder *c) { return CODER(c)->lastAlgorithm(); }
 const int *myldpc_lastIterations(myldpc_coder *c) { return CODER(c)->lastIterations(); }
 int myldpc_lastCodeSize(myldpc_coder *c) { return CODER(c)->lastCodeSize(); }

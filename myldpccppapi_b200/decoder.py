@@ -318,6 +318,9 @@ class Coder:
     def setStrictDecodeType(self, strict: bool) -> int:
         return self._check(self._L.myldpc_setStrictDecodeType(self._c, 1 if strict else 0))
 
+    def setRegisterHostBuffers(self, on: bool) -> int:
+        return self._check(self._L.myldpc_setRegisterHostBuffers(self._c, 1 if on else 0))
+
     def setFusedKernelArithmetic(self, exact: bool) -> int:
         return self._check(self._L.myldpc_setFusedKernelArithmetic(self._c, 1 if exact else 0))
 

@@ -73,6 +73,8 @@ SIGNATURES = {
     "ldpc_b200_edge_tables": (_i, [_i, _i, _vp, _vp, _vp, _vp, _pi, _pi]),
     "ldpc_b200_probe_smem_bandwidth": (_i, [_i, C.POINTER(C.c_double)]),
     "ldpc_b200_launch_count": (_i64, [_vp]),
+    "ldpc_b200_host_alloc": (_vp, [C.c_size_t]),
+    "ldpc_b200_host_free": (_i, [_vp]),
     "ldpc_b200_get_timing": (_i, [_vp, C.POINTER(Timing)]),
     "ldpc_b200_reset_timing": (_i, [_vp]),
     "ldpc_b200_last_error": (C.c_char_p, []),
@@ -126,6 +128,7 @@ CODER_SIGNATURES = {
     "myldpc_setEarlyTermination": (_i, [_vp, _i]),
     "myldpc_setStrictDecodeType": (_i, [_vp, _i]),
     "myldpc_setFusedKernelArithmetic": (_i, [_vp, _i]),
+    "myldpc_setRegisterHostBuffers": (_i, [_vp, _i]),
     "myldpc_lastAlgorithm": (_i, [_vp]),
     "myldpc_lastIterations": (C.POINTER(C.c_int32), [_vp]),
     "myldpc_lastCodeSize": (_i, [_vp]),

@@ -14,6 +14,22 @@
 
 namespace ldpc_b200 {
 namespace {
+// Mean iteration count of a launch, from a sample of its per-word counts: one CTA, one pass.
+__global__ void __launch_bounds__(256) ldpc_iter_stats_kernel(const int32_t* __restrict__ iters, long long ncw, unsigned long long* stats) {
+    const long long nsamp = ncw < 4096 ? ncw : 4096;
+    unsigned long long s = 0;
+    for (long long i = threadIdx.x; i < nsamp; i += 256) s += (unsigned long long)iters[i * ncw / nsamp];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ unsigned long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) s += part[w];
+        stats[0] = s;
+        stats[1] = (unsigned long long)nsamp;
+    }
+}
+
 template <int SW>
 int launch_warp_t(const WarpParams& q, int grid, int threads, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(ldpc_ms_warp_kernel<SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -82,6 +98,11 @@ int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream) {
 
 int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream) {
     ldpc_fused_big_kernel<<<grid, 512, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int k_launch_iter_stats(const int32_t* iters, long long ncw, unsigned long long* stats, cudaStream_t stream) {
+    ldpc_iter_stats_kernel<<<1, 256, 0, stream>>>(iters, ncw, stats);
     return (int)cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@
 #include "ldpc_cluster.cuh"
 #include "ldpc_qc.cuh"
 #include "ldpc_qcg.cuh"
+#include "ldpc_qcw.cuh"
 #include "ldpc_warp.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
@@ -74,6 +75,10 @@ struct Options {
     long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
     long long stream_batch_kb = 0;    // channel values per launch (0 = default)
     long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
+    // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
+    // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
+    int qc_et = -1;
+    int qc_et_pct = 60;               // auto: used while the mean iteration count is at most this share of the cap (measured crossover: profiles/r02_et_kernel.md)
 };
 
 struct OptionName { const char* name; int kind; size_t off; bool runtime; };  // kind 0 bool, 1 int, 2 long long
@@ -85,6 +90,7 @@ const OptionName kOptionNames[] = {
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1),
 };
 #undef OPT
 #undef OPTR
@@ -174,6 +180,16 @@ struct ldpc_b200_decoder {
     size_t qc_smem = 0;
     size_t qc_ring_smem = 0;  // dynamic shared memory of the ring kernel (0: not usable for this profile)
     int qc_ring_per_sm = 0;
+    // the early-termination kernel (ldpc_qcw.cuh: a warp per codeword), prepared next to the main one
+    QcwParams qcw;
+    int qcw_kind = -1, qcw_state = 0, qcw_slot = -1, qcw_warps = 0;
+    uint32_t* d_syn_tab = nullptr;
+    // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
+    int32_t* d_iters_own = nullptr;          // iteration counts when the caller does not ask for them
+    int64_t iters_own_cap = 0;
+    unsigned long long* d_stats = nullptr;   // [0] sum of the sampled counts, [1] words sampled
+    unsigned long long* h_stats = nullptr;   // pinned copy, refreshed after every launch
+    int last_kernel = 0;                     // ldpc_b200_info.kernel_variant of the most recent launch
     // QC tables with a run-time profile (ldpc_qcg.cuh)
     QcgParams qcg;
     QcgWarpTab qcg_tab[kQcgMaxW];
@@ -1212,6 +1228,60 @@ bool qc_prepare(ldpc_b200_decoder* h) {
     return false;
 }
 
+// The early-termination kernel (ldpc_qcw.cuh: a warp per codeword, z <= 32): finds the rate's instantiation, builds its
+// tables, takes a slot of that unit's constant bank.  false = this code has none (the main kernel serves every regime).
+std::mutex g_qcw_mu;
+const void* g_qcw_owner[kQcMaxDevices][kQcTabSlots] = {};
+
+bool qcw_prepare(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    if (h->qc_state != 1) return false;
+    int n = 0;
+    const QcwProfileEntry* profiles = qcw_profiles(&n);
+    std::vector<std::vector<QcBlk>> rows;
+    int rows_z = 0;
+    for (int k = 0; k < n; ++k) {
+        const QcwProfileEntry& pe = profiles[k];
+        if (t.N != 24 * pe.z) continue;
+        if (rows_z != pe.z) { rows.clear(); rows_z = pe.z; if (!qc_blocks(t, pe.z, &rows)) rows.clear(); }
+        if (rows.empty()) continue;
+        std::vector<unsigned char> tab;
+        std::vector<uint32_t> syn;
+        if (!pe.build(t, rows, &tab, &syn)) continue;
+        const int warps = std::min<int>(kQcwMaxWarps, (int)(h->smem_optin / (size_t)pe.warp_bytes));
+        if (warps < 8) return false;
+        DeviceGuard guard(h->device);
+        if (!guard.ok || h->device < 0 || h->device >= kQcMaxDevices) return false;
+        int slot = -1;
+        {
+            std::lock_guard<std::mutex> lk(g_qcw_mu);
+            for (int s2 = 0; s2 < kQcTabSlots && slot < 0; ++s2)
+                if (!g_qcw_owner[h->device][s2]) { g_qcw_owner[h->device][s2] = h; slot = s2; }
+        }
+        if (slot < 0) return false;
+        if (pe.upload(slot, tab.data(), tab.size()) != 0 || cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||
+            cudaMemcpy(h->d_syn_tab, syn.data(), syn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            (!h->d_stats && cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) ||
+            (!h->h_stats && cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)) {
+            (void)cudaGetLastError();
+            std::lock_guard<std::mutex> lk(g_qcw_mu);
+            g_qcw_owner[h->device][slot] = nullptr;
+            return false;
+        }
+        h->h_stats[0] = h->h_stats[1] = 0ull;
+        std::memset(&h->qcw, 0, sizeof(h->qcw));
+        h->qcw.tab_slot = slot;
+        h->qcw.N = t.N;
+        h->qcw.syn_tab = h->d_syn_tab;
+        h->qcw_slot = slot;
+        h->qcw_kind = k;
+        h->qcw_warps = warps;
+        h->table_bytes += tab.size() + syn.size() * 4;
+        return true;
+    }
+    return false;
+}
+
 // Run-time-profile QC path: picks G (most codewords per CTA with two CTAs per SM, else one CTA), builds and uploads.
 bool qcg_prepare(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
@@ -1678,6 +1748,7 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
                 const int n = guard.ok ? pe.ring_ctas_per_sm(need) : 0;
                 if (n >= qc_per_sm) { h->qc_ring_smem = need; h->qc_ring_per_sm = n; }
             }
+            if (h->qcw_state == 0) h->qcw_state = (h->opt.qc_et != 0 && qcw_prepare(h)) ? 1 : -1;
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
             pl.threads = 32 * qc_profiles()[h->qc_kind].W;
@@ -1924,13 +1995,48 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
-        // ring kernel unless its bulk copies cannot be used (channel values not 16-byte aligned)
-        if (h->qc_ring_smem && (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0)
+        // Which kernel: the early-termination kernel (a warp per codeword) when the handle's recent words stopped early
+        // on average -- the mean iteration count of the previous launches, sampled on the device and read from pinned
+        // memory: no synchronisation -- the main kernel otherwise and whenever the regime is unknown.
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0;  // bulk copies of the ring kernel
+        const bool et_ready = h->qcw_state == 1 && h->early && !h->qc_ring_smem;
+        const bool track = et_ready && h->opt.qc_et < 0;   // the regime is tracked through the iteration counts
+        bool use_et = et_ready && h->opt.qc_et > 0;
+        if (track && h->h_stats[1] > 0)
+            use_et = (double)h->h_stats[0] * 100.0 <= (double)h->opt.qc_et_pct * (double)h->max_iter * (double)h->h_stats[1];
+        if (track && !q.iters) {
+            if (h->iters_own_cap < ncw) {
+                cudaFree(h->d_iters_own); h->d_iters_own = nullptr; h->iters_own_cap = 0;
+                CU_TRY(cudaMalloc(&h->d_iters_own, (size_t)ncw * sizeof(int32_t)));
+                h->iters_own_cap = ncw;
+            }
+            q.iters = h->d_iters_own;
+        }
+        if (use_et) {
+            QcwParams& e = h->qcw;
+            e.K = q.K; e.max_iter = q.max_iter; e.early_term = q.early_term;
+            e.llr = q.llr; e.ncw = q.ncw; e.info = q.info; e.hard = q.hard; e.iters = q.iters; e.post = q.post;
+            e.counter64 = q.counter64; e.avail = q.avail; e.status = q.status; e.wait_ns = q.wait_ns;
+            int np = 0;
+            const QcwProfileEntry& pe = qcw_profiles(&np)[h->qcw_kind];
+            const int et_grid = (int)std::min<int64_t>((ncw + h->qcw_warps - 1) / h->qcw_warps, (int64_t)h->sm_count);
+            rc = launch_status(pe.launch(e, et_grid, h->qcw_warps, stream), "quasi-cyclic (warp per codeword)");
+            h->last_kernel = 1;
+        } else if (h->qc_ring_smem && aligned) {  // ring kernel unless its bulk copies cannot be used
             rc = launch_status(qc_profiles()[h->qc_kind].launch_ring(q, grid, h->qc_ring_smem, stream), "quasi-cyclic (ring)");
-        else
+            h->last_kernel = 2;
+        } else {
             rc = launch_status(qc_profiles()[h->qc_kind].launch(q, grid, pl.smem, stream), "quasi-cyclic");
+            h->last_kernel = 0;
+        }
         if (rc) return rc;
         h->launches += 1;
+        if (track) {
+            rc = launch_status(k_launch_iter_stats(q.iters, ncw, h->d_stats, stream), "iteration statistics");
+            if (rc) return rc;
+            CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+            h->launches += 1;
+        }
         return LDPC_B200_OK;
     }
 
@@ -2149,6 +2255,12 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaDeviceSynchronize();
             free_slots(h);
             if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
+            if (h->qcw_slot >= 0 && h->device >= 0 && h->device < kQcMaxDevices) {
+                std::lock_guard<std::mutex> lk(g_qcw_mu);
+                if (g_qcw_owner[h->device][h->qcw_slot] == h) g_qcw_owner[h->device][h->qcw_slot] = nullptr;
+            }
+            cudaFree(h->d_syn_tab); cudaFree(h->d_iters_own); cudaFree(h->d_stats);
+            if (h->h_stats) cudaFreeHost(h->h_stats);
             cudaFree(h->dq_tabs);
             cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);
             cudaFree(h->d_avail);
@@ -2354,6 +2466,8 @@ int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info* info) {
     info->smem_bytes = h->plan.smem;
     info->workspace_bytes = h->plan.ws_stride * sizeof(float) * (size_t)h->plan.ctas;
     info->table_bytes = h->table_bytes;
+    info->kernel_variant = h->last_kernel;
+    info->et_available = h->qcw_state == 1 ? 1 : 0;
     return LDPC_B200_OK;
 }
 

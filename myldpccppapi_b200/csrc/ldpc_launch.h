@@ -25,6 +25,7 @@ struct WarpParams;
 struct ClusterParams;
 struct QcParams;
 struct QcgParams;
+struct QcwParams;
 struct TdmpParams;
 struct BigParams;
 
@@ -44,6 +45,8 @@ int k_launch_stream(const StreamParams& q, int grid, int threads, cudaStream_t s
 int k_launch_sp_big(const BigParams& q, int grid, cudaStream_t stream);    // any size, messages in a global workspace
 int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream);
 int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream);  // the reference's fused kernels, their arithmetic
+// stats[0] = sum of up to 4096 evenly spaced entries of iters[0, ncw), stats[1] = how many (the regime of the last launch)
+int k_launch_iter_stats(const int32_t* iters, long long ncw, unsigned long long* stats, cudaStream_t stream);
 
 // Quasi-cyclic block structure of H for block size z: rows[br] = the circulants (block column, shift) of block
 // row br in ascending column order.
@@ -61,6 +64,15 @@ struct QcProfileEntry {
     int (*launch_ring)(const QcParams&, int grid, size_t smem, cudaStream_t stream);
     int (*ring_ctas_per_sm)(size_t smem);
 };
+// The warp-per-codeword kernel of the early-termination regime (ldpc_qcw.cuh): rate x z, z <= 32.
+struct QcwProfileEntry {
+    int z, warp_bytes;   // shared memory per codeword in flight (= per warp)
+    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, std::vector<unsigned char>* tab, std::vector<uint32_t>* syn_tab);
+    int (*launch)(const QcwParams&, int grid, int warps, cudaStream_t stream);
+    int (*upload)(int slot, const void* tab, size_t bytes);
+};
+const QcwProfileEntry* qcw_profiles(int* n);
+
 // one table per 802.16e rate (k_qc.cu compiled with -DLDPC_QC_RATE=...)
 const QcProfileEntry* qc_profiles_34B(int* n);
 const QcProfileEntry* qc_profiles_34A(int* n);

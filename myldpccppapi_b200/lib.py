@@ -30,6 +30,7 @@ class Info(C.Structure):
         ("path", C.c_int), ("threads_per_cta", C.c_int), ("ctas", C.c_int),
         ("codewords_per_cta", C.c_int),
         ("smem_bytes", C.c_size_t), ("workspace_bytes", C.c_size_t), ("table_bytes", C.c_size_t),
+        ("kernel_variant", C.c_int), ("et_available", C.c_int),
     ]
 
     def asdict(self):

@@ -296,6 +296,58 @@ def test_qc_alternative_kernels(default_code, monkeypatch, env):
     assert np.array_equal(out["info"][late], ref7[0][late])
 
 
+@pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
+def test_qc_early_termination_kernel(rate, name, num, den):
+    """ldpc_ms_qcw_kernel (a warp per codeword, syndrome from packed hard bits, no message clearing): bits, iteration
+    counts and posteriors of the oracle in every regime -- forced on (option qc_et = 1) over inputs from clean to
+    hopeless, on the device path, the streamed host path, tiny batches, caps 1 / 2 / 7 and the special values; and chosen
+    by the handle itself (qc_et = -1) after a launch whose words stopped early, dropped again after one whose words did not."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    N = 576
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    s0 = {0: 0.85, 1: 0.68, 2: 0.68, 3: 0.6, 4: 0.6, 5: 0.52}[rate]   # around the waterfall of each rate
+    llr = np.concatenate([awgn_llr(900, N, s0, seed=71 + rate), awgn_llr(1500, N, s0 * 0.85, seed=72 + rate),
+                          awgn_llr(301, N, 1.2, seed=73 + rate), awgn_llr(200, N, s0 * 0.6, seed=74 + rate)])
+    llr[5] = 0.0                                  # erased word: every posterior stays 0, bits all 1
+    llr[6, ::3] = 0.0
+    llr[7] = np.where(np.arange(N) % 2 == 0, -0.0, 0.0)
+    llr[8] = np.abs(llr[8]) + 0.1                 # all-zero codeword received cleanly: stops at iteration 1
+    llr[9, :7] = [np.inf, -np.inf, 1e30, -1e30, 1e-40, -1e-40, 1000.0]
+    ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(llr, literal=False)
+    dec = m.Decoder.wimax(K, N, rate)
+    assert dec.info()["path_name"] == "qc"
+    dec.reserve(4096)
+    assert dec.info()["et_available"] == 1
+    dec.set_option("qc_et", 1)
+    assert_parity(_run_device(dec, llr), ref, N, what="rate %s device" % name)
+    assert dec.info()["kernel_variant"] == 1
+    pinned = torch.from_numpy(llr).pin_memory().numpy()
+    assert_parity(dec.decode_host(pinned, want_hard=True, want_post=True), ref, N, what="streamed, pinned")
+    assert_parity(dec.decode_host(llr, want_hard=False, want_post=False), ref, N, what="host, pageable, info only")
+    dec.set_option("stream_chunk", 8)
+    assert_parity(dec.decode_host(pinned[:700], want_hard=True, want_post=True), tuple(r[:700] for r in ref), N, what="streamed, tiny chunks")
+    dec.set_option("stream_chunk", 0)
+    for n in (1, 3, 5, 9, 2401):
+        assert_parity(_run_device(dec, llr[:n]), tuple(r[:n] for r in ref), N, what="%d words" % n)
+    for cap in (1, 2, 7):
+        dec.set_max_iter(cap)
+        rc = oracle.Oracle(M, N, K, rp, ci, times=cap).decode(llr[:1200], literal=False)
+        assert_parity(_run_device(dec, llr[:1200]), rc, N, what="cap %d" % cap)
+    dec.set_max_iter(40)
+    # the handle's own choice: main kernel while the regime is unknown or the words run long, the early-termination
+    # kernel after a launch whose words stopped early
+    dec.set_option("qc_et", -1)
+    easy, hard = llr[900:2400], llr[2400:2701]
+    seen = []
+    for part, lo, hi in ((hard, 2400, 2701), (easy, 900, 2400), (easy, 900, 2400), (hard, 2400, 2701), (hard, 2400, 2701)):
+        out = _run_device(dec, part)
+        assert_parity(out, tuple(r[lo:hi] for r in ref), N, what="auto")
+        seen.append(dec.info()["kernel_variant"])
+    assert seen == [0, 0, 1, 1, 0], seen
+
+
 @pytest.mark.parametrize("N,rate,name,num,den", [(1152, 4, "3/4B", 3, 4), (1632, 0, "1/2", 1, 2), (2304, 5, "5/6", 5, 6), (1824, 1, "2/3A", 2, 3)])
 def test_any_size_sum_product_and_layered_kernels(N, rate, name, num, den):
     """The reference's kernels have no size limit (decodeCL.c:25-62, 203-292).  Codes beyond the on-chip layouts --

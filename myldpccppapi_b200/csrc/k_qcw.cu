@@ -1,5 +1,5 @@
-// k_qcw.cu -- the warp-per-codeword quasi-cyclic kernel (ldpc_qcw.cuh): one instantiation per 802.16e rate at z = 24,
-// the host-side table builder, and this unit's __constant__ table bank.
+// k_qcw.cu -- the warp-per-codeword quasi-cyclic kernel (ldpc_qcw.cuh): one instantiation per 802.16e rate at z = 24
+// and z = 32 (N = 576, 768), and the host-side check that a handle's H is the compiled code.
 #include <cstring>
 
 #include "ldpc_launch.h"
@@ -9,30 +9,17 @@
 namespace ldpc_b200 {
 namespace {
 
-// rows[br] = the circulants (block column, shift) of block row br: row r meets column (r + s) mod z.
+// rows[br] = the circulants (block column, shift) of block row br: row r meets column (r + s) mod z.  true = H is
+// exactly the code compiled into P; fills the per-lane table of the syndrome rounds.
 template <class P>
-bool qcw_build(const HostTables& t, const std::vector<std::vector<QcBlk>>& rows, std::vector<unsigned char>* tab_bytes,
-               std::vector<uint32_t>* syn_tab) {
+bool qcw_build(const HostTables& t, const std::vector<std::vector<QcBlk>>& rows, std::vector<uint32_t>* syn_tab) {
     constexpr int z = P::Z, NB = P::NB, MB = P::MB;
     if (t.N != NB * z || t.M != MB * z || (int)rows.size() != MB) return false;
-    struct Col { int br, j, s; };
-    std::vector<std::vector<Col>> cols(NB);
     for (int br = 0; br < MB; ++br) {
         if ((int)rows[br].size() != P::cdeg(br)) return false;
-        for (int j = 0; j < (int)rows[br].size(); ++j) cols[rows[br][j].bc].push_back({br, j, rows[br][j].s});
-    }
-    for (int b = 0; b < NB; ++b)
-        if ((int)cols[b].size() != P::vdeg(b)) return false;
-    tab_bytes->assign(sizeof(QcwTab<P>), 0);
-    QcwTab<P>& tab = *reinterpret_cast<QcwTab<P>*>(tab_bytes->data());
-    for (int br = 0; br < MB; ++br)
         for (int j = 0; j < P::cdeg(br); ++j)
-            tab.cn_t[P::coff(br) + j] = (uint32_t)(rows[br][j].bc * 2 * z + rows[br][j].s) * 4u;
-    for (int b = 0; b < NB; ++b)
-        for (int k = 0; k < P::vdeg(b); ++k) {   // ascending block row = ascending row: the summation order
-            const Col& c = cols[b][k];
-            tab.vn[P::voff(b) + k] = make_uint2(P::T_BYTES + (uint32_t)(P::e0(c.br) + c.j) * z * 4u - (uint32_t)c.s * 4u, (uint32_t)c.s);
-        }
+            if (rows[br][j].bc != P::cbc(P::e0(br) + j) || rows[br][j].s != P::csh(P::e0(br) + j)) return false;
+    }
     syn_tab->assign((size_t)P::ROUNDS * 32, 0xffffffffu);
     for (int r = 0; r < P::ROUNDS; ++r)
         for (int lane = 0; lane < 32; ++lane) {
@@ -51,15 +38,12 @@ int launch_qcw_t(const QcwParams& q, int grid, int warps, cudaStream_t stream) {
     return (int)cudaGetLastError();
 }
 
-int upload_qcw_bank(int slot, const void* tab, size_t bytes) {
-    if (slot < 0 || slot >= kQcTabSlots || bytes > (size_t)kQcwBankBytes) return (int)cudaErrorInvalidValue;
-    return (int)cudaMemcpyToSymbol(g_qcw_bank, tab, bytes, (size_t)slot * kQcwBankBytes, cudaMemcpyHostToDevice);
-}
-
-#define QCW_PROFILE(R, Z) {Z, (int)QcwProfile<R, Z>::WARP_BYTES, &qcw_build<QcwProfile<R, Z>>, &launch_qcw_t<QcwProfile<R, Z>>, &upload_qcw_bank}
+#define QCW_PROFILE(C) {C::Z, (int)QcwProfile<C>::WARP_BYTES, &qcw_build<QcwProfile<C>>, &launch_qcw_t<QcwProfile<C>>}
 const QcwProfileEntry kTable[] = {
-    QCW_PROFILE(QcwRate34B, 24), QCW_PROFILE(QcwRate34A, 24), QCW_PROFILE(QcwRate23B, 24),
-    QCW_PROFILE(QcwRate23A, 24), QCW_PROFILE(QcwRate12, 24),  QCW_PROFILE(QcwRate56, 24),
+    QCW_PROFILE(QcwCode34B_24), QCW_PROFILE(QcwCode34A_24), QCW_PROFILE(QcwCode23B_24),
+    QCW_PROFILE(QcwCode23A_24), QCW_PROFILE(QcwCode12_24),  QCW_PROFILE(QcwCode56_24),
+    QCW_PROFILE(QcwCode34B_32), QCW_PROFILE(QcwCode34A_32), QCW_PROFILE(QcwCode23B_32),
+    QCW_PROFILE(QcwCode23A_32), QCW_PROFILE(QcwCode12_32),  QCW_PROFILE(QcwCode56_32),
 };
 #undef QCW_PROFILE
 

@@ -78,7 +78,8 @@ struct Options {
     // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
-    int qc_et_pct = 60;               // auto: used while the mean iteration count is at most this share of the cap (measured crossover: profiles/r02_et_kernel.md)
+    int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
+                                      // crossover of the code (profiles/r02_et_kernel.md: z = 24 90 %, z = 32 every regime)
 };
 
 struct OptionName { const char* name; int kind; size_t off; bool runtime; };  // kind 0 bool, 1 int, 2 long long
@@ -182,7 +183,7 @@ struct ldpc_b200_decoder {
     int qc_ring_per_sm = 0;
     // the early-termination kernel (ldpc_qcw.cuh: a warp per codeword), prepared next to the main one
     QcwParams qcw;
-    int qcw_kind = -1, qcw_state = 0, qcw_slot = -1, qcw_warps = 0;
+    int qcw_kind = -1, qcw_state = 0, qcw_warps = 0;
     uint32_t* d_syn_tab = nullptr;
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
     int32_t* d_iters_own = nullptr;          // iteration counts when the caller does not ask for them
@@ -1228,11 +1229,8 @@ bool qc_prepare(ldpc_b200_decoder* h) {
     return false;
 }
 
-// The early-termination kernel (ldpc_qcw.cuh: a warp per codeword, z <= 32): finds the rate's instantiation, builds its
-// tables, takes a slot of that unit's constant bank.  false = this code has none (the main kernel serves every regime).
-std::mutex g_qcw_mu;
-const void* g_qcw_owner[kQcMaxDevices][kQcTabSlots] = {};
-
+// The warp-per-codeword kernel (ldpc_qcw.cuh; 802.16e codes with z = 24 or 32, their circulants compiled in): finds the
+// instantiation whose code this handle's H is.  false = there is none (the lockstep kernel serves every regime).
 bool qcw_prepare(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
     if (h->qc_state != 1) return false;
@@ -1245,38 +1243,27 @@ bool qcw_prepare(ldpc_b200_decoder* h) {
         if (t.N != 24 * pe.z) continue;
         if (rows_z != pe.z) { rows.clear(); rows_z = pe.z; if (!qc_blocks(t, pe.z, &rows)) rows.clear(); }
         if (rows.empty()) continue;
-        std::vector<unsigned char> tab;
         std::vector<uint32_t> syn;
-        if (!pe.build(t, rows, &tab, &syn)) continue;
-        const int warps = std::min<int>(kQcwMaxWarps, (int)(h->smem_optin / (size_t)pe.warp_bytes));
+        if (!pe.build(t, rows, &syn)) continue;
+        // a multiple of four warps (one register-file partition each); 16 at z = 24, 12 at z = 32
+        const int warps = std::min<int>(kQcwMaxWarps, (int)(h->smem_optin / (size_t)pe.warp_bytes)) & ~3;
         if (warps < 8) return false;
         DeviceGuard guard(h->device);
-        if (!guard.ok || h->device < 0 || h->device >= kQcMaxDevices) return false;
-        int slot = -1;
-        {
-            std::lock_guard<std::mutex> lk(g_qcw_mu);
-            for (int s2 = 0; s2 < kQcTabSlots && slot < 0; ++s2)
-                if (!g_qcw_owner[h->device][s2]) { g_qcw_owner[h->device][s2] = h; slot = s2; }
-        }
-        if (slot < 0) return false;
-        if (pe.upload(slot, tab.data(), tab.size()) != 0 || cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||
+        if (!guard.ok) return false;
+        if (cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||
             cudaMemcpy(h->d_syn_tab, syn.data(), syn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
             (!h->d_stats && cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) ||
             (!h->h_stats && cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)) {
             (void)cudaGetLastError();
-            std::lock_guard<std::mutex> lk(g_qcw_mu);
-            g_qcw_owner[h->device][slot] = nullptr;
             return false;
         }
         h->h_stats[0] = h->h_stats[1] = 0ull;
         std::memset(&h->qcw, 0, sizeof(h->qcw));
-        h->qcw.tab_slot = slot;
         h->qcw.N = t.N;
         h->qcw.syn_tab = h->d_syn_tab;
-        h->qcw_slot = slot;
         h->qcw_kind = k;
         h->qcw_warps = warps;
-        h->table_bytes += tab.size() + syn.size() * 4;
+        h->table_bytes += syn.size() * 4;
         return true;
     }
     return false;
@@ -2003,7 +1990,11 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         const bool track = et_ready && h->opt.qc_et < 0;   // the regime is tracked through the iteration counts
         bool use_et = et_ready && h->opt.qc_et > 0;
         if (track && h->h_stats[1] > 0)
-            use_et = (double)h->h_stats[0] * 100.0 <= (double)h->opt.qc_et_pct * (double)h->max_iter * (double)h->h_stats[1];
+{
+            int np0 = 0;
+            const int pct = h->opt.qc_et_pct > 0 ? h->opt.qc_et_pct : (qcw_profiles(&np0)[h->qcw_kind].z >= 32 ? 100 : 90);
+            use_et = (double)h->h_stats[0] * 100.0 <= (double)pct * (double)h->max_iter * (double)h->h_stats[1];
+        }
         if (track && !q.iters) {
             if (h->iters_own_cap < ncw) {
                 cudaFree(h->d_iters_own); h->d_iters_own = nullptr; h->iters_own_cap = 0;
@@ -2255,10 +2246,6 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaDeviceSynchronize();
             free_slots(h);
             if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
-            if (h->qcw_slot >= 0 && h->device >= 0 && h->device < kQcMaxDevices) {
-                std::lock_guard<std::mutex> lk(g_qcw_mu);
-                if (g_qcw_owner[h->device][h->qcw_slot] == h) g_qcw_owner[h->device][h->qcw_slot] = nullptr;
-            }
             cudaFree(h->d_syn_tab); cudaFree(h->d_iters_own); cudaFree(h->d_stats);
             if (h->h_stats) cudaFreeHost(h->h_stats);
             cudaFree(h->dq_tabs);

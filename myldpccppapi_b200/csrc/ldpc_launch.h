@@ -64,12 +64,13 @@ struct QcProfileEntry {
     int (*launch_ring)(const QcParams&, int grid, size_t smem, cudaStream_t stream);
     int (*ring_ctas_per_sm)(size_t smem);
 };
-// The warp-per-codeword kernel of the early-termination regime (ldpc_qcw.cuh): rate x z, z <= 32.
+// The warp-per-codeword kernel (ldpc_qcw.cuh): 802.16e rate x z, z = 24 or 32.
 struct QcwProfileEntry {
     int z, warp_bytes;   // shared memory per codeword in flight (= per warp)
-    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, std::vector<unsigned char>* tab, std::vector<uint32_t>* syn_tab);
+    // true if H is exactly the code compiled into the instantiation (its circulants are immediates); fills the per-lane
+    // table of the syndrome rounds
+    bool (*build)(const HostTables&, const std::vector<std::vector<QcBlk>>&, std::vector<uint32_t>* syn_tab);
     int (*launch)(const QcwParams&, int grid, int warps, cudaStream_t stream);
-    int (*upload)(int slot, const void* tab, size_t bytes);
 };
 const QcwProfileEntry* qcw_profiles(int* n);
 

@@ -296,15 +296,15 @@ def test_qc_alternative_kernels(default_code, monkeypatch, env):
     assert np.array_equal(out["info"][late], ref7[0][late])
 
 
+@pytest.mark.parametrize("N", [576, 768])
 @pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
-def test_qc_early_termination_kernel(rate, name, num, den):
+def test_qc_early_termination_kernel(rate, name, num, den, N):
     """ldpc_ms_qcw_kernel (a warp per codeword, syndrome from packed hard bits, no message clearing): bits, iteration
     counts and posteriors of the oracle in every regime -- forced on (option qc_et = 1) over inputs from clean to
     hopeless, on the device path, the streamed host path, tiny batches, caps 1 / 2 / 7 and the special values; and chosen
     by the handle itself (qc_et = -1) after a launch whose words stopped early, dropped again after one whose words did not."""
     import myldpccppapi_b200 as m
     torch = _torch()
-    N = 576
     K = N * num // den
     rp, ci, M = oracle.wimax_H(N, name)
     s0 = {0: 0.85, 1: 0.68, 2: 0.68, 3: 0.6, 4: 0.6, 5: 0.52}[rate]   # around the waterfall of each rate

@@ -27,9 +27,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ncw", type=int, default=65536)
     ap.add_argument("--rate", type=int, default=4)
+    ap.add_argument("--N", type=int, default=576)
     ap.add_argument("--points", default="sigma1,0,1,2,2.5,3,3.5,4,5")
     args = ap.parse_args()
-    N = 576
+    N = args.N
     num, den = {0: (1, 2), 1: (2, 3), 2: (2, 3), 3: (3, 4), 4: (3, 4), 5: (5, 6)}[args.rate]
     K = N * num // den
     dec = m.Decoder.wimax(K, N, args.rate, max_iter=40)

@@ -336,8 +336,9 @@ def test_qc_early_termination_kernel(rate, name, num, den, N):
         rc = oracle.Oracle(M, N, K, rp, ci, times=cap).decode(llr[:1200], literal=False)
         assert_parity(_run_device(dec, llr[:1200]), rc, N, what="cap %d" % cap)
     dec.set_max_iter(40)
-    # the handle's own choice: main kernel while the regime is unknown or the words run long, the early-termination
-    # kernel after a launch whose words stopped early
+    # the handle's own choice: the lockstep kernel while the regime is unknown, afterwards the warp-per-codeword kernel
+    # whenever the previous launch's words stopped early on average (z = 24: mean <= 90 % of the cap; z = 32: always,
+    # it is the faster kernel in every regime there)
     dec.set_option("qc_et", -1)
     easy, hard = llr[900:2400], llr[2400:2701]
     seen = []
@@ -345,7 +346,7 @@ def test_qc_early_termination_kernel(rate, name, num, den, N):
         out = _run_device(dec, part)
         assert_parity(out, tuple(r[lo:hi] for r in ref), N, what="auto")
         seen.append(dec.info()["kernel_variant"])
-    assert seen == [0, 0, 1, 1, 0], seen
+    assert seen == ([0, 0, 1, 1, 0] if N == 576 else [0, 1, 1, 1, 1]), seen
 
 
 @pytest.mark.parametrize("N,rate,name,num,den", [(1152, 4, "3/4B", 3, 4), (1632, 0, "1/2", 1, 2), (2304, 5, "5/6", 5, 6), (1824, 1, "2/3A", 2, 3)])

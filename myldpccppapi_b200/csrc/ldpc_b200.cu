@@ -78,6 +78,7 @@ struct Options {
     // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
+    int qc_et_every = 4;              // auto: the iteration counts are sampled after every n-th launch once the regime is known (13 us each)
     int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
                                       // crossover of the code (profiles/r02_et_kernel.md: z = 24 90 %, z = 32 every regime)
 };
@@ -91,7 +92,7 @@ const OptionName kOptionNames[] = {
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
-    OPTR(qc_et, 1), OPTR(qc_et_pct, 1),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1),
 };
 #undef OPT
 #undef OPTR
@@ -188,8 +189,8 @@ struct ldpc_b200_decoder {
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
     int32_t* d_iters_own = nullptr;          // iteration counts when the caller does not ask for them
     int64_t iters_own_cap = 0;
-    unsigned long long* d_stats = nullptr;   // [0] sum of the sampled counts, [1] words sampled
-    unsigned long long* h_stats = nullptr;   // pinned copy, refreshed after every launch
+    unsigned long long* h_stats = nullptr;   // pinned, written by the device after every launch: [0] sum of the sampled counts, [1] words sampled
+    unsigned stat_tick = 0;
     int last_kernel = 0;                     // ldpc_b200_info.kernel_variant of the most recent launch
     // QC tables with a run-time profile (ldpc_qcg.cuh)
     QcgParams qcg;
@@ -1252,7 +1253,6 @@ bool qcw_prepare(ldpc_b200_decoder* h) {
         if (!guard.ok) return false;
         if (cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||
             cudaMemcpy(h->d_syn_tab, syn.data(), syn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-            (!h->d_stats && cudaMalloc(&h->d_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) ||
             (!h->h_stats && cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)) {
             (void)cudaGetLastError();
             return false;
@@ -2022,10 +2022,10 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         }
         if (rc) return rc;
         h->launches += 1;
-        if (track) {
-            rc = launch_status(k_launch_iter_stats(q.iters, ncw, h->d_stats, stream), "iteration statistics");
+        if (track && (h->h_stats[1] == 0 || h->stat_tick++ % (unsigned)std::max(1, h->opt.qc_et_every) == 0)) {
+            // (written straight into pinned host memory: no copy operation between two decodes of the stream)
+            rc = launch_status(k_launch_iter_stats(q.iters, ncw, h->h_stats, stream), "iteration statistics");
             if (rc) return rc;
-            CU_TRY(cudaMemcpyAsync(h->h_stats, h->d_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
             h->launches += 1;
         }
         return LDPC_B200_OK;
@@ -2246,7 +2246,7 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaDeviceSynchronize();
             free_slots(h);
             if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
-            cudaFree(h->d_syn_tab); cudaFree(h->d_iters_own); cudaFree(h->d_stats);
+            cudaFree(h->d_syn_tab); cudaFree(h->d_iters_own);
             if (h->h_stats) cudaFreeHost(h->h_stats);
             cudaFree(h->dq_tabs);
             cudaFree(h->st_llr); cudaFree(h->st_info); cudaFree(h->st_hard); cudaFree(h->st_iters); cudaFree(h->st_post);

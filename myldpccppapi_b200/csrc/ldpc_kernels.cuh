@@ -307,6 +307,38 @@ __device__ __forceinline__ void sts_u128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// The new messages of one check from S_j = -Q_j (refreshRMS, decodeCL.c:126-147 / MyLdpc.cpp:705-721):
+//   R_j = sign_j * min(1000, min over the OTHER edges of |S|),  sign_j negative iff an odd number of the other Q are
+//   negative = parity ^ 1 ^ signbit(S_j)  (Q_j < 0 <=> !signbit(S_j); px = xor of all S_j, D = degree).
+// The exclude-self minimum is taken as min3(prefix, neighbour, suffix) over PAIRS of edges: two three-input min
+// instructions per edge.  Tracking min1/min2 and selecting by comparison gives the same value bit for bit (ties
+// included: the minimum of the others is the same number either way) but costs 4.5 instructions per edge on the
+// half-rate ALU pipe, which bound the check pass.  The sign is applied by one multiplication with +-1.0 (FMA pipe; exact,
+// and a zero magnitude takes the sign bit as the xor did).
+__device__ __forceinline__ float ms_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+template <int D>
+__device__ __forceinline__ void ms_new_messages(const float* S, uint32_t px, float* rn) {
+    constexpr int H = (D + 1) / 2;
+    const uint32_t one = (((px >> 31) ^ (uint32_t)D ^ 1u) << 31) ^ 0x3f800000u;  // +-1.0f, flipped per edge by signbit(S_j)
+    // pe[t] = min(1000, |S_0| .. |S_{2t-1}|), se[t] = min(1000, |S_{2t}| .. |S_{D-1}|)
+    float pe[H + 1], se[H + 1];
+    pe[0] = kClamp;
+#pragma unroll
+    for (int t = 0; t + 1 < H; ++t) pe[t + 1] = ms_min3(pe[t], fabsf(S[2 * t]), fabsf(S[2 * t + 1]));
+    se[H] = kClamp;
+#pragma unroll
+    for (int t = H - 1; t >= 1; --t)
+        se[t] = (2 * t + 1 < D) ? ms_min3(se[t + 1], fabsf(S[2 * t]), fabsf(S[2 * t + 1])) : fminf(se[t + 1], fabsf(S[2 * t]));
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int t = j >> 1, o = j ^ 1;   // the other edge of the pair (none for the last edge of an odd row)
+        const float m = o < D ? ms_min3(pe[t], fabsf(S[o]), se[t + 1]) : fminf(pe[t], se[t + 1]);
+        uint32_t sg;  // (S_j & 0x80000000) ^ one in ONE LOP3
+        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(sg) : "r"(__float_as_uint(S[j])), "r"(one));
+        rn[j] = __fmul_rn(m, __uint_as_float(sg));
+    }
+}
+
 // CNT consecutive variable-node edges: entries at shared address `q` ({ST row address, 1 << shift}).
 template <int CNT>
 __device__ __forceinline__ void l16_vn_edges(uint32_t q, uint32_t lane16, uint32_t key, float& acc) {
@@ -615,15 +647,9 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
     for (int j = 0; j < D; ++j) tv[j] = ld_node_f32<DSM>(ent[j] + (T16 ? 0u : c4));
 #pragma unroll
     for (int j = 0; j < D; ++j) S[j] = lds_f32(rrow + (uint32_t)j * 128u);
-    float m1 = INFINITY, m2 = INFINITY;
     uint32_t px = 0u, sx = 0u;
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
-        const float a = fabsf(S[j]);
-        m2 = fminf(m2, fmaxf(m1, a));
-        m1 = fminf(m1, a);
-    }
+    for (int j = 0; j < D; ++j) S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
     // sign parities, two edges per 3-input LOP3
 #pragma unroll
     for (int j = 0; j + 1 < D; j += 2) {
@@ -634,19 +660,10 @@ __device__ __forceinline__ uint32_t grp_check(uint32_t tab, const uint32_t* __re
         px ^= __float_as_uint(S[D - 1]);
         sx ^= __float_as_uint(tv[D - 1]);
     }
-    // (Q_j < 0) = !signbit(S_j); parity of the negative Q's = (D & 1) ^ xor signbit(S);
-    // sign(R_j) = parity ^ (Q_j < 0) = parity ^ 1 ^ signbit(S_j)
-    const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
-    uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
-    uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
-    asm("" : "+r"(m1x), "+r"(m2x));  // materialise: keeps the parity flip out of the per-edge selects
+    float rn[D];
+    ms_new_messages<D>(S, px, rn);
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
-        uint32_t rn;  // (S_j & 0x80000000) ^ mag in ONE LOP3 (kept opaque so the sign is not re-derived with FADDs)
-        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(rn) : "r"(__float_as_uint(S[j])), "r"(mag));
-        sts_f32(rrow + (uint32_t)j * 128u, __uint_as_float(rn));
-    }
+    for (int j = 0; j < D; ++j) sts_f32(rrow + (uint32_t)j * 128u, rn[j]);
     return ((sx >> 31) ^ (uint32_t)D) & 1u;  // hard bit = !signbit(T)
 }
 

@@ -173,17 +173,10 @@ __device__ __forceinline__ bool qc_wait_input(const unsigned long long* avail, l
     }
 }
 
-// One check of exact degree D: the T rows come from warp-uniform bases, the R rows are this lane's own column of the
-// block (edge j at + j * RS).  refreshRMS (decodeCL.c:126-147): S_j = T + R_old = -Q_j; R_new_j = sign * min(1000, min
-// over the OTHER edges of |S|), taken as min3(prefix, neighbour, suffix) over pairs of edges -- two three-input min
-// instructions per edge, the same value bit for bit as tracking min1/min2 and selecting by comparison (4.5 ALU-pipe
-// instructions per edge: the check pass was bound by that pipe).  sign(R_new_j) = parity of the other negative Q's =
-// parity ^ 1 ^ signbit(S_j) (Q_j < 0 <=> !signbit(S_j)), applied by one multiplication with +-1.0 (FMA pipe).
-// Returns the row's syndrome bit.
-__device__ __forceinline__ float qc_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// One check of exact degree D (see grp_check / ms_new_messages): the T rows come from warp-uniform bases, the R rows
+// are this lane's own column of the block (edge j at + j * RS).  Returns the row's syndrome bit.
 template <int D, uint32_t RS, uint32_t WRAP, bool DUP>
 __device__ __forceinline__ uint32_t qc_check(const uint32_t* __restrict__ tt, uint32_t rrow, uint32_t la) {
-    constexpr int H = (D + 1) / 2;
     float tv[D + 1], S[D];
 #pragma unroll
     for (int j = 0; j < D; j += 2) {  // two warp-uniform bases per LDCU.64
@@ -205,26 +198,10 @@ __device__ __forceinline__ uint32_t qc_check(const uint32_t* __restrict__ tt, ui
         px ^= __float_as_uint(S[D - 1]);
         sx ^= __float_as_uint(tv[D - 1]);
     }
-    const uint32_t one = (((px >> 31) ^ (uint32_t)D ^ 1u) << 31) ^ 0x3f800000u;  // +-1.0f; flipped per edge by signbit(S_j)
-    // pe[t] = min(1000, |S_0| .. |S_{2t-1}|), se[t] = min(1000, |S_{2t}| .. |S_{D-1}|)
-    float pe[H + 1], se[H + 1];
-    pe[0] = kClamp;
-#pragma unroll
-    for (int t = 0; t + 1 < H; ++t) pe[t + 1] = qc_min3(pe[t], fabsf(S[2 * t]), fabsf(S[2 * t + 1]));
-    se[H] = kClamp;
-#pragma unroll
-    for (int t = H - 1; t >= 1; --t)
-        se[t] = (2 * t + 1 < D) ? qc_min3(se[t + 1], fabsf(S[2 * t]), fabsf(S[2 * t + 1])) : fminf(se[t + 1], fabsf(S[2 * t]));
     float rn[D];
+    ms_new_messages<D>(S, px, rn);
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const int t = j >> 1, o = j ^ 1;   // the other edge of the pair (none for the last edge of an odd row)
-        const float m = o < D ? qc_min3(pe[t], fabsf(S[o]), se[t + 1]) : fminf(pe[t], se[t + 1]);
-        uint32_t sg;
-        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(sg) : "r"(__float_as_uint(S[j])), "r"(one));
-        rn[j] = __fmul_rn(m, __uint_as_float(sg));
-        sts_f32(la + rrow + (uint32_t)j * RS, rn[j]);
-    }
+    for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS, rn[j]);
     if constexpr (DUP) {  // this group owns the block's last rows, which are also read through the leading pad
 #pragma unroll
         for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS - WRAP, rn[j]);

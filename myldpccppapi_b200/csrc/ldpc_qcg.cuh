@@ -69,15 +69,9 @@ __device__ __forceinline__ void qcg_check_load(uint32_t tt, uint32_t rrow, uint3
 }
 template <int D>
 __device__ __forceinline__ uint32_t qcg_check_finish(uint32_t rrow, uint32_t la, uint32_t RS, uint32_t WRAP, bool dup, const float* tv, float* S) {
-    float m1 = INFINITY, m2 = INFINITY;
     uint32_t px = 0u, sx = 0u;
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
-        const float a = fabsf(S[j]);
-        m2 = fminf(m2, fmaxf(m1, a));
-        m1 = fminf(m1, a);
-    }
+    for (int j = 0; j < D; ++j) S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j
 #pragma unroll
     for (int j = 0; j + 1 < D; j += 2) {
         px = px ^ __float_as_uint(S[j]) ^ __float_as_uint(S[j + 1]);
@@ -87,20 +81,13 @@ __device__ __forceinline__ uint32_t qcg_check_finish(uint32_t rrow, uint32_t la,
         px ^= __float_as_uint(S[D - 1]);
         sx ^= __float_as_uint(tv[D - 1]);
     }
-    const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
-    uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
-    uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
-    asm("" : "+r"(m1x), "+r"(m2x));
-    uint32_t rn[D];
+    float rn[D];
+    ms_new_messages<D>(S, px, rn);
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
-        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(rn[j]) : "r"(__float_as_uint(S[j])), "r"(mag));
-        sts_f32(la + rrow + (uint32_t)j * RS, __uint_as_float(rn[j]));
-    }
+    for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS, rn[j]);
     if (dup) {  // warp-uniform
 #pragma unroll
-        for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS - WRAP, __uint_as_float(rn[j]));
+        for (int j = 0; j < D; ++j) sts_f32(la + rrow + (uint32_t)j * RS - WRAP, rn[j]);
     }
     return ((sx >> 31) ^ (uint32_t)D) & 1u;
 }

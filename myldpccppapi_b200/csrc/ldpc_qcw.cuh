@@ -69,13 +69,11 @@ struct QcwParams {
 
 #ifdef LDPC_QCW_DEVICE   // the kernel: only the unit that instantiates it (k_qcw.cu)
 
-__device__ __forceinline__ float qcw_min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
-
 // One block row: lane = row.  refreshRMS (decodeCL.c:126-147): S_j = T + R_old = -Q_j, R_new_j = sign * min(1000, min of
 // the other |S|), sign(R_new_j) = parity of the other negative Q's = parity ^ 1 ^ signbit(S_j).
 template <class P, int I>
 __device__ __forceinline__ void qcw_check(uint32_t la, bool act) {
-    constexpr int D = P::cdeg(I), E0 = P::e0(I), H = (D + 1) / 2;
+    constexpr int D = P::cdeg(I), E0 = P::e0(I);
     float S[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -87,25 +85,11 @@ __device__ __forceinline__ void qcw_check(uint32_t la, bool act) {
 #pragma unroll
     for (int j = 0; j + 1 < D; j += 2) px = px ^ __float_as_uint(S[j]) ^ __float_as_uint(S[j + 1]);
     if (D & 1) px ^= __float_as_uint(S[D - 1]);
-    // +-1.0f: bit 31 = parity ^ D ^ 1, flipped per edge by signbit(S_j)
-    const uint32_t one = (((px >> 31) ^ (uint32_t)D ^ 1u) << 31) ^ 0x3f800000u;
-    // pe[t] = min(1000, |S_0| .. |S_{2t-1}|), se[t] = min(1000, |S_{2t}| .. |S_{D-1}|)
-    float pe[H + 1], se[H + 1];
-    pe[0] = kClamp;
+    float rn[D];
+    ms_new_messages<D>(S, px, rn);   // exclude-self minima by prefix / suffix, sign by multiplication (ldpc_kernels.cuh)
+    if (act) {
 #pragma unroll
-    for (int t = 0; t + 1 < H; ++t) pe[t + 1] = qcw_min3(pe[t], fabsf(S[2 * t]), fabsf(S[2 * t + 1]));
-    se[H] = kClamp;
-#pragma unroll
-    for (int t = H - 1; t >= 1; --t)
-        se[t] = (2 * t + 1 < D) ? qcw_min3(se[t + 1], fabsf(S[2 * t]), fabsf(S[2 * t + 1])) : fminf(se[t + 1], fabsf(S[2 * t]));
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const int t = j >> 1, o = j ^ 1;   // the other edge of the pair (none for the last edge of an odd row)
-        const float m = o < D ? qcw_min3(pe[t], fabsf(S[o]), se[t + 1]) : fminf(pe[t], se[t + 1]);
-        uint32_t sg;
-        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(sg) : "r"(__float_as_uint(S[j])), "r"(one));
-        const float rn = __fmul_rn(m, __uint_as_float(sg));
-        if (act) sts_f32(la + P::T_BYTES + (uint32_t)(E0 + j) * P::ZB, rn);
+        for (int j = 0; j < D; ++j) sts_f32(la + P::T_BYTES + (uint32_t)(E0 + j) * P::ZB, rn[j]);
     }
 }
 

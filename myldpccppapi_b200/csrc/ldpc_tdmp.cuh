@@ -66,30 +66,17 @@ __device__ __forceinline__ void tdmp_check(uint32_t tab, uint32_t rrow, uint32_t
 #pragma unroll
         for (int j = 0; j < D; ++j) S[j] = __fadd_rn(tv[j], S[j]);  // = -Q_j = -(P - R_old)
     }
-    float m1 = INFINITY, m2 = INFINITY;
     uint32_t px = 0u;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const float a = fabsf(S[j]);
-        m2 = fminf(m2, fmaxf(m1, a));
-        m1 = fminf(m1, a);
-    }
 #pragma unroll
     for (int j = 0; j + 1 < D; j += 2) px = px ^ __float_as_uint(S[j]) ^ __float_as_uint(S[j + 1]);
     if (D & 1) px ^= __float_as_uint(S[D - 1]);
-    // (Q_j < 0) = !signbit(S_j); sign(R_j) = xor of the others = total ^ own
-    const uint32_t flip = (((px >> 31) ^ (uint32_t)D ^ 1u) & 1u) << 31;
-    uint32_t m1x = __float_as_uint(fminf(m1, kClamp)) ^ flip;
-    uint32_t m2x = __float_as_uint(fminf(m2, kClamp)) ^ flip;
-    asm("" : "+r"(m1x), "+r"(m2x));
+    float rn[D];
+    ms_new_messages<D>(S, px, rn);   // (Q_j < 0) = !signbit(S_j); sign(R_j) = xor of the others = total ^ own
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        const uint32_t mag = (fabsf(S[j]) == m1) ? m2x : m1x;
-        uint32_t rn;
-        asm("lop3.b32 %0, %1, 0x80000000, %2, 0x6a;" : "=r"(rn) : "r"(__float_as_uint(S[j])), "r"(mag));
         if (act) {
-            sts_f32(rrow + (uint32_t)j * 128u, __uint_as_float(rn));
-            sts_f32(ent[j], __fsub_rn(S[j], __uint_as_float(rn)));  // -(Q + R_new)
+            sts_f32(rrow + (uint32_t)j * 128u, rn[j]);
+            sts_f32(ent[j], __fsub_rn(S[j], rn[j]));  // -(Q + R_new)
         }
     }
 }

@@ -340,6 +340,7 @@ def test_qc_early_termination_kernel(rate, name, num, den, N):
     # whenever the previous launch's words stopped early on average (z = 24: mean <= 90 % of the cap; z = 32: always,
     # it is the faster kernel in every regime there)
     dec.set_option("qc_et", -1)
+    dec.set_option("qc_et_every", 1)   # (default: the counts are sampled after every fourth launch)
     easy, hard = llr[900:2400], llr[2400:2701]
     seen = []
     for part, lo, hi in ((hard, 2400, 2701), (easy, 900, 2400), (easy, 900, 2400), (hard, 2400, 2701), (hard, 2400, 2701)):

@@ -25,6 +25,7 @@
 #include "ldpc_qc.cuh"
 #include "ldpc_qcg.cuh"
 #include "ldpc_qcw.cuh"
+#include "ldpc_qcm.cuh"
 #include "ldpc_warp.cuh"
 #include "ldpc_sp.cuh"
 #include "ldpc_tdmp.cuh"
@@ -62,7 +63,7 @@ constexpr int kCounterRing = 256;  // one work-queue head per in-flight launch
 // decode path calls getenv.
 struct Options {
     // kernel choice: read when a plan is made
-    bool no_qc = false, no_qcg = false, qc_generic = false, qc_ring = false;
+    bool no_qc = false, no_qcg = false, no_qcm = false, qcm_always = false, qc_generic = false, qc_ring = false;
     bool grp_no_profile = false, grp_no_ysmem = false, grp_prefer_16 = false, grp_t16 = false, grp_no_t16 = false;
     bool debug_placement = false, sp_big = false;  // sp_big: sum-product through the any-size kernel even where the on-chip one fits (tests)
     int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0, qc_prefer_g = 0;
@@ -87,7 +88,7 @@ struct OptionName { const char* name; int kind; size_t off; bool runtime; };  //
 #define OPT(n, k) {#n, k, offsetof(Options, n), false}   // shapes the plan: environment only, read at create
 #define OPTR(n, k) {#n, k, offsetof(Options, n), true}   // may change afterwards (ldpc_b200_set_option)
 const OptionName kOptionNames[] = {
-    OPT(no_qc, 0), OPT(no_qcg, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
+    OPT(no_qc, 0), OPT(no_qcg, 0), OPT(no_qcm, 0), OPT(qcm_always, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
@@ -186,6 +187,9 @@ struct ldpc_b200_decoder {
     QcwParams qcw;
     int qcw_kind = -1, qcw_state = 0, qcw_warps = 0;
     uint32_t* d_syn_tab = nullptr;
+    // a group of warps per codeword, any z (ldpc_qcm.cuh): the block sizes without a compiled lockstep profile
+    QcmParams qcm;
+    int qcm_kind = -1, qcm_state = 0, qcm_slot = -1, qcm_groups = 0;
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
     int32_t* d_iters_own = nullptr;          // iteration counts when the caller does not ask for them
     int64_t iters_own_cap = 0;
@@ -1269,6 +1273,49 @@ bool qcw_prepare(ldpc_b200_decoder* h) {
     return false;
 }
 
+// The group-of-warps-per-codeword kernel (ldpc_qcm.cuh): any quasi-cyclic code with 24 block columns and the degree
+// sequences of an 802.16e rate, z <= 96.  Builds the tables, takes a slot of that unit's constant bank.
+std::mutex g_qcm_mu;
+const void* g_qcm_owner[kQcMaxDevices][kQcTabSlots] = {};
+
+bool qcm_prepare(ldpc_b200_decoder* h) {
+    const HostTables& t = h->host;
+    if (t.N % 24) return false;
+    const int z = t.N / 24;
+    std::vector<std::vector<QcBlk>> rows;
+    if (z > 96 || !qc_blocks(t, z, &rows)) return false;
+    int n = 0;
+    const QcmProfileEntry* profiles = qcm_profiles(&n);
+    for (int k = 0; k < n; ++k) {
+        const QcmProfileEntry& pe = profiles[k];
+        std::vector<unsigned char> tab;
+        int groups = 0;
+        if (!pe.build(t, z, rows, h->smem_optin, &h->qcm, &tab, &groups)) continue;
+        DeviceGuard guard(h->device);
+        if (!guard.ok || h->device < 0 || h->device >= kQcMaxDevices) return false;
+        int slot = -1;
+        {
+            std::lock_guard<std::mutex> lk(g_qcm_mu);
+            for (int s2 = 0; s2 < kQcTabSlots && slot < 0; ++s2)
+                if (!g_qcm_owner[h->device][s2]) { g_qcm_owner[h->device][s2] = h; slot = s2; }
+        }
+        if (slot < 0) return false;
+        if (pe.upload(slot, tab.data(), tab.size()) != 0) {
+            (void)cudaGetLastError();
+            std::lock_guard<std::mutex> lk(g_qcm_mu);
+            g_qcm_owner[h->device][slot] = nullptr;
+            return false;
+        }
+        h->qcm.tab_slot = slot;
+        h->qcm_slot = slot;
+        h->qcm_kind = k;
+        h->qcm_groups = groups;
+        h->table_bytes += tab.size();
+        return true;
+    }
+    return false;
+}
+
 // Run-time-profile QC path: picks G (most codewords per CTA with two CTAs per SM, else one CTA), builds and uploads.
 bool qcg_prepare(ldpc_b200_decoder* h) {
     const HostTables& t = h->host;
@@ -1716,7 +1763,7 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
     {   // quasi-cyclic code matching a compiled profile: warp-uniform tables (min-sum only)
         const bool want = flood_alg == LDPC_B200_ALG_MIN_SUM &&
                           (h->forced_path == LDPC_B200_PATH_QC || (h->forced_path < 0 && !h->opt.no_qc));
-        const bool compiled = want && !h->opt.qc_generic;  // (the switch forces the run-time profile: tests)
+        const bool compiled = want && !h->opt.qc_generic && !h->opt.qcm_always;  // (the switches force the run-time profile / the group-of-warps kernel: tests)
         if (compiled && h->qc_state == 0) h->qc_state = qc_prepare(h) ? 1 : -1;
         const bool fits = compiled && h->qc_state == 1 && 2 * (h->qc_smem + 2048) <= h->smem_optin + 1024;
         // (the kernel's launch bounds allow three CTAs per SM up to 288 threads)
@@ -1750,6 +1797,21 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
         // any other quasi-cyclic code: the same kernel with a run-time profile -- when the generic on-chip kernel would
         // have to run one codeword per CTA (z > 24: measured 1.6-2.2x faster); with 8 or 16 words per CTA the group
         // kernel is as fast (z = 24 rates: 1.31-1.67 ms against 1.49-1.56 ms per 16,384 words) and stays the choice
+        // no compiled lockstep profile (z = 28, 36, 44, 52, 56, 60, 68, 72, 76, 84, 88, 92 of the reference's family): a group
+        // of ceil(z / 32) warps per codeword (measured 2-3x the kernels below: profiles/r02_wimax_family.txt)
+        if (want && !h->opt.no_qcm && !h->opt.qc_generic && h->qcm_state == 0) h->qcm_state = qcm_prepare(h) ? 1 : -1;
+        if (want && !h->opt.no_qcm && !h->opt.qc_generic && h->qcm_state == 1) {
+            pl.path = LDPC_B200_PATH_QC;
+            pl.dmax = 2;  // marks the group-of-warps kernel
+            pl.threads = 32 * h->qcm_groups * h->qcm.NW;
+            pl.smem = (size_t)h->qcm_groups * h->qcm.word_bytes;
+            pl.ctas = h->sm_count;
+            pl.cw_per_cta = h->qcm_groups;
+            pl.W = h->qcm_groups * h->qcm.NW; pl.G = h->qcm_groups;
+            h->plan = pl;
+            h->planned = true;
+            return LDPC_B200_OK;
+        }
         bool generic = want && !h->opt.no_qcg;
         if (generic && h->forced_path < 0 && !h->opt.qc_generic) {
             GrpShape sh;
@@ -1950,6 +2012,23 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
         q.counter64 = ctr64;
         rc = launch_status(k_launch_warp(h->w_sw, q, grid, pl.threads, pl.smem, stream), "warp-per-check");
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
+
+    if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
+        QcmParams& q = h->qcm;  // tables and geometry filled by qcm_build; per-launch fields below
+        q.K = h->K;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.counter64 = ctr64;
+        q.avail = h->cur_avail;
+        q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
+        q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
+        int np = 0;
+        rc = launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, grid, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
+        if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
     }
@@ -2246,6 +2325,10 @@ int ldpc_b200_destroy(ldpc_b200_handle h) {
             cudaDeviceSynchronize();
             free_slots(h);
             if (h->qc_slot >= 0) qc_release_slot(h, h->device, h->qc_slot);
+            if (h->qcm_slot >= 0 && h->device >= 0 && h->device < kQcMaxDevices) {
+                std::lock_guard<std::mutex> lk(g_qcm_mu);
+                if (g_qcm_owner[h->device][h->qcm_slot] == h) g_qcm_owner[h->device][h->qcm_slot] = nullptr;
+            }
             cudaFree(h->d_syn_tab); cudaFree(h->d_iters_own);
             if (h->h_stats) cudaFreeHost(h->h_stats);
             cudaFree(h->dq_tabs);

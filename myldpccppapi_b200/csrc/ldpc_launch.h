@@ -26,6 +26,7 @@ struct ClusterParams;
 struct QcParams;
 struct QcgParams;
 struct QcwParams;
+struct QcmParams;
 struct TdmpParams;
 struct BigParams;
 
@@ -73,6 +74,15 @@ struct QcwProfileEntry {
     int (*launch)(const QcwParams&, int grid, int warps, cudaStream_t stream);
 };
 const QcwProfileEntry* qcw_profiles(int* n);
+
+// The group-of-warps-per-codeword kernel (ldpc_qcm.cuh): one instantiation per 802.16e degree profile, any z <= 96.
+struct QcmProfileEntry {
+    bool (*build)(const HostTables&, int z, const std::vector<std::vector<QcBlk>>&, size_t smem_limit, QcmParams*,
+                  std::vector<unsigned char>* tab, int* groups);
+    int (*launch)(const QcmParams&, int grid, int groups, cudaStream_t stream);
+    int (*upload)(int slot, const void* tab, size_t bytes);
+};
+const QcmProfileEntry* qcm_profiles(int* n);
 
 // one table per 802.16e rate (k_qc.cu compiled with -DLDPC_QC_RATE=...)
 const QcProfileEntry* qc_profiles_34B(int* n);

@@ -296,6 +296,49 @@ def test_qc_alternative_kernels(default_code, monkeypatch, env):
     assert np.array_equal(out["info"][late], ref7[0][late])
 
 
+@pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
+def test_qc_group_of_warps_kernel(rate, name, num, den, monkeypatch):
+    """ldpc_ms_qcm_kernel (a codeword per group of ceil(z / 32) warps, run-time tables): the twelve block sizes of the
+    reference's family without a compiled lockstep profile (z = 28 ... 92) as planned, and -- forced -- one, two and
+    three warps per codeword at the profiled sizes z = 24, 48, 96.  Bits, counts and posteriors of the oracle on the
+    device path, the streamed host path, tiny batches, a short cap; special values."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    for z, forced in [(28, False), (36, False), (44, False), (52, False), (56, False), (60, False), (68, False), (72, False),
+                      (76, False), (84, False), (88, False), (92, False), (24, True), (48, True), (96, True)]:
+        N = 24 * z
+        K = N * num // den
+        rp, ci, M = oracle.wimax_H(N, name)
+        if forced:
+            monkeypatch.setenv("LDPC_B200_QCM_ALWAYS", "1")
+        else:
+            monkeypatch.delenv("LDPC_B200_QCM_ALWAYS", raising=False)
+        nw = 70 if z in (36, 60, 96, 24) else 24
+        y = np.concatenate([awgn_llr(nw, N, sigma_from_ebn0(2.2, num / den), seed=N + rate), awgn_llr(nw, N, sigma_from_ebn0(4.0, num / den), seed=N + rate + 1),
+                            awgn_llr(5, N, 1.3, seed=N + rate + 2)])
+        y[3] = 0.0
+        y[4, ::3] = 0.0
+        y[5] = np.where(np.arange(N) % 2 == 0, -0.0, 0.0)
+        y[6, :7] = [np.inf, -np.inf, 1e30, -1e30, 1e-40, -1e-40, 1000.0]
+        ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(y, literal=False)
+        dec = m.Decoder.wimax(K, N, rate)
+        inf = dec.info()
+        assert inf["path_name"] == "qc" and inf["threads_per_cta"] == 32 * inf["codewords_per_cta"] * ((z + 31) // 32), inf
+        what = "z=%d rate %s" % (z, name)
+        assert_parity(_run_device(dec, y), ref, N, what=what)
+        if z in (36, 60, 96, 24):
+            assert_parity(dec.decode_host(y, want_hard=True, want_post=True), ref, N, what=what + " host")
+            pinned = torch.from_numpy(y).pin_memory().numpy()
+            dec.set_option("stream_chunk", 8)
+            assert_parity(dec.decode_host(pinned, want_hard=False, want_post=False), ref, N, what=what + " streamed, tiny chunks")
+            dec.set_option("stream_chunk", 0)
+            for n in (1, 3, 17):
+                assert_parity(_run_device(dec, y[:n]), tuple(r[:n] for r in ref), N, what=what + " %d words" % n)
+            dec.set_max_iter(3)
+            rc = oracle.Oracle(M, N, K, rp, ci, times=3).decode(y, literal=False)
+            assert_parity(_run_device(dec, y), rc, N, what=what + " cap 3")
+
+
 @pytest.mark.parametrize("N", [576, 768])
 @pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
 def test_qc_early_termination_kernel(rate, name, num, den, N):

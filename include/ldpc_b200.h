@@ -106,10 +106,11 @@ typedef struct ldpc_b200_info {
     size_t smem_bytes;   /* dynamic shared memory per CTA                           */
     size_t workspace_bytes;
     size_t table_bytes;  /* device bytes of the check-major + variable-major tables */
-    int kernel_variant;  /* quasi-cyclic path, most recent launch: 0 main kernel, 1 early-termination kernel
-                            (chosen per launch from the previous launches' mean iteration count; option
-                            "qc_et": -1 auto, 0 never, 1 always), 2 ring-staged kernel */
-    int et_available;    /* 1 if this handle can run the early-termination kernel */
+    int kernel_variant;  /* quasi-cyclic path with a compiled lockstep profile, most recent launch: 0 lockstep kernel,
+                            1 warp-per-codeword kernel, 3 group-of-warps kernel (chosen per launch from the previous
+                            launches' mean iteration count; option "qc_et": -1 auto, 0 never, 1 always), 2 ring-staged */
+    int et_available;    /* which per-codeword kernel this handle can switch to: 0 none, 1 warp per codeword (802.16e
+                            codes with z = 24 / 32), 2 group of warps */
 } ldpc_b200_info;
 
 /* Build a decoder for the M x N parity-check matrix given in CSR (row_ptr[M+1],

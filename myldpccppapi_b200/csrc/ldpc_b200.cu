@@ -1256,12 +1256,10 @@ bool qcw_prepare(ldpc_b200_decoder* h) {
         DeviceGuard guard(h->device);
         if (!guard.ok) return false;
         if (cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||
-            cudaMemcpy(h->d_syn_tab, syn.data(), syn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-            (!h->h_stats && cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) != cudaSuccess)) {
+            cudaMemcpy(h->d_syn_tab, syn.data(), syn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
             (void)cudaGetLastError();
             return false;
         }
-        h->h_stats[0] = h->h_stats[1] = 0ull;
         std::memset(&h->qcw, 0, sizeof(h->qcw));
         h->qcw.N = t.N;
         h->qcw.syn_tab = h->d_syn_tab;
@@ -1783,6 +1781,16 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
                 if (n >= qc_per_sm) { h->qc_ring_smem = need; h->qc_ring_per_sm = n; }
             }
             if (h->qcw_state == 0) h->qcw_state = (h->opt.qc_et != 0 && qcw_prepare(h)) ? 1 : -1;
+            if (h->qcw_state != 1 && h->qcm_state == 0) h->qcm_state = (h->opt.qc_et != 0 && !h->opt.no_qcm && qcm_prepare(h)) ? 1 : -1;
+            if ((h->qcw_state == 1 || h->qcm_state == 1) && !h->h_stats) {
+                DeviceGuard guard(h->device);
+                if (!guard.ok || cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    h->h_stats = nullptr; h->qcw_state = -1; h->qcm_state = -1;
+                } else {
+                    h->h_stats[0] = h->h_stats[1] = 0ull;
+                }
+            }
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 1;  // marks the compiled profile
             pl.threads = 32 * qc_profiles()[h->qc_kind].W;
@@ -2016,18 +2024,24 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         return LDPC_B200_OK;
     }
 
-    if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
+    // the group-of-warps kernel (ldpc_qcm.cuh): the plan's kernel for block sizes without a compiled lockstep profile, and
+    // the early-termination alternative of the profiled sizes that have no warp-per-codeword kernel
+    auto launch_qcm = [&](int32_t* iters_out) -> int {
         QcmParams& q = h->qcm;  // tables and geometry filled by qcm_build; per-launch fields below
         q.K = h->K;
         q.max_iter = h->max_iter; q.early_term = h->early;
         q.llr = d_llr; q.ncw = ncw;
-        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = d_post;
+        q.info = d_info; q.hard = d_hard; q.iters = iters_out; q.post = d_post;
         q.counter64 = ctr64;
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
         int np = 0;
-        rc = launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, grid, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
+        const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
+        return launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
+    };
+    if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
+        rc = launch_qcm(d_iters);
         if (rc) return rc;
         h->launches += 1;
         return LDPC_B200_OK;
@@ -2061,18 +2075,21 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
-        // Which kernel: the early-termination kernel (a warp per codeword) when the handle's recent words stopped early
-        // on average -- the mean iteration count of the previous launches, sampled on the device and read from pinned
-        // memory: no synchronisation -- the main kernel otherwise and whenever the regime is unknown.
+        // Which kernel: the lockstep kernel, or -- when the handle's recent words stopped early on average -- the kernel
+        // that decodes every codeword on its own warp(s): ldpc_qcw.cuh where the code has one (z = 24 / 32), else
+        // ldpc_qcm.cuh.  The regime is the mean iteration count of the previous launches, sampled on the device and read
+        // from pinned memory (no synchronisation); unknown = lockstep.  Measured crossovers (share of the cap):
+        // qcw z = 24 90 %, z = 32 every regime; qcm 25 % (profiles/r02_qcw_*.txt, r02_qcm_vs_lockstep.txt).
         const bool aligned = (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0;  // bulk copies of the ring kernel
-        const bool et_ready = h->qcw_state == 1 && h->early && !h->qc_ring_smem;
+        const bool have_w = h->qcw_state == 1, have_m = !have_w && h->qcm_state == 1;
+        const bool et_ready = (have_w || have_m) && h->early && !h->qc_ring_smem;
         const bool track = et_ready && h->opt.qc_et < 0;   // the regime is tracked through the iteration counts
         bool use_et = et_ready && h->opt.qc_et > 0;
-        if (track && h->h_stats[1] > 0)
-{
+        if (track) {
             int np0 = 0;
-            const int pct = h->opt.qc_et_pct > 0 ? h->opt.qc_et_pct : (qcw_profiles(&np0)[h->qcw_kind].z >= 32 ? 100 : 90);
-            use_et = (double)h->h_stats[0] * 100.0 <= (double)pct * (double)h->max_iter * (double)h->h_stats[1];
+            const int pct = h->opt.qc_et_pct > 0 ? h->opt.qc_et_pct : (have_m ? 25 : (qcw_profiles(&np0)[h->qcw_kind].z >= 32 ? 100 : 90));
+            if (pct >= 100) use_et = true;
+            else if (h->h_stats[1] > 0) use_et = (double)h->h_stats[0] * 100.0 <= (double)pct * (double)h->max_iter * (double)h->h_stats[1];
         }
         if (track && !q.iters) {
             if (h->iters_own_cap < ncw) {
@@ -2082,7 +2099,10 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
             }
             q.iters = h->d_iters_own;
         }
-        if (use_et) {
+        if (use_et && have_m) {
+            rc = launch_qcm(q.iters);
+            h->last_kernel = 3;
+        } else         if (use_et) {
             QcwParams& e = h->qcw;
             e.K = q.K; e.max_iter = q.max_iter; e.early_term = q.early_term;
             e.llr = q.llr; e.ncw = q.ncw; e.info = q.info; e.hard = q.hard; e.iters = q.iters; e.post = q.post;
@@ -2537,7 +2557,7 @@ int ldpc_b200_get_info(ldpc_b200_handle h, ldpc_b200_info* info) {
     info->workspace_bytes = h->plan.ws_stride * sizeof(float) * (size_t)h->plan.ctas;
     info->table_bytes = h->table_bytes;
     info->kernel_variant = h->last_kernel;
-    info->et_available = h->qcw_state == 1 ? 1 : 0;
+    info->et_available = h->qcw_state == 1 ? 1 : (h->planned && h->plan.path == LDPC_B200_PATH_QC && h->plan.dmax == 1 && h->qcm_state == 1 ? 2 : 0);
     return LDPC_B200_OK;
 }
 

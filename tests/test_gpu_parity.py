@@ -390,7 +390,32 @@ def test_qc_early_termination_kernel(rate, name, num, den, N):
         out = _run_device(dec, part)
         assert_parity(out, tuple(r[lo:hi] for r in ref), N, what="auto")
         seen.append(dec.info()["kernel_variant"])
-    assert seen == ([0, 0, 1, 1, 0] if N == 576 else [0, 1, 1, 1, 1]), seen
+    assert seen == ([0, 0, 1, 1, 0] if N == 576 else [1, 1, 1, 1, 1]), seen
+
+
+def test_qc_lockstep_hands_over_to_the_group_of_warps_kernel():
+    """A block size with a compiled lockstep profile but no warp-per-codeword kernel (z = 48): after a launch whose words
+    stopped early the handle decodes with ldpc_ms_qcm_kernel (kernel_variant 3), and goes back to the lockstep kernel
+    after one whose words ran long; the oracle's bits, counts and posteriors either way."""
+    import myldpccppapi_b200 as m
+    N, K, rate = 1152, 864, 4
+    rp, ci, M = oracle.wimax_H(N, "3/4B")
+    easy = awgn_llr(600, N, sigma_from_ebn0(4.2, 0.75), seed=91)
+    hard = awgn_llr(200, N, 1.1, seed=92)
+    orc = oracle.Oracle(M, N, K, rp, ci, times=40)
+    ref_e, ref_h = orc.decode(easy, literal=False), orc.decode(hard, literal=False)
+    dec = m.Decoder.wimax(K, N, rate)
+    dec.reserve(1024)
+    assert dec.info()["et_available"] == 2
+    dec.set_option("qc_et_every", 1)
+    seen = []
+    for part, ref in ((hard, ref_h), (easy, ref_e), (easy, ref_e), (hard, ref_h), (hard, ref_h)):
+        assert_parity(_run_device(dec, part), ref, N, what="auto")
+        seen.append(dec.info()["kernel_variant"])
+    assert seen == [0, 0, 3, 3, 0], seen
+    dec.set_option("qc_et", 1)
+    assert_parity(dec.decode_host(easy, want_hard=True, want_post=True), ref_e, N, what="forced, host")
+    assert dec.info()["kernel_variant"] == 3
 
 
 @pytest.mark.parametrize("N,rate,name,num,den", [(1152, 4, "3/4B", 3, 4), (1632, 0, "1/2", 1, 2), (2304, 5, "5/6", 5, 6), (1824, 1, "2/3A", 2, 3)])

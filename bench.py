@@ -59,17 +59,25 @@ WORKLOADS = {
     "cfg3": ("regular_3_6_n8192", 1.0, 40, 131072),
     "cfg4": ("wimax_3_4b_n576_ebn0_3.5dB_early_termination", sigma_from_ebn0(3.5, 0.75), 40, 65536),
     "cfg5": ("ira_n64800_cap50", 1.0, 50, 4736),
+    # two more points of the sweep and of the reference's code family, measured as sub-records only
+    "cfg4_4dB": ("wimax_3_4b_n576_ebn0_4.0dB_early_termination", sigma_from_ebn0(4.0, 0.75), 40, 65536),
+    "family_z60": ("wimax_3_4b_n1440_z60_no_compiled_profile", 1.0, 40, 32768),
 }
 # (steps, warmup, oracle spot-check words) of the sub-records in `workloads`
-SUB = {"cfg3": (5, 3, 32), "cfg5": (3, 3, 2), "cfg4": (20, 3, 512)}
+SUB = {"cfg3": (5, 3, 32), "cfg5": (3, 3, 2), "cfg4": (20, 3, 512), "cfg4_4dB": (20, 3, 512), "family_z60": (10, 3, 128)}
 
 
 def make_code(workload: str):
     """(M, N, K, row_ptr, col_idx).  Host-side only: the 802.16e expansion comes from the oracle package here so that
     the reference arm never loads the product's CUDA library (the product's expansion is checked equal in tests)."""
-    if workload in ("cfg1", "cfg2", "cfg4"):
+    if workload in ("cfg1", "cfg2", "cfg4", "cfg4_4dB"):
         import oracle
         N, K = 576, 432
+        rp, ci, M = oracle.wimax_H(N, "3/4B")
+        return M, N, K, rp, ci
+    if workload == "family_z60":   # a block size Coder::initCheckMatrix accepts that has no compiled lockstep profile
+        import oracle
+        N, K = 1440, 1080
         rp, ci, M = oracle.wimax_H(N, "3/4B")
         return M, N, K, rp, ci
     from myldpccppapi_b200 import codes
@@ -340,7 +348,10 @@ def main() -> None:
         except Exception:
             pass
         r = dict(roof_smem if onchip else roof_hbm)
-        r.update({"kernel": KERNELS.get(info["path_name"], "?") if args.algorithm == 0 else {1: "ldpc_sp_group_kernel", 2: "ldpc_tdmp_group_kernel"}[args.algorithm],
+        kname = KERNELS.get(info["path_name"], "?")
+        if info["path_name"] == "qc":
+            kname = {0: "ldpc_ms_qc_kernel", 1: "ldpc_ms_qcw_kernel", 2: "ldpc_ms_qc_ring_kernel", 3: "ldpc_ms_qcm_kernel"}.get(info.get("kernel_variant", 0), kname)
+        r.update({"kernel": kname if args.algorithm == 0 else {1: "ldpc_sp_group_kernel", 2: "ldpc_tdmp_group_kernel"}[args.algorithm],
                   "launch_ms": ms_step, "traffic": roof_hbm.get("traffic"),
                   "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},
                   "hbm": roof_hbm, "smem": roof_smem,
@@ -370,7 +381,7 @@ def main() -> None:
         code = make_code(workload)
         M, N, K, rp, ci = code
         dec = m.Decoder(M, N, K, rp, ci, device=local_rank, max_iter=cap, early_termination=True)
-        if workload in ("cfg1", "cfg2", "cfg4"):
+        if workload in ("cfg1", "cfg2", "cfg4", "cfg4_4dB", "family_z60"):
             dec.set_layer_height(N // 24)
         if forced_path >= 0:
             dec.set_path(forced_path)
@@ -399,6 +410,7 @@ def main() -> None:
         sampler.region(False)
         barrier()
         ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        info = dec.info()   # (after the launches: kernel_variant says which quasi-cyclic kernel the handle settled on)
         res = {"dec": dec, "info": info, "code": code, "llr": llr, "out": out, "ms_step": ms_step,
                "launches": dec.launches - launches0, "clocks": sampler.summary(reset=True),
                "mean_iters": float(out["iters"].float().mean().item()), "total_cw": sum_over_ranks(float(ncw))}
@@ -556,7 +568,7 @@ def main() -> None:
         del llr
         R["llr"] = None
         torch.cuda.empty_cache()
-        for wl in ("cfg4", "cfg3", "cfg5"):
+        for wl in ("cfg4", "cfg4_4dB", "family_z60", "cfg3", "cfg5"):
             wdesc, wsigma, wcap, wncw = WORKLOADS[wl]
             wsteps, wwarm, wcheck = SUB[wl]
             try:

@@ -2043,6 +2043,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
         rc = launch_qcm(d_iters);
         if (rc) return rc;
+        h->last_kernel = 3;
         h->launches += 1;
         return LDPC_B200_OK;
     }

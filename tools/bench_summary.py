@@ -10,6 +10,6 @@ if d.get("e2e_plugin") and d["e2e_plugin"].get("registered"): r = d["e2e_plugin"
 if d.get("e2e_plugin"): p = d["e2e_plugin"]; print("plugin: %.3f Gbit/s %.3f ms  first %.2f ms  setup %.1f ms  match %s" % (p["value"], p["ms_per_step"], p["first_call_ms"], p["setup_ms"], p["bytes_match_device_path"]))
 for k, v in (d.get("workloads") or {}).items():
     if "error" in v: print(k, "ERROR", v["error"]); continue
-    print("%s: %.3f Gbit/s  %.3f ms  iters %.2f  frac %.3f (%s)  %s  oracle %s" % (k, v["value"], v["ms_per_step"], v["mean_iterations"], v["roofline"]["frac"], v["roofline"]["bound"], v["clocks"], v["gpu_matches_oracle_all_ranks"]))
+    print("%s: %.3f Gbit/s  %.3f ms  iters %.2f  frac %.3f (%s, %s)  %s  oracle %s" % (k, v["value"], v["ms_per_step"], v["mean_iterations"], v["roofline"]["frac"], v["roofline"]["bound"], v["roofline"].get("kernel"), v["clocks"], v["gpu_matches_oracle_all_ranks"]))
 print("parity_all_ranks:", d.get("parity_all_ranks", {}).get("ok"), " setdevices:", d.get("setdevices"))
 print("cpu_baseline:", d.get("cpu_baseline"))

@@ -281,6 +281,8 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # (keeps "NCCL version ..." off stdout: rank 0 prints ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     # CPU-side barrier (gloo) for the leg in which rank 0 alone drives every GPU: ranks parked in an NCCL barrier would
     # keep a spinning kernel on the very GPUs rank 0 is timing

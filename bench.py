@@ -434,6 +434,34 @@ def main() -> None:
                                 "clocks": sampler.summary(reset=True)}
         return res
 
+    def packed_legs(pdec, pllr, pncw, pN, pK, steps, want_f32=False):
+        """End to end through ldpc_b200_decode_host_packed: the same channel values as float16 and as int8 (x 1/8) in pinned
+        host buffers, widened on the device -- half / a quarter of the PCIe bytes.  (Additive API: the reference's is
+        fp32; the quantised values are a different input, so the iteration counts move a little.)"""
+        res = {}
+        legs = [("f16", pllr.to(torch.float16).cpu().pin_memory(), 1.0, 2),
+                ("i8", torch.clamp(torch.round(pllr * 8.0), -127, 127).to(torch.int8).cpu().pin_memory(), 0.125, 1)]
+        if want_f32:
+            legs.insert(0, ("f32", pllr.cpu().pin_memory(), 1.0, 4))
+        h_o = {"info": torch.empty((pncw, pdec.KB), dtype=torch.uint8, pin_memory=True),
+               "iters": torch.empty((pncw,), dtype=torch.int32, pin_memory=True)}
+        for name, buf, scale, esz in legs:
+            call = (lambda: pdec.decode_host(buf, out=h_o)) if name == "f32" else (lambda: pdec.decode_host_packed(buf, scale=scale, out=h_o))
+            for _ in range(3):
+                call()
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                call()
+            torch.cuda.synchronize()
+            dtp = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            res[name] = {"value": sum_over_ranks(float(pncw)) * pK * steps / dtp / 1e9, "unit": UNIT, "ms_per_step": dtp / steps * 1e3,
+                         "h2d_bytes_per_step": int(sum_over_ranks(float(pncw))) * pN * esz, "mean_iterations": float(h_o["iters"].float().mean().item())}
+            del buf
+        return res
+
     # ---- headline: device-resident decode of the chosen workload
     desc, sigma, cap, ncw = WORKLOADS[args.workload]
     sigma = args.sigma if args.sigma is not None else sigma
@@ -507,6 +535,11 @@ def main() -> None:
                                    "the end-to-end step cannot be shorter than bytes / this rate" % world)
         e2e["h2d_bound_ms_per_step"] = round(max(ncw * N * 4 / (v * 1e9) for v in ceil) * 1e3, 3)
         del h_llr, d_tmp
+        if not args.no_extras and args.algorithm == 0:
+            try:
+                e2e["packed_input"] = packed_legs(dec, llr, ncw, N, K, max(5, args.steps // 2))
+            except Exception as e:
+                e2e["packed_input"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- the call a user of the reference makes: Coder::decode of the drop-in C++ class, malloc'd buffers
     plugin = None
@@ -584,6 +617,8 @@ def main() -> None:
                                               if k in ("bound", "achieved", "peak", "unit", "frac", "kernel", "launch_ms", "traffic", "algorithmic_bytes_per_codeword")},
                                  "clocks": W["clocks"], "gpu_launches": W["launches"],
                                  "gpu_matches_oracle_all_ranks": ok, "oracle_words_per_rank": nchk}
+                if wl == "cfg4" and not args.no_e2e:   # the regime in which the PCIe copy, not the kernel, bounds a host call
+                    workloads[wl]["e2e_by_input_format"] = packed_legs(W["dec"], W["llr"], wncw, W["code"][1], wK, 10, want_f32=True)
                 W["dec"].close()
                 del W
             except Exception as e:  # a sub-record must never take the headline down

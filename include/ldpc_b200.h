@@ -183,6 +183,21 @@ int ldpc_b200_encoder_init(ldpc_b200_handle h);
 int ldpc_b200_encode_device(ldpc_b200_handle h, const uint8_t *d_info, int64_t ncw, uint8_t *d_codewords, void *stream);
 int ldpc_b200_encode_host(ldpc_b200_handle h, const uint8_t *info, int64_t ncw, uint8_t *codewords);
 
+/* The same call with the channel values in a PACKED host format, widened to fp32 on the device: the decoder sees
+ * exactly (float)x * scale (one fp32 multiplication; scale = 1 widens fp16 exactly), so results equal
+ * ldpc_b200_decode_host on those floats bit for bit.  Additive: the reference's API has fp32 only (MyLdpc.h:118).
+ * Why: in the early-termination regime and on multi-GPU hosts the host-to-device copy, not the kernel, bounds the
+ * call; fp16 halves those bytes, int8 quarters them.  Pinned buffers (ldpc_b200_host_alloc)
+ * are copied by DMA under the running kernels; pageable ones work but are staged by the driver. */
+enum {
+    LDPC_B200_LLR_F32 = 0,  /* const float*   */
+    LDPC_B200_LLR_F16 = 1,  /* IEEE binary16  */
+    LDPC_B200_LLR_I8 = 2    /* const int8_t*  */
+};
+int ldpc_b200_decode_host_packed(ldpc_b200_handle h, const void *llr, int format, float scale, int64_t ncw,
+                                 uint8_t *info, uint8_t *hard, int32_t *iters, float *post);
+
+
 /* Synthetic BPSK-AWGN channel on the device: y = (bit ? -1 : +1) + sigma * n, n ~ N(0,1)
  * from a counter-based generator keyed by (seed, codeword, position).  d_bits: packed
  * codeword bits [ncw][ceil(N/8)] LSB-first, or NULL for the all-zero codeword.          */

@@ -4,6 +4,8 @@
 // of any size (ldpc_big.cuh).
 #include <algorithm>
 
+#include <cuda_fp16.h>
+
 #include "ldpc_launch.h"
 #include "ldpc_kernels.cuh"
 #include "ldpc_cluster.cuh"
@@ -27,6 +29,18 @@ __global__ void __launch_bounds__(256) ldpc_iter_stats_kernel(const int32_t* __r
         for (int w = 1; w < 8; ++w) s += part[w];
         stats[0] = s;
         stats[1] = (unsigned long long)nsamp;
+    }
+}
+
+// Packed channel values -> fp32 (ldpc_b200_decode_host_packed): y = (float)x * scale, one rounding.
+template <class T>
+__global__ void __launch_bounds__(256) ldpc_widen_kernel(const T* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v;
+        if constexpr (sizeof(T) == 2) v = __half2float(in[i]);
+        else v = (float)in[i];
+        out[i] = __fmul_rn(v, scale);
     }
 }
 
@@ -103,6 +117,14 @@ int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream) {
 
 int k_launch_iter_stats(const int32_t* iters, long long ncw, unsigned long long* stats, cudaStream_t stream) {
     ldpc_iter_stats_kernel<<<1, 256, 0, stream>>>(iters, ncw, stats);
+    return (int)cudaGetLastError();
+}
+
+int k_launch_widen(int format, const void* in, float* out, long long n, float scale, cudaStream_t stream) {
+    const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    if (format == 1) ldpc_widen_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(in), out, n, scale);
+    else if (format == 2) ldpc_widen_kernel<signed char><<<grid, 256, 0, stream>>>(static_cast<const signed char*>(in), out, n, scale);
+    else return kNoKernel;
     return (int)cudaGetLastError();
 }
 

@@ -76,6 +76,7 @@ struct Options {
     long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
     long long stream_batch_kb = 0;    // channel values per launch (0 = default)
     long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
+    int stage_threads = 4;            // host threads that stage a pageable input buffer through the pinned ring
     // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
@@ -93,7 +94,7 @@ const OptionName kOptionNames[] = {
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
-    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(stage_threads, 1),
 };
 #undef OPT
 #undef OPTR
@@ -254,6 +255,8 @@ struct ldpc_b200_decoder {
     uint8_t* s_hard[kSlots] = {nullptr, nullptr, nullptr};
     int32_t* s_iters[kSlots] = {nullptr, nullptr, nullptr};
     float* s_post[kSlots] = {nullptr, nullptr, nullptr};
+    void* s_pack[kSlots] = {nullptr, nullptr, nullptr};   // packed channel values of a chunk (ldpc_b200_decode_host_packed)
+    size_t s_pack_bytes = 0;
 
     // streamed host pipeline (one persistent launch per batch, input chunks announced through *d_avail)
     float* st_llr = nullptr;
@@ -1971,6 +1974,8 @@ int ensure_workspace(ldpc_b200_decoder* h) {
 }
 
 void free_slots(ldpc_b200_decoder* h) {
+    for (int s = 0; s < kSlots; ++s) { cudaFree(h->s_pack[s]); h->s_pack[s] = nullptr; }
+    h->s_pack_bytes = 0;
     for (int s = 0; s < kSlots; ++s) {
         cudaFree(h->s_llr[s]); h->s_llr[s] = nullptr;
         cudaFree(h->s_info[s]); h->s_info[s] = nullptr;
@@ -2807,7 +2812,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
                         next_enq.store(j + 1);
                     }
                 };
-                const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>({4, nch, (int64_t)std::max(1u, std::thread::hardware_concurrency())}));
+                const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::max(1, h->opt.stage_threads), nch, (int64_t)std::max(1u, std::thread::hardware_concurrency())}));
                 std::vector<std::thread> pool;
                 for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
                 work();
@@ -2853,10 +2858,21 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
 // The chunked 3-stream pipeline: H2D, kernel and D2H of consecutive chunks overlap across kSlots streams.
 // (h->mu held, current device = the handle's)
 int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                             int32_t* iters, float* post) {
+                             int32_t* iters, float* post, const void* packed = nullptr, int format = LDPC_B200_LLR_F32, float scale = 1.0f,
+                             int64_t chunk_words = 0) {
     const HostTables& t = h->host;
     const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
-    const int64_t chunk = h->reserved;
+    const int64_t chunk = chunk_words > 0 ? std::min(chunk_words, h->reserved) : h->reserved;
+    const size_t esz = format == LDPC_B200_LLR_F16 ? 2 : (format == LDPC_B200_LLR_I8 ? 1 : 4);
+    if (packed && h->s_pack_bytes < esz * (size_t)chunk * t.N) {   // packed chunks land here and are widened into s_llr
+        for (int s = 0; s < kSlots; ++s) {
+            if (h->streams[s]) CU_TRY(cudaStreamSynchronize(h->streams[s]));
+            cudaFree(h->s_pack[s]); h->s_pack[s] = nullptr;
+        }
+        h->s_pack_bytes = 0;
+        for (int s = 0; s < kSlots; ++s) CU_TRY(cudaMalloc(&h->s_pack[s], esz * (size_t)chunk * t.N));
+        h->s_pack_bytes = esz * (size_t)chunk * t.N;
+    }
     if (post) {
         for (int s = 0; s < kSlots; ++s)
             if (!h->s_post[s]) CU_TRY(cudaMalloc(&h->s_post[s], sizeof(float) * (size_t)chunk * t.N));
@@ -2872,8 +2888,16 @@ int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw
         cudaStream_t st = h->streams[slot];
         const bool tc = timed && ci < ntimed;
         if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci], st));
-        CU_TRY(cudaMemcpyAsync(h->s_llr[slot], llr + (size_t)off * t.N, sizeof(float) * (size_t)n * t.N,
-                               cudaMemcpyHostToDevice, st));
+        if (packed) {
+            CU_TRY(cudaMemcpyAsync(h->s_pack[slot], static_cast<const char*>(packed) + esz * (size_t)off * t.N, esz * (size_t)n * t.N,
+                                   cudaMemcpyHostToDevice, st));
+            const int wrc = launch_status(k_launch_widen(format, h->s_pack[slot], h->s_llr[slot], (long long)n * t.N, scale, st), "widen");
+            if (wrc) return wrc;
+            h->launches += 1;
+        } else {
+            CU_TRY(cudaMemcpyAsync(h->s_llr[slot], llr + (size_t)off * t.N, sizeof(float) * (size_t)n * t.N,
+                                   cudaMemcpyHostToDevice, st));
+        }
         if (tc) CU_TRY(cudaEventRecord(h->tev[4 * ci + 1], st));
         int rc = launch_decode(h, h->s_llr[slot], n, info ? h->s_info[slot] : nullptr, hard ? h->s_hard[slot] : nullptr,
                                iters ? h->s_iters[slot] : nullptr, post ? h->s_post[slot] : nullptr, st);
@@ -2972,6 +2996,47 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
     }
     const int rc = decode_host_chunked_body(h, llr, ncw, info, hard, iters, post);
     if (rc != LDPC_B200_OK) {  // drain the streams: no copy into the caller's buffers may outlive an error return
+        const std::string keep = g_err;
+        for (int s = 0; s < kSlots; ++s) if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
+        (void)cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+
+int ldpc_b200_decode_host_packed(ldpc_b200_handle h, const void* llr, int format, float scale, int64_t ncw, uint8_t* info,
+                                 uint8_t* hard, int32_t* iters, float* post) {
+    if (format == LDPC_B200_LLR_F32 && scale == 1.0f) return ldpc_b200_decode_host(h, static_cast<const float*>(llr), ncw, info, hard, iters, post);
+    if (!h) return fail(LDPC_B200_ERR_ARG, "null handle");
+    if (format != LDPC_B200_LLR_F16 && format != LDPC_B200_LLR_I8) return fail(LDPC_B200_ERR_ARG, "format must be LDPC_B200_LLR_F16 or LDPC_B200_LLR_I8 (fp32 takes scale 1)");
+    if (ncw < 0) return fail(LDPC_B200_ERR_ARG, "ncw must be >= 0");
+    if (ncw == 0) return LDPC_B200_OK;
+    if (!llr) return fail(LDPC_B200_ERR_ARG, "llr is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    struct WallTimer {
+        ldpc_b200_decoder* h; int64_t n; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~WallTimer() {
+            h->timing.wall_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            h->timing.calls += 1; h->timing.codewords += n;
+        }
+    } wall_timer{h, ncw};
+    if (!h->planned) {
+        const int prc = make_plan(h);
+        if (prc) return prc;
+    }
+    // chunks of 3/4 of a wave of the persistent grid on three streams: copy, widen + decode, copy back overlap, and the
+    // kernels of consecutive chunks fill each other's tails (the chunk rule of the fp32 pipeline, tools/e2e_chunk_sweep.py)
+    const int64_t wave = std::max<int64_t>(1, (int64_t)h->plan.ctas * h->plan.cw_per_cta);
+    const int64_t g = std::max<int64_t>(1, h->plan.cw_per_cta);
+    const int64_t chunk = std::max<int64_t>(g, wave * 3 / 4 / g * g);
+    if (h->reserved == 0) {
+        const int rrc = reserve_locked(h, chunk);
+        if (rrc) return rrc;
+    }
+    const int rc = decode_host_chunked_body(h, nullptr, ncw, info, hard, iters, post, llr, format, scale, chunk);
+    if (rc != LDPC_B200_OK) {
         const std::string keep = g_err;
         for (int s = 0; s < kSlots; ++s) if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
         (void)cudaGetLastError();

@@ -47,6 +47,8 @@ int k_launch_sp_big(const BigParams& q, int grid, cudaStream_t stream);    // an
 int k_launch_tdmp_big(const BigParams& q, int grid, cudaStream_t stream);
 int k_launch_fused_big(const BigParams& q, int grid, cudaStream_t stream);  // the reference's fused kernels, their arithmetic
 // stats[0] = sum of up to 4096 evenly spaced entries of iters[0, ncw), stats[1] = how many (the regime of the last launch)
+// format 1: IEEE binary16, 2: int8; out[i] = (float)in[i] * scale
+int k_launch_widen(int format, const void* in, float* out, long long n, float scale, cudaStream_t stream);
 int k_launch_iter_stats(const int32_t* iters, long long ncw, unsigned long long* stats, cudaStream_t stream);
 
 // Quasi-cyclic block structure of H for block size z: rows[br] = the circulants (block column, shift) of block

@@ -189,6 +189,43 @@ class Decoder:
         check(self._L.ldpc_b200_decode_host(self._h, _host_ptr(a), ncw, ptr("info"), ptr("hard"), ptr("iters"), ptr("post")))
         return out
 
+    def decode_host_packed(self, llr, scale: float = 1.0, want_hard: bool = False, want_post: bool = False, out: Optional[dict] = None):
+        """decode_host with the channel values as float16 or int8 (numpy array or pinned torch tensor), widened on the device
+        to (float)x * scale: half / a quarter of the host-to-device bytes (ldpc_b200_decode_host_packed)."""
+        a, fmt = _packed_host_array(llr)
+        ncw = _numel(a) // self.N
+        out = out if out is not None else {}
+        if "info" not in out:
+            out["info"] = np.empty((ncw, self.KB), dtype=np.uint8)
+        if "iters" not in out:
+            out["iters"] = np.empty((ncw,), dtype=np.int32)
+        if want_hard and "hard" not in out:
+            out["hard"] = np.empty((ncw, self.NB), dtype=np.uint8)
+        if want_post and "post" not in out:
+            out["post"] = np.empty((ncw, self.N), dtype=np.float32)
+        ptr = lambda k: _host_ptr(out[k]) if k in out else None  # noqa: E731
+        check(self._L.ldpc_b200_decode_host_packed(self._h, _host_ptr(a), fmt, C.c_float(scale), ncw, ptr("info"), ptr("hard"),
+                                                   ptr("iters"), ptr("post")))
+        return out
+
+
+def _packed_host_array(x):
+    """(array or pinned tensor, format code) for decode_host_packed: float16 -> 1, int8 -> 2."""
+    if hasattr(x, "data_ptr"):
+        import torch
+
+        if x.is_cuda:
+            raise ValueError("expected a host tensor")
+        fmt = {torch.float16: 1, torch.int8: 2}.get(x.dtype)
+        if fmt is None:
+            raise ValueError("expected a float16 or int8 tensor, got %s" % x.dtype)
+        return x.contiguous(), fmt
+    a = np.ascontiguousarray(x)
+    fmt = {np.dtype(np.float16): 1, np.dtype(np.int8): 2}.get(a.dtype)
+    if fmt is None:
+        raise ValueError("expected float16 or int8 data, got %s" % a.dtype)
+    return a, fmt
+
 
 def _as_host_array(x, dtype):
     if hasattr(x, "data_ptr"):  # torch CPU tensor (possibly pinned)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "ldpc_b200_reserve": (_i, [_vp, _i64]),
     "ldpc_b200_decode_device": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ldpc_b200_decode_host": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ldpc_b200_decode_host_packed": (_i, [_vp, _vp, _i, _f, _i64, _vp, _vp, _vp, _vp]),
     "ldpc_b200_synth_llr": (_i, [_vp, _i64, _i, _f, _u64, _vp, _i, _vp]),
     "ldpc_b200_wimax_csr": (_i, [_i, _i, _i, _vp, _vp, _pi, _pi]),
     "ldpc_b200_edge_tables": (_i, [_i, _i, _vp, _vp, _vp, _vp, _pi, _pi]),

@@ -580,6 +580,37 @@ def test_coder_decode_sp_uses_the_sum_product_kernel(default_code):
         assert np.array_equal(out[:srcLength], td_info.reshape(-1))
 
 
+@pytest.mark.parametrize("N,rate,name,num,den", [(576, 4, "3/4B", 3, 4), (1440, 0, "1/2", 1, 2)])
+def test_packed_channel_values(N, rate, name, num, den):
+    """ldpc_b200_decode_host_packed: float16 / int8 channel values widened on the device give exactly what the fp32 call
+    gives on the widened floats ((float)x * scale, one fp32 multiplication) -- bits, counts and posteriors of the oracle;
+    pinned and pageable buffers, many chunks, a ragged tail."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    ncw = 3001
+    y = np.concatenate([awgn_llr(2000, N, sigma_from_ebn0(3.0, num / den), seed=N), awgn_llr(1001, N, sigma_from_ebn0(1.0, num / den), seed=N + 1)])
+    orc = oracle.Oracle(M, N, K, rp, ci, times=40)
+    dec = m.Decoder.wimax(K, N, rate)
+    h = y.astype(np.float16)
+    for scale in (1.0, 0.37):
+        wide = (h.astype(np.float32) * np.float32(scale)).astype(np.float32)
+        ref = orc.decode(wide, literal=False)
+        assert_parity(dec.decode_host_packed(h, scale=scale, want_hard=True, want_post=True), ref, N, what="float16 pageable scale %g" % scale)
+    ref = orc.decode(h.astype(np.float32), literal=False)
+    pinned = torch.from_numpy(h).pin_memory()
+    assert_parity(dec.decode_host_packed(pinned, want_hard=True, want_post=True), ref, N, what="float16 pinned")
+    assert_parity(dec.decode_host(h.astype(np.float32), want_hard=True, want_post=True), ref, N, what="fp32 call on the widened values")
+    q = np.clip(np.rint(y * 8.0), -127, 127).astype(np.int8)         # 4-bit fraction, as a receiver front end would deliver
+    wide = (q.astype(np.float32) * np.float32(0.125)).astype(np.float32)
+    ref = orc.decode(wide, literal=False)
+    assert_parity(dec.decode_host_packed(q, scale=0.125, want_hard=True, want_post=True), ref, N, what="int8")
+    assert_parity(dec.decode_host_packed(torch.from_numpy(q).pin_memory(), scale=0.125), ref, N, what="int8 pinned, info only")
+    with pytest.raises(ValueError):
+        dec.decode_host_packed(y)                                     # fp32 belongs to decode_host
+
+
 def _run_cli(name, *args):
     import pathlib
     import subprocess

@@ -1,11 +1,13 @@
 #!/usr/bin/env python3
 """SASS listing summary of the hot kernels (cuobjdump on the built library; no GPU needed):
-registers / shared / spills and the opcode histogram of each, written to profiles/r01_sass_kernels.txt."""
+registers / shared / spills and the opcode histogram of each, written to profiles/r02_sass_kernels.txt (round 1: r01_sass_kernels.txt)."""
 import collections, pathlib, re, subprocess, sys
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 LIB = ROOT / "myldpccppapi_b200" / "libldpc_b200.so"
 WANT = [
-    ("cfg1/2/4 default", r"ldpc_ms_qc_kernel<ldpc_b200::QcProfile34B<24, 8>"),
+    ("cfg1/2 default (lockstep)", r"ldpc_ms_qc_kernel<ldpc_b200::QcProfile34B<24, 8, 12>"),
+    ("cfg4 default (warp per codeword)", r"ldpc_ms_qcw_kernel<ldpc_b200::QcwProfile<ldpc_b200::QcwCode34B_24>"),
+    ("block sizes without a compiled profile (group of warps per codeword), rate 3/4B", r"ldpc_ms_qcm_kernel<ldpc_b200::QcwCode34B_24>"),
     ("generic on-chip, G=8 static profile", r"ldpc_ms_group_kernel<8, 16, true, 384, false, ldpc_b200::ProfileWimax34B576, false>"),
     ("cfg3 default", r"ldpc_ms_group_kernel<1, 8, false, 1024, false, ldpc_b200::ProfileRegular36N8192, true>"),
     ("cfg5 default", r"ldpc_ms_stream_kernel<1024>"),
@@ -50,5 +52,5 @@ for label, pat in WANT:
             out.append("  memory / cross-lane: " + ", ".join("%s %d" % (k, fam.get(k, 0)) for k in keys if fam.get(k, 0)))
             out.append("")
             break
-(ROOT / "profiles" / "r01_sass_kernels.txt").write_text("\n".join(out) + "\n")
+(ROOT / "profiles" / "r02_sass_kernels.txt").write_text("\n".join(out) + "\n")
 print("\n".join(out))

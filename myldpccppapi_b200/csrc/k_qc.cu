@@ -46,13 +46,17 @@ int upload_bank(int slot, const void* tab, size_t bytes) {
     return (int)cudaMemcpyToSymbol(g_qc_bank, tab, bytes, (size_t)slot * kQcBankBytes, cudaMemcpyHostToDevice);
 }
 
-#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank, &launch_qc_ring_t<T<Z, G, W>>, &ring_ctas_per_sm<T<Z, G, W>>}
+#define QC_PROFILE(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank, nullptr, nullptr}
+// with the ring-staged variant of the kernel (opt-in experiment, measured slower: profiles/r02_ring_kernel.md) -- only
+// where its test and measurements live, z = 24
+#define QC_PROFILE_RING(T, Z, G, W) {Z, G, W, &qc_build<T<Z, G, W>>, &launch_qc_t<T<Z, G, W>>, &upload_bank, &launch_qc_ring_t<T<Z, G, W>>, &ring_ctas_per_sm<T<Z, G, W>>}
 const QcProfileEntry kTable[] = {
-    QC_PROFILE(LDPC_QC_RATE, 24, 8, 12), QC_PROFILE(LDPC_QC_RATE, 48, 4, 12), QC_PROFILE(LDPC_QC_RATE, 96, 2, 12),
+    QC_PROFILE_RING(LDPC_QC_RATE, 24, 8, 12), QC_PROFILE(LDPC_QC_RATE, 48, 4, 12), QC_PROFILE(LDPC_QC_RATE, 96, 2, 12),
     QC_PROFILE(LDPC_QC_RATE, 40, 4, 10), QC_PROFILE(LDPC_QC_RATE, 80, 2, 10),
     QC_PROFILE(LDPC_QC_RATE, 32, 4, 8),  QC_PROFILE(LDPC_QC_RATE, 64, 2, 8),
-    QC_PROFILE(LDPC_QC_RATE, 24, 4, 6),  // experiment (option qc_prefer_g = 4): half-size CTAs, three per SM
+    QC_PROFILE_RING(LDPC_QC_RATE, 24, 4, 6),  // experiment (option qc_prefer_g = 4): half-size CTAs, three per SM
 };
+#undef QC_PROFILE_RING
 #undef QC_PROFILE
 
 }  // namespace

@@ -1777,7 +1777,7 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
             const uint32_t ring_bytes = (uint32_t)std::max(1, pe.G / 2) * (uint32_t)t.N * 4u;
             h->qc.ring_off = ring_off;
             h->qc_ring_smem = 0;
-            if (h->opt.qc_ring) {  // opt-in: measured slower than the loop-top refill (profiles/r02_ring_kernel.md)
+            if (h->opt.qc_ring && pe.launch_ring) {  // opt-in: measured slower than the loop-top refill (profiles/r02_ring_kernel.md)
                 DeviceGuard guard(h->device);
                 const size_t need = (size_t)ring_off + ring_bytes;
                 const int n = guard.ok ? pe.ring_ctas_per_sm(need) : 0;

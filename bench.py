@@ -237,7 +237,19 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit_record(line)
+
+
+_RECORD_FD = None
+
+
+def emit_record(line: dict) -> None:
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _RECORD_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RECORD_FD, data)
 
 
 def main() -> None:
@@ -258,6 +270,12 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true", help="headline only: no sustained / workloads / plugin / setdevices legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print there while the bench runs (NCCL's version
+    # banner, for one) goes to stderr; the record is written to the saved descriptor at the end
+    global _RECORD_FD
+    sys.stdout.flush()
+    _RECORD_FD = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,8 +299,6 @@ def main() -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # (keeps "NCCL version ..." off stdout: rank 0 prints ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
     # CPU-side barrier (gloo) for the leg in which rank 0 alone drives every GPU: ranks parked in an NCCL barrier would
     # keep a spinning kernel on the very GPUs rank 0 is timing
@@ -700,7 +716,7 @@ def main() -> None:
                                                               "what": "info bytes and iteration counts of each rank's first words against the oracle on the same floats"},
         "workloads": workloads or None, "setdevices": setdev, "cpu_baseline": cpu, "pcie_topology": topo,
     }
-    print(json.dumps(line))
+    emit_record(line)
     if world > 1:
         dist.destroy_process_group()
 

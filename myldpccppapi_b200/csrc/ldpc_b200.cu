@@ -272,6 +272,8 @@ struct ldpc_b200_decoder {
     int64_t h_avail_cap = 0;
     cudaEvent_t st_event = nullptr;
     const unsigned long long* cur_avail = nullptr;  // set around a streamed launch (under mu)
+    int cur_fmt = 0;                                // ... whose input buffer holds packed channel values (LDPC_B200_LLR_*)
+    float cur_scale = 1.0f;
     // pageable input: ring of pinned staging buffers filled by host threads
     static constexpr int kStageSlots = 8;
     float* st_pin[kStageSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2041,6 +2043,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.avail = h->cur_avail;
         q.status = h->cur_avail ? reinterpret_cast<int*>(h->d_avail + 1) : nullptr;
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
+        q.fmt = h->cur_fmt; q.scale = h->cur_scale;
         int np = 0;
         const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
         return launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
@@ -2097,6 +2100,10 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
             if (pct >= 100) use_et = true;
             else if (h->h_stats[1] > 0) use_et = (double)h->h_stats[0] * 100.0 <= (double)pct * (double)h->max_iter * (double)h->h_stats[1];
         }
+        if (h->cur_fmt != LDPC_B200_LLR_F32) {   // packed input is widened at the load: only the per-codeword kernels read it
+            if (!have_w && !have_m) return fail(LDPC_B200_ERR_UNSUPPORTED, "packed channel values need a per-codeword kernel");
+            use_et = true;
+        }
         if (track && !q.iters) {
             if (h->iters_own_cap < ncw) {
                 cudaFree(h->d_iters_own); h->d_iters_own = nullptr; h->iters_own_cap = 0;
@@ -2113,6 +2120,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
             e.K = q.K; e.max_iter = q.max_iter; e.early_term = q.early_term;
             e.llr = q.llr; e.ncw = q.ncw; e.info = q.info; e.hard = q.hard; e.iters = q.iters; e.post = q.post;
             e.counter64 = q.counter64; e.avail = q.avail; e.status = q.status; e.wait_ns = q.wait_ns;
+            e.fmt = h->cur_fmt; e.scale = h->cur_scale;
             int np = 0;
             const QcwProfileEntry& pe = qcw_profiles(&np)[h->qcw_kind];
             const int et_grid = (int)std::min<int64_t>((ncw + h->qcw_warps - 1) / h->qcw_warps, (int64_t)h->sm_count);
@@ -2711,7 +2719,11 @@ namespace {
 constexpr int kStreamedRetry = 1;
 // (h->mu held, current device = the handle's; the caller drains the streams when this returns non-zero)
 int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                              int32_t* iters, float* post, bool staged) {
+                              int32_t* iters, float* post, bool staged, const void* packed = nullptr, int format = LDPC_B200_LLR_F32,
+                              float scale = 1.0f) {
+    // packed (pinned only): the chunks are copied as they are and the per-codeword kernels widen them at the load
+    const size_t esz = format == LDPC_B200_LLR_F16 ? 2 : (format == LDPC_B200_LLR_I8 ? 1 : 4);
+    const char* src_bytes = packed ? static_cast<const char*>(packed) : reinterpret_cast<const char*>(llr);
     const HostTables& t = h->host;
     const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
     const int64_t g = h->plan.cw_per_cta;
@@ -2729,7 +2741,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
     // efficient.  Larger chunks lose: the kernel consumes words in order at 70 % of the PCIe rate, so it keeps
     // running into the end of the announced range and waits for a whole chunk (measured, cfg2 end to end:
     // 4.08 ms with 4 MB chunks, 4.11 with 8 MB, 4.27 with 16 MB).
-    auto words_of = [&](int64_t bytes) { return std::max<int64_t>(g, (bytes / ((int64_t)t.N * 4)) / g * g); };
+    auto words_of = [&](int64_t bytes) { return std::max<int64_t>(g, (bytes / ((int64_t)t.N * (int64_t)esz)) / g * g); };
     int64_t chunk0 = words_of((int64_t)1 << 20), chunk_max = words_of((int64_t)4 << 20);
     if (h->opt.stream_chunk >= 1) chunk0 = chunk_max = (h->opt.stream_chunk + g - 1) / g * g;
     if (staged) {
@@ -2770,15 +2782,17 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
             int64_t j = 0, chunk = chunk0;
             for (int64_t c0 = 0; c0 < n; c0 += chunk, chunk = std::min(chunk * 2, chunk_max), ++j) {
                 const int64_t m = std::min(chunk, n - c0);
-                CU_TRY(cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, llr + (size_t)(off + c0) * t.N, sizeof(float) * (size_t)m * t.N,
-                                       cudaMemcpyHostToDevice, cs));
+                CU_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(h->st_llr) + esz * (size_t)c0 * t.N, src_bytes + esz * (size_t)(off + c0) * t.N,
+                                       esz * (size_t)m * t.N, cudaMemcpyHostToDevice, cs));
                 h->h_avail_vals[j] = (unsigned long long)(c0 + m);
                 CU_TRY(cudaMemcpyAsync(h->d_avail, h->h_avail_vals + j, sizeof(unsigned long long), cudaMemcpyHostToDevice, cs));
             }
             h->cur_avail = h->d_avail;
+            h->cur_fmt = packed ? format : LDPC_B200_LLR_F32; h->cur_scale = scale;
             rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
                                iters ? h->st_iters : nullptr, post ? h->st_post : nullptr, ks);
             h->cur_avail = nullptr;
+            h->cur_fmt = LDPC_B200_LLR_F32; h->cur_scale = 1.0f;
         } else {
             h->cur_avail = h->d_avail;
             rc = launch_decode(h, h->st_llr, n, info ? h->st_info : nullptr, hard ? h->st_hard : nullptr,
@@ -2844,8 +2858,10 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
 }
 
 int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
-                         int32_t* iters, float* post, bool staged) {
-    const int rc = decode_host_streamed_body(h, llr, ncw, info, hard, iters, post, staged);
+                         int32_t* iters, float* post, bool staged, const void* packed = nullptr, int format = LDPC_B200_LLR_F32,
+                         float scale = 1.0f) {
+    const int rc = decode_host_streamed_body(h, llr, ncw, info, hard, iters, post, staged, packed, format, scale);
+    h->cur_fmt = LDPC_B200_LLR_F32; h->cur_scale = 1.0f; h->cur_avail = nullptr;
     if (rc != LDPC_B200_OK) {  // no copy into the caller's buffers may still be in flight when an error returns
         const std::string keep = g_err;
         for (int s = 0; s < 2; ++s) if (h->streams[s]) cudaStreamSynchronize(h->streams[s]);
@@ -3025,6 +3041,19 @@ int ldpc_b200_decode_host_packed(ldpc_b200_handle h, const void* llr, int format
     if (!h->planned) {
         const int prc = make_plan(h);
         if (prc) return prc;
+    }
+    // Quasi-cyclic codes with a per-codeword kernel, pinned input: ONE persistent launch fed by the copy stream, exactly as
+    // the fp32 call -- the chunks are copied packed and the kernel widens each value where it loads it.
+    if (h->algorithm == LDPC_B200_ALG_MIN_SUM && h->plan.path == LDPC_B200_PATH_QC && !h->opt.no_streamed && !h->qc_ring_smem &&
+        (h->plan.dmax == 2 || (h->plan.dmax == 1 && (h->qcw_state == 1 || h->qcm_state == 1)))) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
+                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        if (!pinned) (void)cudaGetLastError();
+        if (pinned) {
+            const int src = decode_host_streamed(h, nullptr, ncw, info, hard, iters, post, false, llr, format, scale);
+            if (src != kStreamedRetry) return src;
+        }
     }
     // chunks of 3/4 of a wave of the persistent grid on three streams: copy, widen + decode, copy back overlap, and the
     // kernels of consecutive chunks fill each other's tails (the chunk rule of the fp32 pipeline, tools/e2e_chunk_sweep.py)

@@ -17,6 +17,7 @@
 // y is canonicalised with y + 0.0f (-0.0 -> +0.0): then neither P nor Q can ever be -0.0 and the
 // sign bit of Q equals the reference's (Q < 0) test (see DESIGN.md "zero signs").
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -305,6 +306,14 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
 }
 __device__ __forceinline__ void sts_u128(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Channel value i of a buffer in one of the host formats of ldpc_b200_decode_host_packed (0 fp32, 1 IEEE binary16,
+// 2 int8): (float)x * scale, one fp32 rounding -- what the widening kernel of the chunked pipeline computes.
+__device__ __forceinline__ float llr_at(const void* __restrict__ base, int fmt, float scale, size_t i) {
+    if (fmt == 1) return __fmul_rn(__half2float(__ldg(static_cast<const __half*>(base) + i)), scale);
+    if (fmt == 2) return __fmul_rn((float)__ldg(static_cast<const signed char*>(base) + i), scale);
+    return __ldg(static_cast<const float*>(base) + i);
 }
 
 // The new messages of one check from S_j = -Q_j (refreshRMS, decodeCL.c:126-147 / MyLdpc.cpp:705-721):

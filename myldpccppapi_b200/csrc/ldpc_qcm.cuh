@@ -62,6 +62,8 @@ struct QcmParams {
     const unsigned long long* avail;   // streamed input (see QcParams)
     int* status;
     unsigned long long wait_ns;
+    int fmt;                      // format of llr: 0 fp32, 1 binary16, 2 int8 (ldpc_b200_decode_host_packed), widened at the load
+    float scale;
 };
 
 #ifdef LDPC_QCM_DEVICE   // the kernel and its table bank: only the unit that instantiates them (k_qcm.cu)
@@ -166,12 +168,13 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const
     };
 
     // the leader warp's lane 0 holds a ticket from the work queue one word ahead (see ldpc_qcw.cuh)
+    const int esz = p.fmt == 1 ? 2 : (p.fmt == 2 ? 1 : 4);   // bytes per channel value in p.llr
     auto claim = [&]() -> long long { return (sw == 0 && lane == 0) ? (long long)atomicAdd(p.counter64, 1ull) : 0ll; };
     auto prefetch_y = [&](long long w) {
-        const char* src = reinterpret_cast<const char*>(p.llr + (size_t)w * p.N);
-        for (int o0 = 0; o0 < p.N * 4; o0 += 32 * 128) {   // (same trip count in every lane)
+        const char* src = reinterpret_cast<const char*>(p.llr) + (size_t)w * p.N * esz;
+        for (int o0 = 0; o0 < p.N * esz; o0 += 32 * 128) {   // (same trip count in every lane)
             const int o = o0 + (int)lane * 128;
-            if (o < p.N * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+            if (o < p.N * esz) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
         }
     };
     auto landed = [&](long long w) -> bool {
@@ -200,10 +203,14 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const
         const long long w = s_word[ws];
         if (w >= p.ncw) break;
         // ---- start word w (decodeInitMS, decodeCL.c:113-124): T = -y (canonical zero), R = 0
-        {
+        if (p.fmt == 0) {
             const float* src = p.llr + (size_t)w * p.N + c;
 #pragma unroll
             for (int b = 0; b < NB; ++b) yn[b] = act ? __ldg(src + b * p.z) : 0.0f;
+        } else {   // packed host formats, widened here
+            const size_t i0 = (size_t)w * p.N + c;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) yn[b] = act ? llr_at(p.llr, p.fmt, p.scale, i0 + (size_t)(b * p.z)) : 0.0f;
         }
         if (act) {
 #pragma unroll 8

@@ -64,6 +64,8 @@ struct QcwParams {
     const unsigned long long* avail;   // streamed input (see QcParams)
     int* status;
     unsigned long long wait_ns;
+    int fmt;                           // format of llr: 0 fp32, 1 binary16, 2 int8 (ldpc_b200_decode_host_packed), widened at the load
+    float scale;
     const uint32_t* syn_tab;           // [ROUNDS][32]: (block column << 8) | shift of the circulant a lane rotates, 0xffffffff = none
 };
 
@@ -146,12 +148,13 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
 #pragma unroll
     for (int r = 0; r < P::ROUNDS; ++r) syn[r] = p.syn_tab[r * 32 + (int)lane];
 
+    const int esz = p.fmt == 1 ? 2 : (p.fmt == 2 ? 1 : 4);   // bytes per channel value in p.llr
     // word w's channel values are pulled into L2 one word ahead (a lane per 128-byte line) ...
     auto prefetch_y = [&](long long w) {
-        const char* src = reinterpret_cast<const char*>(p.llr + (size_t)w * p.N);
-        for (int o0 = 0; o0 < p.N * 4; o0 += 32 * 128) {   // (same trip count in every lane)
+        const char* src = reinterpret_cast<const char*>(p.llr) + (size_t)w * p.N * esz;
+        for (int o0 = 0; o0 < p.N * esz; o0 += 32 * 128) {   // (same trip count in every lane)
             const int o = o0 + (int)lane * 128;
-            if (o < p.N * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+            if (o < p.N * esz) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
         }
     };
     // lane 0 takes a ticket from the work queue; it is broadcast only when it is consumed, one word later, so the
@@ -175,10 +178,14 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
         const long long w = wn;
         if (w >= p.ncw) break;
         // ---- start word w (decodeInitMS, decodeCL.c:113-124): T = -y (canonical zero), R = 0
-        {
+        if (p.fmt == 0) {
             const float* src = p.llr + (size_t)w * p.N + lane;
 #pragma unroll
             for (int b = 0; b < NB; ++b) yn[b] = act ? __ldg(src + b * Z) : 0.0f;
+        } else {   // packed host formats, widened here
+            const size_t i0 = (size_t)w * p.N + lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) yn[b] = act ? llr_at(p.llr, p.fmt, p.scale, i0 + (size_t)(b * Z)) : 0.0f;
         }
         if (act) {
 #pragma unroll

@@ -54,9 +54,10 @@ bool qcm_build(const HostTables& t, int z, const std::vector<std::vector<QcBlk>>
 template <class R>
 int launch_qcm_t(const QcmParams& q, int grid, int groups, cudaStream_t stream) {
     const size_t smem = (size_t)groups * q.word_bytes;
-    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_qcm_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = q.fmt == 0 ? ldpc_ms_qcm_kernel<R, false> : ldpc_ms_qcm_kernel<R, true>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    ldpc_ms_qcm_kernel<R><<<grid, groups * q.NW * 32, smem, stream>>>(q);
+    kernel<<<grid, groups * q.NW * 32, smem, stream>>>(q);
     return (int)cudaGetLastError();
 }
 

@@ -32,9 +32,10 @@ bool qcw_build(const HostTables& t, const std::vector<std::vector<QcBlk>>& rows,
 template <class P>
 int launch_qcw_t(const QcwParams& q, int grid, int warps, cudaStream_t stream) {
     const size_t smem = (size_t)warps * P::WARP_BYTES;
-    cudaError_t e = cudaFuncSetAttribute(ldpc_ms_qcw_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = q.fmt == 0 ? ldpc_ms_qcw_kernel<P, false> : ldpc_ms_qcw_kernel<P, true>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    ldpc_ms_qcw_kernel<P><<<grid, warps * 32, smem, stream>>>(q);
+    kernel<<<grid, warps * 32, smem, stream>>>(q);
     return (int)cudaGetLastError();
 }
 

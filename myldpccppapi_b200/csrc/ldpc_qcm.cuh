@@ -99,12 +99,9 @@ __device__ __forceinline__ uint32_t qcm_check(const QcmTab<R>& tb, uint32_t la, 
         px ^= __float_as_uint(S[D - 1]);
         sx ^= __float_as_uint(tv[D - 1]);
     }
-    float rn[D];
-    ms_new_messages<D>(S, px, rn);
-    if (act) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) sts_f32(r0 + (uint32_t)j * zb, rn[j]);
-    }
+    ms_new_messages_each<D>(S, px, [&](int j, float rn) {
+        if (act) sts_f32(r0 + (uint32_t)j * zb, rn);
+    });
     return ((sx >> 31) ^ (uint32_t)D) & 1u;
 }
 
@@ -141,7 +138,8 @@ __device__ __forceinline__ void qcm_vn(const QcmTab<R>& tb, uint32_t la, uint32_
     }
 }
 
-template <class R>
+// PACKED: p.llr holds float16 / int8 values, widened at the load (a separate instantiation, see ldpc_qcw.cuh)
+template <class R, bool PACKED = false>
 __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const __grid_constant__ QcmParams p) {
     constexpr int NB = R::NB;
     static_assert(sizeof(QcmTab<R>) <= kQcmBankBytes, "profile tables exceed a bank slot");
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const
     };
 
     // the leader warp's lane 0 holds a ticket from the work queue one word ahead (see ldpc_qcw.cuh)
-    const int esz = p.fmt == 1 ? 2 : (p.fmt == 2 ? 1 : 4);   // bytes per channel value in p.llr
+    const int esz = !PACKED ? 4 : (p.fmt == 1 ? 2 : 1);   // bytes per channel value in p.llr
     auto claim = [&]() -> long long { return (sw == 0 && lane == 0) ? (long long)atomicAdd(p.counter64, 1ull) : 0ll; };
     auto prefetch_y = [&](long long w) {
         const char* src = reinterpret_cast<const char*>(p.llr) + (size_t)w * p.N * esz;
@@ -203,7 +201,7 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const
         const long long w = s_word[ws];
         if (w >= p.ncw) break;
         // ---- start word w (decodeInitMS, decodeCL.c:113-124): T = -y (canonical zero), R = 0
-        if (p.fmt == 0) {
+        if constexpr (!PACKED) {
             const float* src = p.llr + (size_t)w * p.N + c;
 #pragma unroll
             for (int b = 0; b < NB; ++b) yn[b] = act ? __ldg(src + b * p.z) : 0.0f;

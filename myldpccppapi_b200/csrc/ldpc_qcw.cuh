@@ -21,7 +21,8 @@
 //     min1/min2 tracking plus compare-and-select (4.5), the same value bit for bit; the sign is applied by one
 //     multiplication with +-1.0 on the FMA pipe (the kernel is bound by the half-rate ALU pipe and by issue).
 //   * SYNDROME FROM PACKED BITS.  The variable pass ballots the sign of every posterior it writes: lane b keeps the
-//     z hard bits of block column b in a register.  The syndrome of ALL z rows of a block row is the XOR over its
+//     z hard bits of block column b in a register (a select per block column; keeping the words in shared memory
+//     instead cost 24 wavefronts per iteration of a kernel that is bound by them: +5 %).  The syndrome of ALL z rows of a block row is the XOR over its
 //     circulants of that word rotated by the shift -- one shuffle and one rotate per CIRCULANT (88 for Test.cpp's
 //     code), not per edge, reduced by a butterfly.  A word is finished the moment its syndrome is clean after a
 //     variable pass: it costs exactly `iters` trips (reference stop rule, MyLdpc.cpp:751-755).
@@ -45,8 +46,7 @@ struct QcwProfile : C {
     static constexpr int Z = C::Z, NB = C::NB, MB = C::MB, E = C::E;
     static constexpr uint32_t ZB = (uint32_t)Z * 4u;
     static constexpr uint32_t T_BYTES = (uint32_t)NB * 2u * ZB;   // T[NB][2z]: every block column twice
-    static constexpr uint32_t HB_OFF = T_BYTES + (uint32_t)E * ZB; // R[E][z], then the hard-bit words [NB]
-    static constexpr uint32_t WARP_BYTES = HB_OFF + 128u;          // (idle lanes read up to 32 B past the last circulant)
+    static constexpr uint32_t WARP_BYTES = T_BYTES + (uint32_t)E * ZB + 128u;   // R[E][z] behind T (+ slack: idle lanes read up to 32 B past the last circulant)
     static constexpr int SEG = C::DMAX <= 8 ? 8 : (C::DMAX <= 16 ? 16 : 32);   // lanes per block row in the syndrome rounds
     static constexpr int ROUNDS = (MB * SEG + 31) / 32;
 };
@@ -104,9 +104,9 @@ __device__ __forceinline__ void qcw_cn(uint32_t la, bool act) {
 
 // One block column: lane = column.  refreshPostPMS (decodeCL.c:149-171): T = (-y) - R_1 - R_2 ... in ascending-row
 // order; edge k's message sits at row (lane - s) mod z of its circulant: lane*4 + (circulant - s*4), plus z*4 for the
-// lanes below s (laz = la + z*4).  The z hard bits of the column (bit = !signbit(T)) go to the warp's hard-bit word B.
+// lanes below s (laz = la + z*4).  The z hard bits of the column (bit = !signbit(T)) go to lane B's register.
 template <class P, int B>
-__device__ __forceinline__ void qcw_vn(uint32_t la, uint32_t laz, uint32_t lane, const float* yn, bool act) {
+__device__ __forceinline__ void qcw_vn(uint32_t la, uint32_t laz, uint32_t lane, const float* yn, bool act, uint32_t& hb) {
     if constexpr (B < P::NB) {
         constexpr int D = P::vdeg(B), V0 = P::v0(B);
         float r[D];
@@ -123,8 +123,8 @@ __device__ __forceinline__ void qcw_vn(uint32_t la, uint32_t laz, uint32_t lane,
             sts_f32(la + (uint32_t)B * 2u * P::ZB + P::ZB, acc);
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, act && (__float_as_uint(acc) >> 31) == 0u);
-        if (lane == 0u) qc_sts_u32(la + P::HB_OFF + (uint32_t)B * 4u, bal);
-        qcw_vn<P, B + 1>(la, laz, lane, yn, act);
+        if (lane == (uint32_t)B) hb = bal;   // (a register select: the kernel is bound by shared-memory wavefronts, not by the ALU pipe)
+        qcw_vn<P, B + 1>(la, laz, lane, yn, act, hb);
     }
 }
 
@@ -164,10 +164,11 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
     auto landed = [&](long long w) -> bool {   // streamed input: wait (bounded) until word w is in device memory
         return w < p.ncw && (!p.avail || qc_wait_input(p.avail, w, true, p.status, p.wait_ns));
     };
+    uint32_t hb = 0u;   // lane b: the z hard bits of block column b (bit = !signbit(T)) after the last variable pass
     // hard-bit word of the block column that holds byte b of the codeword, shifted to that byte
     auto byte_of = [&](int b) -> uint32_t {
         const int bc = (8 * b) / Z;
-        return (qc_lds_u32(wb + P::HB_OFF + (uint32_t)(bc < NB ? bc : 0) * 4u) >> (8 * b - bc * Z)) & 0xffu;
+        return (__shfl_sync(0xffffffffu, hb, bc < NB ? bc : 0) >> (8 * b - bc * Z)) & 0xffu;
     };
 
     float yn[NB];
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
         for (;;) {
             qcw_cn<P, 0>(la, act);
             __syncwarp();
-            qcw_vn<P, 0>(la, la + ZB, lane, yn, act);
+            qcw_vn<P, 0>(la, la + ZB, lane, yn, act, hb);
             __syncwarp();
             ++it;
             if (it >= p.max_iter) break;
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
                 for (int r = 0; r < P::ROUNDS; ++r) {
                     const uint32_t e = syn[r];
                     const bool valid = e != 0xffffffffu;
-                    const uint32_t wv = qc_lds_u32(wb + P::HB_OFF + ((e >> 6) & 0x7cu));
+                    const uint32_t wv = __shfl_sync(0xffffffffu, hb, (int)((e >> 8) & 31u));
                     const uint32_t s = valid ? (e & 31u) : 0u;
                     uint32_t x;
                     if constexpr (Z == 32) x = __funnelshift_r(wv, wv, s);

@@ -6,7 +6,8 @@
 // (profiles/r02_ring_kernel.md, r02_et_kernel.md): CTA-wide barriers around every retire/start event, the leaving word's
 // bits packed from shared memory, the starting word's messages cleared, and one extra loop trip per word because the
 // syndrome of iteration t is only seen by the check pass of t + 1.  A CTA-level variant with an incremental syndrome
-// (ldpc_qc_et.cuh) removed the extra trip but not the barriers and paid for it in divergent shared-memory atomics.
+// (built, measured, removed: profiles/r02_et_kernel.md) took the extra trip away but not the barriers and paid for it
+// in divergent shared-memory atomics.
 //
 // Here nothing is shared between codewords, so nothing is synchronised between them:
 //   * a warp owns one codeword: T[24][2z] (negated posterior, each block column stored twice so that the cyclic
@@ -19,12 +20,13 @@
 //   * EXCLUDE-SELF MINIMA BY PREFIX / SUFFIX.  R_e = +-min(1000, min over the other edges |Q|) is taken as
 //     min3(prefix, neighbour, suffix) over pairs of edges: 2 three-input min/max instructions per edge instead of
 //     min1/min2 tracking plus compare-and-select (4.5), the same value bit for bit; the sign is applied by one
-//     multiplication with +-1.0 on the FMA pipe (the kernel is bound by the half-rate ALU pipe and by issue).
+//     multiplication with +-1.0 on the FMA pipe (with min1/min2 tracking the kernel was bound by the half-rate ALU
+//     pipe; now by shared-memory wavefronts: 93 % of peak at the cap, profiles/r02_ncu_qcw_fixed40.txt).
 //   * SYNDROME FROM PACKED BITS.  The variable pass ballots the sign of every posterior it writes: lane b keeps the
 //     z hard bits of block column b in a register (a select per block column; keeping the words in shared memory
-//     instead cost 24 wavefronts per iteration of a kernel that is bound by them: +5 %).  The syndrome of ALL z rows of a block row is the XOR over its
-//     circulants of that word rotated by the shift -- one shuffle and one rotate per CIRCULANT (88 for Test.cpp's
-//     code), not per edge, reduced by a butterfly.  A word is finished the moment its syndrome is clean after a
+//     instead cost 24 wavefronts per iteration of a kernel that is bound by them: +5 %).  The syndrome of ALL z rows
+//     of a block row is the XOR over its circulants of that word rotated by the shift -- one shuffle and one rotate
+//     per CIRCULANT (88 for Test.cpp's code), not per edge, reduced by a butterfly.  A word is finished the moment its syndrome is clean after a
 //     variable pass: it costs exactly `iters` trips (reference stop rule, MyLdpc.cpp:751-755).
 //   * the leaving word's info bytes ARE those registers (toChar, decodeCL.c:188-199: three bytes per block column);
 //     the starting word's channel values were pulled into L2 one word ahead; its messages are cleared by E

@@ -71,6 +71,7 @@ struct Options {
     // launch / host pipeline: read per call
     int refill_wait = 1;              // measured: profiles/r01_refill_sweep.txt
     bool no_streamed = false, streamed_pageable = false, no_staged = false;
+    bool no_warm = false;             // skip the first-launch warm-up of ldpc_b200_reserve (measurements of the cold first call)
     bool register_host = false;       // page-lock a pageable input buffer on first sight (cudaHostRegister) and keep it registered
     long long staged_min_kb = 8 << 10;  // pageable input of 8 MB or more is staged by host threads
     long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
@@ -92,7 +93,7 @@ const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(no_qcm, 0), OPT(qcm_always, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
-    OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(register_host, 0),
+    OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
     OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(stage_threads, 1),
 };
@@ -196,6 +197,7 @@ struct ldpc_b200_decoder {
     int64_t iters_own_cap = 0;
     unsigned long long* h_stats = nullptr;   // pinned, written by the device after every launch: [0] sum of the sampled counts, [1] words sampled
     unsigned stat_tick = 0;
+    unsigned warmed = 0;                     // bit a: the kernels of algorithm a have been launched once (warm_kernels_locked)
     int last_kernel = 0;                     // ldpc_b200_info.kernel_variant of the most recent launch
     // QC tables with a run-time profile (ldpc_qcg.cuh)
     QcgParams qcg;
@@ -2623,9 +2625,72 @@ int ensure_streamed_buffers(ldpc_b200_decoder* h, int64_t want, bool hard, bool 
     return LDPC_B200_OK;
 }
 
+// CUDA loads a kernel's code at its first launch.  Loading needs the device idle, so a kernel first launched behind
+// the persistent launch of the host-buffer path -- which is spinning on input the host has not queued yet -- sat
+// out the kernel's whole wait bound: the first Coder::decode of a process took 4 s (tools/setdevices_first_call.py).
+// Every kernel a decode with the handle's current algorithm can launch is therefore run once here, on a few all-zero
+// words, where the reference compiles its OpenCL kernels (addDecodeType, MyLdpc.cpp:387-437).
+// (h->mu held, current device = the handle's)
+int warm_kernels_locked(ldpc_b200_decoder* h) {
+    const unsigned bit = 1u << (unsigned)h->algorithm;
+    if ((h->warmed & bit) || h->opt.no_warm) return LDPC_B200_OK;
+    if (!h->planned) { const int rc = make_plan(h); if (rc) return rc; }
+    const HostTables& t = h->host;
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    const int64_t n = std::max<int64_t>(1, h->plan.cw_per_cta);
+    // scratch of its own: [channel values | info bytes | hard bytes | iteration counts]
+    const size_t o_info = sizeof(float) * (size_t)n * t.N, o_hard = o_info + (((size_t)n * KB + 15) & ~(size_t)15),
+                 o_iters = o_hard + (((size_t)n * NB + 15) & ~(size_t)15), bytes = o_iters + sizeof(int32_t) * (size_t)n;
+    char* d = nullptr;
+    CU_TRY(cudaMalloc(&d, bytes));
+    float* llr = reinterpret_cast<float*>(d);
+    uint8_t* info = reinterpret_cast<uint8_t*>(d + o_info);
+    uint8_t* hard = reinterpret_cast<uint8_t*>(d + o_hard);
+    int32_t* iters = reinterpret_cast<int32_t*>(d + o_iters);
+    cudaStream_t s = nullptr;  // (the legacy stream: the handle's own streams may not exist yet)
+    const int64_t launches = h->launches;
+    const int last_kernel = h->last_kernel, qc_et = h->opt.qc_et;
+    int rc = cudaMemsetAsync(d, 0, bytes, s) == cudaSuccess ? LDPC_B200_OK : fail(LDPC_B200_ERR_CUDA, "kernel warm-up: memset failed");
+    const bool qc_min_sum = h->algorithm == LDPC_B200_ALG_MIN_SUM && h->plan.path == LDPC_B200_PATH_QC;
+    if (rc == LDPC_B200_OK && qc_min_sum && qc_et < 0) {
+        // lockstep kernel, per-codeword kernel (fp32, float16 and int8 channel values), iteration statistics
+        const int fmts[3] = {LDPC_B200_LLR_F32, LDPC_B200_LLR_F16, LDPC_B200_LLR_I8};
+        for (int et = 0; et <= 1 && rc == LDPC_B200_OK; ++et) {
+            h->opt.qc_et = et;
+            rc = launch_decode(h, llr, n, info, hard, iters, nullptr, s);
+        }
+        const bool per_word = h->qcw_state == 1 || h->qcm_state == 1;
+        for (int f = 1; f < 3 && per_word && h->early && rc == LDPC_B200_OK; ++f) {
+            h->cur_fmt = fmts[f];
+            rc = launch_decode(h, llr, n, info, hard, iters, nullptr, s);
+        }
+        h->cur_fmt = LDPC_B200_LLR_F32;
+        h->opt.qc_et = -1;
+        if (rc == LDPC_B200_OK) rc = launch_decode(h, llr, n, info, hard, nullptr, nullptr, s);
+        h->opt.qc_et = qc_et;
+    } else if (rc == LDPC_B200_OK) {
+        rc = launch_decode(h, llr, n, info, hard, iters, nullptr, s);
+    }
+    const cudaError_t e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    h->launches = launches;          // the caller's launch count and kernel choice start from a clean state
+    h->last_kernel = last_kernel;
+    h->stat_tick = 0;
+    if (h->h_stats) h->h_stats[0] = h->h_stats[1] = 0ull;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(LDPC_B200_ERR_CUDA, std::string("kernel warm-up: ") + cudaGetErrorString(e));
+    h->warmed |= bit;
+    return LDPC_B200_OK;
+}
+
 // (h->mu held)
 int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
-    if (batch <= h->reserved) return LDPC_B200_OK;
+    if (batch <= h->reserved) {
+        if (h->reserved < 1) return LDPC_B200_OK;
+        DeviceGuard guard(h->device);
+        if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+        return warm_kernels_locked(h);   // (a new algorithm since the last reservation)
+    }
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
     CU_TRY(cudaDeviceSynchronize());
@@ -2679,7 +2744,7 @@ int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
             h->st_pin_bytes = need;
         }
     }
-    return LDPC_B200_OK;
+    return warm_kernels_locked(h);
 }
 }  // namespace
 
@@ -2977,7 +3042,9 @@ int ldpc_b200_decode_host(ldpc_b200_handle h, const float* llr, int64_t ncw, uin
                 (void)cudaGetLastError();  // (overlaps an older registration, or the driver refused: staged path below)
             }
         }
-        int rc = kStreamedRetry;
+        int rc = warm_kernels_locked(h);  // (a handle nobody called ldpc_b200_reserve on: the kernels load here, once)
+        if (rc) return rc;
+        rc = kStreamedRetry;
         if (pinned || h->opt.streamed_pageable) {
             rc = decode_host_streamed(h, llr, ncw, info, hard, iters, post, false);
         } else if ((int64_t)ncw * t.N * 4 >= (h->opt.staged_min_kb << 10) && !h->opt.no_staged) {
@@ -3051,6 +3118,8 @@ int ldpc_b200_decode_host_packed(ldpc_b200_handle h, const void* llr, int format
                             (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
         if (!pinned) (void)cudaGetLastError();
         if (pinned) {
+            const int wrc = warm_kernels_locked(h);
+            if (wrc) return wrc;
             const int src = decode_host_streamed(h, nullptr, ncw, info, hard, iters, post, false, llr, format, scale);
             if (src != kStreamedRetry) return src;
         }

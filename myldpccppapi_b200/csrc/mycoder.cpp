@@ -180,16 +180,38 @@ int Coder::forDecoder(int batchSize) {
 }
 
 int Coder::addDecodeType(enum decodeType deType) {
-    (void)deType;  // both kernels are precompiled; decode() picks one per call from its own deType
+    // every kernel is precompiled and decode() picks one per call from its own deType; what happens here is what the
+    // reference does here (it builds and allocates, MyLdpc.cpp:387-437): launch buffers for batchSize words, and one
+    // launch of this deType's kernels so that the first decode() finds their code loaded on the device
     if (impl->handles.empty()) {
         impl->err = "forDecoder must be called before addDecodeType";
         return LDPC_B200_ERR_ARG;
     }
-    if (impl->batchSize > 0)
-        for (ldpc_b200_handle h : impl->handles) {
-            int rc = ldpc_b200_reserve(h, impl->batchSize);
-            if (rc != LDPC_B200_OK) return impl->fail(rc);
+    if (impl->batchSize > 0) {
+        int alg = deType == DecodeSP ? LDPC_B200_ALG_SUM_PRODUCT
+                  : (deType == DecodeTDMP || deType == DecodeTDMPCL) ? LDPC_B200_ALG_LAYERED_MIN_SUM
+                                                                     : LDPC_B200_ALG_MIN_SUM;
+        if (impl->fusedExact && deType == DecodeMSCL) alg = LDPC_B200_ALG_FUSED_MIN_SUM;
+        if (impl->fusedExact && deType == DecodeTDMPCL) alg = LDPC_B200_ALG_FUSED_LAYERED;
+        auto setup = [&](ldpc_b200_handle h) -> int {
+            int rc = ldpc_b200_reserve(h, impl->batchSize);  // min-sum: the host-buffer pipeline's buffers too
+            if (rc == LDPC_B200_OK && alg != LDPC_B200_ALG_MIN_SUM) {
+                if (ldpc_b200_set_algorithm(h, alg) == LDPC_B200_OK) rc = ldpc_b200_reserve(h, impl->batchSize);
+                ldpc_b200_set_algorithm(h, LDPC_B200_ALG_MIN_SUM);  // (a code the kernel cannot hold: decode() reports it)
+            }
+            return rc;
+        };
+        // one host thread per device: a CUDA context loads kernels for its own device only
+        std::vector<int> rcs(impl->handles.size(), LDPC_B200_OK);
+        if (impl->handles.size() == 1) rcs[0] = setup(impl->handles[0]);
+        else {
+            std::vector<std::thread> th;
+            for (size_t g = 0; g < impl->handles.size(); ++g) th.emplace_back([&, g]() { rcs[g] = setup(impl->handles[g]); });
+            for (auto &t : th) t.join();
         }
+        for (int rc : rcs)
+            if (rc != LDPC_B200_OK) return impl->fail(rc);
+    }
     if (impl->batchSize > 0) {  // result staging for a call of batchSize words: the first decode() allocates nothing
         Impl::grow(impl->iters, impl->itersCap, impl->itersPinned, (size_t)impl->batchSize);
         Impl::grow(impl->info, impl->infoCap, impl->infoPinned, (size_t)impl->batchSize * ((impl->K + 7) / 8));

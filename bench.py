@@ -368,7 +368,7 @@ def main() -> None:
         r = dict(roof_smem if onchip else roof_hbm)
         kname = KERNELS.get(info["path_name"], "?")
         if info["path_name"] == "qc":
-            kname = {0: "ldpc_ms_qc_kernel", 1: "ldpc_ms_qcw_kernel", 2: "ldpc_ms_qc_ring_kernel", 3: "ldpc_ms_qcm_kernel"}.get(info.get("kernel_variant", 0), kname)
+            kname = {0: "ldpc_ms_qc_kernel", 1: "ldpc_ms_qcw_kernel", 2: "ldpc_ms_qc_ring_kernel", 3: "ldpc_ms_qcm_kernel", 4: "ldpc_ms_qcm_multi_kernel"}.get(info.get("kernel_variant", 0), kname)
         r.update({"kernel": kname if args.algorithm == 0 else {1: "ldpc_sp_group_kernel", 2: "ldpc_tdmp_group_kernel"}[args.algorithm],
                   "launch_ms": ms_step, "traffic": roof_hbm.get("traffic"),
                   "algorithmic_bytes_per_codeword": {"hbm": b_hbm, "messages": b_msg, "mean_iterations": mean_iters},
@@ -670,6 +670,25 @@ def main() -> None:
                 setdev = {"api": "one process, Coder::setDevices(0..%d), one host thread per GPU, malloc'd buffers" % (world - 1),
                           "codewords": tot, "value": tot * K / dts / 1e9, "unit": UNIT, "ms_per_step": dts * 1e3, "first_call_ms": first_s * 1e3,
                           "gpu_matches_oracle_on_sample": bool(np.array_equal(got, chk[0]))}
+                coder.close()
+                # the same with the caller's buffer page-locked at its first decode: every GPU DMAs its shard straight out of it
+                src2 = np.zeros(src_len + 1, dtype=np.uint8)
+                coder = m.Coder(K, N, m.rate_3_4_b)
+                coder.setMaxIter(cap)
+                coder.setDevices(list(range(world)))
+                coder.setRegisterHostBuffers(True)
+                coder.forDecoder(tot)
+                coder.addDecodeType(m.DecodeMS)
+                t0 = time.perf_counter()
+                coder.decode(post, src2, src_len, m.DecodeMS)
+                first_r = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    coder.decode(post, src2, src_len, m.DecodeMS)
+                dtr = (time.perf_counter() - t0) / 5
+                setdev["registered"] = {"api": "the same after Coder::setRegisterHostBuffers(true)", "value": tot * K / dtr / 1e9, "unit": UNIT,
+                                        "ms_per_step": dtr * 1e3, "first_call_ms": first_r * 1e3,
+                                        "bytes_match_unregistered": bool(np.array_equal(src, src2))}
                 coder.close()
             except Exception as e:
                 setdev = {"error": "%s: %s" % (type(e).__name__, e)}

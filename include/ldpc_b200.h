@@ -108,7 +108,9 @@ typedef struct ldpc_b200_info {
     size_t table_bytes;  /* device bytes of the check-major + variable-major tables */
     int kernel_variant;  /* quasi-cyclic path with a compiled lockstep profile, most recent launch: 0 lockstep kernel,
                             1 warp-per-codeword kernel, 3 group-of-warps kernel (chosen per launch from the previous
-                            launches' mean iteration count; option "qc_et": -1 auto, 0 never, 1 always), 2 ring-staged */
+                            launches' mean iteration count; option "qc_et": -1 auto, 0 never, 1 always), 2 ring-staged,
+                            4 group-of-warps kernel with several codewords per group (block sizes without a lockstep
+                            profile, while the words run long; option "qcm_multi_pct") */
     int et_available;    /* which per-codeword kernel this handle can switch to: 0 none, 1 warp per codeword (802.16e
                             codes with z = 24 / 32), 2 group of warps */
 } ldpc_b200_info;

@@ -48,7 +48,40 @@ bool qcm_build(const HostTables& t, int z, const std::vector<std::vector<QcBlk>>
     if (q.NW > 1) groups = std::min(groups, kQcmMaxGroups);
     if (groups < 2) return false;
     *groups_out = groups;
+    q.PK = 1;
     return true;
+}
+
+// Geometry of ldpc_ms_qcm_multi_kernel for `pack` codewords per group (same tables, same slice layout).
+// false = that many do not fit.
+bool qcm_multi_geometry(const QcmParams& single, int pack, size_t smem_limit, QcmParams* out, int* groups_out) {
+    if (pack < 2 || pack > kQcmMaxPack) return false;
+    QcmParams q = single;
+    q.PK = pack;
+    q.NW = (pack * q.z + 31) / 32;
+    q.RW = (pack * q.z + q.NW - 1) / q.NW;
+    if (q.NW < 2 || q.NW > kQcmMaxWarps) return false;
+    // consecutive slices z words apart modulo the 32 banks: the lanes of a warp that straddles two codewords
+    // (rows z-1-i .. z-1 of one, 0 .. j of the next) then hit consecutive banks as the lanes of one codeword do
+    if (q.z % 4 == 0) q.word_bytes += ((uint32_t)(q.z * 4) % 128u + 128u - q.word_bytes % 128u) % 128u;
+    if (smem_limit < 1024) return false;
+    int groups = (int)((smem_limit - 1024) / ((size_t)pack * q.word_bytes));   // (the kernel's static shared memory counts too)
+    groups = std::min(groups, kQcmMaxWarps / q.NW);
+    groups = std::min(groups, kQcmMaxGroups);
+    if (groups < 1) return false;
+    *out = q;
+    *groups_out = groups;
+    return true;
+}
+
+template <class R>
+int launch_qcm_multi_t(const QcmParams& q, int grid, int groups, cudaStream_t stream) {
+    const size_t smem = (size_t)groups * q.PK * q.word_bytes;
+    auto kernel = ldpc_ms_qcm_multi_kernel<R>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kernel<<<grid, groups * q.NW * 32, smem, stream>>>(q);
+    return (int)cudaGetLastError();
 }
 
 template <class R>
@@ -67,7 +100,7 @@ int upload_qcm_bank(int slot, const void* tab, size_t bytes) {
 }
 
 // (the degree sequences of a rate do not depend on z: the z = 24 code tables carry them)
-#define QCM_PROFILE(C) {&qcm_build<C>, &launch_qcm_t<C>, &upload_qcm_bank}
+#define QCM_PROFILE(C) {&qcm_build<C>, &launch_qcm_t<C>, &upload_qcm_bank, &qcm_multi_geometry, &launch_qcm_multi_t<C>}
 const QcmProfileEntry kTable[] = {
     QCM_PROFILE(QcwCode34B_24), QCM_PROFILE(QcwCode34A_24), QCM_PROFILE(QcwCode23B_24),
     QCM_PROFILE(QcwCode23A_24), QCM_PROFILE(QcwCode12_24),  QCM_PROFILE(QcwCode56_24),

@@ -82,6 +82,8 @@ struct Options {
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
     int qc_et_every = 4;              // auto: the iteration counts are sampled after every n-th launch once the regime is known (13 us each)
+    int qcm_pack = 0;                 // group-of-warps kernel, codewords per group: 0 / 1 = one, 2 / 3 = that many (ldpc_ms_qcm_multi_kernel)
+    int qcm_multi_pct = -1;           // ... used while the mean iteration count is above this share of the cap (-1 = measured crossover, 0 = always)
     int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
                                       // crossover of the code (profiles/r02_et_kernel.md: z = 24 90 %, z = 32 every regime)
 };
@@ -92,10 +94,10 @@ struct OptionName { const char* name; int kind; size_t off; bool runtime; };  //
 const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(no_qcm, 0), OPT(qcm_always, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
-    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(place_effort, 2),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
-    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(stage_threads, 1),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1),
 };
 #undef OPT
 #undef OPTR
@@ -192,6 +194,8 @@ struct ldpc_b200_decoder {
     // a group of warps per codeword, any z (ldpc_qcm.cuh): the block sizes without a compiled lockstep profile
     QcmParams qcm;
     int qcm_kind = -1, qcm_state = 0, qcm_slot = -1, qcm_groups = 0;
+    QcmParams qcm_multi;                     // the same with several codewords per group (ldpc_ms_qcm_multi_kernel); 0 groups = not used
+    int qcm_multi_groups = 0;
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
     int32_t* d_iters_own = nullptr;          // iteration counts when the caller does not ask for them
     int64_t iters_own_cap = 0;
@@ -1315,6 +1319,14 @@ bool qcm_prepare(ldpc_b200_decoder* h) {
         h->qcm_slot = slot;
         h->qcm_kind = k;
         h->qcm_groups = groups;
+        // several codewords per group (ldpc_ms_qcm_multi_kernel): measurements in profiles/r02_qcm_pack.txt
+        h->qcm_multi_groups = 0;
+        {
+            const int pack = h->opt.qcm_pack;
+            QcmParams qm;
+            int gm = 0;
+            if (pack >= 2 && pe.multi_geometry(h->qcm, pack, h->smem_optin, &qm, &gm)) { h->qcm_multi = qm; h->qcm_multi_groups = gm; }
+        }
         h->table_bytes += tab.size();
         return true;
     }
@@ -1816,6 +1828,11 @@ int make_plan_for(ldpc_b200_decoder* h, const int flood_alg) {
         // of ceil(z / 32) warps per codeword (measured 2-3x the kernels below: profiles/r02_wimax_family.txt)
         if (want && !h->opt.no_qcm && !h->opt.qc_generic && h->qcm_state == 0) h->qcm_state = qcm_prepare(h) ? 1 : -1;
         if (want && !h->opt.no_qcm && !h->opt.qc_generic && h->qcm_state == 1) {
+            if (h->qcm_multi_groups > 0 && !h->h_stats) {   // the regime decides between one and several codewords per group
+                DeviceGuard guard(h->device);
+                if (guard.ok && cudaMallocHost(&h->h_stats, 2 * sizeof(unsigned long long)) == cudaSuccess) h->h_stats[0] = h->h_stats[1] = 0ull;
+                else { (void)cudaGetLastError(); h->h_stats = nullptr; }
+            }
             pl.path = LDPC_B200_PATH_QC;
             pl.dmax = 2;  // marks the group-of-warps kernel
             pl.threads = 32 * h->qcm_groups * h->qcm.NW;
@@ -2035,8 +2052,9 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
 
     // the group-of-warps kernel (ldpc_qcm.cuh): the plan's kernel for block sizes without a compiled lockstep profile, and
     // the early-termination alternative of the profiled sizes that have no warp-per-codeword kernel
-    auto launch_qcm = [&](int32_t* iters_out) -> int {
-        QcmParams& q = h->qcm;  // tables and geometry filled by qcm_build; per-launch fields below
+    auto launch_qcm = [&](int32_t* iters_out, bool multi = false) -> int {
+        QcmParams& q = multi ? h->qcm_multi : h->qcm;  // tables and geometry filled by qcm_build; per-launch fields below
+        q.tab_slot = h->qcm.tab_slot;
         q.K = h->K;
         q.max_iter = h->max_iter; q.early_term = h->early;
         q.llr = d_llr; q.ncw = ncw;
@@ -2047,14 +2065,42 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.wait_ns = (unsigned long long)std::max<long long>(1, h->opt.wait_timeout_ms) * 1000000ull;
         q.fmt = h->cur_fmt; q.scale = h->cur_scale;
         int np = 0;
+        if (multi) {
+            const int64_t per_cta = (int64_t)h->qcm_multi_groups * q.PK;
+            const int g = (int)std::min<int64_t>((ncw + per_cta - 1) / per_cta, (int64_t)h->sm_count);
+            return launch_status(qcm_profiles(&np)[h->qcm_kind].launch_multi(q, g, h->qcm_multi_groups, stream), "quasi-cyclic (warps per group of codewords)");
+        }
         const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
         return launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
     };
     if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
-        rc = launch_qcm(d_iters);
+        // several codewords per group while the words run long; one per group (nothing waits for a slower neighbour) once
+        // the previous launches' words stopped early on average -- the regime is sampled as for the lockstep kernel below
+        const bool can_multi = h->qcm_multi_groups > 0 && h->cur_fmt == LDPC_B200_LLR_F32;
+        const int pct = h->opt.qcm_multi_pct < 0 ? 90 : h->opt.qcm_multi_pct;
+        const bool track = can_multi && h->early && h->h_stats && pct > 0;
+        bool use_multi = can_multi;
+        int32_t* it_out = d_iters;
+        if (track) {
+            if (h->h_stats[1] > 0) use_multi = (double)h->h_stats[0] * 100.0 > (double)pct * (double)h->max_iter * (double)h->h_stats[1];
+            if (!it_out) {
+                if (h->iters_own_cap < ncw) {
+                    cudaFree(h->d_iters_own); h->d_iters_own = nullptr; h->iters_own_cap = 0;
+                    CU_TRY(cudaMalloc(&h->d_iters_own, (size_t)ncw * sizeof(int32_t)));
+                    h->iters_own_cap = ncw;
+                }
+                it_out = h->d_iters_own;
+            }
+        }
+        rc = launch_qcm(it_out, use_multi);
         if (rc) return rc;
-        h->last_kernel = 3;
+        h->last_kernel = use_multi ? 4 : 3;
         h->launches += 1;
+        if (track && (h->h_stats[1] == 0 || h->stat_tick++ % (unsigned)std::max(1, h->opt.qc_et_every) == 0)) {
+            rc = launch_status(k_launch_iter_stats(it_out, ncw, h->h_stats, stream), "iteration statistics");
+            if (rc) return rc;
+            h->launches += 1;
+        }
         return LDPC_B200_OK;
     }
 

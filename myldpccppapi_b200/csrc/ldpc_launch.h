@@ -83,6 +83,9 @@ struct QcmProfileEntry {
                   std::vector<unsigned char>* tab, int* groups);
     int (*launch)(const QcmParams&, int grid, int groups, cudaStream_t stream);
     int (*upload)(int slot, const void* tab, size_t bytes);
+    // several codewords per group of warps (ldpc_ms_qcm_multi_kernel): geometry for `pack` codewords, and its launch
+    bool (*multi_geometry)(const QcmParams& single, int pack, size_t smem_limit, QcmParams* out, int* groups);
+    int (*launch_multi)(const QcmParams&, int grid, int groups, cudaStream_t stream);
 };
 const QcmProfileEntry* qcm_profiles(int* n);
 

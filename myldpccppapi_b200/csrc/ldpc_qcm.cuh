@@ -46,7 +46,8 @@ constexpr int kQcmBankBytes = 1152;
 
 struct QcmParams {
     int tab_slot;
-    int z, NW, RW;                // block size, warps per codeword, rows per warp
+    int z, NW, RW;                // block size, warps per group, rows per warp
+    int PK;                       // codewords per group of warps (ldpc_ms_qcm_multi_kernel; 1 = ldpc_ms_qcm_kernel)
     uint32_t zb, t_bytes;         // z * 4; bytes of T (= 24 * 2z * 4): R starts there
     uint32_t bits_off;            // bit buffer of the word's hard decisions (N / 8 bytes + 4), byte offset in its slice
     uint32_t word_bytes;          // shared memory per codeword in flight
@@ -276,6 +277,190 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_kernel(const
         }
         if (p.iters && gl == 0) p.iters[w] = it;
         gsync();   // every read of this word's T and bits is done before the next word overwrites them
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Several codewords per group of warps.  With one codeword per group a block size just above a multiple of 32 leaves
+// most lanes of the last warp idle (z = 36: 2 warps, 18 of 32 lanes each; z = 68: 3 warps, 23 lanes each), and an idle
+// lane costs what a working one does -- a warp's shared-memory access is a wavefront whether 18 or 32 lanes take part.
+// Here the rows of PK = 2 or 3 codewords are laid side by side over the group's lanes (z = 36: 3 codewords = 108 rows on
+// 4 warps; z = 68: 2 codewords = 136 rows on 5 warps): lane (sw, l) serves row (sw * RW + l) mod z of codeword
+// (sw * RW + l) / z, in that codeword's own slice of shared memory, so both passes stay the straight-line code above with
+// per-lane bases.  The slices are z words apart modulo the 32 banks (qcm_multi_geometry), so the lanes of a warp that
+// straddles two codewords still touch 32 different banks.  The group's codewords start together; each stops by its own
+// syndrome (its lanes freeze, reference stop rule MyLdpc.cpp:751-755) and the group takes its next PK words when all
+// have stopped -- the price in the early-termination regime is the spread of the iteration counts inside a group, so the
+// host uses this kernel only while the words run long (ldpc_b200.cu: launch_decode).  Bit-exact with ldpc_ms_qcm_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kQcmMaxPack = 3;
+
+template <class R>
+__global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_ms_qcm_multi_kernel(const __grid_constant__ QcmParams p) {
+    constexpr int NB = R::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_word[kQcmMaxWarps];       // first word of the group's pack
+    __shared__ uint32_t s_flag[kQcmMaxWarps][2];     // bit k: "some check of the group's k-th word is unsatisfied", double buffered
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int ws = warp / p.NW, sw = warp - ws * p.NW;
+    const QcmTab<R>& tb = *reinterpret_cast<const QcmTab<R>*>(&g_qcm_bank[p.tab_slot][0]);
+    const uint32_t cc = (uint32_t)(sw * p.RW) + lane;                         // row of the side-by-side layout
+    const bool inr = lane < (uint32_t)p.RW && cc < (uint32_t)(p.PK * p.z);
+    const uint32_t k = min(cc / (uint32_t)p.z, (uint32_t)(p.PK - 1));         // which of the group's codewords
+    const uint32_t c = cc - k * (uint32_t)p.z;                                // this lane's row / column inside a block
+    const uint32_t gb = smem_u32(smem_raw) + (uint32_t)(ws * p.PK) * p.word_bytes;
+    const uint32_t wb = gb + k * p.word_bytes;
+    const uint32_t zb = p.zb;
+    const uint32_t la = wb + c * 4u, laz = la + zb;
+    const int KB = (p.K + 7) >> 3, NB8 = (p.N + 7) >> 3;
+    const int gl = sw * 32 + (int)lane, gn = p.NW * 32;
+    // this warp's lanes of each codeword (warp-uniform; a codeword's lanes are contiguous)
+    uint32_t km[kQcmMaxPack];
+#pragma unroll
+    for (int kk = 0; kk < kQcmMaxPack; ++kk) km[kk] = __ballot_sync(0xffffffffu, inr && k == (uint32_t)kk);
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(ws + 1), "r"(gn) : "memory"); };
+
+    auto claim = [&]() -> long long { return (sw == 0 && lane == 0) ? (long long)atomicAdd(p.counter64, (unsigned long long)p.PK) : 0ll; };
+    auto prefetch_y = [&](long long w0) {   // the pack's words are consecutive: one contiguous range
+        const long long n = min((long long)p.PK, p.ncw - w0);
+        const char* src = reinterpret_cast<const char*>(p.llr + (size_t)w0 * p.N);
+        const int bytes = (int)n * p.N * 4;
+        for (int o0 = 0; o0 < bytes; o0 += 32 * 128) {
+            const int o = o0 + (int)lane * 128;
+            if (o < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+        }
+    };
+    auto landed = [&](long long w0) -> bool {   // streamed input: the pack's last word has arrived
+        if (w0 >= p.ncw) return false;
+        const long long wl = min(w0 + p.PK, p.ncw) - 1;
+        return !p.avail || qc_wait_input(p.avail, wl, true, p.status, p.wait_ns);
+    };
+
+    float yn[NB];
+    long long wn = 0, tick = 0;
+    if (sw == 0) {
+        if (lane == 0) { s_flag[ws][0] = 0u; s_flag[ws][1] = 0u; }
+        wn = __shfl_sync(0xffffffffu, claim(), 0);
+        tick = claim();
+        if (!landed(wn)) wn = p.ncw;
+        if (wn < p.ncw) prefetch_y(wn);
+    }
+    for (;;) {
+        if (sw == 0) {
+            if (lane == 0) s_word[ws] = wn;
+            for (int kk = 0; kk < p.PK; ++kk)   // hard-bit buffers of the pack: cleared here, filled when the words leave
+                for (int o0 = 0; o0 < NB8 + 4; o0 += 128) {
+                    const int o = o0 + (int)lane * 4;
+                    if (o < NB8 + 4) qc_sts_u32(gb + (uint32_t)kk * p.word_bytes + p.bits_off + (uint32_t)o, 0u);
+                }
+        }
+        gsync();
+        const long long w0 = s_word[ws];
+        if (w0 >= p.ncw) break;
+        const long long w = w0 + (long long)k;
+        const bool has = inr && w < p.ncw;                         // (the last pack of a batch may be short)
+        const uint32_t livemask = (1u << (int)min((long long)p.PK, p.ncw - w0)) - 1u;
+        bool act = has;
+        // ---- start the pack (decodeInitMS, decodeCL.c:113-124): T = -y (canonical zero), R = 0
+        {
+            const float* src = p.llr + (size_t)w * p.N + c;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) yn[b] = has ? __ldg(src + b * p.z) : 0.0f;
+        }
+        if (has) {
+#pragma unroll 8
+            for (int e = 0; e < R::E; ++e) sts_f32(la + p.t_bytes + (uint32_t)e * zb, 0.0f);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            yn[b] = __fadd_rn(-yn[b], 0.0f);
+            if (has) {
+                sts_f32(la + (uint32_t)(2 * b) * zb, yn[b]);
+                sts_f32(la + (uint32_t)(2 * b + 1) * zb, yn[b]);
+            }
+        }
+        if (sw == 0) {   // the next pack's values travel while this one is decoded
+            wn = __shfl_sync(0xffffffffu, tick, 0);
+            if (!landed(wn)) wn = p.ncw;
+            if (wn < p.ncw) prefetch_y(wn);
+            tick = claim();
+        }
+        gsync();
+
+        int it = 0, my_it = 0;
+        uint32_t ph = 0u, donemask = 0u;
+        for (;;) {
+            const uint32_t unsat = qcm_cn<R, 0>(tb, la, p.t_bytes, zb, act);
+            const bool check = p.early_term && it >= 1;
+            if (check) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, act && unsat != 0u);
+                uint32_t f = 0u;
+#pragma unroll
+                for (int kk = 0; kk < kQcmMaxPack; ++kk) f |= (bal & km[kk]) ? (1u << kk) : 0u;
+                if (f && lane == 0) qcm_atoms_or(smem_u32(&s_flag[ws][ph]), f);
+            }
+            gsync();
+            if (check) {
+                const uint32_t stopped = livemask & ~donemask & ~s_flag[ws][ph];   // syndrome zero: T of iteration `it` is final
+                if (act && ((stopped >> k) & 1u)) { act = false; my_it = it; }
+                donemask |= stopped;
+            }
+            if (donemask == livemask) break;
+            if (sw == 0 && lane == 0) s_flag[ws][ph ^ 1u] = 0u;
+            ph ^= 1u;
+            qcm_vn<R, 0>(tb, la, laz, c, zb, yn, act);
+            gsync();
+            ++it;
+            if (it >= p.max_iter) break;
+        }
+        if (act) my_it = it;   // stopped by the cap
+        // (a flag left set by the last trip is cleared by trips 0 / 1 of the next pack before that buffer is used again)
+
+        // ---- the pack leaves (toChar, decodeCL.c:188-199): bit n = !(P > 0) = !signbit(T)
+        for (int b = 0; b < NB; ++b) {
+            const float t = lds_f32(la + (uint32_t)(2 * b) * zb);
+            const uint32_t bal = __ballot_sync(0xffffffffu, has && (__float_as_uint(t) >> 31) == 0u);
+            if (p.post && has) p.post[(size_t)w * p.N + b * p.z + (int)c] = -t;
+            if (lane == 0) {
+#pragma unroll
+                for (int kk = 0; kk < kQcmMaxPack; ++kk) {
+                    if (km[kk]) {
+                        const int f = __ffs((int)km[kk]) - 1;                       // first lane of codeword kk in this warp
+                        const uint32_t c0 = (uint32_t)(sw * p.RW + f) - (uint32_t)(kk * p.z);
+                        const uint32_t g = (uint32_t)(b * p.z) + c0, sh = g & 31u;
+                        const uint32_t v = (bal & km[kk]) >> f;
+                        const uint32_t bits = gb + (uint32_t)kk * p.word_bytes + p.bits_off;
+                        qcm_atoms_or(bits + (g >> 5) * 4u, v << sh);
+                        if (sh) qcm_atoms_or(bits + (g >> 5) * 4u + 4u, v >> (32u - sh));
+                    }
+                }
+            }
+        }
+        gsync();
+        {
+            const int nby = p.hard ? NB8 : KB;
+            for (int kk = 0; kk < p.PK; ++kk) {
+                if (!((livemask >> kk) & 1u)) break;
+                const uint32_t bits = gb + (uint32_t)kk * p.word_bytes + p.bits_off;
+                const long long wk = w0 + kk;
+                for (int b0 = 0; b0 < nby; b0 += gn) {
+                    const int b = b0 + gl;
+                    if (b < nby) {
+                        const uint32_t v = (qc_lds_u32(bits + (uint32_t)(b & ~3)) >> (8 * (b & 3))) & 0xffu;
+                        if (p.hard) p.hard[(size_t)wk * NB8 + b] = (uint8_t)v;
+                        if (p.info && b < KB) {
+                            const uint32_t keep = (b == KB - 1 && (p.K & 7)) ? ((1u << (p.K & 7)) - 1u) : 0xffu;
+                            p.info[(size_t)wk * KB + b] = (uint8_t)(v & keep);
+                        }
+                    }
+                }
+            }
+        }
+        if (p.iters && has && c == 0u) p.iters[w] = my_it;
+        gsync();   // every read of the pack's T and bits is done before the next pack overwrites them
     }
 }
 

@@ -339,6 +339,51 @@ def test_qc_group_of_warps_kernel(rate, name, num, den, monkeypatch):
             assert_parity(_run_device(dec, y), rc, N, what=what + " cap 3")
 
 
+@pytest.mark.parametrize("pack", [2, 3])
+@pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
+def test_qc_group_of_warps_kernel_several_codewords_per_group(rate, name, num, den, pack, monkeypatch):
+    """ldpc_ms_qcm_multi_kernel: two / three codewords side by side on one group of warps (forced for every launch).
+    Words of one group stop at different iterations (mixed Eb/N0), the last group of a batch is short, special values:
+    bits, counts and posteriors of the oracle on the device path and the streamed host path."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    monkeypatch.setenv("LDPC_B200_QCM_PACK", str(pack))
+    for z in (36, 44, 68, 76, 92) if pack == 2 else (36, 28):
+        N = 24 * z
+        K = N * num // den
+        rp, ci, M = oracle.wimax_H(N, name)
+        rng = np.random.default_rng(N + rate)
+        y = np.concatenate([awgn_llr(40, N, sigma_from_ebn0(2.4, num / den), seed=N + rate), awgn_llr(40, N, sigma_from_ebn0(4.0, num / den), seed=N + rate + 1),
+                            awgn_llr(7, N, 1.3, seed=N + rate + 2)])
+        y = y[rng.permutation(len(y))]   # fast and slow words inside one group
+        y[3] = 0.0
+        y[4, ::3] = 0.0
+        y[5] = np.where(np.arange(N) % 2 == 0, -0.0, 0.0)
+        y[6, :7] = [np.inf, -np.inf, 1e30, -1e30, 1e-40, -1e-40, 1000.0]
+        ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(y, literal=False)
+        dec = m.Decoder.wimax(K, N, rate)
+        dec.set_option("qcm_multi_pct", 0)
+        what = "z=%d rate %s pack %d" % (z, name, pack)
+        assert_parity(_run_device(dec, y), ref, N, what=what)
+        assert dec.info()["kernel_variant"] == 4, dec.info()
+        for n in (1, 2, 3, 4, 17):
+            assert_parity(_run_device(dec, y[:n]), tuple(r[:n] for r in ref), N, what=what + " %d words" % n)
+        if z == 36:
+            assert_parity(dec.decode_host(y, want_hard=True, want_post=True), ref, N, what=what + " host")
+            pinned = torch.from_numpy(y).pin_memory().numpy()
+            dec.set_option("stream_chunk", 8)
+            assert_parity(dec.decode_host(pinned, want_hard=False, want_post=False), ref, N, what=what + " streamed, tiny chunks")
+            dec.set_option("stream_chunk", 0)
+            assert dec.info()["kernel_variant"] == 4
+            dec.set_max_iter(3)
+            rc = oracle.Oracle(M, N, K, rp, ci, times=3).decode(y, literal=False)
+            assert_parity(_run_device(dec, y), rc, N, what=what + " cap 3")
+            dec.set_max_iter(5)
+            dec.set_early_termination(False)   # every word runs to the cap; a noiseless word keeps its bits
+            res = _run_device(dec, np.ones((11, N), dtype=np.float32))
+            assert np.all(res["iters"] == 5) and not res["info"].any()
+
+
 @pytest.mark.parametrize("N", [576, 768])
 @pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
 def test_qc_early_termination_kernel(rate, name, num, den, N):

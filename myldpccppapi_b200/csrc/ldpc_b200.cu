@@ -82,7 +82,7 @@ struct Options {
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
     int qc_et_every = 4;              // auto: the iteration counts are sampled after every n-th launch once the regime is known (13 us each)
-    int qcm_pack = 0;                 // group-of-warps kernel, codewords per group: 0 / 1 = one, 2 / 3 = that many (ldpc_ms_qcm_multi_kernel)
+    int qcm_pack = -1;                // group-of-warps kernel, codewords per group: -1 = the measured best of the block size and rate, 0 / 1 = one, 2 / 3 = that many
     int qcm_multi_pct = -1;           // ... used while the mean iteration count is above this share of the cap (-1 = measured crossover, 0 = always)
     int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
                                       // crossover of the code (profiles/r02_et_kernel.md: z = 24 90 %, z = 32 every regime)
@@ -1319,10 +1319,22 @@ bool qcm_prepare(ldpc_b200_decoder* h) {
         h->qcm_slot = slot;
         h->qcm_kind = k;
         h->qcm_groups = groups;
-        // several codewords per group (ldpc_ms_qcm_multi_kernel): measurements in profiles/r02_qcm_pack.txt
+        // several codewords per group (ldpc_ms_qcm_multi_kernel) where one leaves most lanes of the last warp idle and
+        // shared memory has room for more: the measured best of the reference's family (profiles/r02_qcm_pack.txt:
+        // z = 36 3.6-5.5 -> 4.9-7.0 Gbit/s, z = 44 4.5-6.8 -> 5.2-7.4, z = 68 / 72 / 76 +11-15 % where listed; every other
+        // block size is fastest with one codeword per group)
         h->qcm_multi_groups = 0;
         {
-            const int pack = h->opt.qcm_pack;
+            static const int kRateOfKind[6] = {4, 3, 2, 1, 0, 5};   // qcm_profiles() order: 3/4B, 3/4A, 2/3B, 2/3A, 1/2, 5/6
+            struct Best { int z; int pack[6]; };                    // by rate: 1/2, 2/3A, 2/3B, 3/4A, 3/4B, 5/6
+            static const Best kBest[] = {{36, {3, 3, 3, 3, 3, 3}}, {44, {2, 2, 2, 2, 2, 2}}, {68, {3, 3, 3, 3, 3, 1}},
+                                         {72, {3, 3, 3, 1, 1, 1}}, {76, {2, 1, 1, 1, 1, 1}}};
+            int pack = h->opt.qcm_pack;
+            if (pack < 0) {
+                pack = 1;
+                for (const Best& b : kBest)
+                    if (b.z == z && k < 6) pack = b.pack[kRateOfKind[k]];
+            }
             QcmParams qm;
             int gm = 0;
             if (pack >= 2 && pe.multi_geometry(h->qcm, pack, h->smem_optin, &qm, &gm)) { h->qcm_multi = qm; h->qcm_multi_groups = gm; }
@@ -2077,7 +2089,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         // several codewords per group while the words run long; one per group (nothing waits for a slower neighbour) once
         // the previous launches' words stopped early on average -- the regime is sampled as for the lockstep kernel below
         const bool can_multi = h->qcm_multi_groups > 0 && h->cur_fmt == LDPC_B200_LLR_F32;
-        const int pct = h->opt.qcm_multi_pct < 0 ? 90 : h->opt.qcm_multi_pct;
+        const int pct = h->opt.qcm_multi_pct < 0 ? 80 : h->opt.qcm_multi_pct;   // (measured: 2-5 % slower at 70 % of the cap)
         const bool track = can_multi && h->early && h->h_stats && pct > 0;
         bool use_multi = can_multi;
         int32_t* it_out = d_iters;

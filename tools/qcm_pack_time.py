@@ -29,9 +29,9 @@ def main():
     ap.add_argument("--zs", default="28,36,44,52,56,60,68,72,76,84,88,92")
     ap.add_argument("--rates", default="0,4")
     ap.add_argument("--ncw", type=int, default=16384)
-    ap.add_argument("--ebn0", default="2.5,3.5")
+    ap.add_argument("--ebn0", default="2.5,3.5", help="comma list; empty = the cap only")
     args = ap.parse_args()
-    pts = [float(v) for v in args.ebn0.split(",")]
+    pts = [float(v) for v in args.ebn0.split(",") if v]
     print("| z | rate | pack | words x threads per CTA | cap: Gbit/s | " + " | ".join("%.1f dB: ms (mean it)" % e for e in pts) + " | identical |")
     print("|---|---|---|---|---|" + "---|" * (len(pts) + 1))
     for z in (int(v) for v in args.zs.split(",")):

@@ -110,7 +110,8 @@ typedef struct ldpc_b200_info {
                             1 warp-per-codeword kernel, 3 group-of-warps kernel (chosen per launch from the previous
                             launches' mean iteration count; option "qc_et": -1 auto, 0 never, 1 always), 2 ring-staged,
                             4 group-of-warps kernel with several codewords per group (block sizes without a lockstep
-                            profile, while the words run long; option "qcm_multi_pct") */
+                            profile, while the words run long; option "qcm_multi_pct"), 5 quasi-cyclic sum-product
+                            kernel (LDPC_B200_ALG_SUM_PRODUCT on codes the on-chip sum-product layout cannot hold) */
     int et_available;    /* which per-codeword kernel this handle can switch to: 0 none, 1 warp per codeword (802.16e
                             codes with z = 24 / 32), 2 group of warps */
 } ldpc_b200_info;

@@ -32,7 +32,7 @@ QC_RATES = [("34B", "QcProfile34B"), ("34A", "QcProfile34A"), ("23B", "QcProfile
             ("23A", "QcProfile23A"), ("12", "QcProfile12"), ("56", "QcProfile56")]
 UNITS = [("ldpc_b200.cu", "ldpc_b200", []), ("ldpc_tables.cpp", "ldpc_tables", []),
          ("k_group.cu", "k_group", []), ("k_qcg.cu", "k_qcg", []), ("k_sp.cu", "k_sp", []),
-         ("k_tdmp.cu", "k_tdmp", []), ("k_misc.cu", "k_misc", []), ("k_qcw.cu", "k_qcw", []), ("k_qcm.cu", "k_qcm", [])]
+         ("k_tdmp.cu", "k_tdmp", []), ("k_misc.cu", "k_misc", []), ("k_qcw.cu", "k_qcw", []), ("k_qcm.cu", "k_qcm", []), ("k_spq.cu", "k_spq", [])]
 UNITS += [("k_qc.cu", "k_qc_" + tag, ["-DLDPC_QC_RATE=" + prof, "-DLDPC_QC_RATE_FN=qc_profiles_" + tag]) for tag, prof in QC_RATES]
 
 

@@ -65,6 +65,7 @@ struct Options {
     // kernel choice: read when a plan is made
     bool no_qc = false, no_qcg = false, no_qcm = false, qcm_always = false, qc_generic = false, qc_ring = false;
     bool grp_no_profile = false, grp_no_ysmem = false, grp_prefer_16 = false, grp_t16 = false, grp_no_t16 = false;
+    int sp_qc = -1;   // quasi-cyclic sum-product kernel (ldpc_spq.cuh): -1 = where the on-chip kernel does not fit, 0 never, 1 wherever it can run
     bool debug_placement = false, sp_big = false;  // sp_big: sum-product through the any-size kernel even where the on-chip one fits (tests)
     int grp_g = 0, grp_warps = 0, l16_warps = 0, tdmp_g = 0, stream_threads = 0, qc_prefer_g = 0;
     long long place_effort = 12;
@@ -94,7 +95,7 @@ struct OptionName { const char* name; int kind; size_t off; bool runtime; };  //
 const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(no_qcm, 0), OPT(qcm_always, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
-    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(place_effort, 2),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(sp_qc, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
     OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1),
@@ -194,6 +195,8 @@ struct ldpc_b200_decoder {
     // a group of warps per codeword, any z (ldpc_qcm.cuh): the block sizes without a compiled lockstep profile
     QcmParams qcm;
     int qcm_kind = -1, qcm_state = 0, qcm_slot = -1, qcm_groups = 0;
+    std::vector<unsigned char> qcm_tab;      // its table block (also uploaded to the sum-product unit's bank, ldpc_spq.cuh)
+    int spq_state = 0;                       // quasi-cyclic sum-product kernel: 0 not tried, 1 ready, -1 not for this code
     QcmParams qcm_multi;                     // the same with several codewords per group (ldpc_ms_qcm_multi_kernel); 0 groups = not used
     int qcm_multi_groups = 0;
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
@@ -1319,6 +1322,7 @@ bool qcm_prepare(ldpc_b200_decoder* h) {
         h->qcm_slot = slot;
         h->qcm_kind = k;
         h->qcm_groups = groups;
+        h->qcm_tab = tab;
         // several codewords per group (ldpc_ms_qcm_multi_kernel) where one leaves most lanes of the last warp idle and
         // shared memory has room for more: the measured best of the reference's family (profiles/r02_qcm_pack.txt:
         // z = 36 3.6-5.5 -> 4.9-7.0 Gbit/s, z = 44 4.5-6.8 -> 5.2-7.4, z = 68 / 72 / 76 +11-15 % where listed; every other
@@ -1703,6 +1707,35 @@ int upload_tdmp_tables(ldpc_b200_decoder* h) {
 // Sum-product (layered = false) or layered min-sum of a code of any size: 32 codewords per CTA, lane = codeword, every
 // message in a CTA-private slice of a global workspace (ldpc_big.cuh).
 // does the handle's current algorithm run an any-size kernel (global workspace, launches serialise on it)?
+bool sp_group_fits(const ldpc_b200_decoder* h) {   // the on-chip sum-product kernel of ldpc_sp.cuh can hold the code
+    const Plan& pl = h->plan;
+    const HostTables& t = h->host;
+    return pl.path == LDPC_B200_PATH_GROUP && pl.tab_smem && !pl.t16 && (pl.G == 8 || pl.G == 16) &&
+           t.max_col_weight <= 8 && t.max_row_weight <= 20 && !h->opt.sp_big;
+}
+
+// Sum-product on the quasi-cyclic layout (ldpc_spq.cuh): tables and geometry of the group-of-warps min-sum kernel,
+// uploaded to the sum-product unit's own __constant__ bank.  (h->mu held)
+bool spq_prepare(ldpc_b200_decoder* h) {
+    if (h->spq_state != 0) return h->spq_state == 1;
+    h->spq_state = -1;
+    if (h->opt.sp_qc == 0 || h->opt.sp_big) return false;
+    if (h->qcm_state == 0) h->qcm_state = qcm_prepare(h) ? 1 : -1;
+    if (h->qcm_state != 1 || h->qcm_tab.empty()) return false;
+    int n = 0;
+    const SpqProfileEntry* profiles = spq_profiles(&n);
+    if (h->qcm_kind < 0 || h->qcm_kind >= n) return false;
+    DeviceGuard guard(h->device);
+    if (!guard.ok) return false;
+    if (profiles[h->qcm_kind].upload(h->qcm_slot, h->qcm_tab.data(), h->qcm_tab.size()) != 0) { (void)cudaGetLastError(); return false; }
+    h->spq_state = 1;
+    return true;
+}
+// is it the kernel a sum-product decode of this handle runs?  (after spq_prepare; the plan is the sum-product plan)
+bool uses_spq(const ldpc_b200_decoder* h) {
+    return h->algorithm == LDPC_B200_ALG_SUM_PRODUCT && h->spq_state == 1 && (h->opt.sp_qc > 0 || !sp_group_fits(h));
+}
+
 bool uses_big_kernel(const ldpc_b200_decoder* h) {
     const Plan& pl = h->plan;
     const HostTables& t = h->host;
@@ -1710,6 +1743,7 @@ bool uses_big_kernel(const ldpc_b200_decoder* h) {
         case LDPC_B200_ALG_FUSED_MIN_SUM: case LDPC_B200_ALG_FUSED_LAYERED: return true;
         case LDPC_B200_ALG_LAYERED_MIN_SUM: return h->tdmp_big;
         case LDPC_B200_ALG_SUM_PRODUCT:
+            if (uses_spq(h)) return false;
             return !(pl.path == LDPC_B200_PATH_GROUP && pl.tab_smem && !pl.t16 && (pl.G == 8 || pl.G == 16) &&
                      t.max_col_weight <= 8 && t.max_row_weight <= 20 && !h->opt.sp_big);
         default: return false;
@@ -2034,9 +2068,10 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     if (h->algorithm == LDPC_B200_ALG_SUM_PRODUCT) {
         // the on-chip kernel takes short codes (group layout with 8 or 16 words per CTA, variable degree <= 8, check degree
         // <= 20); every other code goes to the any-size kernel -- DecodeSP never decodes with another algorithm
+        (void)spq_prepare(h);   // (quasi-cyclic codes: ldpc_spq.cuh, launched below)
         if (uses_big_kernel(h)) return launch_big(h, kBigSumProduct, d_llr, ncw, d_info, d_hard, d_iters, d_post, stream);
     }
-    int rc = ensure_workspace(h);
+    int rc = uses_spq(h) ? LDPC_B200_OK : ensure_workspace(h);
     if (rc) return rc;
     const int per_group = (pl.path == LDPC_B200_PATH_GROUP || pl.path == LDPC_B200_PATH_QC) ? pl.G : (pl.path == LDPC_B200_PATH_WARP ? 1 : kLanes);
     const int64_t ngroups = (ncw + per_group - 1) / per_group;
@@ -2085,6 +2120,24 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
         return launch_status(qcm_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "quasi-cyclic (warps per codeword)");
     };
+    if (uses_spq(h)) {   // sum-product, quasi-cyclic layout: the group-of-warps geometry with the arithmetic of ldpc_sp.cuh
+        if (d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
+        QcmParams q = h->qcm;
+        q.K = h->K;
+        q.max_iter = h->max_iter; q.early_term = h->early;
+        q.llr = d_llr; q.ncw = ncw;
+        q.info = d_info; q.hard = d_hard; q.iters = d_iters; q.post = nullptr;
+        q.counter64 = ctr64;
+        q.avail = nullptr; q.status = nullptr; q.wait_ns = 0ull;
+        q.fmt = LDPC_B200_LLR_F32; q.scale = 1.0f;
+        int np = 0;
+        const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
+        rc = launch_status(spq_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "sum-product (quasi-cyclic)");
+        if (rc) return rc;
+        h->last_kernel = 5;
+        h->launches += 1;
+        return LDPC_B200_OK;
+    }
     if (pl.path == LDPC_B200_PATH_QC && pl.dmax == 2) {
         // several codewords per group while the words run long; one per group (nothing waits for a slower neighbour) once
         // the previous launches' words stopped early on average -- the regime is sampled as for the lockstep kernel below
@@ -2508,6 +2561,8 @@ int ldpc_b200_set_algorithm(ldpc_b200_handle h, int algorithm) {
         h->algorithm = prev;
         (void)make_plan(h);
         g_err = keep;
+    } else if (algorithm == LDPC_B200_ALG_SUM_PRODUCT) {
+        (void)spq_prepare(h);   // quasi-cyclic codes: the kernel of ldpc_spq.cuh (known before the first decode sizes its chunks)
     }
     return rc;
 }
@@ -2797,6 +2852,7 @@ int reserve_locked(ldpc_b200_decoder* h, int64_t batch) {
             h->st_pin_bytes = 0;
             for (int i = 0; i < ldpc_b200_decoder::kStageSlots; ++i) {
                 CU_TRY(cudaMallocHost(&h->st_pin[i], need));
+                std::memset(h->st_pin[i], 0, need);  // (the host threads' first copy into it should not be the one that maps it)
                 if (!h->st_pin_ev[i]) CU_TRY(cudaEventCreateWithFlags(&h->st_pin_ev[i], cudaEventDisableTiming));
             }
             h->st_pin_bytes = need;

@@ -89,6 +89,13 @@ struct QcmProfileEntry {
 };
 const QcmProfileEntry* qcm_profiles(int* n);
 
+// quasi-cyclic sum-product kernel (k_spq.cu, ldpc_spq.cuh): same tables, geometry and profile order as qcm_profiles()
+struct SpqProfileEntry {
+    int (*launch)(const QcmParams&, int grid, int groups, cudaStream_t stream);
+    int (*upload)(int slot, const void* tab, size_t bytes);
+};
+const SpqProfileEntry* spq_profiles(int* n);
+
 // one table per 802.16e rate (k_qc.cu compiled with -DLDPC_QC_RATE=...)
 const QcProfileEntry* qc_profiles_34B(int* n);
 const QcProfileEntry* qc_profiles_34A(int* n);

@@ -52,6 +52,7 @@ struct Coder::Impl {
         pinned = q != nullptr;
         if (!q) q = std::malloc(n * sizeof(T));
         if (!q) return false;
+        std::memset(q, 0, n * sizeof(T));  // touched here, not by the first decode()
         p = static_cast<T *>(q);
         cap = n;
         return true;

@@ -464,10 +464,12 @@ def test_qc_lockstep_hands_over_to_the_group_of_warps_kernel():
 
 
 @pytest.mark.parametrize("N,rate,name,num,den", [(1152, 4, "3/4B", 3, 4), (1632, 0, "1/2", 1, 2), (2304, 5, "5/6", 5, 6), (1824, 1, "2/3A", 2, 3)])
-def test_any_size_sum_product_and_layered_kernels(N, rate, name, num, den):
+def test_any_size_sum_product_and_layered_kernels(N, rate, name, num, den, monkeypatch):
     """The reference's kernels have no size limit (decodeCL.c:25-62, 203-292).  Codes beyond the on-chip layouts --
-    most of the reference's own family -- run ldpc_sp_big_kernel / ldpc_tdmp_big_kernel (messages in a global workspace):
-    bits and iteration counts of the sum-product oracle; bits, counts and posteriors of the layered oracle."""
+    most of the reference's own family -- run the quasi-cyclic sum-product kernel (ldpc_spq.cuh: a group of warps per
+    codeword) and, forced, ldpc_sp_big_kernel (messages in a global workspace); layered: ldpc_tdmp_big_kernel where the
+    on-chip layout does not fit.  Bits and iteration counts of the sum-product oracle; bits, counts and posteriors of the
+    layered oracle."""
     import myldpccppapi_b200 as m
     torch = _torch()
     K = N * num // den
@@ -482,8 +484,24 @@ def test_any_size_sum_product_and_layered_kernels(N, rate, name, num, den):
     sp = oracle.decode_sp(o, y)
     assert np.array_equal(out["iters"].cpu().numpy(), sp[1]) and np.array_equal(out["info"].cpu().numpy(), sp[0])
     assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(sp[2], axis=1, bitorder="little"))
+    assert dec.info()["kernel_variant"] == 5   # the quasi-cyclic sum-product kernel (ldpc_spq.cuh)
     host = dec.decode_host(y)
     assert np.array_equal(host["iters"], sp[1]) and np.array_equal(host["info"], sp[0])
+    for n in (1, 2, 17):
+        part = dec.decode_device(torch.from_numpy(y[:n]).cuda(), want_hard=True)
+        assert np.array_equal(part["iters"].cpu().numpy(), sp[1][:n]) and np.array_equal(part["info"].cpu().numpy(), sp[0][:n])
+    dec.set_max_iter(3)
+    sp3 = oracle.decode_sp(oracle.Oracle(M, N, K, rp, ci, times=3), y)
+    out3 = dec.decode_device(torch.from_numpy(y).cuda(), want_hard=True)
+    assert np.array_equal(out3["iters"].cpu().numpy(), sp3[1]) and np.array_equal(out3["info"].cpu().numpy(), sp3[0])
+    dec.set_max_iter(40)
+    monkeypatch.setenv("LDPC_B200_SP_BIG", "1")   # the any-size kernel (ldpc_big.cuh): same bytes
+    big = m.Decoder.wimax(K, N, rate)
+    monkeypatch.delenv("LDPC_B200_SP_BIG")
+    big.set_algorithm(1)
+    outb = big.decode_device(torch.from_numpy(y).cuda(), want_hard=True)
+    assert big.info()["kernel_variant"] != 5
+    assert np.array_equal(outb["iters"].cpu().numpy(), sp[1]) and np.array_equal(outb["info"].cpu().numpy(), sp[0])
     dec.set_algorithm(2)
     td = oracle.decode_tdmp(o, y, N // 24)
     assert_parity(_run_device(dec, y), td, N, what="layered, N=%d" % N)
@@ -718,6 +736,41 @@ def test_sum_product_matches_restated_oracle(default_code, sigma):
     dec.set_algorithm(0)
     ref = o.decode(llr)
     assert_parity(_run_device(dec, llr), ref, c["N"], what="min-sum after sum-product")
+
+
+@pytest.mark.parametrize("rate,name,num,den", [(4, "3/4B", 3, 4), (0, "1/2", 1, 2), (1, "2/3A", 2, 3), (2, "2/3B", 2, 3), (3, "3/4A", 3, 4), (5, "5/6", 5, 6)])
+def test_quasi_cyclic_sum_product_kernel(rate, name, num, den, monkeypatch):
+    """ldpc_sp_qcm_kernel (ldpc_spq.cuh) on every rate of the reference's family: forced on the short code the on-chip
+    group kernel also holds (z = 24), and as planned where one, two and three warps serve a codeword (z = 28, 36, 68; idle
+    lanes in the last warp).  Bits and iteration counts of the sum-product oracle (pinned to the reference's own kernels,
+    tests/test_oracle_vs_refcl.py); special values; the streamed host path."""
+    import myldpccppapi_b200 as m
+    torch = _torch()
+    monkeypatch.setenv("LDPC_B200_SP_QC", "1")
+    for z in (24, 28, 36, 68):
+        N = 24 * z
+        K = N * num // den
+        rp, ci, M = oracle.wimax_H(N, name)
+        y = np.concatenate([awgn_llr(14, N, sigma_from_ebn0(2.0, num / den), seed=N + rate), awgn_llr(14, N, sigma_from_ebn0(4.0, num / den), seed=N + rate + 1),
+                            awgn_llr(5, N, 1.3, seed=N + rate + 2)])
+        y[3] = 0.0
+        y[4, ::3] = 0.0
+        y[5] = np.where(np.arange(N) % 2 == 0, -0.0, 0.0)
+        y[6, :7] = [20.0, -20.0, 1e30, -1e30, 1e-40, -1e-40, 11.1]   # exp(8y) overflows / underflows
+        o = oracle.Oracle(M, N, K, rp, ci, times=40)
+        sp = oracle.decode_sp(o, y)
+        dec = m.Decoder.wimax(K, N, rate)
+        dec.set_algorithm(1)
+        out = dec.decode_device(torch.from_numpy(y).cuda(), want_hard=True)
+        torch.cuda.synchronize()
+        what = "z=%d rate %s" % (z, name)
+        assert dec.info()["kernel_variant"] == 5, what
+        assert np.array_equal(out["iters"].cpu().numpy(), sp[1]), what
+        assert np.array_equal(out["info"].cpu().numpy(), sp[0]), what
+        assert np.array_equal(out["hard"].cpu().numpy(), np.packbits(sp[2], axis=1, bitorder="little")), what
+        if z in (24, 36):
+            host = dec.decode_host(torch.from_numpy(y).pin_memory().numpy())
+            assert np.array_equal(host["iters"], sp[1]) and np.array_equal(host["info"], sp[0]), what + " host"
 
 
 def test_sum_product_other_rates_and_caps():

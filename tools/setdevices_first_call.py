@@ -36,9 +36,11 @@ def run(scenario, per):
     coder.setDevices(list(range(n)))
     t0 = time.perf_counter(); coder.forDecoder(tot); coder.addDecodeType(de); setup = time.perf_counter() - t0
     t0 = time.perf_counter(); coder.decode(post, src, src_len, de); first = time.perf_counter() - t0
+    print("           first call phases (s):", {k: round(v, 5) for k, v in coder.lastStepTimes().items()}, flush=True)
     ts = []
     for _ in range(5):
         t0 = time.perf_counter(); coder.decode(post, src, src_len, de); ts.append(time.perf_counter() - t0)
+    print("           steady phases (s):", {k: round(v, 5) for k, v in coder.lastStepTimes().items()}, " calls 2..6 (ms):", [round(t * 1e3, 2) for t in ts], flush=True)
     print("%-10s gpus %d  setup %.1f ms  first call %.1f ms  steady %.2f ms" % (scenario, n, setup * 1e3, first * 1e3, min(ts) * 1e3), flush=True)
 
 

@@ -65,7 +65,7 @@ WORKLOADS = {
 }
 # (steps, warmup, oracle spot-check words) of the sub-records in `workloads`
 PLACE_EFFORT = {"cfg3": 48}   # LDPC_B200_PLACE_EFFORT of the decoder's setup (see measure())
-SUB = {"cfg3": (5, 3, 32), "cfg5": (3, 3, 2), "cfg4": (20, 3, 512), "cfg4_4dB": (20, 3, 512), "family_z60": (10, 3, 128)}
+SUB = {"cfg3": (5, 3, 32), "cfg5": (3, 3, 2), "cfg4": (200, 3, 512), "cfg4_4dB": (200, 3, 512), "family_z60": (10, 3, 128)}
 
 
 def make_code(workload: str):

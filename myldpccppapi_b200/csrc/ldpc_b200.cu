@@ -2952,7 +2952,7 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
     // 3.5 dB, 65,536 words of Test.cpp's code: 4 MB 3.28 ms, 8 MB 3.13, 16 MB 3.09, 32 MB 3.05 against 2.72 for one
     // plain copy; the kernel's tail after the last chunk grows from 0.10 to 0.17 ms)
     if (!staged && h->h_stats && h->h_stats[1] > 0 && h->h_stats[0] * 4ull <= (unsigned long long)h->max_iter * h->h_stats[1])
-        chunk_max = words_of((int64_t)16 << 20);
+        chunk_max = words_of(((int64_t)4 << 20) * (int64_t)esz);   // (packed values: the same words per chunk -- int8 copies are as fast as the kernel)
     if (h->opt.stream_chunk >= 1) chunk0 = chunk_max = (h->opt.stream_chunk + g - 1) / g * g;
     if (staged) {
         chunk0 = chunk_max;  // fixed-size chunks = ring slots

@@ -172,18 +172,22 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
         return (__shfl_sync(0xffffffffu, hb, bc < NB ? bc : 0) >> (8 * b - bc * Z)) & 0xffu;
     };
 
-    // the channel values of the word decoded next are loaded into registers (yq) while the current word is decoded: a
-    // starting word finds them there, no global-memory latency between two words of a warp
-    float yn[NB], yq[NB];
+    // fp32 input: the channel values of the word decoded next are loaded into registers (yq) while the current word is
+    // decoded -- a starting word finds them there, no global-memory latency between two words of a warp.  Packed input
+    // (its widening needs the registers): pulled into L2 one word ahead (a lane per 128-byte line), loaded at the start.
+    float yn[NB], yq[PACKED ? 1 : NB];
     auto load_y = [&](long long w) {
         if constexpr (!PACKED) {
             const float* src = p.llr + (size_t)w * p.N + lane;
 #pragma unroll
             for (int b = 0; b < NB; ++b) yq[b] = act ? __ldg(src + b * Z) : 0.0f;
-        } else {   // packed host formats, widened here
-            const size_t i0 = (size_t)w * p.N + lane;
-#pragma unroll
-            for (int b = 0; b < NB; ++b) yq[b] = act ? llr_at(p.llr, p.fmt, p.scale, i0 + (size_t)(b * Z)) : 0.0f;
+        } else {
+            const int esz = p.fmt == 1 ? 2 : 1;   // bytes per channel value in p.llr
+            const char* src = reinterpret_cast<const char*>(p.llr) + (size_t)w * p.N * esz;
+            for (int o0 = 0; o0 < p.N * esz; o0 += 32 * 128) {   // (same trip count in every lane)
+                const int o = o0 + (int)lane * 128;
+                if (o < p.N * esz) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+            }
         }
     };
     long long wn = __shfl_sync(0xffffffffu, claim(), 0);   // the word decoded next
@@ -194,8 +198,14 @@ __global__ void __launch_bounds__(kQcwMaxWarps * 32, 1) ldpc_ms_qcw_kernel(const
         const long long w = wn;
         if (w >= p.ncw) break;
         // ---- start word w (decodeInitMS, decodeCL.c:113-124): T = -y (canonical zero), R = 0
+        if constexpr (!PACKED) {
 #pragma unroll
-        for (int b = 0; b < NB; ++b) yn[b] = yq[b];
+            for (int b = 0; b < NB; ++b) yn[b] = yq[b];
+        } else {   // packed host formats, widened here
+            const size_t i0 = (size_t)w * p.N + lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) yn[b] = act ? llr_at(p.llr, p.fmt, p.scale, i0 + (size_t)(b * Z)) : 0.0f;
+        }
         // (R = 0 is not stored: the first check pass below takes it as known)
 #pragma unroll
         for (int b = 0; b < NB; ++b) {

@@ -85,6 +85,7 @@ struct Options {
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
     int qc_et_every = 4;              // auto: the iteration counts are sampled after every n-th launch once the regime is known (13 us each)
+    int qcw_warps = 0;                // warp-per-codeword kernel: fewer codewords in flight per SM than fit (occupancy experiments)
     int qcm_pack = -1;                // group-of-warps kernel, codewords per group: -1 = the measured best of the block size and rate, 0 / 1 = one, 2 / 3 = that many
     int qcm_multi_pct = -1;           // ... used while the mean iteration count is above this share of the cap (-1 = measured crossover, 0 = always)
     int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
@@ -97,7 +98,7 @@ struct OptionName { const char* name; int kind; size_t off; bool runtime; };  //
 const OptionName kOptionNames[] = {
     OPT(no_qc, 0), OPT(no_qcg, 0), OPT(no_qcm, 0), OPT(qcm_always, 0), OPT(qc_generic, 0), OPT(qc_ring, 0), OPT(grp_no_profile, 0), OPT(grp_no_ysmem, 0), OPT(grp_prefer_16, 0),
     OPT(grp_t16, 0), OPT(grp_no_t16, 0), OPT(debug_placement, 0), OPT(sp_big, 0), OPT(grp_g, 1), OPT(grp_warps, 1), OPT(l16_warps, 1),
-    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(sp_qc, 1), OPT(place_effort, 2),
+    OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(qcw_warps, 1), OPT(sp_qc, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(avail_memcpy, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
     OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1),
@@ -1267,8 +1268,9 @@ bool qcw_prepare(ldpc_b200_decoder* h) {
         std::vector<uint32_t> syn;
         if (!pe.build(t, rows, &syn)) continue;
         // a multiple of four warps (one register-file partition each); 16 at z = 24, 12 at z = 32
-        const int warps = std::min<int>(kQcwMaxWarps, (int)(h->smem_optin / (size_t)pe.warp_bytes)) & ~3;
-        if (warps < 8) return false;
+        int warps = std::min<int>(kQcwMaxWarps, (int)(h->smem_optin / (size_t)pe.warp_bytes)) & ~3;
+        if (h->opt.qcw_warps >= 4) warps = std::min(warps, h->opt.qcw_warps & ~3);   // (occupancy experiments)
+        if (warps < 8 && h->opt.qcw_warps < 4) return false;
         DeviceGuard guard(h->device);
         if (!guard.ok) return false;
         if (cudaMalloc(&h->d_syn_tab, syn.size() * 4) != cudaSuccess ||

@@ -89,7 +89,7 @@ struct Options {
     int qcm_pack = -1;                // group-of-warps kernel, codewords per group: -1 = the measured best of the block size and rate, 0 / 1 = one, 2 / 3 = that many
     int qcm_multi_pct = -1;           // ... used while the mean iteration count is above this share of the cap (-1 = measured crossover, 0 = always)
     int qc_et_pct = 0;                // auto: used while the mean iteration count is at most this share of the cap; 0 = the measured
-                                      // crossover of the code (profiles/r02_et_kernel.md: z = 24 90 %, z = 32 every regime)
+                                      // crossover of the code (profiles/r02_et_kernel.md: z = 24 97 %, z = 32 every regime)
 };
 
 struct OptionName { const char* name; int kind; size_t off; bool runtime; };  // kind 0 bool, 1 int, 2 long long
@@ -2205,7 +2205,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         // that decodes every codeword on its own warp(s): ldpc_qcw.cuh where the code has one (z = 24 / 32), else
         // ldpc_qcm.cuh.  The regime is the mean iteration count of the previous launches, sampled on the device and read
         // from pinned memory (no synchronisation); unknown = lockstep.  Measured crossovers (share of the cap):
-        // qcw z = 24 90 %, z = 32 every regime; qcm 25 % (profiles/r02_qcw_*.txt, r02_qcm_vs_lockstep.txt).
+        // qcw z = 24 97 % (38.99 of 40: 1.02x, 39.76: 0.95x), z = 32 every regime; qcm 25 % (profiles/r02_qcw_*.txt, r02_qcm_vs_lockstep.txt).
         const bool aligned = (reinterpret_cast<uintptr_t>(d_llr) & 15u) == 0;  // bulk copies of the ring kernel
         const bool have_w = h->qcw_state == 1, have_m = !have_w && h->qcm_state == 1;
         const bool et_ready = (have_w || have_m) && h->early && !h->qc_ring_smem;
@@ -2213,7 +2213,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         bool use_et = et_ready && h->opt.qc_et > 0;
         if (track) {
             int np0 = 0;
-            const int pct = h->opt.qc_et_pct > 0 ? h->opt.qc_et_pct : (have_m ? 25 : (qcw_profiles(&np0)[h->qcw_kind].z >= 32 ? 100 : 90));
+            const int pct = h->opt.qc_et_pct > 0 ? h->opt.qc_et_pct : (have_m ? 25 : (qcw_profiles(&np0)[h->qcw_kind].z >= 32 ? 100 : 97));
             if (pct >= 100) use_et = true;
             else if (h->h_stats[1] > 0) use_et = (double)h->h_stats[0] * 100.0 <= (double)pct * (double)h->max_iter * (double)h->h_stats[1];
         }
@@ -2883,6 +2883,10 @@ int ldpc_b200_decode_device(ldpc_b200_handle h, const float* d_llr, int64_t ncw,
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
     if (!guard.ok) return fail(LDPC_B200_ERR_CUDA, "cudaSetDevice failed");
+    if (ncw > 0) {   // a handle nobody reserved on: its kernels load here, once, not at the launch that first switches kernels
+        const int wrc = warm_kernels_locked(h);   // (3.5 ms in the middle of a stream of decodes: tools/auto_regime_probe.py)
+        if (wrc) return wrc;
+    }
     return launch_decode(h, d_llr, ncw, d_info, d_hard, d_iters, d_post, (cudaStream_t)stream);
 }
 

@@ -425,7 +425,7 @@ def test_qc_early_termination_kernel(rate, name, num, den, N):
         assert_parity(_run_device(dec, llr[:1200]), rc, N, what="cap %d" % cap)
     dec.set_max_iter(40)
     # the handle's own choice: the lockstep kernel while the regime is unknown, afterwards the warp-per-codeword kernel
-    # whenever the previous launch's words stopped early on average (z = 24: mean <= 90 % of the cap; z = 32: always,
+    # whenever the previous launch's words stopped early on average (z = 24: mean <= 97 % of the cap; z = 32: always,
     # it is the faster kernel in every regime there)
     dec.set_option("qc_et", -1)
     dec.set_option("qc_et_every", 1)   # (default: the counts are sampled after every fourth launch)

@@ -55,6 +55,8 @@ def main():
         sigma = float(np.sqrt(1.0 / (2.0 * 0.75 * 10.0 ** (e / 10.0))))
         llr = m.synth_llr(args.ncw, N, sigma, seed=100 + i, bits=bits)
         out = dec.decode_device(llr)
+        for _ in range(4):   # (the handle samples the iteration counts after every fourth launch and picks its kernel from them)
+            dec.decode_device(llr, out=out)
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

@@ -702,6 +702,23 @@ def test_cpp_coder_cli_roundtrip():
     assert int(kv_td["ErrNum"]) <= int(kv_ms["ErrNum"])
 
 
+def test_first_decode_of_a_fresh_process_is_not_slow():
+    """CUDA loads a kernel at its first launch; a kernel first launched behind the spinning persistent launch of the
+    host-buffer path made the first Coder::decode of a process sit out the kernel's 4 s input wait.  addDecodeType (and,
+    for handles nobody reserved on, the first decode) launches every kernel once: in a FRESH process the first decode of
+    32,768 words from malloc'd memory -- and the first C-ABI call on a bare handle -- stay far below a second."""
+    import pathlib
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parents[1]
+    r = subprocess.run([sys.executable, str(root / "tools" / "setdevices_first_call.py"), "32768", "coder", "cabi"], capture_output=True, text=True,
+                       timeout=300, cwd=str(root), env=dict(__import__("os").environ, PYTHONPATH=str(root)))
+    assert r.returncode == 0, r.stdout + r.stderr
+    firsts = [float(line.split("first call")[1].split("ms")[0]) for line in r.stdout.splitlines() if "first call" in line and "phases" not in line]
+    assert len(firsts) == 2, r.stdout
+    assert max(firsts) < 500.0, r.stdout
+
+
 def test_reference_test_cpp_runs_against_the_drop_in():
     """The reference's OWN Test.cpp, compiled unmodified against include/MyLdpc.h at build time
     (myldpccppapi_b200/_build.py: build_harness), decodes its payload without byte errors."""

@@ -200,6 +200,8 @@ struct ldpc_b200_decoder {
     int qcm_kind = -1, qcm_state = 0, qcm_slot = -1, qcm_groups = 0;
     std::vector<unsigned char> qcm_tab;      // its table block (also uploaded to the sum-product unit's bank, ldpc_spq.cuh)
     int spq_state = 0;                       // quasi-cyclic sum-product kernel: 0 not tried, 1 ready, -1 not for this code
+    QcmParams spq;                           // its geometry: the min-sum kernel's with a byte-wide hard-decision array in T's place
+    int spq_groups = 0;
     QcmParams qcm_multi;                     // the same with several codewords per group (ldpc_ms_qcm_multi_kernel); 0 groups = not used
     int qcm_multi_groups = 0;
     // kernel choice per launch: mean iteration count of the previous launches, sampled on the device
@@ -1732,6 +1734,18 @@ bool spq_prepare(ldpc_b200_decoder* h) {
     DeviceGuard guard(h->device);
     if (!guard.ok) return false;
     if (profiles[h->qcm_kind].upload(h->qcm_slot, h->qcm_tab.data(), h->qcm_tab.size()) != 0) { (void)cudaGetLastError(); return false; }
+    // slice of a codeword: [HB bytes | E | 128 B slack | bit buffer] -- E, slack and bit buffer as in the min-sum layout
+    QcmParams q = h->qcm;
+    const uint32_t tail = h->qcm.word_bytes - h->qcm.t_bytes;                 // everything behind T
+    q.hb_bytes = ((uint32_t)(24 * 2 * q.z) + 15u) & ~15u;
+    q.bits_off = h->qcm.bits_off - h->qcm.t_bytes + q.hb_bytes;
+    q.word_bytes = (q.hb_bytes + tail + 15u) & ~15u;
+    int groups = (int)((h->smem_optin - 1024) / q.word_bytes);                // (the kernel's static shared memory counts too)
+    groups = std::min(groups, kQcmMaxWarps / q.NW);
+    if (q.NW > 1) groups = std::min(groups, kQcmMaxGroups);
+    if (groups < 1) return false;
+    h->spq = q;
+    h->spq_groups = groups;
     h->spq_state = 1;
     return true;
 }
@@ -2126,7 +2140,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
     };
     if (uses_spq(h)) {   // sum-product, quasi-cyclic layout: the group-of-warps geometry with the arithmetic of ldpc_sp.cuh
         if (d_post) return fail(LDPC_B200_ERR_UNSUPPORTED, "sum-product mode has no posterior output");
-        QcmParams q = h->qcm;
+        QcmParams q = h->spq;
+        q.tab_slot = h->qcm.tab_slot;
         q.K = h->K;
         q.max_iter = h->max_iter; q.early_term = h->early;
         q.llr = d_llr; q.ncw = ncw;
@@ -2135,8 +2150,8 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
         q.avail = nullptr; q.status = nullptr; q.wait_ns = 0ull;
         q.fmt = LDPC_B200_LLR_F32; q.scale = 1.0f;
         int np = 0;
-        const int g = (int)std::min<int64_t>((ncw + h->qcm_groups - 1) / h->qcm_groups, (int64_t)h->sm_count);
-        rc = launch_status(spq_profiles(&np)[h->qcm_kind].launch(q, g, h->qcm_groups, stream), "sum-product (quasi-cyclic)");
+        const int g = (int)std::min<int64_t>((ncw + h->spq_groups - 1) / h->spq_groups, (int64_t)h->sm_count);
+        rc = launch_status(spq_profiles(&np)[h->qcm_kind].launch(q, g, h->spq_groups, stream), "sum-product (quasi-cyclic)");
         if (rc) return rc;
         h->last_kernel = 5;
         h->launches += 1;

@@ -51,6 +51,8 @@ struct QcmParams {
     uint32_t zb, t_bytes;         // z * 4; bytes of T (= 24 * 2z * 4): R starts there
     uint32_t bits_off;            // bit buffer of the word's hard decisions (N / 8 bytes + 4), byte offset in its slice
     uint32_t word_bytes;          // shared memory per codeword in flight
+    uint32_t hb_bytes;            // sum-product kernel (ldpc_spq.cuh): bytes of its hard-decision array HB[24][2z] (one BYTE per
+                                  // variable); E starts there.  0 in the min-sum launches.
     int N, K;
     int max_iter, early_term;
     const float* __restrict__ llr;

@@ -6,8 +6,9 @@
 // shortest codes of the reference's family fit (N = 576 .. 768); every other block size ran the any-size kernel
 // (ldpc_big.cuh: messages in a global workspace, correctness first) at 0.2 Gbit/s.  Here a codeword's slice of shared
 // memory holds
-//   HB[24][2z]  its hard decisions, one word per variable, every block column stored twice (the cyclic wrap of the
-//               check pass is a plain offset) -- the place of T in ldpc_qcm.cuh, same table entries
+//   HB[24][2z]  its hard decisions, one BYTE per variable (a word each cost a codeword in flight per SM from z = 56 on),
+//               every block column stored twice (the cyclic wrap of the check pass is a plain offset) -- the place of
+//               T in ldpc_qcm.cuh, the same table entries divided by four
 //   E [E ][z]   one float per edge that alternates meaning as in ldpc_sp.cuh: after a variable pass E_e = q0_e - q1_e,
 //               after a check pass E_e = d_e = product over the row's OTHER edges of (q0 - q1), in row-list order
 // and the tables, the geometry and the work queue are those of the group-of-warps min-sum kernel (QcmTab / QcmParams).
@@ -24,6 +25,14 @@ namespace ldpc_b200 {
 #ifdef LDPC_SPQ_DEVICE   // the kernel and its table bank: only the unit that instantiates them (k_spq.cu)
 static __constant__ uint4 g_spq_bank[kQcTabSlots][kQcmBankBytes / 16];
 
+__device__ __forceinline__ uint32_t spq_lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spq_sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void spq_atoms_or(uint32_t a, uint32_t v) {
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -32,14 +41,14 @@ __device__ __forceinline__ void spq_atoms_or(uint32_t a, uint32_t v) {
 // reference's left-to-right product with edge j skipped -- its first j factors are the running prefix shared by all
 // later edges.  Returns the row's syndrome bit over the hard decisions of the previous variable pass (checkResult).
 template <class R, int I>
-__device__ __forceinline__ uint32_t spq_check(const QcmTab<R>& tb, uint32_t la, uint32_t eb, uint32_t zb, bool act) {
+__device__ __forceinline__ uint32_t spq_check(const QcmTab<R>& tb, uint32_t la, uint32_t lb, uint32_t eb, uint32_t zb, bool act) {
     constexpr int D = R::cdeg(I);
     uint32_t syn = 0u;
 #pragma unroll
-    for (int j = 0; j < D; j += 2) {  // two warp-uniform bases per LDCU.64
+    for (int j = 0; j < D; j += 2) {  // two warp-uniform bases per LDCU.64 (byte offsets of the float layout: / 4 here)
         const uint2 e = *reinterpret_cast<const uint2*>(tb.cn_t + QcmLayout<R>::coff(I) + j);
-        syn ^= lds_u32(la + e.x);
-        if (j + 1 < D) syn ^= lds_u32(la + e.y);
+        syn ^= spq_lds_u8(lb + (e.x >> 2));
+        if (j + 1 < D) syn ^= spq_lds_u8(lb + (e.y >> 2));
     }
     const uint32_t r0 = la + eb + (uint32_t)R::e0(I) * zb;   // this lane's row of the block row's first circulant
     float x[D];
@@ -58,10 +67,10 @@ __device__ __forceinline__ uint32_t spq_check(const QcmTab<R>& tb, uint32_t la, 
 }
 
 template <class R, int I>
-__device__ __forceinline__ uint32_t spq_cn(const QcmTab<R>& tb, uint32_t la, uint32_t eb, uint32_t zb, bool act) {
+__device__ __forceinline__ uint32_t spq_cn(const QcmTab<R>& tb, uint32_t la, uint32_t lb, uint32_t eb, uint32_t zb, bool act) {
     if constexpr (I < R::MB) {
-        const uint32_t u = spq_check<R, I>(tb, la, eb, zb, act);
-        return u | spq_cn<R, I + 1>(tb, la, eb, zb, act);
+        const uint32_t u = spq_check<R, I>(tb, la, lb, eb, zb, act);
+        return u | spq_cn<R, I + 1>(tb, la, lb, eb, zb, act);
     } else {
         return 0u;
     }
@@ -71,7 +80,7 @@ __device__ __forceinline__ uint32_t spq_cn(const QcmTab<R>& tb, uint32_t la, uin
 // (decodeCL.c:43-62); edge k's message sits at row (c - s) mod z of its circulant.  `bits` bit B = this column's hard
 // decision of block column B.
 template <class R, int B>
-__device__ __forceinline__ void spq_vn(const QcmTab<R>& tb, uint32_t la, uint32_t laz, uint32_t c, uint32_t zb, const float* tt,
+__device__ __forceinline__ void spq_vn(const QcmTab<R>& tb, uint32_t la, uint32_t laz, uint32_t lb, uint32_t c, uint32_t z, const float* tt,
                                        uint32_t& bits, bool act) {
     if constexpr (B < R::NB) {
         constexpr int D = R::vdeg(B), V0 = R::v0(B);
@@ -108,10 +117,10 @@ __device__ __forceinline__ void spq_vn(const QcmTab<R>& tb, uint32_t la, uint32_
         const uint32_t bit = (pu0 > pu1) ? 0u : ((pu0 < pu1) ? 1u : prev);
         if (act) {
             bits = (bits & ~(1u << B)) | (bit << B);
-            sts_u32(la + (uint32_t)(2 * B) * zb, bit);
-            sts_u32(la + (uint32_t)(2 * B + 1) * zb, bit);
+            spq_sts_u8(lb + (uint32_t)(2 * B) * z, bit);
+            spq_sts_u8(lb + (uint32_t)(2 * B + 1) * z, bit);
         }
-        spq_vn<R, B + 1>(tb, la, laz, c, zb, tt, bits, act);
+        spq_vn<R, B + 1>(tb, la, laz, lb, c, z, tt, bits, act);
     }
 }
 
@@ -131,7 +140,11 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_sp_qcm_kernel(const
     const uint32_t c = (uint32_t)(sw * p.RW) + lane;
     const bool act = lane < (uint32_t)p.RW && c < (uint32_t)p.z;
     const uint32_t zb = p.zb;
-    const uint32_t la = wb + c * 4u, laz = la + zb;
+    const uint32_t la = wb + c * 4u;                      // this lane's row of a float array that starts at the slice base
+    const uint32_t lb = wb + c;                           // ... of the byte array HB
+    // the table entries of the variable pass are offsets in the min-sum layout (messages behind p.t_bytes of posteriors):
+    // here E starts behind p.hb_bytes of hard decisions
+    const uint32_t lav = la + p.hb_bytes - p.t_bytes, laz = lav + zb;
     const uint32_t bitbuf = wb + p.bits_off;
     const int KB = (p.K + 7) >> 3, NB8 = (p.N + 7) >> 3;
     const int gl = sw * 32 + (int)lane, gn = p.NW * 32;
@@ -183,8 +196,8 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_sp_qcm_kernel(const
         if (act) {
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
-                sts_u32(la + (uint32_t)(2 * b) * zb, 0u);
-                sts_u32(la + (uint32_t)(2 * b + 1) * zb, 0u);
+                spq_sts_u8(lb + (uint32_t)(2 * b * p.z), 0u);
+                spq_sts_u8(lb + (uint32_t)((2 * b + 1) * p.z), 0u);
             }
         }
 #pragma unroll
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_sp_qcm_kernel(const
             const float x0 = __fsub_rn(__fdiv_rn(tt[b], one_t), __fdiv_rn(1.0f, one_t));
             for (int k = 0; k < R::vdeg(b); ++k) {
                 const uint2 u = tb.vn[R::v0(b) + k];
-                if (act) sts_f32((c < u.y ? laz : la) + u.x, x0);
+                if (act) sts_f32((c < u.y ? laz : lav) + u.x, x0);
             }
         }
         uint32_t bits = 0u;
@@ -209,14 +222,14 @@ __global__ void __launch_bounds__(kQcmMaxWarps * 32, 1) ldpc_sp_qcm_kernel(const
         uint32_t ph = 0u;
         for (;;) {
             // refreshR + checkResult of the previous hard decision
-            const uint32_t unsat = spq_cn<R, 0>(tb, la, p.t_bytes, zb, act);
+            const uint32_t unsat = spq_cn<R, 0>(tb, la, lb, p.hb_bytes, zb, act);
             const bool check = p.early_term && it >= 1;
             if (check && __any_sync(0xffffffffu, act && unsat != 0u) && lane == 0) s_flag[ws][ph] = 1u;  // same-value race, benign
             gsync();
             if (check && s_flag[ws][ph] == 0u) break;            // the hard decisions of iteration `it` satisfy every check
             if (sw == 0 && lane == 0) s_flag[ws][ph ^ 1u] = 0u;
             ph ^= 1u;
-            spq_vn<R, 0>(tb, la, laz, c, zb, tt, bits, act);     // hardDecision + refreshQ
+            spq_vn<R, 0>(tb, lav, laz, lb, c, (uint32_t)p.z, tt, bits, act);     // hardDecision + refreshQ
             gsync();
             ++it;
             if (it >= p.max_iter) break;

@@ -1726,7 +1726,8 @@ bool spq_prepare(ldpc_b200_decoder* h) {
     if (h->spq_state != 0) return h->spq_state == 1;
     h->spq_state = -1;
     if (h->opt.sp_qc == 0 || h->opt.sp_big) return false;
-    if (h->qcm_state == 0) h->qcm_state = qcm_prepare(h) ? 1 : -1;
+    // (the min-sum plan may have skipped the group-of-warps tables -- option qc_et = 0 --: they are built here then)
+    if (h->qcm_state != 1 && h->qcm_tab.empty()) h->qcm_state = qcm_prepare(h) ? 1 : -1;
     if (h->qcm_state != 1 || h->qcm_tab.empty()) return false;
     int n = 0;
     const SpqProfileEntry* profiles = spq_profiles(&n);
@@ -2409,7 +2410,7 @@ int launch_decode(ldpc_b200_decoder* h, const float* d_llr, int64_t ncw, uint8_t
 extern "C" {
 
 const char* ldpc_b200_last_error(void) { return g_err.c_str(); }
-const char* ldpc_b200_version(void) { return "ldpc_b200 0.1 (sm_100a)"; }
+const char* ldpc_b200_version(void) { return "ldpc_b200 0.2 (sm_100a)"; }
 
 int ldpc_b200_create(ldpc_b200_handle* out, int M, int N, int K, const int32_t* row_ptr, const int32_t* col_idx,
                      int device) {

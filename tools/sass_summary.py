@@ -6,8 +6,10 @@ ROOT = pathlib.Path(__file__).resolve().parents[1]
 LIB = ROOT / "myldpccppapi_b200" / "libldpc_b200.so"
 WANT = [
     ("cfg1/2 default (lockstep)", r"ldpc_ms_qc_kernel<ldpc_b200::QcProfile34B<24, 8, 12>"),
-    ("cfg4 default (warp per codeword)", r"ldpc_ms_qcw_kernel<ldpc_b200::QcwProfile<ldpc_b200::QcwCode34B_24>"),
-    ("block sizes without a compiled profile (group of warps per codeword), rate 3/4B", r"ldpc_ms_qcm_kernel<ldpc_b200::QcwCode34B_24>"),
+    ("cfg4 default (warp per codeword)", r"ldpc_ms_qcw_kernel<ldpc_b200::QcwProfile<ldpc_b200::QcwCode34B_24>, false>"),
+    ("block sizes without a compiled profile (group of warps per codeword), rate 3/4B", r"ldpc_ms_qcm_kernel<ldpc_b200::QcwCode34B_24, false>"),
+    ("... with several codewords per group (z = 36, 44, 68, 72, 76)", r"ldpc_ms_qcm_multi_kernel<ldpc_b200::QcwCode34B_24>"),
+    ("DecodeSP on the quasi-cyclic layout (z >= 32), rate 3/4B", r"ldpc_sp_qcm_kernel<ldpc_b200::QcwCode34B_24>"),
     ("generic on-chip, G=8 static profile", r"ldpc_ms_group_kernel<8, 16, true, 384, false, ldpc_b200::ProfileWimax34B576, false>"),
     ("cfg3 default", r"ldpc_ms_group_kernel<1, 8, false, 1024, false, ldpc_b200::ProfileRegular36N8192, true>"),
     ("cfg5 default", r"ldpc_ms_stream_kernel<1024>"),

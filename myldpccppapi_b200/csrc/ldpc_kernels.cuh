@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(1024, 1) ldpc_ms_lane_kernel(const DecodeParam
         const float* src = p.llr + (size_t)(active ? cw : 0) * N;
 
         // ---- load: y -> Y and P (decodeInitMS, decodeCL.c:113-124: Q_e = y[col(e)], i.e. R = 0)
-        if ((N & 3) == 0) {
+        if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(p.llr) & 15u) == 0) {  // (a caller's pointer may be 4-byte aligned only)
             for (int n4 = warp; n4 < (N >> 2); n4 += W) {
                 float4 v = active ? __ldg(reinterpret_cast<const float4*>(src) + n4) : make_float4(1.f, 1.f, 1.f, 1.f);
                 const float vv[4] = {v.x, v.y, v.z, v.w};

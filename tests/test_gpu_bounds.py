@@ -159,3 +159,101 @@ def test_guard_bands_sum_product_and_layered(N, big, monkeypatch):
     dec.set_algorithm(1)
     _same(_decode_guarded(dec, y[:37], want_post=False, skewed=True), (sp[0][:37], sp[1][:37], sp[2][:37], None),
           "sum-product N=%d big=%d, buffers at odd offsets" % (N, big), post=False)
+
+
+# ---- host-buffer calls --------------------------------------------------------------------------------------------------
+def _host_guarded(nbytes, skew, pinned):
+    """(whole uint8 array, view of nbytes) in host memory; pinned = page-locked through torch."""
+    total = GUARD + skew + nbytes + GUARD
+    if pinned:
+        import torch
+        whole = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
+    else:
+        whole = np.empty(total, dtype=np.uint8)
+    whole[:] = SENTINEL
+    return whole, whole[GUARD + skew:GUARD + skew + nbytes]
+
+
+def _host_intact(whole, nbytes, skew):
+    return bool((whole[:GUARD + skew] == SENTINEL).all()) and bool((whole[GUARD + skew + nbytes:] == SENTINEL).all())
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("skewed", [False, True])
+def test_guard_bands_host_buffers(default_code, pinned, skewed):
+    """ldpc_b200_decode_host (persistent launch fed by the copy stream when pinned, staged chunks when pageable; tiny
+    chunks; the warp-per-codeword kernel) and ldpc_b200_decode_host_packed (float16 / int8): the caller's host buffers sit
+    between sentinel bands, at 16-byte alignment or at the weakest alignment of their element type."""
+    import myldpccppapi_b200 as m
+    c = default_code
+    N, K = c["N"], c["K"]
+    y = np.concatenate([_inputs(N, 0.75, 500), _inputs(N, 0.75, 510), _inputs(N, 0.75, 520)])   # 999 words
+    ref = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"], times=40).decode(y, literal=False)
+    dec = m.Decoder.wimax(K, N, c["rate"])
+    KB, NB = dec.KB, dec.NB
+
+    def run(n, fmt=np.float32, scale=1.0, what=""):
+        esz = np.dtype(fmt).itemsize
+        sk = {"llr": esz if skewed else 0, "info": 1 if skewed else 0, "hard": 1 if skewed else 0, "iters": 4 if skewed else 0,
+              "post": 4 if skewed else 0}
+        sizes = {"llr": n * N * esz, "info": n * KB, "hard": n * NB, "iters": n * 4, "post": n * N * 4}
+        whole, view = {}, {}
+        for k in sizes:
+            whole[k], view[k] = _host_guarded(sizes[k], sk[k], pinned)
+        src = view["llr"].view(fmt).reshape(n, N)
+        src[:] = y[:n] if fmt == np.float32 else (np.clip(np.round(y[:n] / scale), -127, 127) if fmt == np.int8 else y[:n]).astype(fmt)
+        out = {"info": view["info"].reshape(n, KB), "hard": view["hard"].reshape(n, NB), "iters": view["iters"].view(np.int32),
+               "post": view["post"].view(np.float32).reshape(n, N)}
+        before = whole["llr"].copy()
+        if fmt == np.float32:
+            dec.decode_host(src, want_hard=True, want_post=True, out=out)
+            want = tuple(r[:n] for r in ref)
+        else:
+            dec.decode_host_packed(src, scale=scale, want_hard=True, want_post=True, out=out)
+            wide = (src.astype(np.float32) * np.float32(scale)).astype(np.float32)   # the contract: the fp32 call on the widened floats
+            want = oracle.Oracle(c["M"], N, K, c["row_ptr"], c["col_idx"], times=40).decode(wide, literal=False)
+        for k in ("info", "hard", "iters", "post"):
+            assert _host_intact(whole[k], sizes[k], sk[k]), "%s %s: a byte outside the buffer changed (%d words)" % (what, k, n)
+        assert np.array_equal(whole["llr"], before), what + ": the caller's channel values were written"
+        _same(out, want, "%s, %d words" % (what, n))
+
+    for n in (1, 37, 999):
+        run(n, what="host fp32")
+    dec.set_option("stream_chunk", 8)
+    run(333, what="host fp32, 8-word chunks")
+    dec.set_option("stream_chunk", 0)
+    dec.reserve(4096)
+    dec.set_option("qc_et", 1)
+    run(999, what="host fp32, warp-per-codeword kernel")
+    run(37, fmt=np.float16, what="host fp16")
+    run(333, fmt=np.int8, scale=1.0 / 32, what="host int8")
+    dec.set_option("qc_et", -1)
+    run(999, fmt=np.float16, what="host fp16, handle's own kernel choice")
+
+
+@pytest.mark.parametrize("de_type", [1, 2, 3, 4, 5])   # DecodeMS, DecodeSP, DecodeTDMP, DecodeTDMPCL, DecodeMSCL (MyLdpc.h:37-39)
+def test_guard_bands_coder_decode_ragged_src_length(de_type):
+    """The drop-in Coder::decode with a stream that ends inside the last codeword: the reference's guard is
+    `charOffset <= srcLength` and may touch srcCode[srcLength] (MyLdpc.cpp:765-774); the drop-in writes exactly srcLength
+    bytes.  postCode is read only (getPostCodeLength floats, nothing behind them that matters)."""
+    import myldpccppapi_b200 as m
+    N, K, rate = 576, 432, 4
+    ncw = 45
+    y = np.ascontiguousarray(_inputs(N, 0.75, 600 + de_type)[:ncw])
+    src_len = ncw * (K // 8) - 11
+    whole, dst = _host_guarded(src_len, 1, False)
+    gf = GUARD // 4
+    yin = np.full(gf + ncw * N + gf, np.nan, dtype=np.float32)
+    yin[gf:gf + ncw * N] = y.reshape(-1)
+    coder = m.Coder(K, N, rate)
+    coder.forDecoder(16)
+    coder.addDecodeType(de_type)
+    assert coder.decode(yin[gf:gf + ncw * N], dst, src_len, de_type) == 0
+    assert _host_intact(whole, src_len, 1), "Coder::decode wrote outside srcCode[0, srcLength)"
+    plain = np.zeros(src_len + 1, dtype=np.uint8)
+    c2 = m.Coder(K, N, rate)
+    c2.forDecoder(64)
+    c2.addDecodeType(de_type)
+    assert c2.decode(y.reshape(-1), plain, src_len, de_type) == 0
+    assert np.array_equal(dst, plain[:src_len]) and plain[src_len] == 0
+    assert np.array_equal(coder.lastIterations, c2.lastIterations)

@@ -166,6 +166,8 @@ int ldpc_b200_reserve(ldpc_b200_handle h, int64_t batch);
  *   d_hard  : [ncw][ceil(N/8)] bytes, all N hard bits LSB-first (may be NULL)
  *   d_iters : [ncw] int32 iteration count at exit, 1..max_iter (may be NULL)
  *   d_post  : [ncw][N] float32 posterior values lPostP (may be NULL)
+ * Buffers need only the alignment of their element type (4 bytes for floats and counts,
+ * 1 for packed bits): a slice of a larger array is fine (tests/test_gpu_bounds.py).
  * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream).    */
 int ldpc_b200_decode_device(ldpc_b200_handle h, const float *d_llr, int64_t ncw,
                             uint8_t *d_info, uint8_t *d_hard, int32_t *d_iters,

@@ -80,7 +80,9 @@ struct Options {
     long long stream_chunk = 0;       // words per input chunk (0 = 1, 2, then 4 MB)
     long long stream_batch_kb = 0;    // channel values per launch (0 = default)
     long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
-    int stage_threads = 4;            // host threads that stage a pageable input buffer through the pinned ring
+    int stage_threads = 6;            // host threads that stage a pageable input buffer through the pinned ring (6-12 measured alike
+                                      // with streaming stores, profiles/r02_stage_nt.txt; 4 was the optimum of the plain memcpy)
+    int stage_nt = 1;                 // ... with non-temporal stores (stage_copy_nt, ldpc_tables.h); 0 = plain memcpy
     // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
     int qc_et = -1;
@@ -101,7 +103,7 @@ const OptionName kOptionNames[] = {
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(qcw_warps, 1), OPT(sp_qc, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(avail_memcpy, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
-    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1), OPTR(stage_nt, 1),
 };
 #undef OPT
 #undef OPTR
@@ -3047,7 +3049,8 @@ int decode_host_streamed_body(ldpc_b200_decoder* h, const float* llr, int64_t nc
                             if (cudaEventSynchronize(h->st_pin_ev[slot]) != cudaSuccess) { err.store(1); break; }
                         }
                         const int64_t c0 = j * cw, m = std::min(cw, n - c0);
-                        std::memcpy(h->st_pin[slot], src + (size_t)c0 * t.N, sizeof(float) * (size_t)m * t.N);
+                        if (h->opt.stage_nt) stage_copy_nt(h->st_pin[slot], src + (size_t)c0 * t.N, sizeof(float) * (size_t)m * t.N);
+                        else std::memcpy(h->st_pin[slot], src + (size_t)c0 * t.N, sizeof(float) * (size_t)m * t.N);
                         while (next_enq.load() != j && !err.load()) std::this_thread::yield();  // queue in chunk order
                         if (err.load()) break;
                         if (cudaMemcpyAsync(h->st_llr + (size_t)c0 * t.N, h->st_pin[slot], sizeof(float) * (size_t)m * t.N, cudaMemcpyHostToDevice, cs) != cudaSuccess ||

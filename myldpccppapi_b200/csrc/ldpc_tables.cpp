@@ -2,6 +2,10 @@
 #include "ldpc_tables.h"
 
 #include <algorithm>
+#include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "wimax_tables.h"
 
@@ -123,5 +127,52 @@ std::string build_encoder(const HostTables& t, int K, std::vector<uint32_t>* xt,
             if (getbit(r, M + k)) (*xt)[(size_t)(k >> 5) * MP + r] |= 1u << (k & 31);
     return "";
 }
+
+// ---- staging copy with streaming stores (see ldpc_tables.h) ------------------------------------------------------------
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx2"))) void stage_copy_avx2(char* d, const char* s, size_t n) {  // d 32-byte aligned, n % 128 == 0
+    for (size_t i = 0; i < n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 64));
+        const __m256i e = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(s + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(d + i + 96), e);
+    }
+}
+void stage_copy_sse2(char* d, const char* s, size_t n) {  // d 16-byte aligned, n % 64 == 0
+    for (size_t i = 0; i < n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 32));
+        const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(d + i + 48), e);
+    }
+}
+}  // namespace
+
+void stage_copy_nt(void* dst, const void* src, size_t bytes) {
+    char* d = static_cast<char*>(dst);
+    const char* s = static_cast<const char*>(src);
+    const size_t head = std::min(bytes, (size_t)((64u - (reinterpret_cast<uintptr_t>(d) & 63u)) & 63u));
+    if (head) { std::memcpy(d, s, head); d += head; s += head; bytes -= head; }
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    const size_t body = bytes & ~(size_t)127;
+    if (body) {
+        if (avx2) stage_copy_avx2(d, s, body);
+        else stage_copy_sse2(d, s, body);
+    }
+    if (bytes > body) std::memcpy(d + body, s + body, bytes - body);
+    _mm_sfence();
+}
+#else
+void stage_copy_nt(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+#endif
 
 }  // namespace ldpc_b200

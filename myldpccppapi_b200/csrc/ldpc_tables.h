@@ -8,6 +8,7 @@
 //                    the reference's column-list order and therefore the fp32 summation
 //                    order of the posterior (MyLdpc.cpp:723-728).
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -39,5 +40,11 @@ std::string wimax_csr(int K, int N, int rate, std::vector<int32_t>* row_ptr, std
 // through the Richardson-Urbanke split, reference MyLdpc.cpp:137-165, 633-682).  Returns X transposed and packed
 // for the device: xt[w * (MW*32) + r] holds info bits 32w .. 32w+31 of row r; KW = ceil(K/32), MW = ceil(M/32).
 std::string build_encoder(const HostTables& t, int K, std::vector<uint32_t>* xt, int* KW, int* MW);
+
+// Copy of a pageable caller buffer into a page-locked staging slot with NON-TEMPORAL stores (the host-buffer pipeline of
+// ldpc_b200_decode_host): a plain memcpy reads the destination lines for ownership before overwriting them and leaves
+// them in the cache, from where the DMA engine's read forces a write-back -- four memory transfers per byte where
+// three are needed (source read, streaming write, DMA read).  Ends with a store fence: the caller may queue the DMA.
+void stage_copy_nt(void* dst, const void* src, size_t bytes);
 
 }  // namespace ldpc_b200

@@ -174,6 +174,11 @@ int Coder::forDecoder(int batchSize) {
         ldpc_b200_set_max_iter(h, impl->times);
         ldpc_b200_set_early_termination(h, impl->early ? 1 : 0);
         ldpc_b200_set_option(h, "register_host", impl->registerHost ? 1 : 0);
+        if (impl->devices.size() > 1) {
+            // every GPU's handle stages its shard of a pageable postCode with its own host threads: share the cores
+            const long long hw = std::max(1u, std::thread::hardware_concurrency());
+            ldpc_b200_set_option(h, "stage_threads", std::max(2LL, std::min(6LL, hw / (long long)impl->devices.size())));
+        }
         if (impl->rate >= 0) ldpc_b200_set_layer_height(h, impl->N / 24);  // z, reference MyLdpc.cpp:22
         impl->handles.push_back(h);
     }

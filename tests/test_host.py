@@ -145,3 +145,19 @@ def test_shard_ranges_cover_and_are_disjoint():
                 assert r[0][0] == 0 and r[-1][1] == ncw
                 assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
                 assert all(b % align == 0 or b == ncw for b, _ in r)
+
+
+def test_staging_copy_gives_memcpy_bytes(tmp_path):
+    """stage_copy_nt (non-temporal staging copy of the pageable host-buffer path): tests/native/stage_copy_test.cpp built
+    against the product source with g++ and run here -- every alignment, sizes around the vector steps, no stray byte."""
+    import pathlib, shutil, subprocess
+    root = pathlib.Path(__file__).resolve().parent.parent
+    cxx = shutil.which("g++")
+    assert cxx, "g++ missing"
+    exe = tmp_path / "stage_copy_test"
+    csrc = root / "myldpccppapi_b200" / "csrc"
+    r = subprocess.run([cxx, "-O2", "-std=c++17", "-I", str(csrc), "-I", str(root / "include"), str(root / "tests" / "native" / "stage_copy_test.cpp"),
+                        str(csrc / "ldpc_tables.cpp"), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr

@@ -82,6 +82,7 @@ struct Options {
     long long wait_timeout_ms = 4000; // bound of the kernel's wait for streamed input
     int stage_threads = 6;            // host threads that stage a pageable input buffer through the pinned ring (6-12 measured alike
                                       // with streaming stores, profiles/r02_stage_nt.txt; 4 was the optimum of the plain memcpy)
+    int chunk_stage = 1;              // chunked pipeline: a pageable caller buffer is staged by host threads too (0: the driver stages it)
     int stage_nt = 1;                 // ... with non-temporal stores (stage_copy_nt, ldpc_tables.h); 0 = plain memcpy
     // early-termination kernel of the quasi-cyclic path (ldpc_qcw.cuh, a warp per codeword): -1 = chosen per launch from the
     // mean iteration count of the handle's previous launches, 0 = never, 1 = whenever it can run
@@ -103,7 +104,7 @@ const OptionName kOptionNames[] = {
     OPT(tdmp_g, 1), OPT(stream_threads, 1), OPT(qc_prefer_g, 1), OPT(qcm_pack, 1), OPT(qcw_warps, 1), OPT(sp_qc, 1), OPT(place_effort, 2),
     OPTR(refill_wait, 1), OPTR(no_streamed, 0), OPTR(streamed_pageable, 0), OPTR(no_staged, 0), OPTR(no_warm, 0), OPTR(avail_memcpy, 0), OPTR(register_host, 0),
     OPTR(staged_min_kb, 2), OPTR(stream_chunk, 2), OPTR(stream_batch_kb, 2), OPTR(wait_timeout_ms, 2),
-    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1), OPTR(stage_nt, 1),
+    OPTR(qc_et, 1), OPTR(qc_et_pct, 1), OPTR(qc_et_every, 1), OPTR(qcm_multi_pct, 1), OPTR(stage_threads, 1), OPTR(stage_nt, 1), OPTR(chunk_stage, 1),
 };
 #undef OPT
 #undef OPTR
@@ -3104,6 +3105,109 @@ int decode_host_streamed(ldpc_b200_decoder* h, const float* llr, int64_t ncw, ui
     return rc;
 }
 
+// The chunked pipeline below with a PAGEABLE caller buffer.  cudaMemcpyAsync from pageable memory is staged by the driver,
+// synchronously, at ~7.5 GB/s; a long code's kernel wants its input several times faster (regular (3,6) N = 8192:
+// 4.3 GB per 131,072 words in 86 ms).  Here host threads copy pieces of at most one ring slot (>= 4 MB) into the pinned
+// ring with streaming stores, and the thread that holds the next piece IN ORDER queues its DMA on the chunk's stream and,
+// behind a chunk's last piece, the chunk's launch and read-back: streams, device buffers and results are exactly those
+// of the plain loop.  (h->mu held, current device = the handle's; fp32 input only)
+int decode_host_chunked_staged(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
+                               int32_t* iters, float* post, int64_t chunk) {
+    const HostTables& t = h->host;
+    const size_t KB = (h->K + 7) / 8, NB = (t.N + 7) / 8;
+    constexpr int S = ldpc_b200_decoder::kStageSlots;
+    const size_t wbytes = sizeof(float) * (size_t)t.N;
+    const size_t need = std::max<size_t>((size_t)4 << 20, wbytes);
+    if (h->st_pin_bytes < need) {
+        CU_TRY(cudaDeviceSynchronize());
+        for (int i = 0; i < S; ++i) {
+            if (h->st_pin[i]) { cudaFreeHost(h->st_pin[i]); h->st_pin[i] = nullptr; }
+        }
+        h->st_pin_bytes = 0;
+        for (int i = 0; i < S; ++i) {
+            CU_TRY(cudaMallocHost(&h->st_pin[i], need));
+            std::memset(h->st_pin[i], 0, need);
+            if (!h->st_pin_ev[i]) CU_TRY(cudaEventCreateWithFlags(&h->st_pin_ev[i], cudaEventDisableTiming));
+        }
+        h->st_pin_bytes = need;
+    }
+    const int64_t pw = std::max<int64_t>(1, (int64_t)(h->st_pin_bytes / wbytes));   // words per piece
+    const int64_t nchunks = (ncw + chunk - 1) / chunk, ppc = (chunk + pw - 1) / pw;  // pieces per full chunk
+    const int64_t n_last = ncw - (nchunks - 1) * chunk;
+    const int64_t npieces = (nchunks - 1) * ppc + (n_last + pw - 1) / pw;
+    constexpr int64_t kTimedChunks = 64;
+    const int64_t ntimed = std::min(nchunks, kTimedChunks);
+    const bool timed = timing_events(h, (size_t)(4 * ntimed));
+    std::atomic<int64_t> next_piece{0}, next_enq{0};
+    std::atomic<int> err{0};
+    int err_rc = LDPC_B200_ERR_CUDA;
+    std::string err_msg;
+    auto cuda_failed = [&](const char* what) {   // (called by the thread whose turn it is, or before any queueing: no race on err_msg)
+        if (!err.exchange(1)) { err_rc = LDPC_B200_ERR_CUDA; err_msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()); }
+    };
+    auto work = [&]() {
+        if (cudaSetDevice(h->device) != cudaSuccess) { cuda_failed("cudaSetDevice"); return; }
+        for (;;) {
+            const int64_t j = next_piece.fetch_add(1);
+            if (j >= npieces || err.load()) break;
+            const int rs = (int)(j % S);
+            const int64_t c = j / ppc, k = j % ppc;
+            const int64_t c_first = c * chunk, c_n = std::min(chunk, ncw - c_first);
+            const int64_t w0 = k * pw, m = std::min(pw, c_n - w0);            // words [w0, w0 + m) of chunk c
+            const bool last_of_chunk = w0 + m == c_n;
+            if (j >= S) {  // the ring slot's previous piece must have been queued and its DMA finished
+                while (next_enq.load() <= j - S && !err.load()) std::this_thread::yield();
+                if (err.load()) break;
+                if (cudaEventSynchronize(h->st_pin_ev[rs]) != cudaSuccess) { cuda_failed("staging ring"); break; }
+            }
+            const float* src = llr + (size_t)(c_first + w0) * t.N;
+            if (h->opt.stage_nt) stage_copy_nt(h->st_pin[rs], src, wbytes * (size_t)m);
+            else std::memcpy(h->st_pin[rs], src, wbytes * (size_t)m);
+            while (next_enq.load() != j && !err.load()) std::this_thread::yield();  // queue in piece order
+            if (err.load()) break;
+            const int slot = (int)(c % kSlots);
+            cudaStream_t st = h->streams[slot];
+            const bool tc = timed && c < ntimed;
+            bool ok = true;
+            if (k == 0 && tc) ok = cudaEventRecord(h->tev[4 * c], st) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(h->s_llr[slot] + (size_t)w0 * t.N, h->st_pin[rs], wbytes * (size_t)m, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            ok = ok && cudaEventRecord(h->st_pin_ev[rs], st) == cudaSuccess;
+            if (ok && last_of_chunk) {
+                if (tc) ok = cudaEventRecord(h->tev[4 * c + 1], st) == cudaSuccess;
+                if (ok) {
+                    const int rc = launch_decode(h, h->s_llr[slot], c_n, info ? h->s_info[slot] : nullptr, hard ? h->s_hard[slot] : nullptr,
+                                                 iters ? h->s_iters[slot] : nullptr, post ? h->s_post[slot] : nullptr, st);
+                    if (rc) { if (!err.exchange(1)) { err_rc = rc; err_msg = g_err; } break; }
+                }
+                if (ok && tc) ok = cudaEventRecord(h->tev[4 * c + 2], st) == cudaSuccess;
+                if (ok && info) ok = cudaMemcpyAsync(info + (size_t)c_first * KB, h->s_info[slot], (size_t)c_n * KB, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                if (ok && hard) ok = cudaMemcpyAsync(hard + (size_t)c_first * NB, h->s_hard[slot], (size_t)c_n * NB, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                if (ok && iters) ok = cudaMemcpyAsync(iters + c_first, h->s_iters[slot], sizeof(int32_t) * (size_t)c_n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                if (ok && post) ok = cudaMemcpyAsync(post + (size_t)c_first * t.N, h->s_post[slot], wbytes * (size_t)c_n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+                if (ok && tc) ok = cudaEventRecord(h->tev[4 * c + 3], st) == cudaSuccess;
+            }
+            if (!ok) { cuda_failed("staged chunk"); break; }
+            next_enq.store(j + 1);
+        }
+    };
+    const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::max(1, h->opt.stage_threads), npieces, (int64_t)std::max(1u, std::thread::hardware_concurrency())}));
+    std::vector<std::thread> pool;
+    for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    if (err.load()) return fail(err_rc, err_msg);
+    for (int s2 = 0; s2 < kSlots; ++s2) CU_TRY(cudaStreamSynchronize(h->streams[s2]));
+    if (timed) {
+        const double scale = (double)nchunks / (double)ntimed;
+        for (int64_t c = 0; c < ntimed; ++c) {
+            h->timing.h2d_s += scale * event_seconds(h->tev[4 * c], h->tev[4 * c + 1]);
+            h->timing.kernel_s += scale * event_seconds(h->tev[4 * c + 1], h->tev[4 * c + 2]);
+            h->timing.d2h_s += scale * event_seconds(h->tev[4 * c + 2], h->tev[4 * c + 3]);
+        }
+    }
+    return LDPC_B200_OK;
+}
+
 // The chunked 3-stream pipeline: H2D, kernel and D2H of consecutive chunks overlap across kSlots streams.
 // (h->mu held, current device = the handle's)
 int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw, uint8_t* info, uint8_t* hard,
@@ -3125,6 +3229,15 @@ int decode_host_chunked_body(ldpc_b200_decoder* h, const float* llr, int64_t ncw
     if (post) {
         for (int s = 0; s < kSlots; ++s)
             if (!h->s_post[s]) CU_TRY(cudaMalloc(&h->s_post[s], sizeof(float) * (size_t)chunk * t.N));
+    }
+    if (!packed && h->opt.chunk_stage && !h->opt.no_staged && (int64_t)ncw * t.N * 4 >= (h->opt.staged_min_kb << 10)) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, llr) == cudaSuccess &&
+                            (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        if (!pinned) {  // pageable input of some size: staged by host threads instead of by the driver
+            (void)cudaGetLastError();
+            return decode_host_chunked_staged(h, llr, ncw, info, hard, iters, post, chunk);
+        }
     }
     // phase timers: four events per chunk for the first kTimedChunks chunks (a sample when there are more)
     constexpr int64_t kTimedChunks = 64;

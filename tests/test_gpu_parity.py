@@ -954,3 +954,42 @@ def test_coder_shards_over_every_visible_gpu(default_code):
     kv1, _ = _run_cli("mytest", 54000, 256, 5.5, "MS", 23, 1)
     kvn, out = _run_cli("mytest", 54000, 256, 5.5, "MS", 23, shards, ngpu)
     assert kvn["ErrNum"] == kv1["ErrNum"] and kvn["MeanIterations"] == kv1["MeanIterations"], out
+
+
+def test_chunked_pipeline_stages_pageable_input(default_code):
+    """ldpc_b200_decode_host on the chunked pipeline (codes that are not quasi-cyclic; sum-product and layered decoding) with
+    a pageable caller buffer: host threads stage pieces of it through the pinned ring (decode_host_chunked_staged) instead
+    of the driver.  Same bytes, counts and posteriors as the oracle -- chunks smaller than a ring slot, chunks of several
+    pieces, a ragged last chunk, one staging thread and many, plain memcpy staging, and the driver-staged loop (option off)."""
+    import myldpccppapi_b200 as m
+    M, N, K, rp, ci = m.codes.regular_code()
+    y = awgn_llr(150, N, 0.84, seed=21)          # 150 words x 32 KB, pageable
+    ref = oracle.Oracle(M, N, K, rp, ci, times=40).decode(y, literal=False)
+    dec = m.Decoder(M, N, K, rp, ci)
+    assert dec.info()["path_name"] != "qc"
+    dec.set_option("staged_min_kb", 0)           # (default: calls of 8 MB or more)
+    for batch, threads, nt in ((16, 6, 1), (37, 3, 0), (64, 1, 1), (200, 6, 1)):   # 200 words = 6.5 MB: two pieces per chunk
+        dec.reserve(batch)
+        dec.set_option("stage_threads", threads)
+        dec.set_option("stage_nt", nt)
+        assert_parity(dec.decode_host(y, want_hard=True, want_post=True), ref, N, what="staged chunks of %d words, %d threads" % (batch, threads))
+        assert_parity(dec.decode_host(y[:1], want_hard=True, want_post=True), tuple(r[:1] for r in ref), N, what="one word")
+    dec.set_option("chunk_stage", 0)
+    assert_parity(dec.decode_host(y, want_hard=True, want_post=True), ref, N, what="driver-staged")
+    dec.set_option("chunk_stage", 1)
+    t = dec.timing(reset=True)
+    dec.decode_host(y)
+    t = dec.timing()
+    assert t["calls"] == 1 and t["codewords"] == 150 and t["h2d_s"] > 0 and t["kernel_s"] > 0
+    # sum-product and layered decoding of Test.cpp's code run the chunked pipeline too
+    c = default_code
+    yd = np.concatenate([awgn_llr(400, c["N"], 0.62, seed=31), awgn_llr(301, c["N"], 0.5, seed=32)])
+    o = oracle.Oracle(c["M"], c["N"], c["K"], c["row_ptr"], c["col_idx"], times=40)
+    d2 = m.Decoder.wimax(c["K"], c["N"], c["rate"])
+    d2.set_option("staged_min_kb", 0)
+    d2.set_algorithm(1)
+    sp = oracle.decode_sp(o, yd)
+    out = d2.decode_host(yd, want_hard=True)
+    assert np.array_equal(out["iters"], sp[1]) and np.array_equal(out["info"], sp[0])
+    d2.set_algorithm(2)
+    assert_parity(d2.decode_host(yd, want_hard=True, want_post=True), oracle.decode_tdmp(o, yd, 24), c["N"], what="layered, staged")

@@ -125,3 +125,51 @@ def test_layered_restatement_basics():
     assert oracle.lib().oracle_tdmp_layering_ok(o._t, 48) == 0
     with pytest.raises(ValueError):
         oracle.decode_tdmp(o, y[:1], 48)
+
+
+def _gf2_codewords(rp, ci, M, N, K, count, seed):
+    """Random codewords of H = [A | B] (B = the last M columns): parity p solves B p = A u over GF(2)."""
+    H = np.zeros((M, N), dtype=np.uint8)
+    for r in range(M):
+        H[r, ci[rp[r]:rp[r + 1]]] = 1
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, 2, (count, K)).astype(np.uint8)
+    aug = np.concatenate([H[:, K:], (H[:, :K] @ u.T) % 2], axis=1).astype(np.uint8)   # [B | A u]
+    for col in range(M):                                                                # Gauss-Jordan mod 2
+        piv = col + int(np.nonzero(aug[col:, col])[0][0])
+        if piv != col:
+            aug[[col, piv]] = aug[[piv, col]]
+        rows = np.nonzero(aug[:, col])[0]
+        rows = rows[rows != col]
+        aug[rows] ^= aug[col]
+    cw = np.concatenate([u, aug[:, M:].T], axis=1).astype(np.uint8)
+    assert not ((H.astype(np.int64) @ cw.T.astype(np.int64)) % 2).any()
+    return cw
+
+
+@pytest.mark.parametrize("name,num,den", [("3/4B", 3, 4), ("1/2", 1, 2), ("5/6", 5, 6)])
+def test_channel_symmetry_of_min_sum_and_layered(name, num, den):
+    """A size-independent property of the algorithm (Coder::decodeCPU, MyLdpc.cpp:684-784, and the layered schedule): sending
+    codeword c over the same noise instead of the all-zero word flips exactly the signs of c's positions -- every message,
+    posterior and hard bit -- so hard bits are XORed with c, posteriors negated there (bit for bit: fp32 negation is exact),
+    and the iteration counts are equal.  (Exact zeros, where `P > 0 ? 0 : 1` is not symmetric, do not occur in random noise.)"""
+    N = 576
+    K = N * num // den
+    rp, ci, M = oracle.wimax_H(N, name)
+    cw = _gf2_codewords(rp, ci, M, N, K, 48, seed=5)
+    rng = np.random.default_rng(6)
+    sig = {"3/4B": 0.52, "1/2": 0.75, "5/6": 0.45}[name]
+    y0 = (1.0 + sig * rng.standard_normal((48, N))).astype(np.float32)
+    y0[40:] = (1.0 + 1.2 * rng.standard_normal((8, N))).astype(np.float32)      # words that run into the cap
+    s = (1.0 - 2.0 * cw).astype(np.float32)
+    y1 = y0 * s
+    o = oracle.Oracle(M, N, K, rp, ci, times=40)
+    for what, dec in (("min-sum", lambda y: o.decode(y)), ("layered", lambda y: oracle.decode_tdmp(o, y, N // 24))):
+        i0, t0, h0, p0 = dec(y0)
+        i1, t1, h1, p1 = dec(y1)
+        assert not (p0 == 0).any()
+        assert np.array_equal(t0, t1), what + ": iteration counts"
+        assert np.array_equal(h1, h0 ^ cw), what + ": hard bits"
+        assert np.array_equal(p1, p0 * s), what + ": posteriors"
+        assert np.array_equal(np.unpackbits(i1, axis=1, bitorder="little")[:, :K], h1[:, :K]), what + ": info bytes"
+        assert (t0[:40] < 40).sum() >= 30 and (t0[40:] == 40).all()   # both regimes are in the sample
